@@ -1,0 +1,102 @@
+"""Generate the committed golden vectors by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+Writes small .npz fixtures next to this file.  The reference modules are imported by
+file path (oracle/reference_loader.py); the OT solver runs through its own shipped
+libot.so (C inner loop, use_C=True), i.e. exactly what `SpaDOT train` executes
+(SpaDOT/utils/_train_utils.py:318) and the vendored twin of what wot runs in
+`SpaDOT analyze` (SpaDOT/utils/_analyze_utils.py:124-126).
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ot_dense, reference_loader  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CFG = dict(ot_dense.DEFAULT_OT_CONFIG)
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def ot_case(ref, name, n, m, d, seed, cfg, G=None, full_plan=True, n_samples=4000):
+    a, b, la, lb = ot_dense.synthetic_embeddings(n, m, d, seed=seed)
+    C = ref.sklearn.metrics.pairwise.pairwise_distances(a, b, metric="sqeuclidean", n_jobs=1)
+    med = float(np.median(C))
+    Cn = C / med
+    G0 = np.ones(n) if G is None else G
+    # (1) single duality-gap solve on the median-normalised cost (ot_solvers.py:164)
+    plan_gap = quiet(ref.optimal_transport_duality_gap, C=Cn.copy(), G=G0.copy(), **cfg)
+    # (2) growth loop as SpaDOT calls it (returns gammas[0], ot_solvers.py:121) and the growth trace
+    gamma0 = quiet(ref.compute_transport_map, a, b, dict(cfg), G=None if G is None else G.copy())
+    growth = [G0.copy()]
+    for _ in range(cfg["growth_iters"]):
+        growth.append(quiet(ref.optimal_transport_duality_gap, C=Cn.copy(), G=growth[-1].copy(), **cfg).sum(axis=1))
+    last_plan = quiet(ref.optimal_transport_duality_gap, C=Cn.copy(), G=growth[-2].copy(), **cfg)
+    # (3) fixed-schedule solver (ot_solvers.py:452)
+    plan_v2 = quiet(ref.transport_stablev2, C=Cn.copy(), G=G0.copy(), **cfg)
+    out = dict(a=a, b=b, labels_a=la, labels_b=lb, median=med, G=G0,
+               gap_row_sums=plan_gap.sum(1), gap_col_sums=plan_gap.sum(0),
+               v2_row_sums=plan_v2.sum(1), v2_col_sums=plan_v2.sum(0),
+               growth_row_sums=np.stack(growth[1:]),
+               table_gap=ot_dense.transition_table(plan_gap, la, lb, 10, 10),
+               table_last=ot_dense.transition_table(last_plan, la, lb, 10, 10),
+               cfg_keys=np.array(sorted(cfg)), cfg_vals=np.array([float(cfg[k]) for k in sorted(cfg)]))
+    assert np.allclose(gamma0, plan_gap, rtol=1e-12, atol=0)  # shipped libot.so is alignment-dependent at 1e-16
+    if full_plan:
+        out.update(plan_gap=plan_gap, plan_v2=plan_v2)
+    else:
+        rng = np.random.default_rng(seed + 1)
+        ii = rng.integers(0, n, n_samples)
+        jj = rng.integers(0, m, n_samples)
+        out.update(sample_i=ii, sample_j=jj, plan_gap_samples=plan_gap[ii, jj], plan_v2_samples=plan_v2[ii, jj])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "written;", "plan sum", plan_gap.sum(), "v2-vs-gap", np.abs(plan_v2 - plan_gap).max() / plan_gap.max())
+
+
+def svgp_case(svgp_mod, name="svgp_small", seed=7):
+    g = torch.Generator().manual_seed(seed)
+    dt = torch.float64
+    n, m, b = 57, 23, 40
+    x = torch.rand(n, 2, generator=g, dtype=dt) * 2 - 1
+    z = torch.rand(m, 2, generator=g, dtype=dt) * 2 - 1
+    out = dict(x=x.numpy(), z=z.numpy())
+    for kt in ("Gaussian", "Cauchy", "Quadratic"):
+        k = svgp_mod.Kernel(kernel_type=kt, scale=0.1, dtype=dt, device="cpu")
+        out["K_" + kt] = k(x, z).numpy()
+        out["Kxx_" + kt] = k(x, x).numpy()
+    cfg = dict(dtype=dt, device="cpu", kernel_type="Gaussian", kernel_scale=0.1)
+    model = svgp_mod.SVGP(cfg, z.numpy(), N_train=n, jitter=1e-2)
+    xb = x[:b]
+    y = torch.randn(b, generator=g, dtype=dt)
+    noise = torch.rand(b, generator=g, dtype=dt) + 0.5
+    mean, B, mu_hat, A_hat = model.approximate_posterior_params(xb, xb, y, noise)
+    l3, kl = model.variational_loss(xb, y, noise, mu_hat, A_hat)
+    out.update(y=y.numpy(), noise=noise.numpy(), post_mean=mean.numpy(), post_var=B.numpy(), mu_hat=mu_hat.numpy(),
+               A_hat=A_hat.numpy(), l3=np.array(float(l3)), kl=np.array(float(kl)), N_train=np.array(n), b=np.array(b))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "written; l3", float(l3), "kl", float(kl))
+
+
+if __name__ == "__main__":
+    assert reference_loader.available(), "reference not mounted"
+    ref = reference_loader.load_ot_solvers()
+    ot_case(ref, "ot_small_48x61_d6", 48, 61, 6, 11, CFG)
+    rng = np.random.default_rng(5)
+    ot_case(ref, "ot_growth_90x70_d20", 90, 70, 20, 12, CFG, G=np.exp(rng.normal(0, 1.0, 90)))
+    ot_case(ref, "ot_medium_300x411_d20", 300, 411, 20, 1993, CFG, full_plan=False)
+    wot_cfg = dict(CFG, lambda1=1.0, lambda2=50.0, epsilon=0.02)
+    ot_case(ref, "ot_wotcfg_130x97_d32", 130, 97, 32, 13, wot_cfg, full_plan=False)
+    svgp_case(reference_loader.load_svgp())
