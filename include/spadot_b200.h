@@ -1,0 +1,162 @@
+/*
+ * spadot_b200.h — C ABI of libspadot_b200.so (sm_100a).
+ *
+ * Drop-in boundary for SpaDOT's optimal-transport hot path.  Every
+ * entry point is `extern "C"`, takes plain pointers / sizes / scalars, returns an int
+ * status (0 = ok, >0 = cudaError_t, <0 = SDB_E_*; sdb_error_string() decodes) and is
+ * asynchronous on the `stream` argument (a cudaStream_t passed as void*).  The caller
+ * owns every buffer including workspaces; nothing is allocated behind its back and
+ * there is no global state.  Pointers are DEVICE pointers unless the name ends in
+ * `_host`.  There is no CPU fallback anywhere in this library.
+ *
+ * Citations `ref:` are relative to /root/reference/SpaDOT/.
+ *
+ * Conventions of the streamed ("flash") Sinkhorn:
+ *   - points are centred and stored feature-major fp32:  xt[k*ld + i]  (k < dpad, i < n),
+ *     ld a multiple of 64 and >= round_up(n,64)+64, padding zero-filled;
+ *   - cost  C_ij = (|x_i|^2 + |y_j|^2 - 2 x_i.y_j) * inv_med      (ref: utils/OT_loss/ot_solvers.py:102-103)
+ *   - a pass over rows i and columns j computes, in base 2,
+ *         L2_i = log2 sum_j 2^( bias_j + scale * x_i.y_j ),   scale = 2*c1*log2(e),  c1 = inv_med/eps
+ *         bias_j = log2(e) * ( g_j/eps - |y_j|^2 * c1 )
+ *     which is the reference's  K(b*dy)  matvec (ref: utils/OT_loss/ot_func.cpp:43-170, 610-636)
+ *     without ever forming K; the column pass is the same kernel with the roles swapped
+ *     (ref: ot_func.cpp:173-249, 642-668).
+ *   - potentials f,g, norms, marginals and every N- or M-length reduction are fp64.
+ */
+#ifndef SPADOT_B200_H
+#define SPADOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_VERSION 100
+
+#define SDB_E_INVALID   (-1)  /* bad argument (null pointer, size, alignment) */
+#define SDB_E_UNSUPPORTED (-2)/* shape outside what the kernel was built for */
+#define SDB_E_NOTFINITE (-3)  /* NaN / overflow detected (ref: ot_solvers.py:446-447) */
+#define SDB_E_DRIVER    (-4)  /* CUDA driver entry point unavailable */
+
+#define SDB_NEG_SENTINEL (-1.0e30f) /* finite stand-in for -inf in fp32 bias vectors */
+
+int sdb_version(void);
+const char* sdb_error_string(int status);
+/* 0 when a CUDA device of compute capability 10.x is usable, else a status. */
+int sdb_device_check(void);
+
+/* ------------------------------------------------------------------ point preparation */
+/* out[k] += sum_i x[i*d+k]   (x row-major n x d, fp64).  out must be zeroed by the caller. */
+int sdb_column_sums_f64(const double* x, int64_t n, int d, double* out, void* stream);
+/* xt[k*ld+i] = (float)(x[i*d+k] - center[k]);  norms[i] = sum_k (double)xt[k*ld+i]^2
+ * (norms of the ROUNDED coordinates, so the streamed cost is the exact squared distance of
+ * the points the kernels actually see).  Rows k in [d,dpad) and columns i in [n,ld) are zeroed. */
+int sdb_prep_points_f64(const double* x, int64_t n, int d, const double* center,
+                        float* xt, int64_t ld, int dpad, double* norms, void* stream);
+
+/* ------------------------------------------------------------------ K3: streamed LSE pass (SIMT fp32) */
+/* partial[(s*n_p + i)*2 + {0,1}] = (max, sum) of 2^(bias_j + scale*x_i.y_j - max) over the
+ * columns j in [split_bounds[s], split_bounds[s+1]) (device array of n_splits+1 entries; keep
+ * each split <= 65536 columns so the fp32 running sums stay below 1e-6 relative error).
+ * dpad <= 128, dpad % 4 == 0.  Grid = ceil(n_p/64) x n_splits CTAs of 256 threads.
+ * replaces: gemv/gemtv + update_k of ref: utils/OT_loss/ot_func.cpp:43-249,547-568. */
+int sdb_lse_pass_simt(const float* pt, int64_t ldp, int64_t n_p,
+                      const float* qt, int64_t ldq, int64_t n_q, int dpad,
+                      const float* bias, float scale,
+                      const int64_t* split_bounds, int n_splits,
+                      float* partial, void* stream);
+
+/* L[i] = ln2 * log2( sum_s sum_s,i * 2^(max_s,i - M_i) ) + ln2*M_i - norms[i]*c1   (fp64)
+ *      = LSE_j[(g_j - C_ij)/eps]; -inf when every partial is empty. */
+int sdb_lse_finalize(const float* partial, int n_splits, int64_t n, const double* norms,
+                     double c1, double* L, void* stream);
+
+/* Potential update of one side (ref: ot_func.cpp:610-668 in total potentials):
+ *   la_old[i] = (pot[i] - frame[i]) / eps                       (log of the reference's old_a)
+ *   pot[i]    = eps*alpha*( logmarg[i] - LA_i ),  LA_i = L[i] - log_n_other, or with the fixed-schedule
+ *               solver's 1e-10 floor (ref: ot_solvers.py:498-502): logaddexp(LA_i, log_floor - frame[i]/eps)
+ *               (pass log_floor = -inf to disable)
+ *   bias[i]   = log2(e)*( pot[i]/eps - norms[i]*c1 )            (fp32, clamped to SDB_NEG_SENTINEL)
+ *   if (pot[i]-frame[i])/eps > log_tau: atomicMax(absorb_flag, iter)   (ref: ot_func.cpp:778-790)
+ * la_old / bias / absorb_flag may be NULL. */
+int sdb_potential_update(int64_t n, const double* L, const double* logmarg, const double* norms,
+                         double eps, double alpha, double log_n_other, double c1,
+                         double* pot, const double* frame, double* la_old, float* bias,
+                         int* absorb_flag, int iter, double log_tau, double log_floor, void* stream);
+/* bias[i] = log2(e)*( pot[i]/eps - norms[i]*c1 ) only (stage changes, first iteration). */
+int sdb_make_bias(int64_t n, const double* pot, const double* norms, double eps, double c1,
+                  float* bias, void* stream);
+/* if (*absorb_flag == iter) { u = f; v = g; }      (ref: ot_func.cpp:792-819) */
+int sdb_absorb(int64_t n, int64_t m, const int* absorb_flag, int iter,
+               const double* f, const double* g, double* u, double* v, void* stream);
+
+/* ------------------------------------------------------------------ K4: stopping rules */
+/* Stage 0-4 rule (ref: ot_func.cpp:897-922).  out[0..3] =
+ *   sum (a~ - old_a e^{u/eps})^2, sum a~^2, sum (b~ - old_b e^{v/eps})^2, sum b~^2
+ * with a~ = exp((f-u)/eps)*exp(u/eps).  scratch: >= 4*SDB_REDUCE_BLOCKS doubles + 1 uint. */
+#define SDB_REDUCE_BLOCKS 1024
+int sdb_stage_criterion(int64_t n, int64_t m, const double* f, const double* u, const double* la_old,
+                        const double* g, const double* v, const double* lb_old, double eps,
+                        double* out4, void* scratch, void* stream);
+/* Final-stage duality-gap ingredients (ref: ot_func.cpp:358-544, ot_solvers.py:132-158).  out[0..9]:
+ *  [0] sum_i Rrow_i  [1] sum_i f_i Rrow_i  [2] sum_i dx (r log(r/p) - r + p), r = Rrow_i/m
+ *  [3] sum_i p_i dx (exp(-f_i/lam1) - 1)
+ *  [4] sum_j Rcol_j  [5] sum_j g_j Rcol_j  [6] sum_j dy (c log(c/q) - c + q), c = Rcol_j/n
+ *  [7] sum_j q_j dy (exp(-g_j/lam2) - 1)   [8],[9] spare
+ * with Rrow_i = exp(f_i/eps + Lr_i), Rcol_j = exp(g_j/eps + Lc_j); dx = 1/N_total, dy = 1/M are explicit
+ * because n may be one rank's row slice.  scratch as above (10 wide). */
+int sdb_gap_terms(int64_t n, int64_t m, const double* f, const double* Lr, const double* logp,
+                  const double* g, const double* Lc, const double* logq,
+                  double eps, double lam1, double lam2, double dx, double dy,
+                  double* out10, void* scratch, void* stream);
+/* out[0] = sum_i exp(L[i] + add[i]/eps_or_1)  generic fp64 sum of exp (used for sum_K and masses);
+ * add may be NULL. */
+int sdb_sum_exp(int64_t n, const double* L, const double* add, double add_scale, double* out1,
+                void* scratch, void* stream);
+
+/* ------------------------------------------------------------------ plan / marginals */
+/* plan[i*m+j] = exp((f_i + g_j - C_ij)/eps) * inv_m with C_ij = sum_k (x_ik-y_jk)^2 * inv_med computed
+ * by direct fp64 differences (ref: ot_solvers.py:102-103,449; ot_func.cpp:571-584). x,y row-major fp64. */
+int sdb_plan_dense_f64(const double* x, const double* y, int64_t n, int64_t m, int d,
+                       const double* f, const double* g, double inv_med, double eps, double inv_m,
+                       double* plan, void* stream);
+/* out[i] = exp(f_i/eps + Lr_i) * inv_m   — plan row sums = next growth vector (ref: ot_solvers.py:116). */
+int sdb_row_mass(int64_t n, const double* f, const double* Lr, double eps, double inv_m, double* out,
+                 void* stream);
+
+/* ------------------------------------------------------------------ K5: exact median of all N*M costs */
+/* dist[s] = sum_k (x[ii[s]*d+k] - y[jj[s]*d+k])^2   fp64, for sampled index pairs. */
+int sdb_pair_distances_f64(const double* x, const double* y, int d, const int64_t* ii, const int64_t* jj,
+                           int64_t n_pairs, double* dist, void* stream);
+/* One streamed sweep over all pairs (fp32 direct differences on the prepared points):
+ *   counts[0] += #pairs with D32 <  lo;  pairs with lo <= D32 < hi are binned uniformly into
+ *   hist[0..n_bins) (counts[1] = their total).  n_bins <= 4096. */
+int sdb_cost_histogram(const float* pt, int64_t ldp, int64_t n_p, const float* qt, int64_t ldq, int64_t n_q,
+                       int dpad, const int64_t* split_bounds, int n_splits, float lo, float hi, int n_bins,
+                       unsigned long long* hist, unsigned long long* counts2, void* stream);
+/* Final sweep: counts[0] += #pairs with D32 < lo; every pair with lo <= D32 < hi has its cost
+ * recomputed by direct fp64 differences from x,y (row-major fp64, ORIGINAL coordinates) and is
+ * appended to cand (capacity cap; counts[1] = number appended, may exceed cap => overflow). */
+int sdb_cost_collect(const float* pt, int64_t ldp, int64_t n_p, const float* qt, int64_t ldq, int64_t n_q,
+                     int dpad, const int64_t* split_bounds, int n_splits, float lo, float hi,
+                     const double* x, const double* y, int d,
+                     double* cand, unsigned long long cap, unsigned long long* counts2, void* stream);
+/* hist256[b] = #{ i : (key(cand[i]) >> shift) & 255 == b and key(cand[i]) >> (shift+8) == prefix }
+ * (key = IEEE bits of a non-negative double); one radix-select digit. hist256 must be zeroed. */
+int sdb_radix_digit_hist(const double* cand, unsigned long long n, int shift, unsigned long long prefix,
+                         unsigned long long* hist256, void* stream);
+
+/* ------------------------------------------------------------------ K6: domain transition table */
+/* table[a*k1+b] += sum_{i: label_row[i]=a} exp(f_i/eps + ln2*(M + log2 S) - norms_i*c1) * inv_m
+ * where (M,S) = partial of column segment b (columns sorted by label; one split per label).
+ * replaces wot transition_table  P0^T . T . P1  (ref: utils/_analyze_utils.py:135-137). */
+int sdb_transition_accumulate(const float* partial, int k1, int64_t n, const double* norms, double c1,
+                              const double* f, double eps, double inv_m, const int* label_row, int k0,
+                              double* table, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPADOT_B200_H */

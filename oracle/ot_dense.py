@@ -101,7 +101,7 @@ def duality_gap_solve(C, G, lambda1, lambda2, epsilon, batch_size=5, tolerance=1
         K = np.exp((u[:, None] - C + v[None, :]) / eps_i)        # :272 / ot_func.cpp:563
         gap = np.inf
         stage_iters = 0   # the reference passes cur_iter by value: max_iter is per stage
-        n_inner = batch_size if e == EPSILON_SCALINGS else 5     # ot_func.cpp:867
+        n_inner = int(batch_size) if e == EPSILON_SCALINGS else 5  # ot_func.cpp:867
         while gap > threshold:                                   # ot_func.cpp:866
             hit_max = False
             for _ in range(n_inner):                             # step1_process :726
@@ -166,7 +166,7 @@ def transport_stablev2(C, lambda1, lambda2, epsilon, scaling_iter, G, tau, epsil
     eps_index, since = 0, 0
     floor = 1e-10                                                # :498
     n_absorb = 0
-    for _ in range(scaling_iter):
+    for _ in range(int(scaling_iter)):
         a = (p / (K @ (b * dy) + floor)) ** alpha1 * np.exp(-u / (lambda1 + eps_i))
         b = (q / (K.T @ (a * dx) + floor)) ** alpha2 * np.exp(-v / (lambda2 + eps_i))
         since += 1
@@ -186,7 +186,7 @@ def transport_stablev2(C, lambda1, lambda2, epsilon, scaling_iter, G, tau, epsil
             alpha2 = lambda2 / (lambda2 + eps_i)
             K = np.exp((u[:, None] - C + v[None, :]) / eps_i)
             a, b = np.ones(I), np.ones(J)
-    for _ in range(extra_iter):                                  # :525-527
+    for _ in range(int(extra_iter)):                             # :525-527
         a = (p / (K @ (b * dy) + floor)) ** alpha1 * np.exp(-u / (lambda1 + eps_i))
         b = (q / (K.T @ (a * dx) + floor)) ** alpha2 * np.exp(-v / (lambda2 + eps_i))
     R = (K.T * a).T * b

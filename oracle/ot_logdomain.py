@@ -118,7 +118,7 @@ def duality_gap_solve(cost: CostOperator, G, lambda1, lambda2, epsilon, batch_si
         la_old, lb_old = np.zeros(I), np.zeros(J)
         final = e == ot_dense.EPSILON_SCALINGS
         threshold = tolerance if final else 1e-6
-        n_inner = batch_size if final else 5
+        n_inner = int(batch_size) if final else 5
         sumK = None
         gap, n_it = np.inf, 0
         Lr = None   # row LSE at the current g, when already known (re-used by the next update)

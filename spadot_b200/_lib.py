@@ -1,0 +1,89 @@
+"""ctypes binding of libspadot_b200.so (include/spadot_b200.h).
+
+The library is the product: there is NO CPU fallback.  Importing this module without the
+built shared object raises ImportError; calling into it without a B200-class device
+raises RuntimeError (see `require_device`).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspadot_b200.so")
+
+c_p = ctypes.c_void_p
+c_i = ctypes.c_int
+c_l = ctypes.c_int64
+c_u = ctypes.c_uint64
+c_d = ctypes.c_double
+c_f = ctypes.c_float
+
+# name -> argtypes; every function returns int status unless noted.  Kept in the same order as
+# include/spadot_b200.h; tests/test_abi.py checks that header and table agree symbol by symbol.
+SIGNATURES = {
+    "sdb_device_check": [],
+    "sdb_column_sums_f64": [c_p, c_l, c_i, c_p, c_p],
+    "sdb_prep_points_f64": [c_p, c_l, c_i, c_p, c_p, c_l, c_i, c_p, c_p],
+    "sdb_lse_pass_simt": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_p, c_i, c_p, c_p],
+    "sdb_lse_finalize": [c_p, c_i, c_l, c_p, c_d, c_p, c_p],
+    "sdb_potential_update": [c_l, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
+    "sdb_make_bias": [c_l, c_p, c_p, c_d, c_d, c_p, c_p],
+    "sdb_absorb": [c_l, c_l, c_p, c_i, c_p, c_p, c_p, c_p, c_p],
+    "sdb_stage_criterion": [c_l, c_l, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_p, c_p, c_p],
+    "sdb_gap_terms": [c_l, c_l, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_d, c_p, c_p, c_p],
+    "sdb_sum_exp": [c_l, c_p, c_p, c_d, c_p, c_p, c_p],
+    "sdb_plan_dense_f64": [c_p, c_p, c_l, c_l, c_i, c_p, c_p, c_d, c_d, c_d, c_p, c_p],
+    "sdb_row_mass": [c_l, c_p, c_p, c_d, c_d, c_p, c_p],
+    "sdb_pair_distances_f64": [c_p, c_p, c_i, c_p, c_p, c_l, c_p, c_p],
+    "sdb_cost_histogram": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_i, c_f, c_f, c_i, c_p, c_p, c_p],
+    "sdb_cost_collect": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_i, c_f, c_f, c_p, c_p, c_i, c_p, c_u, c_p, c_p],
+    "sdb_radix_digit_hist": [c_p, c_u, c_i, c_u, c_p, c_p],
+    "sdb_transition_accumulate": [c_p, c_i, c_l, c_p, c_d, c_p, c_d, c_d, c_p, c_i, c_p, c_p],
+}
+
+_lib = None
+
+
+class SpadotB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared object (no GPU needed to load it or to resolve its symbols)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(spadot_b200 has no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.sdb_version.restype = c_i
+    lib.sdb_version.argtypes = []
+    lib.sdb_error_string.restype = ctypes.c_char_p
+    lib.sdb_error_string.argtypes = [c_i]
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_i
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = load().sdb_error_string(status).decode()
+        raise SpadotB200Error(f"{what or 'libspadot_b200'} failed: {msg} (status {status})")
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args), name)
+
+
+def require_device():
+    """Fail loudly when the CUDA path cannot run (no silent fallback)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("spadot_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    check(load().sdb_device_check(), "sdb_device_check")

@@ -1,0 +1,268 @@
+// K3 (SIMT fp32 form) and K5 sweeps: one tile engine that streams 64x64 tiles of point pairs.
+//
+// The cost / kernel matrix is never materialised: a CTA keeps a 64-row slab of the "row" point
+// set in shared memory (feature-major, so the inner product loop reads conflict-free float4s),
+// streams 64-column slabs of the other set through a cp.async double buffer, forms the 4x4
+// register micro-tile of x_i.y_j (or |x_i-y_j|^2) per thread and hands it to an epilogue functor:
+//   LseEpi      online (max, sum 2^(t-max)) per row           -> Sinkhorn half-iteration
+//   HistEpi     count-below + uniform histogram of the costs   -> median bracketing
+//   CollectEpi  count-below + fp64 re-evaluation of bracket    -> exact median candidates
+// Replaces gemv/gemtv/update_k of ref: SpaDOT/utils/OT_loss/ot_func.cpp:43-249,547-568 and the
+// cost + np.median of ref: SpaDOT/utils/OT_loss/ot_solvers.py:102-103.
+#include "sdb_common.cuh"
+
+namespace {
+
+constexpr int BM = 64;   // rows per CTA
+constexpr int BN = 64;   // columns per streamed tile
+constexpr int NT = 256;  // 16 x 16 threads, 4x4 micro-tile each
+constexpr int MAX_DPAD = 128;
+
+struct PairArgs {
+    const float* pt; int64_t ldp; int64_t n_p;
+    const float* qt; int64_t ldq; int64_t n_q;
+    int dpad;
+    const float* bias;            // may be null (treated as 0 / valid)
+    const int64_t* split_bounds;  // device, n_splits+1 entries
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// --------------------------------------------------------------------------------------------
+template <bool DIRECT, class Epi>
+__global__ void __launch_bounds__(NT) pair_tile_kernel(PairArgs a, typename Epi::Params ep) {
+    extern __shared__ __align__(16) float smem[];
+    const int dpad = a.dpad;
+    float* Ps = smem;                       // [dpad][BM]
+    float* Qs = Ps + dpad * BM;             // [2][dpad][BN]
+    float* Bs = Qs + 2 * dpad * BN;         // [2][BN]
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t row0 = (int64_t)blockIdx.x * BM;
+    const int split = blockIdx.y;
+    const int64_t c0 = a.split_bounds[split], c1 = a.split_bounds[split + 1];
+    const int64_t j_begin = c0 & ~int64_t(3);
+    const int n_tiles = (c1 > c0) ? (int)((c1 - j_begin + BN - 1) / BN) : 0;
+
+    Epi epi(ep, row0 + ty * 4, split, a.n_p);
+
+    // rows slab, once
+    for (int idx = tid; idx < dpad * (BM / 4); idx += NT) {
+        int k = idx / (BM / 4), c4 = idx % (BM / 4);
+        cp_async16(Ps + k * BM + c4 * 4, a.pt + (int64_t)k * a.ldp + row0 + c4 * 4);
+    }
+    auto load_q = [&](int t, int buf) {
+        const int64_t j0 = j_begin + (int64_t)t * BN;
+        float* q = Qs + buf * dpad * BN;
+        for (int idx = tid; idx < dpad * (BN / 4); idx += NT) {
+            int k = idx / (BN / 4), c4 = idx % (BN / 4);
+            cp_async16(q + k * BN + c4 * 4, a.qt + (int64_t)k * a.ldq + j0 + c4 * 4);
+        }
+        if (tid < BN) {
+            int64_t j = j0 + tid;
+            float b = SDB_NEG_SENTINEL;
+            if (j >= c0 && j < c1) b = a.bias ? a.bias[j] : 0.f;
+            Bs[buf * BN + tid] = b;
+        }
+    };
+    if (n_tiles > 0) load_q(0, 0);
+    cp_async_commit();
+
+    for (int t = 0; t < n_tiles; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < n_tiles) load_q(t + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+
+        const float* q = Qs + buf * dpad * BN;
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+
+#pragma unroll 4
+        for (int k = 0; k < dpad; ++k) {
+            const float4 pa = *reinterpret_cast<const float4*>(Ps + k * BM + ty * 4);
+            const float4 qb = *reinterpret_cast<const float4*>(q + k * BN + tx * 4);
+            const float pr[4] = {pa.x, pa.y, pa.z, pa.w};
+            const float qc[4] = {qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (DIRECT) {
+                        const float df = pr[r] - qc[c];
+                        acc[r][c] = fmaf(df, df, acc[r][c]);
+                    } else {
+                        acc[r][c] = fmaf(pr[r], qc[c], acc[r][c]);
+                    }
+                }
+        }
+        const float4 bv = *reinterpret_cast<const float4*>(Bs + buf * BN + tx * 4);
+        const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+        epi.tile(acc, bb, j_begin + (int64_t)t * BN + tx * 4);
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    epi.finish(tx);
+}
+
+// -------------------------------------------------------------------------------------------- LSE
+struct LseEpi {
+    struct Params { float scale; float2* partial; };
+    Params p; int64_t row; int split; int64_t n_p;
+    float m[4], s[4];
+    __device__ LseEpi(const Params& p_, int64_t row_, int split_, int64_t n_p_) : p(p_), row(row_), split(split_), n_p(n_p_) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { m[r] = SDB_NEG_SENTINEL; s[r] = 0.f; }
+    }
+    __device__ __forceinline__ void tile(const float (&acc)[4][4], const float (&b)[4], int64_t) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float t0 = fmaf(p.scale, acc[r][0], b[0]);
+            const float t1 = fmaf(p.scale, acc[r][1], b[1]);
+            const float t2 = fmaf(p.scale, acc[r][2], b[2]);
+            const float t3 = fmaf(p.scale, acc[r][3], b[3]);
+            const float mn = fmaxf(m[r], fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)));
+            s[r] = s[r] * sdb_ex2(m[r] - mn) + ((sdb_ex2(t0 - mn) + sdb_ex2(t1 - mn)) + (sdb_ex2(t2 - mn) + sdb_ex2(t3 - mn)));
+            m[r] = mn;
+        }
+    }
+    __device__ __forceinline__ void finish(int tx) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                const float m2 = __shfl_xor_sync(0xffffffffu, m[r], o);
+                const float s2 = __shfl_xor_sync(0xffffffffu, s[r], o);
+                const float mn = fmaxf(m[r], m2);
+                s[r] = s[r] * sdb_ex2(m[r] - mn) + s2 * sdb_ex2(m2 - mn);
+                m[r] = mn;
+            }
+            if (tx == 0 && row + r < n_p) p.partial[(int64_t)split * n_p + row + r] = make_float2(m[r], s[r]);
+        }
+    }
+};
+
+// -------------------------------------------------------------------------------------------- median sweeps
+struct HistEpi {
+    struct Params { float lo, hi, inv_width; int n_bins; unsigned long long* hist; unsigned long long* counts; };
+    Params p; int64_t row; int64_t n_p;
+    unsigned long long below, inside;
+    __device__ HistEpi(const Params& p_, int64_t row_, int, int64_t n_p_) : p(p_), row(row_), n_p(n_p_), below(0), inside(0) {}
+    __device__ __forceinline__ void tile(const float (&acc)[4][4], const float (&b)[4], int64_t) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (row + r >= n_p) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (b[c] < -1e29f) continue;
+                const float dist = acc[r][c];
+                if (dist < p.lo) { ++below; }
+                else if (dist < p.hi) {
+                    int bin = (int)((dist - p.lo) * p.inv_width);
+                    bin = min(max(bin, 0), p.n_bins - 1);
+                    atomicAdd(p.hist + bin, 1ull);
+                    ++inside;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void finish(int) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            below += __shfl_xor_sync(0xffffffffu, below, o);
+            inside += __shfl_xor_sync(0xffffffffu, inside, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (below) atomicAdd(p.counts, below);
+            if (inside) atomicAdd(p.counts + 1, inside);
+        }
+    }
+};
+
+struct CollectEpi {
+    struct Params { float lo, hi; const double* x; const double* y; int d; double* cand; unsigned long long cap; unsigned long long* counts; };
+    Params p; int64_t row; int64_t n_p;
+    unsigned long long below;
+    __device__ CollectEpi(const Params& p_, int64_t row_, int, int64_t n_p_) : p(p_), row(row_), n_p(n_p_), below(0) {}
+    __device__ __forceinline__ void tile(const float (&acc)[4][4], const float (&b)[4], int64_t col) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (row + r >= n_p) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (b[c] < -1e29f) continue;
+                const float dist = acc[r][c];
+                if (dist < p.lo) { ++below; }
+                else if (dist < p.hi) {
+                    const double* xi = p.x + (row + r) * p.d;
+                    const double* yj = p.y + (col + c) * p.d;
+                    double s = 0.0;
+                    for (int k = 0; k < p.d; ++k) { const double df = xi[k] - yj[k]; s = __dadd_rn(s, __dmul_rn(df, df)); }
+                    const unsigned long long slot = atomicAdd(p.counts + 1, 1ull);
+                    if (slot < p.cap) p.cand[slot] = s;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void finish(int) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+        if ((threadIdx.x & 31) == 0 && below) atomicAdd(p.counts, below);
+    }
+};
+
+template <bool DIRECT, class Epi>
+int launch_pairs(const PairArgs& a, const typename Epi::Params& ep, int n_splits, cudaStream_t st) {
+    if (!a.pt || !a.qt || !a.split_bounds) return SDB_E_INVALID;
+    if (a.dpad <= 0 || a.dpad > MAX_DPAD || (a.dpad & 3)) return SDB_E_UNSUPPORTED;
+    if ((a.ldp & 3) || (a.ldq & 3) || n_splits <= 0 || n_splits > 65535) return SDB_E_INVALID;
+    if (a.ldp < ((a.n_p + BM - 1) / BM) * BM || a.ldq < ((a.n_q + BN - 1) / BN) * BN + BN) return SDB_E_INVALID;
+    if (a.n_p <= 0) return 0;
+    const size_t smem = sizeof(float) * ((size_t)a.dpad * BM + 2 * (size_t)a.dpad * BN + 2 * BN);
+    auto kern = pair_tile_kernel<DIRECT, Epi>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((unsigned)((a.n_p + BM - 1) / BM), (unsigned)n_splits);
+    kern<<<grid, NT, smem, st>>>(a, ep);
+    SDB_LAUNCH_STATUS();
+}
+
+}  // namespace
+
+extern "C" int sdb_lse_pass_simt(const float* pt, int64_t ldp, int64_t n_p, const float* qt, int64_t ldq, int64_t n_q,
+                                 int dpad, const float* bias, float scale, const int64_t* split_bounds, int n_splits,
+                                 float* partial, void* stream) {
+    SDB_CHECK_ARG(bias && partial);
+    PairArgs a{pt, ldp, n_p, qt, ldq, n_q, dpad, bias, split_bounds};
+    LseEpi::Params ep{scale, reinterpret_cast<float2*>(partial)};
+    return launch_pairs<false, LseEpi>(a, ep, n_splits, sdb_stream(stream));
+}
+
+extern "C" int sdb_cost_histogram(const float* pt, int64_t ldp, int64_t n_p, const float* qt, int64_t ldq, int64_t n_q,
+                                  int dpad, const int64_t* split_bounds, int n_splits, float lo, float hi, int n_bins,
+                                  unsigned long long* hist, unsigned long long* counts2, void* stream) {
+    SDB_CHECK_ARG(hist && counts2 && n_bins > 0 && hi > lo);
+    PairArgs a{pt, ldp, n_p, qt, ldq, n_q, dpad, nullptr, split_bounds};
+    HistEpi::Params ep{lo, hi, (float)n_bins / (hi - lo), n_bins, hist, counts2};
+    return launch_pairs<true, HistEpi>(a, ep, n_splits, sdb_stream(stream));
+}
+
+extern "C" int sdb_cost_collect(const float* pt, int64_t ldp, int64_t n_p, const float* qt, int64_t ldq, int64_t n_q,
+                                int dpad, const int64_t* split_bounds, int n_splits, float lo, float hi,
+                                const double* x, const double* y, int d, double* cand, unsigned long long cap,
+                                unsigned long long* counts2, void* stream) {
+    SDB_CHECK_ARG(x && y && cand && counts2 && d > 0);
+    PairArgs a{pt, ldp, n_p, qt, ldq, n_q, dpad, nullptr, split_bounds};
+    CollectEpi::Params ep{lo, hi, x, y, d, cand, cap, counts2};
+    return launch_pairs<true, CollectEpi>(a, ep, n_splits, sdb_stream(stream));
+}

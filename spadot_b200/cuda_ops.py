@@ -1,0 +1,248 @@
+"""Device-side operations of the streamed Sinkhorn, one thin method per C-ABI entry point.
+
+`CudaOps` owns the device buffers of one coupling problem (the local row slice of the
+source spots `x`, all target spots `y`) and launches libspadot_b200.so kernels on torch's
+current CUDA stream.  torch is used for allocation, streams and collectives only.
+
+There is no CPU implementation of this interface in the product: the drivers in
+`sinkhorn.py` are written against it so that the multi-rank logic can be exercised on
+CPU by the test-suite, which injects an oracle-backed stand-in (tests/_numpy_ops.py).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+NEG_INF = float("-inf")
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+class PointSet:
+    """One spot set on the device: original fp64 coordinates (row-major), centred fp32 copy
+    stored feature-major for the tile kernels, and fp64 squared norms of that copy."""
+
+    def __init__(self, x64: torch.Tensor, center: torch.Tensor):
+        assert x64.dtype == torch.float64 and x64.is_cuda and x64.is_contiguous()
+        self.x64 = x64
+        self.n, self.d = x64.shape
+        self.dpad = _round_up(self.d, 4)
+        self.ld = _round_up(self.n, 64) + 64
+        self.xt = torch.empty((self.dpad, self.ld), dtype=torch.float32, device=x64.device)
+        self.norms = torch.empty(self.n, dtype=torch.float64, device=x64.device)
+        st = torch.cuda.current_stream(x64.device).cuda_stream
+        _lib.call("sdb_prep_points_f64", _ptr(x64), self.n, self.d, _ptr(center), _ptr(self.xt), self.ld, self.dpad,
+                  _ptr(self.norms), st)
+
+
+class CudaOps:
+    SIMT_MAX_D = 128
+    MAX_SPLIT_COLS = 65536   # keeps fp32 running sums < 1e-6 relative (include/spadot_b200.h)
+    TARGET_CTAS = 148 * 6
+
+    def __init__(self, x_local, y, device=None):
+        _lib.require_device()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.launches = 0
+        x64 = self._to_dev(x_local)
+        y64 = self._to_dev(y)
+        if x64.shape[1] != y64.shape[1]:
+            raise ValueError("x and y must have the same feature dimension")
+        if x64.shape[1] > self.SIMT_MAX_D:
+            raise ValueError(f"latent dimension {x64.shape[1]} > {self.SIMT_MAX_D} is not supported by the SIMT pass")
+        self.n, self.d = x64.shape
+        self.m = y64.shape[0]
+        # centre on the mean of y (replicated on every rank, so no collective is needed)
+        center = torch.zeros(self.d, dtype=torch.float64, device=self.device)
+        self._call("sdb_column_sums_f64", _ptr(y64), self.m, self.d, _ptr(center))
+        center /= max(self.m, 1)
+        self.center = center
+        self.X = PointSet(x64, center)
+        self.Y = PointSet(y64, center)
+        self.launches += 2
+        self.bias_x = torch.empty(self.n, dtype=torch.float32, device=self.device)
+        self.bias_y = torch.empty(self.m, dtype=torch.float32, device=self.device)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.scratch = torch.zeros(10 * 1024 + 2, dtype=torch.float64, device=self.device)
+        self.out10 = torch.zeros(10, dtype=torch.float64, device=self.device)
+        self._splits = {}
+        self._partials = {}
+        self.inv_med = 1.0
+        self._tick = 0
+
+    # ------------------------------------------------------------------ plumbing
+    def _to_dev(self, a):
+        if isinstance(a, torch.Tensor):
+            t = a.detach()
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(device=self.device, dtype=torch.float64).contiguous()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _call(self, name, *args):
+        _lib.call(name, *args, self._stream())
+        self.launches += 1
+
+    def tick(self):
+        """Monotonic sweep counter; the absorb flag stores the last sweep that exceeded tau."""
+        self._tick += 1
+        return self._tick
+
+    def zeros(self, n, dtype=torch.float64):
+        return torch.zeros(n, dtype=dtype, device=self.device)
+
+    def tensor(self, a, dtype=torch.float64):
+        return torch.as_tensor(np.asarray(a), dtype=dtype).to(self.device)
+
+    def set_median(self, median: float):
+        self.inv_med = 1.0 / float(median)
+
+    def _split_plan(self, n_p, n_q):
+        key = (n_p, n_q)
+        if key not in self._splits:
+            row_tiles = max(1, (n_p + 63) // 64)
+            want = max(1, -(-self.TARGET_CTAS // row_tiles))
+            lo = max(1, -(-n_q // self.MAX_SPLIT_COLS))
+            hi = max(1, n_q // 256)
+            ns = int(min(max(want, lo), max(hi, lo), 65535))
+            bounds = torch.tensor([(n_q * s) // ns for s in range(ns + 1)], dtype=torch.int64, device=self.device)
+            self._splits[key] = (bounds, ns)
+        return self._splits[key]
+
+    def _partial(self, ns, n_p):
+        key = (ns, n_p)
+        if key not in self._partials:
+            self._partials[key] = torch.empty((ns, n_p, 2), dtype=torch.float32, device=self.device)
+        return self._partials[key]
+
+    # ------------------------------------------------------------------ K3 passes
+    def _lse(self, P: PointSet, Q: PointSet, bias, eps, out=None, bounds=None, ns=None, finalize=True):
+        c1 = self.inv_med / eps
+        scale = 2.0 * c1 * math.log2(math.e)
+        if bounds is None:
+            bounds, ns = self._split_plan(P.n, Q.n)
+        partial = self._partial(ns, P.n)
+        self._call("sdb_lse_pass_simt", _ptr(P.xt), P.ld, P.n, _ptr(Q.xt), Q.ld, Q.n, P.dpad, _ptr(bias), scale,
+                   _ptr(bounds), ns, _ptr(partial))
+        if not finalize:
+            return partial
+        if out is None:
+            out = torch.empty(P.n, dtype=torch.float64, device=self.device)
+        self._call("sdb_lse_finalize", _ptr(partial), ns, P.n, _ptr(P.norms), c1, _ptr(out))
+        return out
+
+    def row_lse(self, g, eps, out=None):
+        """Lr_i = LSE_j[(g_j - C_ij)/eps] over all columns (natural log, fp64).  g=None means g=0."""
+        self._call("sdb_make_bias", self.m, _ptr(g), _ptr(self.Y.norms), eps, self.inv_med / eps, _ptr(self.bias_y))
+        return self._lse(self.X, self.Y, self.bias_y, eps, out)
+
+    def col_lse(self, f, eps, out=None):
+        """Lc_j = LSE_{i local}[(f_i - C_ij)/eps] over this rank's rows."""
+        self._call("sdb_make_bias", self.n, _ptr(f), _ptr(self.X.norms), eps, self.inv_med / eps, _ptr(self.bias_x))
+        return self._lse(self.Y, self.X, self.bias_x, eps, out)
+
+    # ------------------------------------------------------------------ vector updates
+    def potential_update(self, side, L, logmarg, eps, alpha, log_n_other, pot, frame, la_old, it, log_tau,
+                         log_floor=NEG_INF):
+        """side='row' updates f (local rows), side='col' updates g; see sdb_potential_update."""
+        norms = self.X.norms if side == "row" else self.Y.norms
+        self._call("sdb_potential_update", pot.numel(), _ptr(L), _ptr(logmarg), _ptr(norms), eps, alpha, log_n_other,
+                   self.inv_med / eps, _ptr(pot), _ptr(frame), _ptr(la_old), 0, _ptr(self.flag), it, log_tau, log_floor)
+
+    def absorb_flag_tensor(self):
+        return self.flag
+
+    def absorb(self, it, f, g, u, v):
+        self._call("sdb_absorb", f.numel(), g.numel(), _ptr(self.flag), it, _ptr(f), _ptr(g), _ptr(u), _ptr(v))
+
+    def stage_criterion(self, f, u, la_old, g, v, lb_old, eps):
+        self._call("sdb_stage_criterion", f.numel(), g.numel(), _ptr(f), _ptr(u), _ptr(la_old), _ptr(g), _ptr(v),
+                   _ptr(lb_old), eps, _ptr(self.out10), _ptr(self.scratch))
+        return self.out10[:4].clone()
+
+    def gap_terms(self, f, Lr, logp, g, Lc, logq, eps, lam1, lam2, dx, dy):
+        self._call("sdb_gap_terms", f.numel(), g.numel(), _ptr(f), _ptr(Lr), _ptr(logp), _ptr(g), _ptr(Lc), _ptr(logq),
+                   eps, lam1, lam2, dx, dy, _ptr(self.out10), _ptr(self.scratch))
+        return self.out10.clone()
+
+    def sum_exp(self, L):
+        self._call("sdb_sum_exp", L.numel(), _ptr(L), 0, 0.0, _ptr(self.out10), _ptr(self.scratch))
+        return self.out10[:1].clone()
+
+    def row_mass(self, f, Lr, eps):
+        out = torch.empty_like(f)
+        self._call("sdb_row_mass", f.numel(), _ptr(f), _ptr(Lr), eps, 1.0 / self.m, _ptr(out))
+        return out
+
+    def plan_dense(self, f, g, eps):
+        plan = torch.empty((self.n, self.m), dtype=torch.float64, device=self.device)
+        self._call("sdb_plan_dense_f64", _ptr(self.X.x64), _ptr(self.Y.x64), self.n, self.m, self.d, _ptr(f), _ptr(g),
+                   self.inv_med, eps, 1.0 / self.m, _ptr(plan))
+        return plan
+
+    # ------------------------------------------------------------------ K5 median primitives
+    def pair_distances(self, ii, jj):
+        ii = torch.as_tensor(ii, dtype=torch.int64).to(self.device)
+        jj = torch.as_tensor(jj, dtype=torch.int64).to(self.device)
+        out = torch.empty(ii.numel(), dtype=torch.float64, device=self.device)
+        self._call("sdb_pair_distances_f64", _ptr(self.X.x64), _ptr(self.Y.x64), self.d, _ptr(ii), _ptr(jj), ii.numel(),
+                   _ptr(out))
+        return out
+
+    def cost_histogram(self, lo, hi, n_bins):
+        hist = torch.zeros(n_bins, dtype=torch.int64, device=self.device)
+        counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        bounds, ns = self._split_plan(self.n, self.m)
+        self._call("sdb_cost_histogram", _ptr(self.X.xt), self.X.ld, self.n, _ptr(self.Y.xt), self.Y.ld, self.m,
+                   self.X.dpad, _ptr(bounds), ns, lo, hi, n_bins, _ptr(hist), _ptr(counts))
+        return hist, counts
+
+    def cost_collect(self, lo, hi, cap):
+        cand = torch.empty(cap, dtype=torch.float64, device=self.device)
+        counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        bounds, ns = self._split_plan(self.n, self.m)
+        self._call("sdb_cost_collect", _ptr(self.X.xt), self.X.ld, self.n, _ptr(self.Y.xt), self.Y.ld, self.m,
+                   self.X.dpad, _ptr(bounds), ns, lo, hi, _ptr(self.X.x64), _ptr(self.Y.x64), self.d, _ptr(cand), cap,
+                   _ptr(counts))
+        return cand, counts
+
+    def radix_digit_hist(self, cand, n, shift, prefix):
+        hist = torch.zeros(256, dtype=torch.int64, device=self.device)
+        self._call("sdb_radix_digit_hist", _ptr(cand), n, shift, prefix, _ptr(hist))
+        return hist
+
+    # ------------------------------------------------------------------ K6 transition table
+    def transition_table(self, f, g, eps, labels_x, labels_y, k0, k1):
+        """table[a,b] = sum_{i in a, j in b} exp((f_i+g_j-C_ij)/eps)/M for this rank's rows."""
+        ly = torch.as_tensor(np.asarray(labels_y), dtype=torch.int64).to(self.device)
+        lx = torch.as_tensor(np.asarray(labels_x), dtype=torch.int32).to(self.device)
+        perm = torch.argsort(ly, stable=True)
+        counts = torch.bincount(ly, minlength=k1)[:k1]
+        bounds = torch.zeros(k1 + 1, dtype=torch.int64, device=self.device)
+        bounds[1:] = torch.cumsum(counts, 0)
+        Yp = PointSet.__new__(PointSet)
+        Yp.n, Yp.d, Yp.dpad, Yp.ld = self.Y.n, self.Y.d, self.Y.dpad, self.Y.ld
+        Yp.xt = torch.zeros_like(self.Y.xt)
+        Yp.xt[:, :self.m] = self.Y.xt[:, :self.m].index_select(1, perm)
+        Yp.norms = self.Y.norms.index_select(0, perm)
+        gp = g.index_select(0, perm).contiguous()
+        bias = torch.empty(self.m, dtype=torch.float32, device=self.device)
+        c1 = self.inv_med / eps
+        self._call("sdb_make_bias", self.m, _ptr(gp), _ptr(Yp.norms), eps, c1, _ptr(bias))
+        partial = self._lse(self.X, Yp, bias, eps, bounds=bounds, ns=k1, finalize=False)
+        table = torch.zeros((k0, k1), dtype=torch.float64, device=self.device)
+        self._call("sdb_transition_accumulate", _ptr(partial), k1, self.n, _ptr(self.X.norms), c1, _ptr(f), eps,
+                   1.0 / self.m, _ptr(lx), k0, _ptr(table))
+        return table

@@ -1,0 +1,311 @@
+"""Host drivers of the streamed unbalanced Sinkhorn (the reference's OT hot path).
+
+What the reference does with dense N x M fp64 matrices K, _K, R on one CPU thread
+(SpaDOT/utils/OT_loss/ot_solvers.py:164-531 driving ot_func.cpp:587-930) is done here in
+total potentials  f = u + eps*log a,  g = v + eps*log b  (SURVEY.md §3.3):
+
+    f_i <- eps*alpha1*( log p_i - LSE_j[(g_j - C_ij)/eps] + log J )
+    g_j <- eps*alpha2*( log q_j - LSE_i[(f_i - C_ij)/eps] + log I )
+
+Each LSE is one streamed device pass that recomputes cost tiles from the embeddings, so
+nothing of size N x M exists unless the caller asks for the dense plan.  Rows (source
+spots) may be partitioned across ranks: the row pass is local, the column pass produces a
+per-rank partial LSE over M columns that is combined with two small all-reduces
+(max, then sum) — the only data-path collectives.
+
+The drivers are written against the `ops` interface of cuda_ops.CudaOps.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+EPSILON_SCALINGS = 5   # ot_solvers.py:217
+NEG_INF = float("-inf")
+
+
+def _safe_ratio(num2, den2):
+    """sqrt(num2) / (1 + sqrt(den2)) with inf/inf -> nan like the reference's fp64 arithmetic."""
+    a, b = math.sqrt(num2) if num2 == num2 else float("nan"), math.sqrt(den2) if den2 == den2 else float("nan")
+    if math.isinf(a) and math.isinf(b):
+        return float("nan")
+    return a / (1.0 + b)
+
+
+class Dist:
+    """Thin wrapper over torch.distributed for the row-partitioned solve (no-op when single)."""
+
+    def __init__(self, group=None, enabled=None):
+        import torch.distributed as td
+        self.td = td
+        self.enabled = (td.is_available() and td.is_initialized()) if enabled is None else enabled
+        self.group = group
+        self.world = td.get_world_size(group) if self.enabled else 1
+        self.rank = td.get_rank(group) if self.enabled else 0
+        self.collectives = 0
+
+    def sum_(self, t):
+        if self.world > 1:
+            self.td.all_reduce(t, op=self.td.ReduceOp.SUM, group=self.group)
+            self.collectives += 1
+        return t
+
+    def max_(self, t):
+        if self.world > 1:
+            self.td.all_reduce(t, op=self.td.ReduceOp.MAX, group=self.group)
+            self.collectives += 1
+        return t
+
+    def gather_cat(self, t):
+        """Concatenate variable-length 1-D tensors from all ranks (used by the median only)."""
+        if self.world == 1:
+            return t
+        n = torch.tensor([t.numel()], dtype=torch.int64, device=t.device)
+        sizes = [torch.zeros_like(n) for _ in range(self.world)]
+        self.td.all_gather(sizes, n, group=self.group)
+        mx = int(max(int(s.item()) for s in sizes))
+        pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
+        pad[:t.numel()] = t
+        bufs = [torch.empty_like(pad) for _ in range(self.world)]
+        self.td.all_gather(bufs, pad, group=self.group)
+        self.collectives += 2
+        return torch.cat([b[:int(s.item())] for b, s in zip(bufs, sizes)])
+
+
+def combine_col_lse(Lc_partial, dist: Dist):
+    """LSE over all ranks' rows from per-rank partial LSEs: max all-reduce, then sum all-reduce."""
+    if dist.world == 1:
+        return Lc_partial
+    mx = dist.max_(Lc_partial.clone())
+    safe = torch.where(torch.isfinite(mx), mx, torch.zeros_like(mx))
+    s = dist.sum_(torch.exp(Lc_partial - safe))
+    return safe + torch.log(s)
+
+
+class _State:
+    """Per-solve device vectors."""
+
+    def __init__(self, ops, G_local, dist: Dist):
+        self.n, self.m = ops.n, ops.m
+        nt = torch.tensor([float(self.n)], dtype=torch.float64, device=ops.device)
+        self.N = int(round(float(dist.sum_(nt).item())))
+        p = ops.tensor(G_local)
+        if p.numel() != self.n:
+            raise ValueError("G must have one entry per (local) source spot")
+        gsum = dist.sum_(p.sum().reshape(1).clone())
+        self.q_value = float(gsum.item()) / self.N               # ot_solvers.py:224  np.average(G)
+        self.p = p
+        self.logp = torch.log(p)
+        self.logq = torch.full((self.m,), math.log(self.q_value) if self.q_value > 0 else NEG_INF,
+                               dtype=torch.float64, device=ops.device)
+        self.f, self.g = ops.zeros(self.n), ops.zeros(self.m)
+        self.u, self.v = ops.zeros(self.n), ops.zeros(self.m)
+        self.la_old, self.lb_old = ops.zeros(self.n), ops.zeros(self.m)
+        self.Lr = ops.zeros(self.n)
+        self.Lc = ops.zeros(self.m)
+
+
+def _sweep(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_known, log_floor=NEG_INF):
+    """One Sinkhorn iteration = row update + column update (ot_func.cpp:587-687) + tau bookkeeping."""
+    it = ops.tick()
+    if not lr_known:
+        ops.row_lse(st.g, eps, out=st.Lr)
+    ops.potential_update("row", st.Lr, st.logp, eps, alpha1, math.log(st.m), st.f, st.u, st.la_old, it, log_tau, log_floor)
+    ops.col_lse(st.f, eps, out=st.Lc)
+    if dist.world > 1:
+        st.Lc.copy_(combine_col_lse(st.Lc, dist))
+    ops.potential_update("col", st.Lc, st.logq, eps, alpha2, math.log(st.N), st.g, st.v, st.lb_old, it, log_tau, log_floor)
+    if dist.world > 1:
+        dist.max_(ops.absorb_flag_tensor())
+    ops.absorb(it, st.f, st.g, st.u, st.v)                        # ot_func.cpp:778-819
+
+
+def solve_duality_gap(ops, G_local, lambda1, lambda2, epsilon, batch_size=5, tolerance=1e-8, tau=1000.0,
+                      epsilon0=1.0, max_iter=1e7, dist: Dist | None = None, info: dict | None = None, **ignored):
+    """optimal_transport_duality_gap (ot_solvers.py:164-449) on the device.
+
+    Returns the state (potentials f,g on the device, row LSE at the final g) and the final epsilon.
+    Raises RuntimeError on a NaN gap like the reference (ot_solvers.py:446-447)."""
+    dist = dist or Dist(enabled=False)
+    st = _State(ops, G_local, dist)
+    scale_factor = math.exp(-math.log(epsilon) / EPSILON_SCALINGS)
+    eps_i = epsilon0 * scale_factor
+    log_tau = math.log(tau)
+    iters, total, gap = [], 0, math.inf
+    for e in range(EPSILON_SCALINGS + 1):
+        st.u.copy_(st.f)                                          # absorb, ot_solvers.py:249-252
+        st.v.copy_(st.g)
+        eps_i = eps_i / scale_factor
+        alpha1 = lambda1 / (lambda1 + eps_i)
+        alpha2 = lambda2 / (lambda2 + eps_i)
+        final = e == EPSILON_SCALINGS
+        threshold = tolerance if final else 1e-6                  # ot_solvers.py:262
+        n_inner = int(batch_size) if final else 5                 # ot_func.cpp:867
+        st.la_old.zero_()
+        st.lb_old.zero_()
+        sumK, lr_known, gap, n_it = None, False, math.inf, 0
+        while gap > threshold:
+            for _ in range(n_inner):
+                n_it += 1
+                _sweep(ops, st, dist, eps_i, alpha1, alpha2, log_tau, lr_known)
+                lr_known = False
+            if final:
+                if sumK is None:
+                    Lk = ops.row_lse(None, eps_i)
+                    sumK = float(dist.sum_(ops.sum_exp(Lk)).item())
+                ops.row_lse(st.g, eps_i, out=st.Lr)               # also the next iteration's row pass
+                lr_known = True
+                t = ops.gap_terms(st.f, st.Lr, st.logp, st.g, st.Lc, st.logq, eps_i, lambda1, lambda2,
+                                  1.0 / st.N, 1.0 / st.m)
+                if dist.world > 1:
+                    rows = dist.sum_(t[:4].clone())
+                    t = torch.cat([rows, t[4:]])
+                t = t.cpu().numpy()
+                IJ = float(st.N) * float(st.m)
+                pri = lambda1 * t[2] + lambda2 * t[6] + (t[1] + t[5] - eps_i * t[0] + eps_i * sumK) / IJ
+                dua = -lambda1 * t[3] - lambda2 * t[7] - eps_i * (t[0] - sumK) / IJ
+                gap = (pri - dua) / abs(pri)                      # ot_func.cpp:543
+            else:
+                c = ops.stage_criterion(st.f, st.u, st.la_old, st.g, st.v, st.lb_old, eps_i)
+                if dist.world > 1:
+                    rows = dist.sum_(c[:2].clone())
+                    c = torch.cat([rows, c[2:]])
+                c = c.cpu().numpy()
+                va = _safe_ratio(c[0], c[1])
+                vb = _safe_ratio(c[2], c[3])
+                gap = vb if vb > va else va                       # std::max(v1, v2), NaN semantics included
+                if math.isnan(gap):
+                    break        # `while (nan > threshold)` is false in the reference as well
+            if n_it >= max_iter:
+                break
+        iters.append(n_it)
+        total += n_it
+    if math.isnan(gap):
+        raise RuntimeError("Overflow encountered in duality gap computation, please report this incident")
+    if not lr_known:
+        ops.row_lse(st.g, eps_i, out=st.Lr)
+    if info is not None:
+        info.update(iters_per_stage=iters, total_iters=total, gap=float(gap), epsilon_final=eps_i)
+    return st, eps_i
+
+
+def solve_stablev2(ops, G_local, lambda1, lambda2, epsilon, scaling_iter=3000, tau=1000.0, epsilon0=1.0,
+                   extra_iter=1000, inner_iter_max=50, dist: Dist | None = None, info: dict | None = None, **ignored):
+    """transport_stablev2 (ot_solvers.py:452-531): fixed epsilon schedule, 1e-10 floor, no host syncs."""
+    dist = dist or Dist(enabled=False)
+    st = _State(ops, G_local, dist)
+    warm = tau is not None
+    eps_i = float(epsilon0 if warm else epsilon)
+    log_tau = math.log(tau) if warm else math.inf
+    log_floor = math.log(1e-10)                                   # ot_solvers.py:498
+    alpha1 = lambda1 / (lambda1 + eps_i)
+    alpha2 = lambda2 / (lambda2 + eps_i)
+    idx = since = 0
+    for _ in range(int(scaling_iter)):
+        _sweep(ops, st, dist, eps_i, alpha1, alpha2, log_tau, False, log_floor)
+        since += 1
+        if warm and since == inner_iter_max:                      # ot_solvers.py:513-523
+            idx += 1
+            since = 0
+            st.u.copy_(st.f)
+            st.v.copy_(st.g)
+            eps_i = (epsilon0 - epsilon) * math.exp(-idx) + epsilon
+            alpha1 = lambda1 / (lambda1 + eps_i)
+            alpha2 = lambda2 / (lambda2 + eps_i)
+    # the extra iterations never absorb (ot_solvers.py:525-527)
+    for _ in range(int(extra_iter)):
+        _sweep(ops, st, dist, eps_i, alpha1, alpha2, math.inf, False, log_floor)
+    ops.row_lse(st.g, eps_i, out=st.Lr)
+    if info is not None:
+        info.update(total_iters=int(scaling_iter) + int(extra_iter), epsilon_final=eps_i)
+    return st, eps_i
+
+
+# ------------------------------------------------------------------------------------------ median (K5)
+def _select_rank(ops, cand, n_cand, k):
+    """k-th smallest (0-based) of cand[:n_cand] (non-negative doubles) by 8 radix-256 digit passes."""
+    prefix, remaining = 0, int(k)
+    for shift in range(56, -1, -8):
+        hist = ops.radix_digit_hist(cand, n_cand, shift, prefix).cpu().numpy()
+        csum = np.cumsum(hist)
+        digit = int(np.searchsorted(csum, remaining, side="right"))
+        remaining -= int(csum[digit - 1]) if digit > 0 else 0
+        prefix = (prefix << 8) | digit
+    return float(np.array([prefix], dtype=np.uint64).view(np.float64)[0])
+
+
+def median_cost(ops, dist: Dist | None = None, n_samples=262144, n_bins=4096, seed=0, small_limit=1 << 22,
+                info: dict | None = None):
+    """Exact np.median of all N*M squared distances (ot_solvers.py:103) without materialising them.
+
+    1. bracket the median from a random sample of pairs (fp64 distances);
+    2. one streamed sweep: count costs below the bracket and histogram the bracket uniformly;
+    3. one streamed sweep: count below the selected bin and re-evaluate its members by direct fp64
+       differences; 4. radix-select the two middle order statistics among those candidates.
+    Sweeps classify with fp32 distances of the centred points; brackets are widened by REL_MARGIN so the
+    classification can never disagree with the exact fp64 value about membership of the true median."""
+    dist = dist or Dist(enabled=False)
+    REL_MARGIN = 2e-5
+    n, m = ops.n, ops.m
+    N = int(round(float(dist.sum_(torch.tensor([float(n)], dtype=torch.float64, device=ops.device)).item())))
+    total = N * m
+    k_lo, k_hi = (total - 1) // 2, total // 2
+    sweeps = 0
+
+    def collect(lo, hi, cap):
+        nonlocal sweeps
+        sweeps += 1
+        cand, counts = ops.cost_collect(float(lo), float(hi), int(cap))
+        below = int(dist.sum_(counts[:1].clone()).item())
+        n_local = int(counts[1].item())
+        if n_local > cap:
+            return None, below, n_local
+        allc = dist.gather_cat(cand[:n_local].contiguous())
+        return allc, below, int(allc.numel())
+
+    lo, hi = 0.0, math.inf
+    if total > small_limit:
+        rng = np.random.default_rng(seed + 7919 * dist.rank)
+        ns = max(1024, n_samples // dist.world)
+        ii = rng.integers(0, max(n, 1), ns)
+        jj = rng.integers(0, m, ns)
+        samp = torch.sort(dist.gather_cat(ops.pair_distances(ii, jj)))[0].cpu().numpy() if n > 0 else np.zeros(0)
+        S = samp.size
+        width = 6.0 * 0.5 / math.sqrt(S)
+        lo = float(samp[max(0, int((0.5 - width) * S))]) * (1 - REL_MARGIN)
+        hi = float(samp[min(S - 1, int((0.5 + width) * S))]) * (1 + REL_MARGIN)
+        if hi > lo > 0:
+            sweeps += 1
+            hist, counts = ops.cost_histogram(float(np.float32(lo)), float(np.float32(hi)), n_bins)
+            hist = dist.sum_(hist).cpu().numpy()
+            below = int(dist.sum_(counts[:1].clone()).item())
+            csum = below + np.cumsum(hist)
+            if below <= k_lo and csum[-1] > k_hi:
+                b_lo = int(np.searchsorted(csum, k_lo, side="right"))
+                b_hi = int(np.searchsorted(csum, k_hi, side="right"))
+                w = (float(np.float32(hi)) - float(np.float32(lo))) / n_bins
+                lo, hi = (float(np.float32(lo)) + (b_lo - 1) * w) * (1 - REL_MARGIN), \
+                         (float(np.float32(lo)) + (b_hi + 2) * w) * (1 + REL_MARGIN)
+            else:
+                lo, hi = 0.0, math.inf     # sample bracket missed (vanishing probability): full collect
+        else:
+            lo, hi = 0.0, math.inf
+    cap = max(1 << 16, int(min(total, 1 << 26)) if not math.isfinite(hi) else 1 << 24)
+    while True:
+        cand, below, n_cand = collect(max(lo, 0.0), hi if math.isfinite(hi) else 3.0e38, cap)
+        if cand is not None and below <= k_lo and k_hi < below + n_cand:
+            break
+        if cand is None and math.isfinite(hi) and cap < (1 << 28):
+            cap *= 4
+            continue
+        if not math.isfinite(hi) and lo <= 0.0:
+            raise RuntimeError("median_cost: candidate buffer too small for an exhaustive collect")
+        lo, hi = 0.0, math.inf
+        cap = int(min(total, 1 << 28))
+    v_lo = _select_rank(ops, cand, n_cand, k_lo - below)
+    v_hi = v_lo if k_hi == k_lo else _select_rank(ops, cand, n_cand, k_hi - below)
+    if info is not None:
+        info.update(sweeps=sweeps, candidates=n_cand, below=below)
+    return 0.5 * (v_lo + v_hi)

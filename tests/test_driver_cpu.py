@@ -1,0 +1,117 @@
+"""Host-side logic of spadot_b200/sinkhorn.py on CPU: the drivers run against an oracle-backed `ops`
+stand-in (tests/_numpy_ops.py) so stage schedule, stopping rules, growth loop, exact-median selection
+and the row-partitioned multi-rank path (gloo, world_size 2) are covered without a GPU."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+from _numpy_ops import NumpyOps
+from oracle import ot_dense
+from spadot_b200 import sinkhorn
+
+CFG = dict(ot_dense.DEFAULT_OT_CONFIG)
+
+
+def test_single_rank_driver_matches_dense_oracle():
+    a, b, la, lb = ot_dense.synthetic_embeddings(90, 75, 7, seed=31)
+    Cn, med = ot_dense.median_normalised_cost(a, b)
+    ops = NumpyOps(a, b)
+    assert sinkhorn.median_cost(ops, small_limit=100, n_samples=2048) == med
+    ops.set_median(med)
+    info, info_ref = {}, {}
+    st, eps = sinkhorn.solve_duality_gap(ops, np.ones(90), info=info, **CFG)
+    want = ot_dense.duality_gap_solve(Cn, np.ones(90), info=info_ref, **CFG)
+    assert info["iters_per_stage"] == info_ref["iters_per_stage"]
+    np.testing.assert_allclose(ops.plan_dense(st.f, st.g, eps).numpy(), want, rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(ops.row_mass(st.f, st.Lr, eps).numpy(), want.sum(1), rtol=1e-10)
+    st2, eps2 = sinkhorn.solve_stablev2(ops, np.ones(90), **dict(CFG, scaling_iter=300, extra_iter=60, tau=3.0))
+    want2 = ot_dense.transport_stablev2(C=Cn, G=np.ones(90), **dict(CFG, scaling_iter=300, extra_iter=60, tau=3.0))
+    np.testing.assert_allclose(ops.plan_dense(st2.f, st2.g, eps2).numpy(), want2, rtol=1e-9, atol=1e-300)
+
+
+@pytest.mark.parametrize("n,m", [(7, 6), (8, 8), (33, 30), (1, 1), (2, 1)])
+def test_median_selection_even_and_odd(n, m):
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, 3, seed=n * 10 + m)
+    want = float(np.median(ot_dense.sqeuclidean(a, b)))
+    assert sinkhorn.median_cost(NumpyOps(a, b)) == want
+    assert sinkhorn.median_cost(NumpyOps(a, b), small_limit=0, n_samples=1024, n_bins=16) == want
+
+
+def test_median_with_ties_and_zero_costs():
+    a = np.zeros((20, 3))
+    b = np.zeros((30, 3))
+    assert sinkhorn.median_cost(NumpyOps(a, b), small_limit=0, n_samples=1024) == 0.0
+    b[:10] = 1.0
+    want = float(np.median(ot_dense.sqeuclidean(a, b)))
+    assert sinkhorn.median_cost(NumpyOps(a, b), small_limit=0, n_samples=1024) == want
+
+
+def test_nan_gap_raises_like_reference():
+    a, b, _, _ = ot_dense.synthetic_embeddings(10, 12, 3, seed=1)
+    ops = NumpyOps(a, b)
+    ops.set_median(float(np.median(ot_dense.sqeuclidean(a, b))))
+    G = np.ones(10)
+    G[3] = 0.0      # r log(r/p) with p = 0 -> NaN in the reference's primal (ot_func.cpp:309-322)
+    with pytest.raises(RuntimeError, match="Overflow encountered in duality gap computation"):
+        sinkhorn.solve_duality_gap(ops, G, **CFG)
+
+
+# ---------------------------------------------------------------------------- world_size 2, gloo
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, a, b, G, la, lb, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = a.shape[0]
+        r0, r1 = (n * rank) // world, (n * (rank + 1)) // world
+        dist = sinkhorn.Dist()
+        ops = NumpyOps(a[r0:r1], b)
+        med = sinkhorn.median_cost(ops, dist, small_limit=0, n_samples=2048, n_bins=64)
+        ops.set_median(med)
+        info = {}
+        st, eps = sinkhorn.solve_duality_gap(ops, G[r0:r1], dist=dist, info=info, **CFG)
+        plan_rows = ops.plan_dense(st.f, st.g, eps).numpy()
+        tab = dist.sum_(ops.transition_table(st.f, st.g, eps, la[r0:r1], lb, 10, 10)).numpy()
+        st2, eps2 = sinkhorn.solve_stablev2(ops, G[r0:r1], dist=dist, **dict(CFG, scaling_iter=120, extra_iter=30))
+        out[rank] = dict(med=med, rows=(r0, r1), plan=plan_rows, iters=info["iters_per_stage"], tab=tab,
+                         plan2=ops.plan_dense(st2.f, st2.g, eps2).numpy(), collectives=dist.collectives)
+    finally:
+        td.destroy_process_group()
+
+
+def test_row_partitioned_solve_world2_gloo():
+    a, b, la, lb = ot_dense.synthetic_embeddings(61, 47, 6, seed=77)   # 61 rows: ragged split 30 / 31
+    G = np.exp(np.random.default_rng(2).normal(0, 0.5, 61))
+    Cn, med = ot_dense.median_normalised_cost(a, b)
+    info_ref = {}
+    want = ot_dense.duality_gap_solve(Cn, G, info=info_ref, **CFG)
+    want2 = ot_dense.transport_stablev2(C=Cn, G=G, **dict(CFG, scaling_iter=120, extra_iter=30))
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), a, b, G, la, lb, out), nprocs=2, join=True)
+    assert set(out.keys()) == {0, 1}
+    plan = np.zeros_like(want)
+    plan2 = np.zeros_like(want)
+    for r in (0, 1):
+        o = out[r]
+        assert o["med"] == med
+        assert o["iters"] == info_ref["iters_per_stage"]
+        plan[o["rows"][0]:o["rows"][1]] = o["plan"]
+        plan2[o["rows"][0]:o["rows"][1]] = o["plan2"]
+        assert o["collectives"] > 0
+    np.testing.assert_allclose(plan, want, rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(plan2, want2, rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(out[0]["tab"], ot_dense.transition_table(want, la, lb, 10, 10), rtol=1e-9)
+    np.testing.assert_allclose(out[0]["tab"], out[1]["tab"], rtol=1e-14)

