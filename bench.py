@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--d", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=8192, help="rows=cols of the dense CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tc", default="auto", choices=["auto", "on", "off"], help="tensor-core (tcgen05) pass")
     return ap.parse_args()
 
 
@@ -187,7 +188,7 @@ def gpu_main(a):
             td.barrier()
         torch.cuda.synchronize()
 
-    ops = CudaOps(x, y, device=dev)
+    ops = CudaOps(x, y, device=dev, tc=a.tc)
     ops.set_median(median)
     st = sinkhorn._State(ops, np.ones(ops.n), dist)
     st.u.copy_(st.f)
@@ -247,7 +248,7 @@ def gpu_main(a):
     e2e_steps = max(2, a.steps // 2)
     barrier()
     t0 = time.perf_counter()
-    ops2 = CudaOps(xh, yh, device=dev)           # H2D + point preparation
+    ops2 = CudaOps(xh, yh, device=dev, tc=a.tc)  # H2D + point preparation
     ops2.set_median(median)
     st2 = sinkhorn._State(ops2, np.ones(ops2.n), dist)
     st2.u.copy_(st2.f)

@@ -68,6 +68,23 @@ int sdb_lse_pass_simt(const float* pt, int64_t ldp, int64_t n_p,
                       const int64_t* split_bounds, int n_splits,
                       float* partial, void* stream);
 
+/* ------------------------------------------------------------------ K3: streamed LSE pass (tcgen05 / TMEM / TMA) */
+/* max over all entries of |x[i*d+k] - center[k]|, written as a double (out must be zeroed). */
+int sdb_absmax_centered_f64(const double* x, int64_t n, int d, const double* center, double* out_max, void* stream);
+/* fp16 hi/lo split of the centred points scaled by 2^pow2_exp:  out16[i*(2*dp) + k] = hi, out16[i*(2*dp) + dp + k] = lo
+ * with hi = fp16(v), lo = fp16(v - hi), v = (x[i*d+k]-center[k]) * 2^pow2_exp (|v| must stay < 32768);
+ * norms[i] = sum_k ((hi+lo) * 2^-pow2_exp)^2 in fp64.  dp in {16,32,64} >= d; rows [n, n_pad) are zero; n_pad % 256 == 0. */
+int sdb_prep_points_split_f16(const double* x, int64_t n, int d, const double* center, int pow2_exp,
+                              void* out16, int64_t n_pad, int dp, double* norms, void* stream);
+/* Same contract as sdb_lse_pass_simt with scale already multiplied by 2^(-2*pow2_exp); splits are
+ * runs of `tiles_per_split` 256-column tiles: n_splits = ceil(ceil(n_q/256)/tiles_per_split) and
+ * partial holds n_splits*n_p (max,sum) pairs.  bias_padded has n_q_pad entries (see sdb_make_bias).
+ * Persistent grid of n_ctas CTAs (use the SM count), 320 threads, one CTA per SM, 512 TMEM columns.
+ * x.y^T = hi*hi + hi*lo + lo*hi on tcgen05.mma kind::f16 with fp32 accumulation in TMEM. */
+int sdb_lse_pass_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad,
+                    int dp, const float* bias_padded, float scale, int tiles_per_split, int n_ctas,
+                    float* partial, void* stream);
+
 /* L[i] = ln2 * log2( sum_s sum_s,i * 2^(max_s,i - M_i) ) + ln2*M_i - norms[i]*c1   (fp64)
  *      = LSE_j[(g_j - C_ij)/eps]; -inf when every partial is empty. */
 int sdb_lse_finalize(const float* partial, int n_splits, int64_t n, const double* norms,
@@ -85,8 +102,9 @@ int sdb_potential_update(int64_t n, const double* L, const double* logmarg, cons
                          double eps, double alpha, double log_n_other, double c1,
                          double* pot, const double* frame, double* la_old, float* bias,
                          int* absorb_flag, int iter, double log_tau, double log_floor, void* stream);
-/* bias[i] = log2(e)*( pot[i]/eps - norms[i]*c1 ) only (stage changes, first iteration). */
-int sdb_make_bias(int64_t n, const double* pot, const double* norms, double eps, double c1,
+/* bias[i] = log2(e)*( pot[i]/eps - norms[i]*c1 ) for i < n (pot may be NULL = 0);
+ * bias[i] = SDB_NEG_SENTINEL for n <= i < n_pad (column padding of the tensor-core pass). */
+int sdb_make_bias(int64_t n, int64_t n_pad, const double* pot, const double* norms, double eps, double c1,
                   float* bias, void* stream);
 /* if (*absorb_flag == iter) { u = f; v = g; }      (ref: ot_func.cpp:792-819) */
 int sdb_absorb(int64_t n, int64_t m, const int* absorb_flag, int iter,

@@ -28,7 +28,10 @@ SIGNATURES = {
     "sdb_lse_pass_simt": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_p, c_i, c_p, c_p],
     "sdb_lse_finalize": [c_p, c_i, c_l, c_p, c_d, c_p, c_p],
     "sdb_potential_update": [c_l, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
-    "sdb_make_bias": [c_l, c_p, c_p, c_d, c_d, c_p, c_p],
+    "sdb_make_bias": [c_l, c_l, c_p, c_p, c_d, c_d, c_p, c_p],
+    "sdb_absmax_centered_f64": [c_p, c_l, c_i, c_p, c_p, c_p],
+    "sdb_prep_points_split_f16": [c_p, c_l, c_i, c_p, c_i, c_p, c_l, c_i, c_p, c_p],
+    "sdb_lse_pass_tc": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_i, c_i, c_p, c_p],
     "sdb_absorb": [c_l, c_l, c_p, c_i, c_p, c_p, c_p, c_p, c_p],
     "sdb_stage_criterion": [c_l, c_l, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_p, c_p, c_p],
     "sdb_gap_terms": [c_l, c_l, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_d, c_p, c_p, c_p],

@@ -1,0 +1,454 @@
+// K3, tensor-core form: streamed "flash-Sinkhorn" half-iteration on tcgen05 / TMEM / TMA (sm_100a).
+//
+//   L2_i = log2 sum_j 2^( bias_j + scale * x_i . y_j )
+//
+// A persistent, warp-specialised CTA per SM owns 128 rows at a time and streams 256-column tiles:
+//   warp 0      TMA producer  : cp.async.bulk.tensor tiles of the fp16 hi/lo split embeddings (SWIZZLE_32/64/128B)
+//                               and the 256-float bias slice, into mbarrier rings
+//   warp 1      MMA issuer    : x.y^T as three tcgen05.mma chains (hi*hi + hi*lo + lo*hi, fp32 accumulate) into one
+//                               of two 128x256 fp32 TMEM accumulators
+//   warps 2..9  epilogue      : two warpgroups ping-pong on the TMEM buffers: tcgen05.ld -> t = scale*d + bias_j ->
+//                               online (max, sum ex2) per row in registers; one (max,sum) pair per row leaves the SM.
+// The N x M cost / kernel matrix never exists in any memory.  The 2-term fp16 split keeps 22 mantissa
+// bits of every coordinate, so the tile math is fp32-accurate (plain TF32/BF16 is not).
+// Replaces gemv/gemtv + update_k of ref: SpaDOT/utils/OT_loss/ot_func.cpp:43-249,547-568.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "sdb_common.cuh"
+
+namespace {
+
+constexpr int TILE_M = 128;          // rows per CTA item (UMMA M)
+constexpr int TILE_N = 256;          // columns per streamed tile (UMMA N)
+constexpr int N_EPI_WARPS = 8;
+constexpr int NT_TC = 32 * (2 + N_EPI_WARPS);
+constexpr int BIAS_STAGES = 4;
+
+// ------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, swizzled UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor layout, version 1):
+//   [0,14) start>>4, [16,30) LBO>>4 (=1: unused for swizzled K-major), [32,46) SBO>>4 (8 rows * row bytes),
+//   [46,48) version=1, [61,64) layout: 2=SW128, 4=SW64, 6=SW32.
+template <int DP>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    constexpr uint64_t row_bytes = DP * 2;
+    constexpr uint64_t layout = (DP == 64) ? 2 : (DP == 32) ? 4 : 6;
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((8 * row_bytes) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= layout << 61;
+    return d;
+}
+
+template <int DP>
+struct TcSmem {
+    static constexpr int STAGES = (DP == 64) ? 2 : 4;
+    static constexpr int A_BYTES = TILE_M * DP * 2;     // one of (hi, lo)
+    static constexpr int B_BYTES = TILE_N * DP * 2;
+    static constexpr int OFF_A = 0;                                     // [2][A_BYTES]
+    static constexpr int OFF_B = OFF_A + 2 * A_BYTES;                   // [STAGES][2][B_BYTES]
+    static constexpr int OFF_BIAS = OFF_B + STAGES * 2 * B_BYTES;       // [BIAS_STAGES][TILE_N] float
+    static constexpr int OFF_MERGE = OFF_BIAS + BIAS_STAGES * TILE_N * 4;  // [TILE_M] float2
+    static constexpr int OFF_BAR = OFF_MERGE + TILE_M * 8;              // barriers
+    static constexpr int N_BARS = 2 * STAGES + 2 + 4 + 2 * BIAS_STAGES;
+    static constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
+    static constexpr int TOTAL = OFF_TMEM + 16 + 1024;                  // + alignment slack
+};
+
+struct TcArgs {
+    const float* bias;       // padded to a multiple of TILE_N with SDB_NEG_SENTINEL
+    float scale;
+    int64_t n_p;
+    int n_row_tiles, n_col_tiles, tiles_per_split, n_splits;
+    float2* partial;         // [n_splits][n_p]
+};
+
+template <int DP>
+__global__ void __launch_bounds__(NT_TC, 1)
+lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, TcArgs a) {
+    using S = TcSmem<DP>;
+    constexpr int STAGES = S::STAGES;
+    constexpr int KSTEPS = DP / 16;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem + S::OFF_A;
+    uint8_t* sB = smem + S::OFF_B;
+    float* sBias = reinterpret_cast<float*>(smem + S::OFF_BIAS);
+    float2* sMerge = reinterpret_cast<float2*>(smem + S::OFF_MERGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+    uint64_t* full = bars;                      // [STAGES]
+    uint64_t* empty = full + STAGES;            // [STAGES]
+    uint64_t* a_full = empty + STAGES;
+    uint64_t* a_empty = a_full + 1;
+    uint64_t* t_full = a_empty + 1;             // [2]
+    uint64_t* t_empty = t_full + 2;             // [2]
+    uint64_t* b_full = t_empty + 2;             // [BIAS_STAGES]
+    uint64_t* b_empty = b_full + BIAS_STAGES;   // [BIAS_STAGES]
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + S::OFF_TMEM);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
+        for (int i = 0; i < BIAS_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_holder)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    const int n_items = a.n_row_tiles * a.n_splits;
+
+    if (warp == 0) {
+        // =============================================================== TMA producer
+        if (lane == 0) {
+            uint32_t tile_ctr = 0, item_ctr = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
+                const int rt = item % a.n_row_tiles, sp = item / a.n_row_tiles;
+                const int t0 = sp * a.tiles_per_split;
+                const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
+                mbar_wait(a_empty, (item_ctr & 1) ^ 1);
+                mbar_expect_tx(a_full, 2 * S::A_BYTES);
+                tma_load_2d(sA, &tmP, a_full, 0, rt * TILE_M);
+                tma_load_2d(sA + S::A_BYTES, &tmP, a_full, DP, rt * TILE_M);
+                for (int t = t0; t < t1; ++t, ++tile_ctr) {
+                    const int s = tile_ctr % STAGES;
+                    mbar_wait(empty + s, ((tile_ctr / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(full + s, 2 * S::B_BYTES);
+                    uint8_t* dst = sB + (size_t)s * 2 * S::B_BYTES;
+                    tma_load_2d(dst, &tmQ, full + s, 0, t * TILE_N);
+                    tma_load_2d(dst + S::B_BYTES, &tmQ, full + s, DP, t * TILE_N);
+                    const int bs = tile_ctr % BIAS_STAGES;
+                    mbar_wait(b_empty + bs, ((tile_ctr / BIAS_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(b_full + bs, TILE_N * 4);
+                    bulk_load_1d(sBias + bs * TILE_N, a.bias + (size_t)t * TILE_N, TILE_N * 4, b_full + bs);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================================================== MMA issuer
+        // instruction descriptor: D=f32 (bit 4), A=B=f16 K-major, N>>3 at [17,23), M>>4 at [24,29)
+        constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+        uint32_t tile_ctr = 0, item_ctr = 0;
+        const uint64_t dAh = make_desc<DP>(smem_u32(sA));
+        const uint64_t dAl = make_desc<DP>(smem_u32(sA + S::A_BYTES));
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
+            const int sp = item / a.n_row_tiles;
+            const int t0 = sp * a.tiles_per_split;
+            const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
+            mbar_wait(a_full, item_ctr & 1);
+            for (int t = t0; t < t1; ++t, ++tile_ctr) {
+                const int s = tile_ctr % STAGES;
+                const int acc = tile_ctr & 1;
+                mbar_wait(full + s, (tile_ctr / STAGES) & 1);
+                mbar_wait(t_empty + acc, ((tile_ctr >> 1) & 1) ^ 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t bsm = smem_u32(sB + (size_t)s * 2 * S::B_BYTES);
+                    const uint64_t dBh = make_desc<DP>(bsm);
+                    const uint64_t dBl = make_desc<DP>(bsm + S::B_BYTES);
+                    const uint32_t d_tmem = tmem_base + acc * TILE_N;
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) umma_f16(d_tmem, dAh + 2 * k, dBh + 2 * k, idesc, k > 0);
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) umma_f16(d_tmem, dAh + 2 * k, dBl + 2 * k, idesc, 1);
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) umma_f16(d_tmem, dAl + 2 * k, dBh + 2 * k, idesc, 1);
+                    umma_commit(empty + s);
+                    umma_commit(t_full + acc);
+                    if (t == t1 - 1) umma_commit(a_empty);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // =============================================================== epilogue warpgroups
+        const int ew = warp - 2;                 // 0..7
+        const int wg = ew >> 2;                  // accumulator buffer this warpgroup drains
+        const int quad = warp & 3;               // TMEM lane quadrant accessible to this warp
+        const int row_in_tile = quad * 32 + lane;
+        const float scale = a.scale;
+        uint32_t tile_ctr = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int rt = item % a.n_row_tiles, sp = item / a.n_row_tiles;
+            const int t0 = sp * a.tiles_per_split;
+            const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
+            float m = SDB_NEG_SENTINEL, ssum = 0.f;
+            for (int t = t0; t < t1; ++t, ++tile_ctr) {
+                const int acc = tile_ctr & 1;
+                if (acc != wg) continue;
+                const int bs = tile_ctr % BIAS_STAGES;
+                mbar_wait(b_full + bs, (tile_ctr / BIAS_STAGES) & 1);
+                mbar_wait(t_full + acc, (tile_ctr >> 1) & 1);
+                tc_fence_after();
+                const float* bias_s = sBias + bs * TILE_N;
+                const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TILE_N;
+#pragma unroll 1
+                for (int c = 0; c < TILE_N; c += 64) {
+                    uint32_t d0[32], d1[32];
+                    tmem_ld32(tbase + c, d0);
+                    tmem_ld32(tbase + c + 32, d1);
+                    tmem_ld_wait();
+                    float tv[64];
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias_s + c + k4 * 4);
+                        tv[k4 * 4 + 0] = fmaf(scale, __uint_as_float(d0[k4 * 4 + 0]), b.x);
+                        tv[k4 * 4 + 1] = fmaf(scale, __uint_as_float(d0[k4 * 4 + 1]), b.y);
+                        tv[k4 * 4 + 2] = fmaf(scale, __uint_as_float(d0[k4 * 4 + 2]), b.z);
+                        tv[k4 * 4 + 3] = fmaf(scale, __uint_as_float(d0[k4 * 4 + 3]), b.w);
+                    }
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias_s + c + 32 + k4 * 4);
+                        tv[32 + k4 * 4 + 0] = fmaf(scale, __uint_as_float(d1[k4 * 4 + 0]), b.x);
+                        tv[32 + k4 * 4 + 1] = fmaf(scale, __uint_as_float(d1[k4 * 4 + 1]), b.y);
+                        tv[32 + k4 * 4 + 2] = fmaf(scale, __uint_as_float(d1[k4 * 4 + 2]), b.z);
+                        tv[32 + k4 * 4 + 3] = fmaf(scale, __uint_as_float(d1[k4 * 4 + 3]), b.w);
+                    }
+                    float cm0 = tv[0], cm1 = tv[1], cm2 = tv[2], cm3 = tv[3];
+#pragma unroll
+                    for (int k = 4; k < 64; k += 4) {
+                        cm0 = fmaxf(cm0, tv[k]); cm1 = fmaxf(cm1, tv[k + 1]);
+                        cm2 = fmaxf(cm2, tv[k + 2]); cm3 = fmaxf(cm3, tv[k + 3]);
+                    }
+                    const float mn = fmaxf(m, fmaxf(fmaxf(cm0, cm1), fmaxf(cm2, cm3)));
+                    float s0 = ssum * sdb_ex2(m - mn), s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                    m = mn;
+#pragma unroll
+                    for (int k = 0; k < 64; k += 4) {
+                        s0 += sdb_ex2(tv[k] - mn); s1 += sdb_ex2(tv[k + 1] - mn);
+                        s2 += sdb_ex2(tv[k + 2] - mn); s3 += sdb_ex2(tv[k + 3] - mn);
+                    }
+                    ssum = (s0 + s1) + (s2 + s3);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(t_empty + acc); mbar_arrive(b_empty + bs); }
+            }
+            // merge the two warpgroups' row statistics and emit one (max, sum) per row
+            if (wg == 1) sMerge[row_in_tile] = make_float2(m, ssum);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (wg == 0) {
+                const float2 o = sMerge[row_in_tile];
+                const float mn = fmaxf(m, o.x);
+                const float sv = ssum * sdb_ex2(m - mn) + o.y * sdb_ex2(o.x - mn);
+                const int64_t row = (int64_t)rt * TILE_M + row_in_tile;
+                if (row < a.n_p) a.partial[(int64_t)sp * a.n_p + row] = make_float2(mn, sv);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------- fp16 split preparation
+__global__ void prep_split_kernel(const double* __restrict__ x, int64_t n, int d, const double* __restrict__ center,
+                                  double pow2, __half* __restrict__ out, int64_t n_pad, int dp, double* __restrict__ norms) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    __half* row = out + i * (2 * dp);
+    double nn = 0.0;
+    const double inv = 1.0 / pow2;
+    for (int k = 0; k < dp; ++k) {
+        __half hi = __float2half_rn(0.f), lo = hi;
+        if (i < n && k < d) {
+            const double v = (x[i * d + k] - center[k]) * pow2;
+            hi = __double2half(v);
+            const double rem = v - (double)__half2float(hi);
+            lo = __double2half(rem);
+            const double rep = ((double)__half2float(hi) + (double)__half2float(lo)) * inv;
+            nn += rep * rep;
+        }
+        row[k] = hi;
+        row[dp + k] = lo;
+    }
+    if (i < n) norms[i] = nn;
+}
+
+__global__ void absmax_centered_kernel(const double* __restrict__ x, int64_t n, int d, const double* __restrict__ center,
+                                       unsigned long long* __restrict__ out_bits) {
+    double mx = 0.0;
+    const int64_t total = n * d;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride)
+        mx = fmax(mx, fabs(x[e] - center[e % d]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx > 0.0) atomicMax(out_bits, (unsigned long long)__double_as_longlong(mx));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+int make_tmap(CUtensorMap* tm, const void* base, int64_t rows_pad, int dp, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return SDB_E_DRIVER;
+    cuuint64_t gdim[2] = {(cuuint64_t)(2 * dp), (cuuint64_t)rows_pad};
+    cuuint64_t gstride[1] = {(cuuint64_t)(2 * dp) * 2};
+    cuuint32_t box[2] = {(cuuint32_t)dp, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapSwizzle sw = dp == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : dp == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : SDB_E_DRIVER;
+}
+
+template <int DP>
+int launch_tc(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
+    auto kern = lse_pass_tc_kernel<DP>;
+    constexpr int smem = TcSmem<DP>::TOTAL;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<n_ctas, NT_TC, smem, st>>>(tmP, tmQ, a);
+    SDB_LAUNCH_STATUS();
+}
+
+}  // namespace
+
+extern "C" {
+
+int sdb_absmax_centered_f64(const double* x, int64_t n, int d, const double* center, double* out_max, void* stream) {
+    SDB_CHECK_ARG(x && center && out_max && d > 0 && n >= 0);
+    if (n == 0) return 0;
+    int grid = (int)((n * d + 256 * 8 - 1) / (256 * 8));
+    if (grid > 1184) grid = 1184;
+    absmax_centered_kernel<<<grid, 256, 0, sdb_stream(stream)>>>(x, n, d, center, reinterpret_cast<unsigned long long*>(out_max));
+    SDB_LAUNCH_STATUS();
+}
+
+int sdb_prep_points_split_f16(const double* x, int64_t n, int d, const double* center, int pow2_exp, void* out16, int64_t n_pad,
+                              int dp, double* norms, void* stream) {
+    SDB_CHECK_ARG(x && center && out16 && norms && d > 0 && dp >= d && (dp == 16 || dp == 32 || dp == 64) && n_pad >= n &&
+                  (n_pad % TILE_N) == 0);
+    prep_split_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, sdb_stream(stream)>>>(x, n, d, center, ldexp(1.0, pow2_exp),
+                                                                                       reinterpret_cast<__half*>(out16), n_pad, dp, norms);
+    SDB_LAUNCH_STATUS();
+}
+
+int sdb_lse_pass_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad, int dp,
+                    const float* bias_padded, float scale, int tiles_per_split, int n_ctas, float* partial, void* stream) {
+    SDB_CHECK_ARG(p16 && q16 && bias_padded && partial && n_p > 0 && n_q > 0 && tiles_per_split > 0 && n_ctas > 0);
+    SDB_CHECK_ARG((n_p_pad % TILE_N) == 0 && (n_q_pad % TILE_N) == 0 && n_p_pad >= n_p && n_q_pad >= n_q);
+    SDB_CHECK_ARG(((uintptr_t)p16 % 128) == 0 && ((uintptr_t)q16 % 128) == 0 && ((uintptr_t)bias_padded % 16) == 0);
+    if (!(dp == 16 || dp == 32 || dp == 64)) return SDB_E_UNSUPPORTED;
+    CUtensorMap tmP, tmQ;
+    int rc = make_tmap(&tmP, p16, n_p_pad, dp, TILE_M);
+    if (rc) return rc;
+    rc = make_tmap(&tmQ, q16, n_q_pad, dp, TILE_N);
+    if (rc) return rc;
+    TcArgs a;
+    a.bias = bias_padded;
+    a.scale = scale;
+    a.n_p = n_p;
+    a.n_row_tiles = (int)((n_p + TILE_M - 1) / TILE_M);
+    a.n_col_tiles = (int)((n_q + TILE_N - 1) / TILE_N);
+    a.tiles_per_split = tiles_per_split;
+    a.n_splits = (a.n_col_tiles + tiles_per_split - 1) / tiles_per_split;   // never empty, by construction
+    a.partial = reinterpret_cast<float2*>(partial);
+    cudaStream_t st = sdb_stream(stream);
+    switch (dp) {
+        case 16: return launch_tc<16>(tmP, tmQ, a, n_ctas, st);
+        case 32: return launch_tc<32>(tmP, tmQ, a, n_ctas, st);
+        default: return launch_tc<64>(tmP, tmQ, a, n_ctas, st);
+    }
+}
+
+}  // extern "C"

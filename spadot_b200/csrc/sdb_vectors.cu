@@ -86,10 +86,11 @@ __global__ void potential_update_kernel(int64_t n, const double* __restrict__ L,
     if (absorb_flag && (nv - fr) / eps > log_tau) atomicMax(absorb_flag, iter);
 }
 
-__global__ void make_bias_kernel(int64_t n, const double* __restrict__ pot, const double* __restrict__ norms, double eps,
-                                 double c1, float* __restrict__ bias) {
+__global__ void make_bias_kernel(int64_t n, int64_t n_pad, const double* __restrict__ pot, const double* __restrict__ norms,
+                                 double eps, double c1, float* __restrict__ bias) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n_pad) return;
+    if (i >= n) { bias[i] = SDB_NEG_SENTINEL; return; }
     const double p = pot ? pot[i] : 0.0;
     double b = SDB_LOG2E * (p / eps - norms[i] * c1);
     bias[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
@@ -320,10 +321,11 @@ int sdb_potential_update(int64_t n, const double* L, const double* logmarg, cons
     SDB_LAUNCH_STATUS();
 }
 
-int sdb_make_bias(int64_t n, const double* pot, const double* norms, double eps, double c1, float* bias, void* stream) {
-    SDB_CHECK_ARG(norms && bias && n >= 0 && eps > 0.0);
-    if (n == 0) return 0;
-    make_bias_kernel<<<blocks_for(n), 256, 0, sdb_stream(stream)>>>(n, pot, norms, eps, c1, bias);
+int sdb_make_bias(int64_t n, int64_t n_pad, const double* pot, const double* norms, double eps, double c1, float* bias,
+                  void* stream) {
+    SDB_CHECK_ARG(norms && bias && n >= 0 && n_pad >= n && eps > 0.0);
+    if (n_pad == 0) return 0;
+    make_bias_kernel<<<blocks_for(n_pad), 256, 0, sdb_stream(stream)>>>(n, n_pad, pot, norms, eps, c1, bias);
     SDB_LAUNCH_STATUS();
 }
 

@@ -43,14 +43,27 @@ class PointSet:
         st = torch.cuda.current_stream(x64.device).cuda_stream
         _lib.call("sdb_prep_points_f64", _ptr(x64), self.n, self.d, _ptr(center), _ptr(self.xt), self.ld, self.dpad,
                   _ptr(self.norms), st)
+        self.x16 = None          # fp16 hi/lo split for the tensor-core pass (built on demand)
+
+    def build_split(self, center, pow2_exp):
+        """fp16 hi/lo split [n_pad][2*dp] (+ fp64 norms of the represented points) for sdb_lse_pass_tc."""
+        self.dp = 16 if self.d <= 16 else 32 if self.d <= 32 else 64
+        self.n_pad = _round_up(max(self.n, 1), 256)
+        self.x16 = torch.empty((self.n_pad, 2 * self.dp), dtype=torch.float16, device=self.x64.device)
+        self.norms16 = torch.empty(self.n, dtype=torch.float64, device=self.x64.device)
+        st = torch.cuda.current_stream(self.x64.device).cuda_stream
+        _lib.call("sdb_prep_points_split_f16", _ptr(self.x64), self.n, self.d, _ptr(center), pow2_exp, _ptr(self.x16),
+                  self.n_pad, self.dp, _ptr(self.norms16), st)
 
 
 class CudaOps:
     SIMT_MAX_D = 128
+    TC_MAX_D = 64
+    TC_MIN_PAIRS = 1 << 22   # below this the tensor-core pipeline cannot fill; the SIMT pass is used
     MAX_SPLIT_COLS = 65536   # keeps fp32 running sums < 1e-6 relative (include/spadot_b200.h)
     TARGET_CTAS = 148 * 6
 
-    def __init__(self, x_local, y, device=None):
+    def __init__(self, x_local, y, device=None, tc="auto"):
         _lib.require_device()
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         self.launches = 0
@@ -70,8 +83,24 @@ class CudaOps:
         self.X = PointSet(x64, center)
         self.Y = PointSet(y64, center)
         self.launches += 2
-        self.bias_x = torch.empty(self.n, dtype=torch.float32, device=self.device)
-        self.bias_y = torch.empty(self.m, dtype=torch.float32, device=self.device)
+        self.bias_x = torch.empty(_round_up(max(self.n, 1), 256), dtype=torch.float32, device=self.device)
+        self.bias_y = torch.empty(_round_up(max(self.m, 1), 256), dtype=torch.float32, device=self.device)
+        if tc not in ("auto", "on", "off"):
+            raise ValueError("tc must be 'auto', 'on' or 'off'")
+        self.use_tc = tc == "on" or (tc == "auto" and self.d <= self.TC_MAX_D and self.n * self.m >= self.TC_MIN_PAIRS)
+        if self.use_tc:
+            if self.d > self.TC_MAX_D or self.n == 0:
+                raise ValueError("the tensor-core pass needs 1 <= d <= 64 and at least one row")
+            amax = torch.zeros(1, dtype=torch.float64, device=self.device)
+            self._call("sdb_absmax_centered_f64", _ptr(x64), self.n, self.d, _ptr(center), _ptr(amax))
+            self._call("sdb_absmax_centered_f64", _ptr(y64), self.m, self.d, _ptr(center), _ptr(amax))
+            amax = float(amax.item())
+            # scale so that the largest |coordinate| lands in [2^13, 2^14): fp16 hi+lo then carries 22 bits
+            self.pow2_exp = 14 - (math.frexp(amax)[1] if amax > 0 else 0)
+            self.X.build_split(center, self.pow2_exp)
+            self.Y.build_split(center, self.pow2_exp)
+            self.launches += 2
+            self.n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.scratch = torch.zeros(10 * 1024 + 2, dtype=torch.float64, device=self.device)
         self.out10 = torch.zeros(10, dtype=torch.float64, device=self.device)
@@ -128,29 +157,54 @@ class CudaOps:
         return self._partials[key]
 
     # ------------------------------------------------------------------ K3 passes
-    def _lse(self, P: PointSet, Q: PointSet, bias, eps, out=None, bounds=None, ns=None, finalize=True):
+    def _norms(self, P: PointSet):
+        return P.norms16 if self.use_tc else P.norms
+
+    def _tc_split_plan(self, n_p, n_q):
+        row_tiles = (n_p + 127) // 128
+        col_tiles = (n_q + 255) // 256
+        want = max(1, -(-4 * self.n_sm // row_tiles))                # enough items to balance a persistent grid
+        ns = min(want, max(1, col_tiles // 8))                        # ... but at least 8 tiles per item
+        ns = max(ns, -(-col_tiles // (self.MAX_SPLIT_COLS // 256)))   # fp32 running-sum accuracy cap
+        tps = -(-col_tiles // ns)
+        return tps, -(-col_tiles // tps)
+
+    def _lse(self, P: PointSet, Q: PointSet, bias, eps, out=None, bounds=None, ns=None, finalize=True, simt=False):
         c1 = self.inv_med / eps
         scale = 2.0 * c1 * math.log2(math.e)
-        if bounds is None:
-            bounds, ns = self._split_plan(P.n, Q.n)
-        partial = self._partial(ns, P.n)
-        self._call("sdb_lse_pass_simt", _ptr(P.xt), P.ld, P.n, _ptr(Q.xt), Q.ld, Q.n, P.dpad, _ptr(bias), scale,
-                   _ptr(bounds), ns, _ptr(partial))
+        if self.use_tc and not simt:
+            tps, ns = self._tc_split_plan(P.n, Q.n)
+            partial = self._partial(ns, P.n)
+            self._call("sdb_lse_pass_tc", _ptr(P.x16), P.n, P.n_pad, _ptr(Q.x16), Q.n, Q.n_pad, P.dp, _ptr(bias),
+                       scale * 2.0 ** (-2 * self.pow2_exp), tps, self.n_sm, _ptr(partial))
+            norms = P.norms16
+        else:
+            if bounds is None:
+                bounds, ns = self._split_plan(P.n, Q.n)
+            partial = self._partial(ns, P.n)
+            self._call("sdb_lse_pass_simt", _ptr(P.xt), P.ld, P.n, _ptr(Q.xt), Q.ld, Q.n, P.dpad, _ptr(bias), scale,
+                       _ptr(bounds), ns, _ptr(partial))
+            norms = P.norms
         if not finalize:
             return partial
         if out is None:
             out = torch.empty(P.n, dtype=torch.float64, device=self.device)
-        self._call("sdb_lse_finalize", _ptr(partial), ns, P.n, _ptr(P.norms), c1, _ptr(out))
+        self._call("sdb_lse_finalize", _ptr(partial), ns, P.n, _ptr(norms), c1, _ptr(out))
         return out
 
     def row_lse(self, g, eps, out=None):
         """Lr_i = LSE_j[(g_j - C_ij)/eps] over all columns (natural log, fp64).  g=None means g=0."""
-        self._call("sdb_make_bias", self.m, _ptr(g), _ptr(self.Y.norms), eps, self.inv_med / eps, _ptr(self.bias_y))
+        self._call("sdb_make_bias", self.m, self.bias_y.numel(), _ptr(g), _ptr(self._norms(self.Y)), eps,
+                   self.inv_med / eps, _ptr(self.bias_y))
         return self._lse(self.X, self.Y, self.bias_y, eps, out)
 
     def col_lse(self, f, eps, out=None):
         """Lc_j = LSE_{i local}[(f_i - C_ij)/eps] over this rank's rows."""
-        self._call("sdb_make_bias", self.n, _ptr(f), _ptr(self.X.norms), eps, self.inv_med / eps, _ptr(self.bias_x))
+        if self.n == 0:
+            out = torch.empty(self.m, dtype=torch.float64, device=self.device) if out is None else out
+            return out.fill_(NEG_INF)
+        self._call("sdb_make_bias", self.n, self.bias_x.numel(), _ptr(f), _ptr(self._norms(self.X)), eps,
+                   self.inv_med / eps, _ptr(self.bias_x))
         return self._lse(self.Y, self.X, self.bias_x, eps, out)
 
     # ------------------------------------------------------------------ vector updates
@@ -240,8 +294,8 @@ class CudaOps:
         gp = g.index_select(0, perm).contiguous()
         bias = torch.empty(self.m, dtype=torch.float32, device=self.device)
         c1 = self.inv_med / eps
-        self._call("sdb_make_bias", self.m, _ptr(gp), _ptr(Yp.norms), eps, c1, _ptr(bias))
-        partial = self._lse(self.X, Yp, bias, eps, bounds=bounds, ns=k1, finalize=False)
+        self._call("sdb_make_bias", self.m, self.m, _ptr(gp), _ptr(Yp.norms), eps, c1, _ptr(bias))
+        partial = self._lse(self.X, Yp, bias, eps, bounds=bounds, ns=k1, finalize=False, simt=True)
         table = torch.zeros((k0, k1), dtype=torch.float64, device=self.device)
         self._call("sdb_transition_accumulate", _ptr(partial), k1, self.n, _ptr(self.X.norms), c1, _ptr(f), eps,
                    1.0 / self.m, _ptr(lx), k0, _ptr(table))

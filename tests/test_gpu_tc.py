@@ -1,0 +1,113 @@
+"""GPU parity of the tcgen05/TMEM/TMA form of the streamed LSE pass (sdb_lse_pass_tc) against the fp64
+oracle and against the SIMT form, then full solves with the tensor-core pass forced on."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ot_dense, ot_logdomain
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+CFG = dict(ot_dense.DEFAULT_OT_CONFIG)
+
+
+@pytest.fixture(scope="module")
+def ot():
+    from spadot_b200 import ot_solvers, sinkhorn
+    from spadot_b200.cuda_ops import CudaOps
+    torch.cuda.set_device(0)
+    return ot_solvers, sinkhorn, CudaOps
+
+
+@pytest.mark.parametrize("n,m,d", [(128, 256, 32), (747, 1966, 20), (1966, 1916, 20), (300, 5000, 32), (130, 97, 6),
+                                   (1000, 1300, 48), (1, 1, 3), (5000, 40000, 32), (40000, 3000, 16)])
+@pytest.mark.parametrize("eps", [1.0, 0.05])
+def test_tc_pass_matches_oracle(ot, n, m, d, eps):
+    _, _, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, d, seed=n + m)
+    rng = np.random.default_rng(3)
+    if n * m <= 4_000_000:
+        C = ot_dense.sqeuclidean(a, b)
+        med = float(np.median(C))
+        rows = np.arange(n)
+        cols = np.arange(m)
+    else:
+        med = 2.0 * d * 2.5
+        rows = rng.integers(0, n, 96)
+        cols = rng.integers(0, m, 96)
+    g = rng.normal(0, 0.3, m)
+    f = rng.normal(0, 0.3, n)
+    ops = CudaOps(a, b, tc="on")
+    ops.set_median(med)
+    Lr = ops.row_lse(ops.tensor(g), eps).cpu().numpy()
+    Lc = ops.col_lse(ops.tensor(f), eps).cpu().numpy()
+    want_r = ot_logdomain.CostOperator(a[rows], b, median=med).row_lse(g / eps, eps)
+    want_c = ot_logdomain.CostOperator(a, b[cols], median=med).col_lse(f / eps, eps)
+    assert np.abs(Lr[rows] - want_r).max() < 2e-5
+    assert np.abs(Lc[cols] - want_c).max() < 2e-5
+
+
+def test_tc_and_simt_passes_agree(ot):
+    _, _, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(3000, 2900, 32, seed=12)
+    g = np.random.default_rng(0).normal(0, 0.3, 2900)
+    o1 = CudaOps(a, b, tc="on")
+    o2 = CudaOps(a, b, tc="off")
+    for o in (o1, o2):
+        o.set_median(160.0)
+    L1 = o1.row_lse(o1.tensor(g), 0.05)
+    L2 = o2.row_lse(o2.tensor(g), 0.05)
+    assert float((L1 - L2).abs().max()) < 2e-5
+
+
+def test_tc_masked_columns_and_empty_rows(ot):
+    _, _, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(200, 700, 8, seed=5)
+    ops = CudaOps(a, b, tc="on")
+    ops.set_median(20.0)
+    g = np.zeros(700)
+    g[300:] = -np.inf
+    cost = ot_logdomain.CostOperator(a, b, median=20.0)
+    Lr = ops.row_lse(ops.tensor(g), 0.5).cpu().numpy()
+    assert np.abs(Lr - cost.row_lse(g / 0.5, 0.5)).max() < 2e-5
+    g[:] = -np.inf
+    assert np.all(np.isneginf(ops.row_lse(ops.tensor(g), 0.5).cpu().numpy()))
+
+
+@pytest.mark.parametrize("n,m,d,seed", [(1966, 1916, 20, 2), (2500, 2048, 32, 3)])
+def test_tc_full_solve_matches_oracle(ot, n, m, d, seed):
+    ot_solvers, sinkhorn, CudaOps = ot
+    a, b, la, lb = ot_dense.synthetic_embeddings(n, m, d, seed=seed)
+    Cn, med = ot_dense.median_normalised_cost(a, b)
+    info_ref = {}
+    want = ot_dense.duality_gap_solve(Cn, np.ones(n), info=info_ref, **CFG)
+    ops = CudaOps(a, b, tc="on")
+    cp = ot_solvers.solve_coupling(a, b, CFG, ops=ops)
+    got = cp.plan().cpu().numpy()
+    assert cp.info["iters_per_stage"] == info_ref["iters_per_stage"]
+    assert np.abs(got.sum(1) - want.sum(1)).max() / want.sum(1).max() < 1e-5
+    assert np.abs(got.sum(0) - want.sum(0)).max() / want.sum(0).max() < 1e-5
+    big = want > 1e-8 * want.max()
+    assert (np.abs(got - want)[big] / want[big]).max() < 1e-4
+    tab = cp.transition_table(la, lb, 10, 10).cpu().numpy()
+    tab_ref = ot_dense.transition_table(want, la, lb, 10, 10)
+    assert np.abs(tab - tab_ref).max() / tab_ref.max() < 1e-4
+    assert np.array_equal(tab.argmax(1), tab_ref.argmax(1))
+
+
+def test_tc_large_properties(ot):
+    """At a size no CPU oracle can hold densely: shift equivariance + spot rows against fp64."""
+    _, _, CudaOps = ot
+    n, m, d = 60000, 50000, 32
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, d, seed=77)
+    ops = CudaOps(a, b)
+    assert ops.use_tc
+    ops.set_median(160.0)
+    eps = 0.05
+    g = ops.tensor(np.random.default_rng(0).normal(0, 0.2, m))
+    L0 = ops.row_lse(g, eps).clone()
+    L1 = ops.row_lse(g + 0.125, eps)
+    assert float((L1 - L0 - 0.125 / eps).abs().max()) < 2e-5
+    idx = np.random.default_rng(1).integers(0, n, 64)
+    want = ot_logdomain.CostOperator(a[idx], b, median=160.0).row_lse(g.cpu().numpy() / eps, eps)
+    assert np.abs(L0.cpu().numpy()[idx] - want).max() < 2e-5
