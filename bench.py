@@ -279,19 +279,34 @@ def gpu_main(a):
         pairs = float(n_loc) * float(a.m)
         flop_per_pair = 2 * ops.X.dpad + 8
         avg_pass_s = (sum(pass_ms) / len(pass_ms)) / 1e3 if pass_ms else float("nan")
-        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12
-        achieved = pairs * flop_per_pair / avg_pass_s / 1e12
-        roofline = dict(bound="fp32", kernel="pair_tile_kernel<LseEpi> (sdb_lse_pass_simt)", achieved=achieved,
-                        peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak, traffic=None,
-                        peak_source=f"148 SM x 128 FMA x 2 x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json; "
-                                    "MEASURED_PEAKS.json has no fp32/SFU entry)",
-                        pass_ms_avg=avg_pass_s * 1e3, pass_launches=len(pass_ms),
-                        share_of_step=(sum(pass_ms) / 1e3) / elapsed,
-                        ex2_per_s=pairs / avg_pass_s, sfu_peak_ex2_per_s=148 * 16 * sm_max * 1e6,
-                        hbm_gbs_algorithmic=((n_loc + a.m) * (ops.X.dpad + 2) * 4) / avg_pass_s / 1e9)
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        common = dict(traffic=None, pass_ms_avg=avg_pass_s * 1e3, pass_launches=len(pass_ms),
+                      share_of_step=(sum(pass_ms) / 1e3) / elapsed,
+                      hbm_gbs_algorithmic=((n_loc + a.m) * (ops.X.dpad + 2) * 4) / avg_pass_s / 1e9,
+                      pairs_per_launch=pairs)
+        if ops.use_tc:
+            # tensor-core form: the dot product runs on tcgen05; what is left per pair is one ex2 (SFU, 16/clk/SM)
+            # and ~4 fp32 instructions, so the binding pipe is the SFU.
+            sfu_peak = n_sm * 16 * sm_max * 1e6 / 1e12
+            achieved = pairs / avg_pass_s / 1e12
+            roofline = dict(bound="sfu", kernel="lse_pass_tc_kernel<%d> (sdb_lse_pass_tc)" % ops.X.dp, achieved=achieved,
+                            peak=sfu_peak, unit="Tex2/s", frac=achieved / sfu_peak,
+                            peak_source=f"{n_sm} SM x 16 MUFU lanes x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json; "
+                                        "that file has no SFU entry)",
+                            tensor_tflops=pairs * 6 * ops.X.dp / avg_pass_s / 1e12,
+                            tensor_frac_of_measured_bf16=(pairs * 6 * ops.X.dp / avg_pass_s / 1e12) / float(peaks.get("bf16_tflops", 1640.6)),
+                            **common)
+        else:
+            fp32_peak = n_sm * 128 * 2 * sm_max * 1e6 / 1e12
+            achieved = pairs * flop_per_pair / avg_pass_s / 1e12
+            roofline = dict(bound="fp32", kernel="pair_tile_kernel<LseEpi> (sdb_lse_pass_simt)", achieved=achieved,
+                            peak=fp32_peak, unit="TFLOP/s", frac=achieved / fp32_peak,
+                            peak_source=f"{n_sm} SM x 128 FMA x 2 x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json; "
+                                        "that file has no fp32 entry)",
+                            ex2_per_s=pairs / avg_pass_s, **common)
         line = dict(metric=METRIC, value=a.steps / elapsed, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
                     ms_per_step=elapsed * 1e3 / a.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
-                    dtype="f32 tiles / f64 vectors", data="synthetic", impl="spadot_b200",
+                    dtype="f16x2-split tensor tiles + f32 epilogue / f64 vectors" if ops.use_tc else "f32 tiles / f64 vectors", data="synthetic", impl="spadot_b200",
                     config=dict(workload=workload_name(a), rows_per_rank=n_loc, parallelism=f"row-partition x{world}",
                                 l2_policy="inputs per pass (>=136 MB at 1M) exceed reuse; potentials rewritten every step",
                                 median="analytic (K5 exact median untimed)", finite=finite,

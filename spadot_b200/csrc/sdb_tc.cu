@@ -7,13 +7,15 @@
 //                               and the 256-float bias slice, into mbarrier rings
 //   warp 1      MMA issuer    : x.y^T as three tcgen05.mma chains (hi*hi + hi*lo + lo*hi, fp32 accumulate) into one
 //                               of two 128x256 fp32 TMEM accumulators
-//   warps 2..9  epilogue      : two warpgroups ping-pong on the TMEM buffers: tcgen05.ld -> t = scale*d + bias_j ->
-//                               online (max, sum ex2) per row in registers; one (max,sum) pair per row leaves the SM.
+//   warps 2..9  epilogue      : all 8 warps drain each accumulator (32 TMEM lanes x 128 columns per warp) while the
+//                               MMA of the next tile fills the other one: tcgen05.ld -> t = scale*d + bias_j ->
+//                               lazily stabilised sum of ex2 per row in registers; one (max,sum) pair per row leaves the SM.
 // The N x M cost / kernel matrix never exists in any memory.  The 2-term fp16 split keeps 22 mantissa
 // bits of every coordinate, so the tile math is fp32-accurate (plain TF32/BF16 is not).
 // Replaces gemv/gemtv + update_k of ref: SpaDOT/utils/OT_loss/ot_func.cpp:43-249,547-568.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "sdb_common.cuh"
 
@@ -21,9 +23,8 @@ namespace {
 
 constexpr int TILE_M = 128;          // rows per CTA item (UMMA M)
 constexpr int TILE_N = 256;          // columns per streamed tile (UMMA N)
-constexpr int N_EPI_WARPS = 8;
-constexpr int NT_TC = 32 * (2 + N_EPI_WARPS);
 constexpr int BIAS_STAGES = 4;
+constexpr int MAX_EPI_WARPS = 16;
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -93,6 +94,41 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+template <int W>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[W]) {
+    if constexpr (W == 32) tmem_ld32(taddr, r); else tmem_ld16(taddr, r);
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 issue one instruction for two lanes of work)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // K-major, swizzled UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor layout, version 1):
 //   [0,14) start>>4, [16,30) LBO>>4 (=1: unused for swizzled K-major), [32,46) SBO>>4 (8 rows * row bytes),
 //   [46,48) version=1, [61,64) layout: 2=SW128, 4=SW64, 6=SW32.
@@ -117,8 +153,8 @@ struct TcSmem {
     static constexpr int OFF_A = 0;                                     // [2][A_BYTES]
     static constexpr int OFF_B = OFF_A + 2 * A_BYTES;                   // [STAGES][2][B_BYTES]
     static constexpr int OFF_BIAS = OFF_B + STAGES * 2 * B_BYTES;       // [BIAS_STAGES][TILE_N] float
-    static constexpr int OFF_MERGE = OFF_BIAS + BIAS_STAGES * TILE_N * 4;  // [TILE_M] float2
-    static constexpr int OFF_BAR = OFF_MERGE + TILE_M * 8;              // barriers
+    static constexpr int OFF_MERGE = OFF_BIAS + BIAS_STAGES * TILE_N * 4;  // [3][TILE_M] float2
+    static constexpr int OFF_BAR = OFF_MERGE + 3 * TILE_M * 8;          // barriers
     static constexpr int N_BARS = 2 * STAGES + 2 + 4 + 2 * BIAS_STAGES;
     static constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
     static constexpr int TOTAL = OFF_TMEM + 16 + 1024;                  // + alignment slack
@@ -132,10 +168,11 @@ struct TcArgs {
     float2* partial;         // [n_splits][n_p]
 };
 
-template <int DP>
-__global__ void __launch_bounds__(NT_TC, 1)
+template <int DP, int EPI_WARPS, bool PACKED>
+__global__ void __launch_bounds__(32 * (2 + EPI_WARPS), 1)
 lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, TcArgs a) {
     using S = TcSmem<DP>;
+    constexpr int N_EPI_WARPS = EPI_WARPS;
     constexpr int STAGES = S::STAGES;
     constexpr int KSTEPS = DP / 16;
     extern __shared__ uint8_t smem_raw[];
@@ -161,8 +198,8 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, 4); }
-        for (int i = 0; i < BIAS_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, N_EPI_WARPS); }
+        for (int i = 0; i < BIAS_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, N_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
@@ -241,81 +278,115 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             }
         }
     } else {
-        // =============================================================== epilogue warpgroups
-        const int ew = warp - 2;                 // 0..7
-        const int wg = ew >> 2;                  // accumulator buffer this warpgroup drains
-        const int quad = warp & 3;               // TMEM lane quadrant accessible to this warp
+        // =============================================================== epilogue warps
+        // Every tile is drained by all epilogue warps: warp (quad, part) owns TMEM lanes [32*quad, +32) and a
+        // 256/PARTS-column slice of the current accumulator, so the MMA of tile t+1 (other accumulator) overlaps
+        // the epilogue of tile t.  tcgen05.ld of the next chunk is in flight while this one is processed.  The
+        // stabiliser m_used only moves when a chunk maximum exceeds it by more than 2^64 (floating point is
+        // scale-free: no precision is lost, terms 2^-126 below the stabiliser are irrelevant to the sum).
+        constexpr int PARTS = EPI_WARPS / 4;
+        constexpr int COLS = TILE_N / PARTS;         // columns per warp per tile
+        constexpr int CH = (EPI_WARPS == 8) ? 32 : 16;
+        constexpr int NCH = COLS / CH;
+        const int ew = warp - 2;
+        const int part = ew >> 2;
+        const int quad = warp & 3;                   // TMEM lane quadrant accessible to this warp
         const int row_in_tile = quad * 32 + lane;
         const float scale = a.scale;
+        const uint64_t scale2 = pack2(scale, scale);
+        const uint32_t bias_base = smem_u32(sBias) + part * COLS * 4;
         uint32_t tile_ctr = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int rt = item % a.n_row_tiles, sp = item / a.n_row_tiles;
             const int t0 = sp * a.tiles_per_split;
             const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
-            float m = SDB_NEG_SENTINEL, ssum = 0.f;
+            float m_used = SDB_NEG_SENTINEL, ssum = 0.f;
             for (int t = t0; t < t1; ++t, ++tile_ctr) {
                 const int acc = tile_ctr & 1;
-                if (acc != wg) continue;
                 const int bs = tile_ctr % BIAS_STAGES;
                 mbar_wait(b_full + bs, (tile_ctr / BIAS_STAGES) & 1);
                 mbar_wait(t_full + acc, (tile_ctr >> 1) & 1);
                 tc_fence_after();
-                const float* bias_s = sBias + bs * TILE_N;
-                const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TILE_N;
-#pragma unroll 1
-                for (int c = 0; c < TILE_N; c += 64) {
-                    uint32_t d0[32], d1[32];
-                    tmem_ld32(tbase + c, d0);
-                    tmem_ld32(tbase + c + 32, d1);
+                const uint32_t bias_s = bias_base + bs * TILE_N * 4;
+                const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TILE_N + part * COLS;
+                uint32_t d[2][CH];
+                tmem_ld<CH>(tbase, d[0]);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
                     tmem_ld_wait();
-                    float tv[64];
+                    if (c + 1 < NCH) tmem_ld<CH>(tbase + (c + 1) * CH, d[(c + 1) & 1]);
+                    float tv[CH];
 #pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4) {
-                        const float4 b = *reinterpret_cast<const float4*>(bias_s + c + k4 * 4);
-                        tv[k4 * 4 + 0] = fmaf(scale, __uint_as_float(d0[k4 * 4 + 0]), b.x);
-                        tv[k4 * 4 + 1] = fmaf(scale, __uint_as_float(d0[k4 * 4 + 1]), b.y);
-                        tv[k4 * 4 + 2] = fmaf(scale, __uint_as_float(d0[k4 * 4 + 2]), b.z);
-                        tv[k4 * 4 + 3] = fmaf(scale, __uint_as_float(d0[k4 * 4 + 3]), b.w);
-                    }
-#pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4) {
-                        const float4 b = *reinterpret_cast<const float4*>(bias_s + c + 32 + k4 * 4);
-                        tv[32 + k4 * 4 + 0] = fmaf(scale, __uint_as_float(d1[k4 * 4 + 0]), b.x);
-                        tv[32 + k4 * 4 + 1] = fmaf(scale, __uint_as_float(d1[k4 * 4 + 1]), b.y);
-                        tv[32 + k4 * 4 + 2] = fmaf(scale, __uint_as_float(d1[k4 * 4 + 2]), b.z);
-                        tv[32 + k4 * 4 + 3] = fmaf(scale, __uint_as_float(d1[k4 * 4 + 3]), b.w);
+                    for (int k4 = 0; k4 < CH / 4; ++k4) {
+                        const float4 b = lds128(bias_s + (c * CH + k4 * 4) * 4);
+                        if constexpr (PACKED) {
+                            const uint64_t r0 = ffma2(scale2, pack2(__uint_as_float(d[c & 1][k4 * 4 + 0]), __uint_as_float(d[c & 1][k4 * 4 + 1])), pack2(b.x, b.y));
+                            const uint64_t r1 = ffma2(scale2, pack2(__uint_as_float(d[c & 1][k4 * 4 + 2]), __uint_as_float(d[c & 1][k4 * 4 + 3])), pack2(b.z, b.w));
+                            unpack2(r0, tv[k4 * 4 + 0], tv[k4 * 4 + 1]);
+                            unpack2(r1, tv[k4 * 4 + 2], tv[k4 * 4 + 3]);
+                        } else {
+                            tv[k4 * 4 + 0] = fmaf(scale, __uint_as_float(d[c & 1][k4 * 4 + 0]), b.x);
+                            tv[k4 * 4 + 1] = fmaf(scale, __uint_as_float(d[c & 1][k4 * 4 + 1]), b.y);
+                            tv[k4 * 4 + 2] = fmaf(scale, __uint_as_float(d[c & 1][k4 * 4 + 2]), b.z);
+                            tv[k4 * 4 + 3] = fmaf(scale, __uint_as_float(d[c & 1][k4 * 4 + 3]), b.w);
+                        }
                     }
                     float cm0 = tv[0], cm1 = tv[1], cm2 = tv[2], cm3 = tv[3];
 #pragma unroll
-                    for (int k = 4; k < 64; k += 4) {
+                    for (int k = 4; k < CH; k += 4) {
                         cm0 = fmaxf(cm0, tv[k]); cm1 = fmaxf(cm1, tv[k + 1]);
                         cm2 = fmaxf(cm2, tv[k + 2]); cm3 = fmaxf(cm3, tv[k + 3]);
                     }
-                    const float mn = fmaxf(m, fmaxf(fmaxf(cm0, cm1), fmaxf(cm2, cm3)));
-                    float s0 = ssum * sdb_ex2(m - mn), s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                    m = mn;
-#pragma unroll
-                    for (int k = 0; k < 64; k += 4) {
-                        s0 += sdb_ex2(tv[k] - mn); s1 += sdb_ex2(tv[k + 1] - mn);
-                        s2 += sdb_ex2(tv[k + 2] - mn); s3 += sdb_ex2(tv[k + 3] - mn);
+                    const float cm = fmaxf(fmaxf(cm0, cm1), fmaxf(cm2, cm3));
+                    if (cm > m_used + 64.f) {          // rare: first chunk of an item, or a much closer column shows up
+                        ssum *= sdb_ex2(m_used - cm);
+                        m_used = cm;
                     }
-                    ssum = (s0 + s1) + (s2 + s3);
+                    if constexpr (PACKED) {
+                        const uint64_t nm2 = pack2(-m_used, -m_used);
+                        uint64_t acc2[CH / 2];
+#pragma unroll
+                        for (int k = 0; k < CH; k += 2) {
+                            float a0, a1;
+                            unpack2(fadd2(pack2(tv[k], tv[k + 1]), nm2), a0, a1);
+                            acc2[k / 2] = pack2(sdb_ex2(a0), sdb_ex2(a1));
+                        }
+#pragma unroll
+                        for (int w = CH / 4; w > 0; w >>= 1)
+#pragma unroll
+                            for (int k = 0; k < w; ++k) acc2[k] = fadd2(acc2[k], acc2[k + w]);
+                        float e0, e1;
+                        unpack2(acc2[0], e0, e1);
+                        ssum += e0 + e1;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < CH; ++k) tv[k] = sdb_ex2(tv[k] - m_used);
+#pragma unroll
+                        for (int w = CH / 2; w > 0; w >>= 1)
+#pragma unroll
+                            for (int k = 0; k < w; ++k) tv[k] += tv[k + w];
+                        ssum += tv[0];
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(t_empty + acc); mbar_arrive(b_empty + bs); }
             }
-            // merge the two warpgroups' row statistics and emit one (max, sum) per row
-            if (wg == 1) sMerge[row_in_tile] = make_float2(m, ssum);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (wg == 0) {
-                const float2 o = sMerge[row_in_tile];
-                const float mn = fmaxf(m, o.x);
-                const float sv = ssum * sdb_ex2(m - mn) + o.y * sdb_ex2(o.x - mn);
+            // merge the column slices' row statistics and emit one (max, sum) per row
+            if (part > 0) sMerge[(part - 1) * TILE_M + row_in_tile] = make_float2(m_used, ssum);
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            if (part == 0) {
+#pragma unroll
+                for (int q = 0; q < PARTS - 1; ++q) {
+                    const float2 o = sMerge[q * TILE_M + row_in_tile];
+                    const float mn = fmaxf(m_used, o.x);
+                    ssum = ssum * sdb_ex2(m_used - mn) + o.y * sdb_ex2(o.x - mn);
+                    m_used = mn;
+                }
                 const int64_t row = (int64_t)rt * TILE_M + row_in_tile;
-                if (row < a.n_p) a.partial[(int64_t)sp * a.n_p + row] = make_float2(mn, sv);
+                if (row < a.n_p) a.partial[(int64_t)sp * a.n_p + row] = make_float2(m_used, ssum);
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
         }
     }
 
@@ -391,14 +462,34 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows_pad, int dp, int b
     return r == CUDA_SUCCESS ? 0 : SDB_E_DRIVER;
 }
 
-template <int DP>
-int launch_tc(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
-    auto kern = lse_pass_tc_kernel<DP>;
+template <int DP, int EPI_WARPS, bool PACKED>
+int launch_tc_v(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
+    auto kern = lse_pass_tc_kernel<DP, EPI_WARPS, PACKED>;
     constexpr int smem = TcSmem<DP>::TOTAL;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    kern<<<n_ctas, NT_TC, smem, st>>>(tmP, tmQ, a);
+    kern<<<n_ctas, 32 * (2 + EPI_WARPS), smem, st>>>(tmP, tmQ, a);
     SDB_LAUNCH_STATUS();
+}
+
+// Tuning variant (development knob, SDB_TC_VARIANT=0..3): bit0 = packed f32x2 epilogue, bit1 = 16 epilogue warps.
+int tc_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SDB_TC_VARIANT");
+        v = e ? atoi(e) & 3 : 1;
+    }
+    return v;
+}
+
+template <int DP>
+int launch_tc(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
+    switch (tc_variant()) {
+        case 1: return launch_tc_v<DP, 8, true>(tmP, tmQ, a, n_ctas, st);
+        case 2: return launch_tc_v<DP, 16, false>(tmP, tmQ, a, n_ctas, st);
+        case 3: return launch_tc_v<DP, 16, true>(tmP, tmQ, a, n_ctas, st);
+        default: return launch_tc_v<DP, 8, false>(tmP, tmQ, a, n_ctas, st);
+    }
 }
 
 }  // namespace
