@@ -174,6 +174,19 @@ int sdb_transition_accumulate(const float* partial, int k1, int64_t n, const dou
                               const double* f, double eps, double inv_m, const int* label_row, int k0,
                               double* table, void* stream);
 
+/* ------------------------------------------------------------------ dense-cost path (caller supplies C) */
+/* For the reference signatures that take an explicit cost matrix (ref: utils/OT_loss/ot_solvers.py:164,452).
+ * C is row-major fp64 with leading dimension ldc; one sweep reads C once.  fp64 throughout.
+ * L[i] = LSE_j[(g_j - C_ij)/eps]  (g may be NULL = 0). */
+int sdb_dense_row_lse_f64(const double* C, int64_t ldc, int64_t n, int64_t m, const double* g, double eps,
+                          double* L, void* stream);
+/* L[j] = LSE_i[(f_i - C_ij)/eps]; partial: workspace of 2*n_chunks*m doubles (rows are swept in n_chunks chunks). */
+int sdb_dense_col_lse_f64(const double* C, int64_t ldc, int64_t n, int64_t m, const double* f, double eps,
+                          double* L, double* partial, int n_chunks, void* stream);
+/* plan[i*m+j] = exp((f_i + g_j - C_ij)/eps) * inv_m   (R / J, ref: ot_solvers.py:449); n <= 65535 per call. */
+int sdb_dense_plan_f64(const double* C, int64_t ldc, int64_t n, int64_t m, const double* f, const double* g,
+                       double eps, double inv_m, double* plan, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

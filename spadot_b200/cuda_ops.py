@@ -56,7 +56,119 @@ class PointSet:
                   self.n_pad, self.dp, _ptr(self.norms16), st)
 
 
-class CudaOps:
+class VectorOps:
+    """O(N+M) fp64 device vector kernels shared by the streamed and the dense-cost solvers."""
+
+    def _init_vectors(self, device):
+        _lib.require_device()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.launches = 0
+        self._tick = 0
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.scratch = torch.zeros(10 * 1024 + 2, dtype=torch.float64, device=self.device)
+        self.out10 = torch.zeros(10, dtype=torch.float64, device=self.device)
+
+    def _to_dev(self, a):
+        if isinstance(a, torch.Tensor):
+            t = a.detach()
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.to(device=self.device, dtype=torch.float64).contiguous()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _call(self, name, *args):
+        _lib.call(name, *args, self._stream())
+        self.launches += 1
+
+    def tick(self):
+        """Monotonic sweep counter; the absorb flag stores the last sweep that exceeded tau."""
+        self._tick += 1
+        return self._tick
+
+    def zeros(self, n, dtype=torch.float64):
+        return torch.zeros(n, dtype=dtype, device=self.device)
+
+    def tensor(self, a, dtype=torch.float64):
+        return torch.as_tensor(np.asarray(a), dtype=dtype).to(self.device)
+
+    def _side_norms(self, side, pot):
+        return pot          # only read when a bias vector is requested (streamed solver overrides)
+
+    def _c1(self, eps):
+        return 0.0
+
+    def potential_update(self, side, L, logmarg, eps, alpha, log_n_other, pot, frame, la_old, it, log_tau,
+                         log_floor=NEG_INF):
+        """side='row' updates f (local rows), side='col' updates g; see sdb_potential_update."""
+        self._call("sdb_potential_update", pot.numel(), _ptr(L), _ptr(logmarg), _ptr(self._side_norms(side, pot)), eps,
+                   alpha, log_n_other, self._c1(eps), _ptr(pot), _ptr(frame), _ptr(la_old), 0, _ptr(self.flag), it,
+                   log_tau, log_floor)
+
+    def absorb_flag_tensor(self):
+        return self.flag
+
+    def absorb(self, it, f, g, u, v):
+        self._call("sdb_absorb", f.numel(), g.numel(), _ptr(self.flag), it, _ptr(f), _ptr(g), _ptr(u), _ptr(v))
+
+    def stage_criterion(self, f, u, la_old, g, v, lb_old, eps):
+        self._call("sdb_stage_criterion", f.numel(), g.numel(), _ptr(f), _ptr(u), _ptr(la_old), _ptr(g), _ptr(v),
+                   _ptr(lb_old), eps, _ptr(self.out10), _ptr(self.scratch))
+        return self.out10[:4].clone()
+
+    def gap_terms(self, f, Lr, logp, g, Lc, logq, eps, lam1, lam2, dx, dy):
+        self._call("sdb_gap_terms", f.numel(), g.numel(), _ptr(f), _ptr(Lr), _ptr(logp), _ptr(g), _ptr(Lc), _ptr(logq),
+                   eps, lam1, lam2, dx, dy, _ptr(self.out10), _ptr(self.scratch))
+        return self.out10.clone()
+
+    def sum_exp(self, L):
+        self._call("sdb_sum_exp", L.numel(), _ptr(L), 0, 0.0, _ptr(self.out10), _ptr(self.scratch))
+        return self.out10[:1].clone()
+
+    def row_mass(self, f, Lr, eps):
+        out = torch.empty_like(f)
+        self._call("sdb_row_mass", f.numel(), _ptr(f), _ptr(Lr), eps, 1.0 / self.m, _ptr(out))
+        return out
+
+
+class DenseOps(VectorOps):
+    """`ops` for a caller-supplied dense cost matrix C (N x M fp64): every sweep reads C once from HBM."""
+
+    def __init__(self, C, device=None):
+        self._init_vectors(device)
+        self.C = self._to_dev(C)
+        if self.C.dim() != 2:
+            raise ValueError("C must be a 2-D cost matrix")
+        self.n, self.m = self.C.shape
+        self.n_chunks = int(max(1, min(256, (self.n + 255) // 256, max(1, (148 * 8 * 256) // max(self.m, 1)))))
+        self.partial = torch.empty(2 * self.n_chunks * max(self.m, 1), dtype=torch.float64, device=self.device)
+
+    def set_median(self, median):
+        pass
+
+    def row_lse(self, g, eps, out=None):
+        out = torch.empty(self.n, dtype=torch.float64, device=self.device) if out is None else out
+        self._call("sdb_dense_row_lse_f64", _ptr(self.C), self.m, self.n, self.m, _ptr(g), eps, _ptr(out))
+        return out
+
+    def col_lse(self, f, eps, out=None):
+        out = torch.empty(self.m, dtype=torch.float64, device=self.device) if out is None else out
+        self._call("sdb_dense_col_lse_f64", _ptr(self.C), self.m, self.n, self.m, _ptr(f), eps, _ptr(out),
+                   _ptr(self.partial), self.n_chunks)
+        self.launches += 1
+        return out
+
+    def plan_dense(self, f, g, eps):
+        plan = torch.empty((self.n, self.m), dtype=torch.float64, device=self.device)
+        for r0 in range(0, self.n, 65535):
+            r1 = min(self.n, r0 + 65535)
+            self._call("sdb_dense_plan_f64", _ptr(self.C[r0:r1]), self.m, r1 - r0, self.m, _ptr(f[r0:r1]), _ptr(g), eps,
+                       1.0 / self.m, _ptr(plan[r0:r1]))
+        return plan
+
+
+class CudaOps(VectorOps):
     SIMT_MAX_D = 128
     TC_MAX_D = 64
     TC_MIN_PAIRS = 1 << 22   # below this the tensor-core pipeline cannot fill; the SIMT pass is used
@@ -64,9 +176,7 @@ class CudaOps:
     TARGET_CTAS = 148 * 6
 
     def __init__(self, x_local, y, device=None, tc="auto"):
-        _lib.require_device()
-        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
-        self.launches = 0
+        self._init_vectors(device)
         x64 = self._to_dev(x_local)
         y64 = self._to_dev(y)
         if x64.shape[1] != y64.shape[1]:
@@ -101,40 +211,11 @@ class CudaOps:
             self.Y.build_split(center, self.pow2_exp)
             self.launches += 2
             self.n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
-        self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self.scratch = torch.zeros(10 * 1024 + 2, dtype=torch.float64, device=self.device)
-        self.out10 = torch.zeros(10, dtype=torch.float64, device=self.device)
         self._splits = {}
         self._partials = {}
         self.inv_med = 1.0
-        self._tick = 0
 
     # ------------------------------------------------------------------ plumbing
-    def _to_dev(self, a):
-        if isinstance(a, torch.Tensor):
-            t = a.detach()
-        else:
-            t = torch.from_numpy(np.ascontiguousarray(a))
-        return t.to(device=self.device, dtype=torch.float64).contiguous()
-
-    def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
-
-    def _call(self, name, *args):
-        _lib.call(name, *args, self._stream())
-        self.launches += 1
-
-    def tick(self):
-        """Monotonic sweep counter; the absorb flag stores the last sweep that exceeded tau."""
-        self._tick += 1
-        return self._tick
-
-    def zeros(self, n, dtype=torch.float64):
-        return torch.zeros(n, dtype=dtype, device=self.device)
-
-    def tensor(self, a, dtype=torch.float64):
-        return torch.as_tensor(np.asarray(a), dtype=dtype).to(self.device)
-
     def set_median(self, median: float):
         self.inv_med = 1.0 / float(median)
 
@@ -208,37 +289,11 @@ class CudaOps:
         return self._lse(self.Y, self.X, self.bias_x, eps, out)
 
     # ------------------------------------------------------------------ vector updates
-    def potential_update(self, side, L, logmarg, eps, alpha, log_n_other, pot, frame, la_old, it, log_tau,
-                         log_floor=NEG_INF):
-        """side='row' updates f (local rows), side='col' updates g; see sdb_potential_update."""
-        norms = self.X.norms if side == "row" else self.Y.norms
-        self._call("sdb_potential_update", pot.numel(), _ptr(L), _ptr(logmarg), _ptr(norms), eps, alpha, log_n_other,
-                   self.inv_med / eps, _ptr(pot), _ptr(frame), _ptr(la_old), 0, _ptr(self.flag), it, log_tau, log_floor)
+    def _side_norms(self, side, pot):
+        return self._norms(self.X if side == "row" else self.Y)
 
-    def absorb_flag_tensor(self):
-        return self.flag
-
-    def absorb(self, it, f, g, u, v):
-        self._call("sdb_absorb", f.numel(), g.numel(), _ptr(self.flag), it, _ptr(f), _ptr(g), _ptr(u), _ptr(v))
-
-    def stage_criterion(self, f, u, la_old, g, v, lb_old, eps):
-        self._call("sdb_stage_criterion", f.numel(), g.numel(), _ptr(f), _ptr(u), _ptr(la_old), _ptr(g), _ptr(v),
-                   _ptr(lb_old), eps, _ptr(self.out10), _ptr(self.scratch))
-        return self.out10[:4].clone()
-
-    def gap_terms(self, f, Lr, logp, g, Lc, logq, eps, lam1, lam2, dx, dy):
-        self._call("sdb_gap_terms", f.numel(), g.numel(), _ptr(f), _ptr(Lr), _ptr(logp), _ptr(g), _ptr(Lc), _ptr(logq),
-                   eps, lam1, lam2, dx, dy, _ptr(self.out10), _ptr(self.scratch))
-        return self.out10.clone()
-
-    def sum_exp(self, L):
-        self._call("sdb_sum_exp", L.numel(), _ptr(L), 0, 0.0, _ptr(self.out10), _ptr(self.scratch))
-        return self.out10[:1].clone()
-
-    def row_mass(self, f, Lr, eps):
-        out = torch.empty_like(f)
-        self._call("sdb_row_mass", f.numel(), _ptr(f), _ptr(Lr), eps, 1.0 / self.m, _ptr(out))
-        return out
+    def _c1(self, eps):
+        return self.inv_med / eps
 
     def plan_dense(self, f, g, eps):
         plan = torch.empty((self.n, self.m), dtype=torch.float64, device=self.device)
