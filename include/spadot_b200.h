@@ -187,6 +187,36 @@ int sdb_dense_col_lse_f64(const double* C, int64_t ldc, int64_t n, int64_t m, co
 int sdb_dense_plan_f64(const double* C, int64_t ldc, int64_t n, int64_t m, const double* f, const double* g,
                        double eps, double inv_m, double* plan, void* stream);
 
+/* ------------------------------------------------------------------ K1: SVGP kernel blocks (train inner loop) */
+/* out[i*ldo+j] = k(|x_i - y_j|^2) (+ jitter when i == j), x (n,dim), y (m,dim) row-major fp64, dim <= 3.
+ * kernel_type 0 Gaussian exp(-d2/scale), 1 Cauchy 1/(1+d2/scale), 2 Quadratic 1 - d2/(d2+scale)
+ * replaces Kernel.forward + _add_diagonal_jitter (ref: model/svgp.py:116-125, 33-41). */
+int sdb_kernel_block_f64(const double* x, int64_t n, const double* y, int64_t m, int dim, int kernel_type,
+                         double scale, double jitter, double* out, int64_t ldo, void* stream);
+/* out[i] = k(|x_i - y_i|^2): kernel_matrix(..., diag_only=True) without the n x n block (ref: svgp.py:43-45). */
+int sdb_kernel_diag_f64(const double* x, const double* y, int64_t n, int dim, int kernel_type, double scale,
+                        double* out, void* stream);
+/* out[i] = w_i^T A w_i for the rows w_i of W (b,m), A (m,m) row-major: the O(b m^2) form of the (b,m,m)
+ * batched product in _compute_l3_term (ref: svgp.py:96-104). */
+int sdb_quad_form_rows_f64(const double* W, const double* A, int64_t b, int m, double* out, void* stream);
+
+/* ------------------------------------------------------------------ K2 / K2b: GAT edge-softmax + aggregation */
+/* Graph in CSR by destination: rowptr (n+1, int64), col (E, int32) = source node of each incoming edge
+ * (self loops included, PyG GATConv add_self_loops semantics are the caller's job).  feat (n,H,C),
+ * a_src / a_dst (n,H) in float or double (is_double).  Writes out (n,H,C) = sum_j alpha_ij feat_j and
+ * alpha (E,H) = softmax_j(leaky_relu(a_src[j]+a_dst[i])) with PyG's +1e-16 denominator.
+ * replaces torch_geometric GATConv message passing used at ref: model/encoder.py:41-45,56-58. */
+int sdb_gat_forward(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
+                    int64_t n, int H, int C, double negative_slope, int is_double, void* out, void* alpha,
+                    void* stream);
+/* Backward of the above.  src_rowptr / src_dst / src_eid: the same edges grouped by SOURCE node
+ * (destination node and position in the by-destination order).  dlogit (E,H) is workspace.
+ * Outputs grad_feat (n,H,C), grad_a_src (n,H), grad_a_dst (n,H).  Deterministic (no atomics). */
+int sdb_gat_backward(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
+                     const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, int64_t n, int H, int C,
+                     double negative_slope, int is_double, const void* alpha, const void* grad_out, void* dlogit,
+                     void* grad_feat, void* grad_a_src, void* grad_a_dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

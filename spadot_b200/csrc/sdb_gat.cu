@@ -1,0 +1,192 @@
+// K2 / K2b: fused GAT edge-softmax + aggregation, forward and backward, over a CSR-by-destination graph.
+//
+// Restates what torch_geometric.nn.GATConv does between its linear layer and its bias add
+// (used at ref: SpaDOT/model/encoder.py:41-45,56-58): per edge j->i and head h
+//     e_ij = leaky_relu(a_src[j,h] + a_dst[i,h], slope);  alpha_ij = softmax_j(e_ij) (+1e-16 in the denominator)
+//     out[i,h,:] = sum_j alpha_ij * feat[j,h,:]
+// PyG materialises (E,H) logits, (E,H,C) messages and scatters them; here one CTA per destination node
+// does the segment softmax in registers/warp shuffles and gathers each source row exactly once
+// (coalesced, 16 B per thread where C allows), writing only out (n,H,C) and alpha (E,H).  The
+// backward uses the by-source CSR so there are no atomics and results are deterministic.
+// HBM/L2 gather-bound:  bytes ~ E*H*C*s (row gathers) + n*H*C*s (write) + E*(4 + 2*H*s).
+#include "sdb_common.cuh"
+
+namespace {
+
+template <typename T> __device__ __forceinline__ T t_exp(T x);
+template <> __device__ __forceinline__ float t_exp<float>(float x) { return __expf(x); }
+template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
+
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_sum_t(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------- forward
+template <typename T>
+__global__ void __launch_bounds__(128) gat_fwd_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
+                                                      const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
+                                                      const int32_t* __restrict__ col, int64_t n, int H, int C, T slope,
+                                                      T* __restrict__ out, T* __restrict__ alpha) {
+    const int64_t i = blockIdx.x;
+    const int64_t e0 = rowptr[i], e1 = rowptr[i + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // segment softmax: one warp per head (round-robin when H > 4)
+    for (int h = warp; h < H; h += 4) {
+        const T ad = a_dst[i * H + h];
+        T mx = -INFINITY;
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            T r = a_src[(int64_t)col[e] * H + h] + ad;
+            r = r > T(0) ? r : r * slope;
+            mx = max(mx, r);
+        }
+        mx = warp_max(mx);
+        T sum = T(0);
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            T r = a_src[(int64_t)col[e] * H + h] + ad;
+            r = r > T(0) ? r : r * slope;
+            sum += t_exp(r - mx);
+        }
+        sum = warp_sum_t(sum) + T(1e-16);
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            T r = a_src[(int64_t)col[e] * H + h] + ad;
+            r = r > T(0) ? r : r * slope;
+            alpha[e * H + h] = t_exp(r - mx) / sum;
+        }
+    }
+    __syncthreads();
+    // aggregation: thread owns feature columns c, c+128, ...; each source row is read once, coalesced
+    const int HC = H * C;
+    for (int c = threadIdx.x; c < HC; c += 128) {
+        const int h = c / C;
+        T acc = T(0);
+        for (int64_t e = e0; e < e1; ++e) acc += alpha[e * H + h] * feat[(int64_t)col[e] * HC + c];
+        out[i * HC + c] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------- backward, by destination
+// dlogit[e,h] = d loss / d (a_src[j,h] + a_dst[i,h]);  grad_a_dst[i,h] = sum_e dlogit[e,h]
+template <typename T>
+__global__ void __launch_bounds__(128) gat_bwd_dst_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
+                                                          const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
+                                                          const int32_t* __restrict__ col, int64_t n, int H, int C, T slope,
+                                                          const T* __restrict__ alpha, const T* __restrict__ grad_out,
+                                                          T* __restrict__ dlogit, T* __restrict__ grad_a_dst) {
+    const int64_t i = blockIdx.x;
+    const int64_t e0 = rowptr[i], e1 = rowptr[i + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int HC = H * C;
+    const int64_t n_eh = (e1 - e0) * H;
+    // d alpha[e,h] = <grad_out[i,h,:], feat[j,h,:]>  (one warp per (edge, head), coalesced over C)
+    for (int64_t p = warp; p < n_eh; p += 4) {
+        const int64_t e = e0 + p / H;
+        const int h = (int)(p % H);
+        const T* go = grad_out + i * HC + h * C;
+        const T* fj = feat + (int64_t)col[e] * HC + h * C;
+        T acc = T(0);
+        for (int c = lane; c < C; c += 32) acc += go[c] * fj[c];
+        acc = warp_sum_t(acc);
+        if (lane == 0) dlogit[e * H + h] = acc;
+    }
+    __syncthreads();
+    for (int h = warp; h < H; h += 4) {
+        T s = T(0);
+        for (int64_t e = e0 + lane; e < e1; e += 32) s += alpha[e * H + h] * dlogit[e * H + h];
+        s = warp_sum_t(s);
+        const T ad = a_dst[i * H + h];
+        T gd = T(0);
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
+            const T r = a_src[(int64_t)col[e] * H + h] + ad;
+            T g = alpha[e * H + h] * (dlogit[e * H + h] - s);
+            g = r > T(0) ? g : g * slope;
+            dlogit[e * H + h] = g;
+            gd += g;
+        }
+        gd = warp_sum_t(gd);
+        if (lane == 0) grad_a_dst[i * H + h] = gd;
+    }
+}
+
+// ---------------------------------------------------------------------------------------- backward, by source
+// grad_feat[j,h,:] = sum_{e: j->i} alpha[e,h] * grad_out[i,h,:];  grad_a_src[j,h] = sum_e dlogit[e,h]
+template <typename T>
+__global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restrict__ src_rowptr, const int32_t* __restrict__ src_dst,
+                                                          const int32_t* __restrict__ src_eid, int64_t n, int H, int C,
+                                                          const T* __restrict__ alpha, const T* __restrict__ dlogit,
+                                                          const T* __restrict__ grad_out, T* __restrict__ grad_feat,
+                                                          T* __restrict__ grad_a_src) {
+    const int64_t j = blockIdx.x;
+    const int64_t p0 = src_rowptr[j], p1 = src_rowptr[j + 1];
+    const int HC = H * C;
+    for (int c = threadIdx.x; c < HC; c += 128) {
+        const int h = c / C;
+        T acc = T(0);
+        for (int64_t p = p0; p < p1; ++p) acc += alpha[(int64_t)src_eid[p] * H + h] * grad_out[(int64_t)src_dst[p] * HC + c];
+        grad_feat[j * HC + c] = acc;
+    }
+    for (int h = threadIdx.x; h < H; h += 128) {
+        T acc = T(0);
+        for (int64_t p = p0; p < p1; ++p) acc += dlogit[(int64_t)src_eid[p] * H + h];
+        grad_a_src[j * H + h] = acc;
+    }
+}
+
+template <typename T>
+int gat_forward_t(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col, int64_t n, int H,
+                  int C, double slope, void* out, void* alpha, cudaStream_t st) {
+    gat_fwd_kernel<T><<<(unsigned)n, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, n, H, C, (T)slope,
+                                                  (T*)out, (T*)alpha);
+    SDB_LAUNCH_STATUS();
+}
+
+template <typename T>
+int gat_backward_t(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
+                   const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, int64_t n, int H, int C, double slope,
+                   const void* alpha, const void* grad_out, void* dlogit, void* grad_feat, void* grad_a_src, void* grad_a_dst,
+                   cudaStream_t st) {
+    gat_bwd_dst_kernel<T><<<(unsigned)n, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, n, H, C, (T)slope,
+                                                      (const T*)alpha, (const T*)grad_out, (T*)dlogit, (T*)grad_a_dst);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    gat_bwd_src_kernel<T><<<(unsigned)n, 128, 0, st>>>(src_rowptr, src_dst, src_eid, n, H, C, (const T*)alpha, (const T*)dlogit,
+                                                      (const T*)grad_out, (T*)grad_feat, (T*)grad_a_src);
+    SDB_LAUNCH_STATUS();
+}
+
+}  // namespace
+
+extern "C" {
+
+int sdb_gat_forward(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col, int64_t n,
+                    int H, int C, double negative_slope, int is_double, void* out, void* alpha, void* stream) {
+    SDB_CHECK_ARG(feat && a_src && a_dst && rowptr && col && out && alpha && n >= 0 && H > 0 && C > 0);
+    if (n == 0) return 0;
+    if (n > 2147483647LL) return SDB_E_UNSUPPORTED;
+    return is_double ? gat_forward_t<double>(feat, a_src, a_dst, rowptr, col, n, H, C, negative_slope, out, alpha, sdb_stream(stream))
+                     : gat_forward_t<float>(feat, a_src, a_dst, rowptr, col, n, H, C, negative_slope, out, alpha, sdb_stream(stream));
+}
+
+int sdb_gat_backward(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
+                     const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, int64_t n, int H, int C,
+                     double negative_slope, int is_double, const void* alpha, const void* grad_out, void* dlogit, void* grad_feat,
+                     void* grad_a_src, void* grad_a_dst, void* stream) {
+    SDB_CHECK_ARG(feat && a_src && a_dst && rowptr && col && src_rowptr && src_dst && src_eid && alpha && grad_out && dlogit &&
+                  grad_feat && grad_a_src && grad_a_dst && n >= 0 && H > 0 && C > 0);
+    if (n == 0) return 0;
+    if (n > 2147483647LL) return SDB_E_UNSUPPORTED;
+    return is_double ? gat_backward_t<double>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, n, H, C, negative_slope, alpha,
+                                              grad_out, dlogit, grad_feat, grad_a_src, grad_a_dst, sdb_stream(stream))
+                     : gat_backward_t<float>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, n, H, C, negative_slope, alpha,
+                                             grad_out, dlogit, grad_feat, grad_a_src, grad_a_dst, sdb_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+"""Drop-in GATConv / GATEncoder (SpaDOT/model/encoder.py:37-61) without torch_geometric.
+
+`GATConv(in_channels, out_channels, heads, concat)` keeps PyG's parameter names and shapes
+(`lin.weight (H*C, in)`, `att_src`, `att_dst (1,H,C)`, `bias`) so state_dicts saved by the reference
+(`train.py:39-41`) load unchanged.  The linear layer stays a cuBLAS GEMM; everything between it and the
+bias add — gather a_src[j]+a_dst[i], LeakyReLU(0.2), segment softmax over incoming edges, weighted
+aggregation, and the whole backward — runs in the fused CSR kernels of csrc/sdb_gat.cu (K2/K2b)
+through one autograd Function.  Self-loop handling = PyG's remove_self_loops + add_self_loops.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+
+class CsrGraph:
+    """Edges (source -> target) with self loops, grouped by destination (forward) and by source (backward)."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, add_self_loops: bool = True):
+        src, dst = edge_index[0].long(), edge_index[1].long()
+        if add_self_loops:
+            keep = src != dst
+            loops = torch.arange(num_nodes, dtype=torch.long, device=edge_index.device)
+            src, dst = torch.cat([src[keep], loops]), torch.cat([dst[keep], loops])
+        order = torch.argsort(dst, stable=True)
+        self.n = num_nodes
+        self.E = int(src.numel())
+        self.col = src[order].to(torch.int32).contiguous()                   # source of each edge, by-destination order
+        dst_sorted = dst[order]
+        self.rowptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=edge_index.device)
+        self.rowptr[1:] = torch.cumsum(torch.bincount(dst_sorted, minlength=num_nodes), 0)
+        by_src = torch.argsort(self.col.long(), stable=True)                 # positions (edge ids) grouped by source
+        self.src_eid = by_src.to(torch.int32).contiguous()
+        self.src_dst = dst_sorted[by_src].to(torch.int32).contiguous()
+        self.src_rowptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=edge_index.device)
+        self.src_rowptr[1:] = torch.cumsum(torch.bincount(self.col.long(), minlength=num_nodes), 0)
+
+
+_GRAPH_CACHE: dict = {}
+
+
+def graph_for(edge_index, num_nodes, add_self_loops=True):
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, num_nodes, add_self_loops, str(edge_index.device))
+    g = _GRAPH_CACHE.get(key)
+    if g is None:
+        if len(_GRAPH_CACHE) > 64:
+            _GRAPH_CACHE.clear()
+        g = _GRAPH_CACHE[key] = CsrGraph(edge_index, num_nodes, add_self_loops)
+    return g
+
+
+def _st(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _EdgeSoftmaxAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, a_src, a_dst, graph, slope):
+        _lib.require_device()
+        if not feat.is_cuda:
+            raise RuntimeError("spadot_b200.gat needs CUDA tensors; there is no CPU fallback")
+        n, H, C = feat.shape
+        feat, a_src, a_dst = feat.contiguous(), a_src.contiguous(), a_dst.contiguous()
+        out = torch.empty_like(feat)
+        alpha = torch.empty((graph.E, H), dtype=feat.dtype, device=feat.device)
+        is_double = int(feat.dtype == torch.float64)
+        if feat.dtype not in (torch.float32, torch.float64):
+            raise TypeError("GATConv supports float32 and float64")
+        _lib.call("sdb_gat_forward", feat.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(), graph.rowptr.data_ptr(),
+                  graph.col.data_ptr(), n, H, C, float(slope), is_double, out.data_ptr(), alpha.data_ptr(), _st(feat))
+        ctx.save_for_backward(feat, a_src, a_dst, alpha)
+        ctx.graph, ctx.slope, ctx.is_double = graph, float(slope), is_double
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        feat, a_src, a_dst, alpha = ctx.saved_tensors
+        g = ctx.graph
+        n, H, C = feat.shape
+        grad_out = grad_out.contiguous()
+        dlogit = torch.empty_like(alpha)
+        grad_feat = torch.empty_like(feat)
+        grad_a_src = torch.empty_like(a_src)
+        grad_a_dst = torch.empty_like(a_dst)
+        _lib.call("sdb_gat_backward", feat.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(), g.rowptr.data_ptr(), g.col.data_ptr(),
+                  g.src_rowptr.data_ptr(), g.src_dst.data_ptr(), g.src_eid.data_ptr(), n, H, C, ctx.slope, ctx.is_double,
+                  alpha.data_ptr(), grad_out.data_ptr(), dlogit.data_ptr(), grad_feat.data_ptr(), grad_a_src.data_ptr(),
+                  grad_a_dst.data_ptr(), _st(feat))
+        return grad_feat, grad_a_src, grad_a_dst, None, None
+
+
+class GATConv(nn.Module):
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, add_self_loops=True, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
+        self.negative_slope, self.add_self_loops = negative_slope, add_self_loops
+        self.lin = nn.Linear(in_channels, heads * out_channels, bias=False)
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(heads * out_channels if concat else out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.xavier_uniform_(self.lin.weight)
+        nn.init.xavier_uniform_(self.att_src)
+        nn.init.xavier_uniform_(self.att_dst)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def forward(self, x, edge_index):
+        H, C, N = self.heads, self.out_channels, x.shape[0]
+        h = self.lin(x).view(N, H, C)
+        a_src = (h * self.att_src).sum(-1)
+        a_dst = (h * self.att_dst).sum(-1)
+        graph = graph_for(edge_index, N, self.add_self_loops)
+        out = _EdgeSoftmaxAggregate.apply(h, a_src, a_dst, graph, self.negative_slope)
+        out = out.reshape(N, H * C) if self.concat else out.mean(dim=1)
+        return out + self.bias if self.bias is not None else out
+
+
+class GATEncoder(nn.Module):
+    """SpaDOT/model/encoder.py:37-61 with the fused GATConv."""
+
+    def __init__(self, input_dim, GAT_z_dim, hidden_dim=512, num_heads=4):
+        super().__init__()
+        self.gat1 = GATConv(input_dim, hidden_dim, heads=num_heads, concat=True)
+        self.gat2 = GATConv(hidden_dim * num_heads, hidden_dim, heads=num_heads, concat=True)
+        self.gat3 = GATConv(hidden_dim * num_heads, hidden_dim, heads=num_heads, concat=False)
+        self.GAT_fc = nn.Linear(hidden_dim, GAT_z_dim * 2)
+        nn.init.xavier_uniform_(self.GAT_fc.weight)
+
+    def forward(self, x, edge_index):
+        h = F.leaky_relu(self.gat1(x, edge_index))
+        h = F.leaky_relu(self.gat2(h, edge_index))
+        h = self.gat3(h, edge_index)
+        GAT_z = self.GAT_fc(h)
+        GAT_enc_mu, GAT_enc_logvar = torch.chunk(GAT_z, 2, dim=1)
+        return GAT_enc_mu, torch.exp(GAT_enc_logvar)

@@ -1,0 +1,99 @@
+"""GAT edge-softmax message passing (K2/K2b).  Oracle: oracle/gat_ref.py (PyG semantics; parity
+unpinned by the reference — torch_geometric is un-vendored).  Forward and every gradient are compared
+in float64 (tight) and float32 (fp32 tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import gat_ref, graph_ref
+
+
+def make_graph(n, seed=0):
+    rng = np.random.default_rng(seed)
+    coords = rng.uniform(0, 30, size=(n, 2))
+    k = max(2, graph_ref.knn_cutoff(n)) if n >= 1000 else 6
+    return torch.from_numpy(graph_ref.spatial_edge_index(coords, k))
+
+
+def test_graph_oracle_shape_and_self_loops():
+    ei = make_graph(200).numpy()
+    assert ei.shape[0] == 2 and ei.shape[1] == 200 * 6 + 200
+    assert np.all(np.bincount(ei[0], minlength=200) == 7)          # every node sends k edges + its self loop
+    assert np.all((ei[0] == ei[1]).sum() == 200)
+    # dense_to_sparse order: sorted by source, then target
+    assert np.all(np.diff(ei[0]) >= 0)
+
+
+def test_oracle_softmax_rows_sum_to_one_and_concat_mean_shapes():
+    torch.manual_seed(0)
+    ei = make_graph(50)
+    conv = gat_ref.GATConvRef(7, 5, heads=3, concat=True).double()
+    x = torch.randn(50, 7, dtype=torch.float64)
+    assert conv(x, ei).shape == (50, 15)
+    conv2 = gat_ref.GATConvRef(7, 5, heads=3, concat=False).double()
+    assert conv2(x, ei).shape == (50, 5)
+    assert set(conv.state_dict().keys()) == {"att_src", "att_dst", "bias", "lin.weight"}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 2e-4)])
+@pytest.mark.parametrize("n,fin,C,H,concat", [(300, 40, 16, 4, True), (257, 33, 24, 3, False), (1200, 64, 512, 4, True)])
+def test_gatconv_forward_backward_match_oracle(dtype, tol, n, fin, C, H, concat):
+    from spadot_b200 import gat
+    dev = torch.device("cuda:0")
+    torch.manual_seed(n)
+    ei = make_graph(n, seed=n)
+    ref = gat_ref.GATConvRef(fin, C, heads=H, concat=concat).to(dtype)
+    mine = gat.GATConv(fin, C, heads=H, concat=concat).to(dtype).to(dev)
+    assert set(mine.state_dict().keys()) == set(ref.state_dict().keys())
+    mine.load_state_dict({k: v.to(dev) for k, v in ref.state_dict().items()})
+    with torch.no_grad():
+        ref.bias.normal_()
+        mine.bias.copy_(ref.bias.to(dev))
+    x = torch.randn(n, fin, dtype=dtype)
+    xr = x.clone().requires_grad_(True)
+    xm = x.clone().to(dev).requires_grad_(True)
+    w = torch.randn(n, C * H if concat else C, dtype=dtype)
+    out_r = ref(xr, ei)
+    out_m = mine(xm, ei.to(dev))
+    scale = float(out_r.abs().max())
+    assert float((out_m.cpu() - out_r).abs().max()) < tol * max(scale, 1.0)
+    (out_r * w).sum().backward()
+    (out_m * w.to(dev)).sum().backward()
+    for (name, pr), (_, pm) in zip(ref.named_parameters(), mine.named_parameters()):
+        gs = float(pr.grad.abs().max())
+        assert float((pm.grad.cpu() - pr.grad).abs().max()) < tol * 50 * max(gs, 1.0), name
+    assert float((xm.grad.cpu() - xr.grad).abs().max()) < tol * 50 * max(float(xr.grad.abs().max()), 1.0)
+
+
+@pytest.mark.gpu
+def test_gat_encoder_matches_oracle_and_loads_reference_style_state_dict():
+    from spadot_b200 import gat
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    n = 400
+    ei = make_graph(n, seed=3)
+    ref = gat_ref.GATEncoderRef(60, 10, hidden_dim=32, num_heads=4).double()
+    mine = gat.GATEncoder(60, 10, hidden_dim=32, num_heads=4).double().to(dev)
+    mine.load_state_dict(ref.state_dict())          # same keys: gatN.lin.weight, gatN.att_src, gatN.att_dst, gatN.bias, GAT_fc.*
+    x = torch.randn(n, 60, dtype=torch.float64)
+    mu_r, var_r = ref(x, ei)
+    mu_m, var_m = mine(x.to(dev), ei.to(dev))
+    np.testing.assert_allclose(mu_m.detach().cpu().numpy(), mu_r.detach().numpy(), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(var_m.detach().cpu().numpy(), var_r.detach().numpy(), rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.gpu
+def test_gat_isolated_and_high_degree_nodes():
+    """A hub with > 32 incoming edges (several warp strides) and a node whose only edge is its self loop."""
+    from spadot_b200 import gat
+    dev = torch.device("cuda:0")
+    n = 120
+    src = torch.arange(1, 100)
+    ei = torch.stack([src, torch.zeros_like(src)])          # 99 edges into node 0; nodes 100..119 isolated
+    torch.manual_seed(0)
+    ref = gat_ref.GATConvRef(9, 8, heads=2).double()
+    mine = gat.GATConv(9, 8, heads=2).double().to(dev)
+    mine.load_state_dict(ref.state_dict())
+    x = torch.randn(n, 9, dtype=torch.float64)
+    np.testing.assert_allclose(mine(x.to(dev), ei.to(dev)).detach().cpu().numpy(), ref(x, ei).detach().numpy(), rtol=1e-10, atol=1e-12)
