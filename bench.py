@@ -280,7 +280,16 @@ def gpu_main(a):
         flop_per_pair = 2 * ops.X.dpad + 8
         avg_pass_s = (sum(pass_ms) / len(pass_ms)) / 1e3 if pass_ms else float("nan")
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        common = dict(traffic=None, pass_ms_avg=avg_pass_s * 1e3, pass_launches=len(pass_ms),
+        traffic = None
+        try:
+            tj = _json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            key = f"lse_pass_{'tc' if ops.use_tc else 'simt'} n={a.n} m={a.m} d={a.d} world={world}"
+            traffic = tj.get(key, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        common = dict(traffic=traffic, traffic_source="ncu --set full, profiles/r1_traffic.json" if traffic else None,
+                      algorithmic_hbm_bytes_per_launch=(n_loc + a.m) * (ops.X.dpad + 2) * 4,
+                      pass_ms_avg=avg_pass_s * 1e3, pass_launches=len(pass_ms),
                       share_of_step=(sum(pass_ms) / 1e3) / elapsed,
                       hbm_gbs_algorithmic=((n_loc + a.m) * (ops.X.dpad + 2) * 4) / avg_pass_s / 1e9,
                       pairs_per_launch=pairs)

@@ -129,6 +129,34 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
     return r;
 }
 
+// 2^x for a packed pair on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f, |f| <= 0.5, degree-5 minimax
+// polynomial for 2^f (max rel. error 2.4e-7 in fp32, the same class as ex2.approx's 2^-22), then the integer n is
+// added into the exponent field.  Used for a fixed fraction of the exponentials so that the SFU (16 ex2/clk/SM)
+// and the FMA pipe share the load.  x must be <= 127; values below -126 are clamped (they are 0 in the sum).
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
+    float x0, x1;
+    unpack2(x2, x0, x1);
+    x0 = fmaxf(x0, -126.f);
+    x1 = fmaxf(x1, -126.f);
+    x2 = pack2(x0, x1);
+    const uint64_t magic = pack2(12582912.f, 12582912.f);        // 1.5 * 2^23: rounds to nearest integer
+    const uint64_t r2 = fadd2(x2, magic);
+    const uint64_t n2 = fadd2(r2, pack2(-12582912.f, -12582912.f));
+    const uint64_t f2 = ffma2(n2, pack2(-1.f, -1.f), x2);
+    uint64_t p2 = pack2(0.0013390863314270973f, 0.0013390863314270973f);
+    p2 = ffma2(p2, f2, pack2(0.009676031768321991f, 0.009676031768321991f));
+    p2 = ffma2(p2, f2, pack2(0.055503569543361664f, 0.055503569543361664f));
+    p2 = ffma2(p2, f2, pack2(0.2402210682630539f, 0.2402210682630539f));
+    p2 = ffma2(p2, f2, pack2(0.6931471824645996f, 0.6931471824645996f));
+    p2 = ffma2(p2, f2, pack2(1.0000001192092896f, 1.0000001192092896f));
+    float r0, r1, p0, p1;
+    unpack2(r2, r0, r1);
+    unpack2(p2, p0, p1);
+    const float e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+    const float e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+    return pack2(e0, e1);
+}
+
 // K-major, swizzled UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor layout, version 1):
 //   [0,14) start>>4, [16,30) LBO>>4 (=1: unused for swizzled K-major), [32,46) SBO>>4 (8 rows * row bytes),
 //   [46,48) version=1, [61,64) layout: 2=SW128, 4=SW64, 6=SW32.
@@ -168,7 +196,7 @@ struct TcArgs {
     float2* partial;         // [n_splits][n_p]
 };
 
-template <int DP, int EPI_WARPS, bool PACKED>
+template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0>
 __global__ void __launch_bounds__(32 * (2 + EPI_WARPS), 1)
 lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, TcArgs a) {
     using S = TcSmem<DP>;
@@ -347,9 +375,14 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                         uint64_t acc2[CH / 2];
 #pragma unroll
                         for (int k = 0; k < CH; k += 2) {
-                            float a0, a1;
-                            unpack2(fadd2(pack2(tv[k], tv[k + 1]), nm2), a0, a1);
-                            acc2[k / 2] = pack2(sdb_ex2(a0), sdb_ex2(a1));
+                            const uint64_t x2 = fadd2(pack2(tv[k], tv[k + 1]), nm2);
+                            if (POLY_EVERY > 0 && ((k / 2) % POLY_EVERY) == POLY_EVERY - 1) {
+                                acc2[k / 2] = exp2_poly2(x2);       // FMA-pipe exponential
+                            } else {
+                                float a0, a1;
+                                unpack2(x2, a0, a1);
+                                acc2[k / 2] = pack2(sdb_ex2(a0), sdb_ex2(a1));
+                            }
                         }
 #pragma unroll
                         for (int w = CH / 4; w > 0; w >>= 1)
@@ -462,9 +495,9 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows_pad, int dp, int b
     return r == CUDA_SUCCESS ? 0 : SDB_E_DRIVER;
 }
 
-template <int DP, int EPI_WARPS, bool PACKED>
+template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0>
 int launch_tc_v(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
-    auto kern = lse_pass_tc_kernel<DP, EPI_WARPS, PACKED>;
+    auto kern = lse_pass_tc_kernel<DP, EPI_WARPS, PACKED, POLY_EVERY>;
     constexpr int smem = TcSmem<DP>::TOTAL;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
@@ -472,12 +505,14 @@ int launch_tc_v(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a,
     SDB_LAUNCH_STATUS();
 }
 
-// Tuning variant (development knob, SDB_TC_VARIANT=0..3): bit0 = packed f32x2 epilogue, bit1 = 16 epilogue warps.
+// Tuning variant (development knob SDB_TC_VARIANT): 0 scalar epilogue, 1 packed f32x2 (all exponentials on the SFU),
+// 2/3/4 packed with every 2nd/3rd/4th pair of exponentials evaluated by the FMA-pipe polynomial.
 int tc_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SDB_TC_VARIANT");
-        v = e ? atoi(e) & 3 : 1;
+        v = e ? atoi(e) : 1;
+        if (v < 0 || v > 4) v = 1;
     }
     return v;
 }
@@ -485,10 +520,11 @@ int tc_variant() {
 template <int DP>
 int launch_tc(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
     switch (tc_variant()) {
-        case 1: return launch_tc_v<DP, 8, true>(tmP, tmQ, a, n_ctas, st);
-        case 2: return launch_tc_v<DP, 16, false>(tmP, tmQ, a, n_ctas, st);
-        case 3: return launch_tc_v<DP, 16, true>(tmP, tmQ, a, n_ctas, st);
-        default: return launch_tc_v<DP, 8, false>(tmP, tmQ, a, n_ctas, st);
+        case 0: return launch_tc_v<DP, 8, false>(tmP, tmQ, a, n_ctas, st);
+        case 2: return launch_tc_v<DP, 8, true, 2>(tmP, tmQ, a, n_ctas, st);
+        case 3: return launch_tc_v<DP, 8, true, 3>(tmP, tmQ, a, n_ctas, st);
+        case 4: return launch_tc_v<DP, 8, true, 4>(tmP, tmQ, a, n_ctas, st);
+        default: return launch_tc_v<DP, 8, true>(tmP, tmQ, a, n_ctas, st);
     }
 }
 
