@@ -217,6 +217,11 @@ int sdb_gat_backward(const void* feat, const void* a_src, const void* a_dst, con
                      double negative_slope, int is_double, const void* alpha, const void* grad_out, void* dlogit,
                      void* grad_feat, void* grad_a_src, void* grad_a_dst, void* stream);
 
+/* k nearest OTHER points (self excluded) of every point, sorted by (distance, index); pts (n,dim) fp64, dim <= 3,
+ * k <= 32 and k <= n-1.  out_idx (n,k) int32, out_dist (n,k) fp64 Euclidean distances (may be NULL).
+ * replaces sklearn NearestNeighbors in _Cal_Spatial_Net (ref: utils/_utils.py:65-69). */
+int sdb_knn_f64(const double* pts, int64_t n, int dim, int k, int32_t* out_idx, double* out_dist, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -190,3 +190,62 @@ int sdb_gat_backward(const void* feat, const void* a_src, const void* a_dst, con
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------- spatial kNN graph
+// Brute-force k nearest neighbours in 2-D/3-D (k <= 32) for the GAT's spatial graph
+// (ref: SpaDOT/utils/_utils.py:52-100 _Cal_Spatial_Net: sklearn NearestNeighbors(k+1) minus self).
+// One thread per query keeps its k best (distance, index) pairs sorted by (distance, index); candidate
+// coordinates are streamed through shared memory.  fp64 distances so pixel-scale coordinates do not collide.
+namespace {
+
+constexpr int KNN_MAX_K = 32;
+constexpr int KNN_TILE = 1024;
+
+__global__ void __launch_bounds__(128) knn_kernel(const double* __restrict__ pts, int64_t n, int dim, int k, int32_t* __restrict__ out_idx,
+                                                  double* __restrict__ out_dist) {
+    __shared__ double tile[KNN_TILE * 3];
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double qx[3] = {0.0, 0.0, 0.0};
+    if (q < n) for (int d = 0; d < dim; ++d) qx[d] = pts[q * dim + d];
+    double bd[KNN_MAX_K];
+    int32_t bi[KNN_MAX_K];
+    for (int t = 0; t < KNN_MAX_K; ++t) { bd[t] = INFINITY; bi[t] = 0x7fffffff; }
+    for (int64_t base = 0; base < n; base += KNN_TILE) {
+        const int cnt = (int)min((int64_t)KNN_TILE, n - base);
+        __syncthreads();
+        for (int e = threadIdx.x; e < cnt * dim; e += blockDim.x) tile[e] = pts[base * dim + e];
+        __syncthreads();
+        if (q >= n) continue;
+        for (int c = 0; c < cnt; ++c) {
+            const int64_t j = base + c;
+            if (j == q) continue;
+            double d2 = 0.0;
+            for (int d = 0; d < dim; ++d) { const double df = qx[d] - tile[c * dim + d]; d2 += df * df; }
+            if (d2 < bd[k - 1] || (d2 == bd[k - 1] && (int32_t)j < bi[k - 1])) {
+                int pos = k - 1;
+                while (pos > 0 && (bd[pos - 1] > d2 || (bd[pos - 1] == d2 && bi[pos - 1] > (int32_t)j))) {
+                    bd[pos] = bd[pos - 1];
+                    bi[pos] = bi[pos - 1];
+                    --pos;
+                }
+                bd[pos] = d2;
+                bi[pos] = (int32_t)j;
+            }
+        }
+    }
+    if (q < n)
+        for (int t = 0; t < k; ++t) {
+            out_idx[q * k + t] = bi[t];
+            if (out_dist) out_dist[q * k + t] = sqrt(bd[t]);
+        }
+}
+
+}  // namespace
+
+extern "C" int sdb_knn_f64(const double* pts, int64_t n, int dim, int k, int32_t* out_idx, double* out_dist, void* stream) {
+    SDB_CHECK_ARG(pts && out_idx && n >= 0 && dim >= 1 && dim <= 3 && k >= 1 && k <= KNN_MAX_K);
+    if (n == 0) return 0;
+    if (k > n - 1) return SDB_E_INVALID;
+    knn_kernel<<<(unsigned)((n + 127) / 128), 128, 0, sdb_stream(stream)>>>(pts, n, dim, k, out_idx, out_dist);
+    SDB_LAUNCH_STATUS();
+}

@@ -1,0 +1,84 @@
+"""Spatial kNN graph and deterministic 2-hop mini-batches for the GAT encoder, without dense N x N
+adjacency and without torch_geometric.
+
+* `spatial_edge_index(coords, k)`  = `_Cal_Spatial_Net` + `dense_to_sparse`
+  (SpaDOT/utils/_utils.py:52-100, utils/_train_utils.py:69-72): directed edges query -> neighbour for the
+  k nearest other spots plus one self loop per spot, ordered like the non-zeros of the dense adjacency
+  (by source, then target).
+* `knn_cutoff(n)` = `min(30, 6 * round(n / 1000))`  (utils/_train_utils.py:69).
+* `two_hop_batches(...)` stands in for `NeighborLoader(num_neighbors=[f, f], batch_size, input_nodes=None)`
+  (utils/_train_utils.py:80-85) for the case the reference always runs in (fan-out >= every in-degree, no
+  shuffling): seeds first, then newly reached nodes; edges = every edge into a seed or into a 1-hop node.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def knn_cutoff(n, max_neighbors=30, knn_cutoff_base=6):
+    return int(min(max_neighbors, knn_cutoff_base * round(n / 1000)))
+
+
+def knn(coords, k, device=None):
+    """(n,k) int64 indices of the k nearest other points, nearest first (CUDA brute force, fp64)."""
+    _lib.require_device()
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    pts = torch.as_tensor(np.asarray(coords) if not isinstance(coords, torch.Tensor) else coords).to(dev, torch.float64).contiguous()
+    n, dim = pts.shape
+    idx = torch.empty((n, k), dtype=torch.int32, device=dev)
+    _lib.call("sdb_knn_f64", pts.data_ptr(), n, dim, int(k), idx.data_ptr(), 0, torch.cuda.current_stream(dev).cuda_stream)
+    return idx.long()
+
+
+def spatial_edge_index(coords, k_cutoff, device=None):
+    nbr = knn(coords, k_cutoff, device)
+    n = nbr.shape[0]
+    src = torch.arange(n, device=nbr.device).repeat_interleave(k_cutoff + 1)
+    dst = torch.cat([nbr, torch.arange(n, device=nbr.device)[:, None]], dim=1).reshape(-1)
+    order = torch.argsort(src * n + dst)                      # dense_to_sparse order
+    return torch.stack([src[order], dst[order]])
+
+
+class InNeighbours:
+    """CSR of in-neighbours (sources of the edges pointing to each node)."""
+
+    def __init__(self, edge_index, num_nodes):
+        src, dst = edge_index[0].long(), edge_index[1].long()
+        order = torch.argsort(dst * num_nodes + src)
+        self.src = src[order]
+        self.rowptr = torch.zeros(num_nodes + 1, dtype=torch.long, device=edge_index.device)
+        self.rowptr[1:] = torch.cumsum(torch.bincount(dst, minlength=num_nodes), 0)
+        self.n = num_nodes
+
+    def edges_into(self, nodes):
+        """All edges (source, target) whose target is in `nodes` (1-D long tensor)."""
+        start, end = self.rowptr[nodes], self.rowptr[nodes + 1]
+        deg = end - start
+        tgt = nodes.repeat_interleave(deg)
+        offs = torch.arange(int(deg.sum()), device=nodes.device) - torch.cumsum(deg, 0).repeat_interleave(deg) + deg.repeat_interleave(deg)
+        return self.src[start.repeat_interleave(deg) + offs], tgt
+
+
+def two_hop_batches(edge_index, num_nodes, batch_size=512, num_hops=2):
+    """Yields (node_ids, local_edge_index, n_seeds): seeds are node_ids[:n_seeds] in sequential order."""
+    nb = InNeighbours(edge_index, num_nodes)
+    dev = edge_index.device
+    for s0 in range(0, num_nodes, batch_size):
+        seeds = torch.arange(s0, min(num_nodes, s0 + batch_size), device=dev)
+        nodes, frontier = seeds, seeds
+        local = torch.full((num_nodes,), -1, dtype=torch.long, device=dev)
+        local[seeds] = torch.arange(seeds.numel(), device=dev)
+        es, et = [], []
+        for _ in range(num_hops):
+            s, t = nb.edges_into(frontier)
+            es.append(s)
+            et.append(t)
+            new = torch.unique(s[local[s] < 0])
+            local[new] = torch.arange(nodes.numel(), nodes.numel() + new.numel(), device=dev)
+            nodes = torch.cat([nodes, new])
+            frontier = new
+        s, t = torch.cat(es), torch.cat(et)
+        yield nodes, torch.stack([local[s], local[t]]), int(seeds.numel())
