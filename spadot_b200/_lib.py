@@ -93,9 +93,16 @@ def call(name: str, *args):
     check(getattr(load(), name)(*args), name)
 
 
+_device_ok = set()
+
+
 def require_device():
-    """Fail loudly when the CUDA path cannot run (no silent fallback)."""
+    """Fail loudly when the CUDA path cannot run (no silent fallback).  The (slow) device-property query
+    runs once per device per process."""
     import torch
     if not torch.cuda.is_available():
         raise RuntimeError("spadot_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-    check(load().sdb_device_check(), "sdb_device_check")
+    dev = torch.cuda.current_device()
+    if dev not in _device_ok:
+        check(load().sdb_device_check(), "sdb_device_check")
+        _device_ok.add(dev)
