@@ -245,18 +245,22 @@ def gpu_main(a):
     # ---- e2e: host buffers in, potentials out, through the public API, copies inside the timed region
     xh = torch.from_numpy(x).pin_memory()
     yh = torch.from_numpy(y).pin_memory()
-    e2e_steps = max(2, a.steps // 2)
+    e2e_steps = a.steps
+
+    def e2e_call(n_steps):
+        ops2 = CudaOps(xh, yh, device=dev, tc=a.tc)  # H2D of both spot sets + point preparation
+        ops2.set_median(median)
+        st2 = sinkhorn._State(ops2, np.ones(ops2.n), dist)
+        st2.u.copy_(st2.f)
+        st2.v.copy_(st2.g)
+        for _ in range(n_steps):
+            sinkhorn._sweep(ops2, st2, dist, EPS, a1, a2, log_tau, False)
+        return st2.f.cpu(), (st2.g.cpu() if rank == 0 else None)      # D2H of the result
+
+    e2e_call(1)                                      # warm-up call (allocator growth, first-use costs), untimed
     barrier()
     t0 = time.perf_counter()
-    ops2 = CudaOps(xh, yh, device=dev, tc=a.tc)  # H2D + point preparation
-    ops2.set_median(median)
-    st2 = sinkhorn._State(ops2, np.ones(ops2.n), dist)
-    st2.u.copy_(st2.f)
-    st2.v.copy_(st2.g)
-    for _ in range(e2e_steps):
-        sinkhorn._sweep(ops2, st2, dist, EPS, a1, a2, log_tau, False)
-    f_host = st2.f.cpu()
-    g_host = st2.g.cpu() if rank == 0 else None
+    f_host, g_host = e2e_call(e2e_steps)
     barrier()
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
