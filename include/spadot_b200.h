@@ -113,8 +113,10 @@ int sdb_absorb(int64_t n, int64_t m, const int* absorb_flag, int iter,
 /* ------------------------------------------------------------------ K4: stopping rules */
 /* Stage 0-4 rule (ref: ot_func.cpp:897-922).  out[0..3] =
  *   sum (a~ - old_a e^{u/eps})^2, sum a~^2, sum (b~ - old_b e^{v/eps})^2, sum b~^2
- * with a~ = exp((f-u)/eps)*exp(u/eps).  scratch: >= 4*SDB_REDUCE_BLOCKS doubles + 1 uint. */
+ * with a~ = exp((f-u)/eps)*exp(u/eps).
+ * scratch (all reductions): SDB_REDUCE_WIDTH*SDB_REDUCE_BLOCKS doubles + one zero-initialised uint after them. */
 #define SDB_REDUCE_BLOCKS 1024
+#define SDB_REDUCE_WIDTH 10
 int sdb_stage_criterion(int64_t n, int64_t m, const double* f, const double* u, const double* la_old,
                         const double* g, const double* v, const double* lb_old, double eps,
                         double* out4, void* scratch, void* stream);

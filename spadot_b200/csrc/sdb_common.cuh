@@ -26,12 +26,14 @@ __device__ __forceinline__ double sdb_warp_sum(double v) {
 }
 
 // Deterministic K-wide fp64 grid reduction finished by the last block to arrive.
-// scratch: K*SDB_REDUCE_BLOCKS doubles followed by one unsigned counter (zero before first use;
-// the kernel leaves it zero again).  gridDim.x <= SDB_REDUCE_BLOCKS, blockDim.x == 256.
+// scratch: SDB_REDUCE_WIDTH*SDB_REDUCE_BLOCKS doubles of per-block partials followed by one unsigned counter
+// at a FIXED offset shared by every K (zero before first use; the kernel leaves it zero again), so reductions of
+// different widths can share one scratch buffer on a stream.  gridDim.x <= SDB_REDUCE_BLOCKS, blockDim.x == 256.
 template <int K>
 __device__ void sdb_grid_reduce(double (&vals)[K], void* scratch_v, double* out) {
     double* scratch = reinterpret_cast<double*>(scratch_v);
-    unsigned* counter = reinterpret_cast<unsigned*>(scratch + K * SDB_REDUCE_BLOCKS);
+    static_assert(K <= SDB_REDUCE_WIDTH, "reduction wider than the scratch layout");
+    unsigned* counter = reinterpret_cast<unsigned*>(scratch + SDB_REDUCE_WIDTH * SDB_REDUCE_BLOCKS);
     __shared__ double sm[8][K];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

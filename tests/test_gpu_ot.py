@@ -215,3 +215,27 @@ def test_large_pass_linearity_properties(ot):
     cost = ot_logdomain.CostOperator(a[idx], b, median=160.0)
     want = cost.row_lse(g.cpu().numpy() / eps, eps)
     assert np.abs(L0.cpu().numpy()[idx] - want).max() < 2e-5
+
+
+def test_reductions_of_different_width_share_scratch(ot):
+    """Regression: with > 256 reduction blocks the 4-wide / 10-wide partials used to overwrite the counter of
+    the narrower reductions.  Interleave all three at a size that needs ~1000 blocks."""
+    _, _, CudaOps = ot
+    n, m = 250_000, 240_000
+    a = np.zeros((n, 2))
+    b = np.zeros((m, 2))
+    ops = CudaOps(a, b, tc="off")
+    rng = np.random.default_rng(0)
+    f, g = rng.normal(0, 0.1, n), rng.normal(0, 0.1, m)
+    L = rng.normal(0, 0.1, n)
+    ft, gt, Lt = ops.tensor(f), ops.tensor(g), ops.tensor(L)
+    z_n, z_m = ops.zeros(n), ops.zeros(m)
+    for _ in range(3):
+        t10 = ops.gap_terms(ft, Lt, z_n, gt, z_m, z_m, 0.5, 0.1, 5.0, 1.0 / n, 1.0 / m).cpu().numpy()
+        c4 = ops.stage_criterion(ft, z_n, z_n, gt, z_m, z_m, 0.5).cpu().numpy()
+        s1 = float(ops.sum_exp(Lt).item())
+        assert s1 == pytest.approx(np.exp(L).sum(), rel=1e-12)
+        assert c4[1] == pytest.approx(np.sum(np.exp(f / 0.5) ** 2), rel=1e-12)
+        assert c4[3] == pytest.approx(np.sum(np.exp(g / 0.5) ** 2), rel=1e-12)
+        assert t10[0] == pytest.approx(np.sum(np.exp(f / 0.5 + L)), rel=1e-12)
+        assert t10[4] == pytest.approx(np.sum(np.exp(g / 0.5)), rel=1e-12)
