@@ -163,6 +163,17 @@ int sdb_cost_collect(const float* pt, int64_t ldp, int64_t n_p, const float* qt,
                      int dpad, const int64_t* split_bounds, int n_splits, float lo, float hi,
                      const double* x, const double* y, int d,
                      double* cand, unsigned long long cap, unsigned long long* counts2, void* stream);
+/* Tensor-core forms of the two sweeps above for the fp16 hi/lo split points of sdb_prep_points_split_f16:
+ * dist = row_norms[i] + col_norms_padded[j] - 2 x_i.y_j with fp32 norms (col_norms_padded[j] >= 3e38 for j >= n_q),
+ * scale = -2 * 2^(-2*pow2_exp); same persistent tcgen05/TMEM/TMA pipeline as sdb_lse_pass_tc, n_bins <= 4096. */
+int sdb_cost_histogram_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad,
+                          int dp, const float* row_norms, const float* col_norms_padded, float scale,
+                          int tiles_per_split, int n_ctas, float lo, float hi, int n_bins,
+                          unsigned long long* hist, unsigned long long* counts2, void* stream);
+int sdb_cost_collect_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad,
+                        int dp, const float* row_norms, const float* col_norms_padded, float scale,
+                        int tiles_per_split, int n_ctas, float lo, float hi, const double* x, const double* y, int d,
+                        double* cand, unsigned long long cap, unsigned long long* counts2, void* stream);
 /* hist256[b] = #{ i : (key(cand[i]) >> shift) & 255 == b and key(cand[i]) >> (shift+8) == prefix }
  * (key = IEEE bits of a non-negative double); one radix-select digit. hist256 must be zeroed. */
 int sdb_radix_digit_hist(const double* cand, unsigned long long n, int shift, unsigned long long prefix,

@@ -25,6 +25,8 @@ constexpr int TILE_M = 128;          // rows per CTA item (UMMA M)
 constexpr int TILE_N = 256;          // columns per streamed tile (UMMA N)
 constexpr int BIAS_STAGES = 4;
 constexpr int MAX_EPI_WARPS = 16;
+constexpr int SWEEP_BINS = 4096;     // shared-memory histogram of the median sweeps
+enum { MODE_LSE = 0, MODE_HIST = 1, MODE_COLLECT = 2 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -185,7 +187,9 @@ struct TcSmem {
     static constexpr int OFF_BAR = OFF_MERGE + 3 * TILE_M * 8;          // barriers
     static constexpr int N_BARS = 2 * STAGES + 2 + 4 + 2 * BIAS_STAGES;
     static constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
-    static constexpr int TOTAL = OFF_TMEM + 16 + 1024;                  // + alignment slack
+    static constexpr int OFF_HIST = OFF_TMEM + 16;                      // [SWEEP_BINS] uint32 (median sweeps only)
+    static constexpr int TOTAL = OFF_HIST + 1024;                       // + alignment slack (LSE pass)
+    static constexpr int TOTAL_SWEEP = OFF_HIST + SWEEP_BINS * 4 + 1024;
 };
 
 struct TcArgs {
@@ -194,9 +198,21 @@ struct TcArgs {
     int64_t n_p;
     int n_row_tiles, n_col_tiles, tiles_per_split, n_splits;
     float2* partial;         // [n_splits][n_p]
+    // median sweeps (MODE_HIST / MODE_COLLECT): bias carries |y_j|^2 (+huge padding), scale = -2 * 2^(-2*pow2_exp)
+    const float* row_norms;  // |x_i|^2 as float, n_p entries
+    float lo, hi, inv_width;
+    int n_bins;
+    unsigned long long* hist;     // [n_bins]
+    unsigned long long* counts;   // [2]: below, inside/appended
+    const double* x64;            // original coordinates, row-major (n_p, d) / (n_q, d)
+    const double* y64;
+    int d;
+    int64_t n_q;
+    double* cand;
+    unsigned long long cap;
 };
 
-template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0>
+template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, int MODE = MODE_LSE>
 __global__ void __launch_bounds__(32 * (2 + EPI_WARPS), 1)
 lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, TcArgs a) {
     using S = TcSmem<DP>;
@@ -323,6 +339,85 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         const float scale = a.scale;
         const uint64_t scale2 = pack2(scale, scale);
         const uint32_t bias_base = smem_u32(sBias) + part * COLS * 4;
+        if constexpr (MODE != MODE_LSE) {
+            // ----------------------------------------------------------- median sweeps (K5 on the tensor cores)
+            // dist = |x_i|^2 + |y_j|^2 - 2 x_i.y_j from the same accumulator tiles; count dist < lo, and for the few
+            // pairs inside [lo, hi) either bin them (shared-memory histogram) or re-evaluate them exactly in fp64
+            // from the original coordinates and append them to the candidate list.
+            uint32_t* shist = reinterpret_cast<uint32_t*>(smem + S::OFF_HIST);
+            if constexpr (MODE == MODE_HIST) {
+                for (int bI = threadIdx.x - 64; bI < SWEEP_BINS; bI += 32 * EPI_WARPS) shist[bI] = 0u;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            }
+            unsigned long long below = 0ull, inside = 0ull;
+            uint32_t tile_ctr = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int rt = item % a.n_row_tiles, sp = item / a.n_row_tiles;
+                const int t0 = sp * a.tiles_per_split;
+                const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
+                const int64_t row = (int64_t)rt * TILE_M + row_in_tile;
+                const float nx = row < a.n_p ? a.row_norms[row] : 3.0e38f;
+                for (int t = t0; t < t1; ++t, ++tile_ctr) {
+                    const int acc = tile_ctr & 1;
+                    const int bs = tile_ctr % BIAS_STAGES;
+                    mbar_wait(b_full + bs, (tile_ctr / BIAS_STAGES) & 1);
+                    mbar_wait(t_full + acc, (tile_ctr >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t bias_s = bias_base + bs * TILE_N * 4;
+                    const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TILE_N + part * COLS;
+                    uint32_t d[2][CH];
+                    tmem_ld<CH>(tbase, d[0]);
+                    uint32_t cnt = 0;
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        tmem_ld_wait();
+                        if (c + 1 < NCH) tmem_ld<CH>(tbase + (c + 1) * CH, d[(c + 1) & 1]);
+#pragma unroll
+                        for (int k4 = 0; k4 < CH / 4; ++k4) {
+                            const float4 b = lds128(bias_s + (c * CH + k4 * 4) * 4);
+                            const float ny[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float dist = fmaf(scale, __uint_as_float(d[c & 1][k4 * 4 + q]), ny[q]) + nx;
+                                cnt += (dist < a.lo) ? 1u : 0u;
+                                if (dist >= a.lo && dist < a.hi) {
+                                    ++inside;
+                                    if constexpr (MODE == MODE_HIST) {
+                                        int bin = (int)((dist - a.lo) * a.inv_width);
+                                        bin = min(max(bin, 0), a.n_bins - 1);
+                                        atomicAdd(shist + bin, 1u);
+                                    } else {
+                                        const int64_t col = (int64_t)t * TILE_N + part * COLS + c * CH + k4 * 4 + q;
+                                        const double* xi = a.x64 + row * a.d;
+                                        const double* yj = a.y64 + col * a.d;
+                                        double s2 = 0.0;
+                                        for (int k = 0; k < a.d; ++k) { const double df = xi[k] - yj[k]; s2 = __dadd_rn(s2, __dmul_rn(df, df)); }
+                                        const unsigned long long slot = atomicAdd(a.counts + 1, 1ull);
+                                        if (slot < a.cap) a.cand[slot] = s2;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    below += cnt;
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(t_empty + acc); mbar_arrive(b_empty + bs); }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                below += __shfl_xor_sync(0xffffffffu, below, o);
+                inside += __shfl_xor_sync(0xffffffffu, inside, o);
+            }
+            if (lane == 0 && below) atomicAdd(a.counts, below);
+            if constexpr (MODE == MODE_HIST) {
+                if (lane == 0 && inside) atomicAdd(a.counts + 1, inside);
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+                for (int bI = threadIdx.x - 64; bI < a.n_bins; bI += 32 * EPI_WARPS)
+                    if (shist[bI]) atomicAdd(a.hist + bI, (unsigned long long)shist[bI]);
+            }
+        } else {
         uint32_t tile_ctr = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int rt = item % a.n_row_tiles, sp = item / a.n_row_tiles;
@@ -421,6 +516,7 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
         }
+        }  // MODE_LSE
     }
 
     tc_fence_before();
@@ -505,6 +601,16 @@ int launch_tc_v(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a,
     SDB_LAUNCH_STATUS();
 }
 
+template <int DP, int MODE>
+int launch_tc_sweep(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
+    auto kern = lse_pass_tc_kernel<DP, 8, false, 0, MODE>;
+    constexpr int smem = TcSmem<DP>::TOTAL_SWEEP;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<n_ctas, 32 * (2 + 8), smem, st>>>(tmP, tmQ, a);
+    SDB_LAUNCH_STATUS();
+}
+
 // Tuning variant (development knob SDB_TC_VARIANT): 0 scalar epilogue, 1 packed f32x2 (all exponentials on the SFU),
 // 2/3/4 packed with every 2nd/3rd/4th pair of exponentials evaluated by the FMA-pipe polynomial.
 int tc_variant() {
@@ -561,7 +667,7 @@ int sdb_lse_pass_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q
     if (rc) return rc;
     rc = make_tmap(&tmQ, q16, n_q_pad, dp, TILE_N);
     if (rc) return rc;
-    TcArgs a;
+    TcArgs a{};
     a.bias = bias_padded;
     a.scale = scale;
     a.n_p = n_p;
@@ -576,6 +682,67 @@ int sdb_lse_pass_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q
         case 32: return launch_tc<32>(tmP, tmQ, a, n_ctas, st);
         default: return launch_tc<64>(tmP, tmQ, a, n_ctas, st);
     }
+}
+
+// Tensor-core forms of sdb_cost_histogram / sdb_cost_collect (same contract; distances from the fp16 hi/lo split
+// points: dist = row_norms[i] + col_norms_padded[j] - 2 x_i.y_j, col_norms_padded = |y_j|^2 for j < n_q and
+// >= 3e38 for the padding).  scale must be -2 * 2^(-2*pow2_exp).  hist / counts accumulate (zero them first).
+static int tc_sweep_common(int mode, const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad,
+                           int dp, const float* row_norms, const float* col_norms_padded, float scale, int tiles_per_split,
+                           int n_ctas, TcArgs& a, void* stream) {
+    if (!p16 || !q16 || !row_norms || !col_norms_padded || n_p <= 0 || n_q <= 0 || tiles_per_split <= 0 || n_ctas <= 0)
+        return SDB_E_INVALID;
+    if ((n_p_pad % TILE_N) || (n_q_pad % TILE_N) || n_p_pad < n_p || n_q_pad < n_q) return SDB_E_INVALID;
+    if (!(dp == 16 || dp == 32 || dp == 64)) return SDB_E_UNSUPPORTED;
+    CUtensorMap tmP, tmQ;
+    int rc = make_tmap(&tmP, p16, n_p_pad, dp, TILE_M);
+    if (rc) return rc;
+    rc = make_tmap(&tmQ, q16, n_q_pad, dp, TILE_N);
+    if (rc) return rc;
+    a.bias = col_norms_padded;
+    a.scale = scale;
+    a.n_p = n_p;
+    a.n_q = n_q;
+    a.row_norms = row_norms;
+    a.n_row_tiles = (int)((n_p + TILE_M - 1) / TILE_M);
+    a.n_col_tiles = (int)((n_q + TILE_N - 1) / TILE_N);
+    a.tiles_per_split = tiles_per_split;
+    a.n_splits = (a.n_col_tiles + tiles_per_split - 1) / tiles_per_split;
+    a.partial = nullptr;
+    cudaStream_t st = sdb_stream(stream);
+    if (mode == MODE_HIST) {
+        switch (dp) {
+            case 16: return launch_tc_sweep<16, MODE_HIST>(tmP, tmQ, a, n_ctas, st);
+            case 32: return launch_tc_sweep<32, MODE_HIST>(tmP, tmQ, a, n_ctas, st);
+            default: return launch_tc_sweep<64, MODE_HIST>(tmP, tmQ, a, n_ctas, st);
+        }
+    }
+    switch (dp) {
+        case 16: return launch_tc_sweep<16, MODE_COLLECT>(tmP, tmQ, a, n_ctas, st);
+        case 32: return launch_tc_sweep<32, MODE_COLLECT>(tmP, tmQ, a, n_ctas, st);
+        default: return launch_tc_sweep<64, MODE_COLLECT>(tmP, tmQ, a, n_ctas, st);
+    }
+}
+
+int sdb_cost_histogram_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad, int dp,
+                          const float* row_norms, const float* col_norms_padded, float scale, int tiles_per_split, int n_ctas,
+                          float lo, float hi, int n_bins, unsigned long long* hist, unsigned long long* counts2, void* stream) {
+    SDB_CHECK_ARG(hist && counts2 && n_bins > 0 && n_bins <= SWEEP_BINS && hi > lo);
+    TcArgs a{};
+    a.lo = lo; a.hi = hi; a.inv_width = (float)n_bins / (hi - lo); a.n_bins = n_bins; a.hist = hist; a.counts = counts2;
+    return tc_sweep_common(MODE_HIST, p16, n_p, n_p_pad, q16, n_q, n_q_pad, dp, row_norms, col_norms_padded, scale, tiles_per_split,
+                           n_ctas, a, stream);
+}
+
+int sdb_cost_collect_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad, int dp,
+                        const float* row_norms, const float* col_norms_padded, float scale, int tiles_per_split, int n_ctas,
+                        float lo, float hi, const double* x, const double* y, int d, double* cand, unsigned long long cap,
+                        unsigned long long* counts2, void* stream) {
+    SDB_CHECK_ARG(x && y && cand && counts2 && d > 0);
+    TcArgs a{};
+    a.lo = lo; a.hi = hi; a.counts = counts2; a.x64 = x; a.y64 = y; a.d = d; a.cand = cand; a.cap = cap;
+    return tc_sweep_common(MODE_COLLECT, p16, n_p, n_p_pad, q16, n_q, n_q_pad, dp, row_norms, col_norms_padded, scale,
+                           tiles_per_split, n_ctas, a, stream);
 }
 
 }  // extern "C"

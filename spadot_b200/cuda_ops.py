@@ -310,9 +310,24 @@ class CudaOps(VectorOps):
                    _ptr(out))
         return out
 
+    def _sweep_norms(self):
+        """fp32 |x_i|^2 and padded |y_j|^2 (+3e38 padding) of the fp16-split points, for the tensor-core sweeps."""
+        if getattr(self, "_nx32", None) is None:
+            self._nx32 = self.X.norms16.to(torch.float32).contiguous()
+            self._ny32 = torch.full((self.Y.n_pad,), 3.0e38, dtype=torch.float32, device=self.device)
+            self._ny32[:self.m] = self.Y.norms16.to(torch.float32)
+        return self._nx32, self._ny32
+
     def cost_histogram(self, lo, hi, n_bins):
         hist = torch.zeros(n_bins, dtype=torch.int64, device=self.device)
         counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        if self.use_tc and n_bins <= 4096:
+            nx, ny = self._sweep_norms()
+            tps, _ = self._tc_split_plan(self.n, self.m)
+            self._call("sdb_cost_histogram_tc", _ptr(self.X.x16), self.n, self.X.n_pad, _ptr(self.Y.x16), self.m, self.Y.n_pad,
+                       self.X.dp, _ptr(nx), _ptr(ny), -2.0 * 2.0 ** (-2 * self.pow2_exp), tps, self.n_sm, lo, hi, n_bins,
+                       _ptr(hist), _ptr(counts))
+            return hist, counts
         bounds, ns = self._split_plan(self.n, self.m)
         self._call("sdb_cost_histogram", _ptr(self.X.xt), self.X.ld, self.n, _ptr(self.Y.xt), self.Y.ld, self.m,
                    self.X.dpad, _ptr(bounds), ns, lo, hi, n_bins, _ptr(hist), _ptr(counts))
@@ -321,6 +336,13 @@ class CudaOps(VectorOps):
     def cost_collect(self, lo, hi, cap):
         cand = torch.empty(cap, dtype=torch.float64, device=self.device)
         counts = torch.zeros(2, dtype=torch.int64, device=self.device)
+        if self.use_tc:
+            nx, ny = self._sweep_norms()
+            tps, _ = self._tc_split_plan(self.n, self.m)
+            self._call("sdb_cost_collect_tc", _ptr(self.X.x16), self.n, self.X.n_pad, _ptr(self.Y.x16), self.m, self.Y.n_pad,
+                       self.X.dp, _ptr(nx), _ptr(ny), -2.0 * 2.0 ** (-2 * self.pow2_exp), tps, self.n_sm, lo, hi,
+                       _ptr(self.X.x64), _ptr(self.Y.x64), self.d, _ptr(cand), cap, _ptr(counts))
+            return cand, counts
         bounds, ns = self._split_plan(self.n, self.m)
         self._call("sdb_cost_collect", _ptr(self.X.xt), self.X.ld, self.n, _ptr(self.Y.xt), self.Y.ld, self.m,
                    self.X.dpad, _ptr(bounds), ns, lo, hi, _ptr(self.X.x64), _ptr(self.Y.x64), self.d, _ptr(cand), cap,

@@ -266,6 +266,7 @@ def median_cost(ops, dist: Dist | None = None, n_samples=262144, n_bins=4096, se
         return allc, below, int(allc.numel())
 
     lo, hi = 0.0, math.inf
+    expect = None
     if total > small_limit:
         rng = np.random.default_rng(seed + 7919 * dist.rank)
         ns = max(1024, n_samples // dist.world)
@@ -285,14 +286,21 @@ def median_cost(ops, dist: Dist | None = None, n_samples=262144, n_bins=4096, se
             if below <= k_lo and csum[-1] > k_hi:
                 b_lo = int(np.searchsorted(csum, k_lo, side="right"))
                 b_hi = int(np.searchsorted(csum, k_hi, side="right"))
-                w = (float(np.float32(hi)) - float(np.float32(lo))) / n_bins
-                lo, hi = (float(np.float32(lo)) + (b_lo - 1) * w) * (1 - REL_MARGIN), \
-                         (float(np.float32(lo)) + (b_hi + 2) * w) * (1 + REL_MARGIN)
+                lo0 = float(np.float32(lo))
+                w = (float(np.float32(hi)) - lo0) / n_bins
+                lo, hi = (lo0 + (b_lo - 1) * w) * (1 - REL_MARGIN), (lo0 + (b_hi + 2) * w) * (1 + REL_MARGIN)
+                # the histogram already says how many candidates the refined bracket holds (per rank at most that)
+                first = max(int(math.floor((lo - lo0) / w)) - 1, 0)
+                last = min(int(math.ceil((hi - lo0) / w)) + 1, n_bins)
+                expect = int(hist[first:last].sum())
             else:
                 lo, hi = 0.0, math.inf     # sample bracket missed (vanishing probability): full collect
         else:
             lo, hi = 0.0, math.inf
-    cap = max(1 << 16, int(min(total, 1 << 26)) if not math.isfinite(hi) else 1 << 24)
+    if not math.isfinite(hi):
+        cap = max(1 << 16, int(min(total, 1 << 26)))
+    else:
+        cap = max(1 << 16, int(1.25 * expect) + (1 << 16)) if expect is not None else 1 << 24
     while True:
         cand, below, n_cand = collect(max(lo, 0.0), hi if math.isfinite(hi) else 3.0e38, cap)
         if cand is not None and below <= k_lo and k_hi < below + n_cand:

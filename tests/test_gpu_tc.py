@@ -111,3 +111,25 @@ def test_tc_large_properties(ot):
     idx = np.random.default_rng(1).integers(0, n, 64)
     want = ot_logdomain.CostOperator(a[idx], b, median=160.0).row_lse(g.cpu().numpy() / eps, eps)
     assert np.abs(L0.cpu().numpy()[idx] - want).max() < 2e-5
+
+
+@pytest.mark.parametrize("n,m,d", [(3000, 2500, 32), (2047, 4099, 20), (5000, 6000, 10), (9000, 7000, 48)])
+def test_tc_median_sweeps_are_exact(ot, n, m, d):
+    """K5 on the tensor cores: same exact median as numpy, 2 sweeps."""
+    _, sinkhorn, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, d, seed=n)
+    want = float(np.median(ot_dense.sqeuclidean(a, b)))
+    ops = CudaOps(a, b, tc="on")
+    info = {}
+    got = sinkhorn.median_cost(ops, small_limit=1 << 20, info=info)
+    assert got == pytest.approx(want, rel=1e-15)
+    assert info["sweeps"] == 2 and info["candidates"] < n * m // 100
+    # counts of the tensor-core and SIMT sweeps agree away from the bracket edges
+    lo, hi = want * 0.9, want * 1.1
+    h1, c1 = ops.cost_histogram(lo, hi, 64)
+    ops.use_tc = False
+    h2, c2 = ops.cost_histogram(lo, hi, 64)
+    ops.use_tc = True
+    total = n * m
+    assert abs(int(c1[0]) - int(c2[0])) <= max(4, total // 100000)
+    assert int((h1 - h2).abs().max()) <= max(8, total // 50000)
