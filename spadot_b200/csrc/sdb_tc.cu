@@ -189,8 +189,35 @@ struct TcSmem {
     static constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
     static constexpr int OFF_HIST = OFF_TMEM + 16;                      // [SWEEP_BINS] uint32 (median sweeps only)
     static constexpr int TOTAL = OFF_HIST + 1024;                       // + alignment slack (LSE pass)
-    static constexpr int TOTAL_SWEEP = OFF_HIST + SWEEP_BINS * 4 + 1024;
+    static constexpr int OFF_SDIST = OFF_HIST + SWEEP_BINS * 4;        // [32][256] float (histogram sweep only)
+    static constexpr int TOTAL_SWEEP = OFF_SDIST + 32 * 256 * 4 + 1024;
 };
+
+// Rare paths of the median sweeps, kept out of line so the hot loop stays small (an inlined fp64 loop per
+// accumulator element blew the instruction cache: the sweep ran 20x slower than the LSE pass).
+__device__ __noinline__ void sweep_hist_rare(uint32_t mask, const float* sd, float lo, float inv_width, int n_bins,
+                                             uint32_t* shist, unsigned long long* inside) {
+    while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        int bin = (int)((sd[k * 256] - lo) * inv_width);
+        bin = min(max(bin, 0), n_bins - 1);
+        atomicAdd(shist + bin, 1u);
+        ++(*inside);
+    }
+}
+__device__ __noinline__ void sweep_collect_rare(uint32_t mask, const double* xi, const double* y64, int64_t col0, int d,
+                                                double* cand, unsigned long long cap, unsigned long long* counter) {
+    while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const double* yj = y64 + (col0 + k) * d;
+        double s2 = 0.0;
+        for (int q = 0; q < d; ++q) { const double df = xi[q] - yj[q]; s2 = __dadd_rn(s2, __dmul_rn(df, df)); }
+        const unsigned long long slot = atomicAdd(counter, 1ull);
+        if (slot < cap) cand[slot] = s2;
+    }
+}
 
 struct TcArgs {
     const float* bias;       // padded to a multiple of TILE_N with SDB_NEG_SENTINEL
@@ -372,30 +399,29 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                     for (int c = 0; c < NCH; ++c) {
                         tmem_ld_wait();
                         if (c + 1 < NCH) tmem_ld<CH>(tbase + (c + 1) * CH, d[(c + 1) & 1]);
+                        float dist[CH];
+                        uint32_t mask = 0;
 #pragma unroll
                         for (int k4 = 0; k4 < CH / 4; ++k4) {
                             const float4 b = lds128(bias_s + (c * CH + k4 * 4) * 4);
                             const float ny[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                const float dist = fmaf(scale, __uint_as_float(d[c & 1][k4 * 4 + q]), ny[q]) + nx;
-                                cnt += (dist < a.lo) ? 1u : 0u;
-                                if (dist >= a.lo && dist < a.hi) {
-                                    ++inside;
-                                    if constexpr (MODE == MODE_HIST) {
-                                        int bin = (int)((dist - a.lo) * a.inv_width);
-                                        bin = min(max(bin, 0), a.n_bins - 1);
-                                        atomicAdd(shist + bin, 1u);
-                                    } else {
-                                        const int64_t col = (int64_t)t * TILE_N + part * COLS + c * CH + k4 * 4 + q;
-                                        const double* xi = a.x64 + row * a.d;
-                                        const double* yj = a.y64 + col * a.d;
-                                        double s2 = 0.0;
-                                        for (int k = 0; k < a.d; ++k) { const double df = xi[k] - yj[k]; s2 = __dadd_rn(s2, __dmul_rn(df, df)); }
-                                        const unsigned long long slot = atomicAdd(a.counts + 1, 1ull);
-                                        if (slot < a.cap) a.cand[slot] = s2;
-                                    }
-                                }
+                                const float dv = fmaf(scale, __uint_as_float(d[c & 1][k4 * 4 + q]), ny[q]) + nx;
+                                dist[k4 * 4 + q] = dv;
+                                cnt += (dv < a.lo) ? 1u : 0u;
+                                mask |= (dv >= a.lo && dv < a.hi) ? (1u << (k4 * 4 + q)) : 0u;
+                            }
+                        }
+                        if (mask) {
+                            const int64_t col0 = (int64_t)t * TILE_N + part * COLS + c * CH;
+                            if constexpr (MODE == MODE_HIST) {
+                                float* sd = reinterpret_cast<float*>(smem + S::OFF_SDIST) + (threadIdx.x - 64);
+#pragma unroll
+                                for (int k = 0; k < CH; ++k) sd[k * 256] = dist[k];
+                                sweep_hist_rare(mask, sd, a.lo, a.inv_width, a.n_bins, shist, &inside);
+                            } else {
+                                sweep_collect_rare(mask, a.x64 + row * a.d, a.y64, col0, a.d, a.cand, a.cap, a.counts + 1);
                             }
                         }
                     }

@@ -236,7 +236,7 @@ def _select_rank(ops, cand, n_cand, k):
     return float(np.array([prefix], dtype=np.uint64).view(np.float64)[0])
 
 
-def median_cost(ops, dist: Dist | None = None, n_samples=262144, n_bins=4096, seed=0, small_limit=1 << 22,
+def median_cost(ops, dist: Dist | None = None, n_samples=1 << 22, n_bins=4096, seed=0, small_limit=1 << 22,
                 info: dict | None = None):
     """Exact np.median of all N*M squared distances (ot_solvers.py:103) without materialising them.
 
@@ -247,7 +247,7 @@ def median_cost(ops, dist: Dist | None = None, n_samples=262144, n_bins=4096, se
     Sweeps classify with fp32 distances of the centred points; brackets are widened by REL_MARGIN so the
     classification can never disagree with the exact fp64 value about membership of the true median."""
     dist = dist or Dist(enabled=False)
-    REL_MARGIN = 2e-5
+    REL_MARGIN = 1e-5     # >= 4x the worst-case relative error of the fp32 / fp16-split distances
     n, m = ops.n, ops.m
     N = int(round(float(dist.sum_(torch.tensor([float(n)], dtype=torch.float64, device=ops.device)).item())))
     total = N * m
@@ -268,15 +268,15 @@ def median_cost(ops, dist: Dist | None = None, n_samples=262144, n_bins=4096, se
     lo, hi = 0.0, math.inf
     expect = None
     if total > small_limit:
-        rng = np.random.default_rng(seed + 7919 * dist.rank)
-        ns = max(1024, n_samples // dist.world)
-        ii = rng.integers(0, max(n, 1), ns)
-        jj = rng.integers(0, m, ns)
-        samp = torch.sort(dist.gather_cat(ops.pair_distances(ii, jj)))[0].cpu().numpy() if n > 0 else np.zeros(0)
-        S = samp.size
+        ns = int(max(1024, min(n_samples, total // 16) // dist.world))
+        gen = torch.Generator(device="cpu").manual_seed(seed + 7919 * dist.rank)
+        ii = torch.randint(0, max(n, 1), (ns,), generator=gen)
+        jj = torch.randint(0, m, (ns,), generator=gen)
+        samp = torch.sort(dist.gather_cat(ops.pair_distances(ii, jj)))[0] if n > 0 else torch.zeros(0, dtype=torch.float64)
+        S = int(samp.numel())
         width = 6.0 * 0.5 / math.sqrt(S)
-        lo = float(samp[max(0, int((0.5 - width) * S))]) * (1 - REL_MARGIN)
-        hi = float(samp[min(S - 1, int((0.5 + width) * S))]) * (1 + REL_MARGIN)
+        lo = float(samp[max(0, int((0.5 - width) * S))].item()) * (1 - REL_MARGIN)
+        hi = float(samp[min(S - 1, int((0.5 + width) * S))].item()) * (1 + REL_MARGIN)
         if hi > lo > 0:
             sweeps += 1
             hist, counts = ops.cost_histogram(float(np.float32(lo)), float(np.float32(hi)), n_bins)
