@@ -218,17 +218,20 @@ int sdb_quad_form_rows_f64(const double* W, const double* A, int64_t b, int m, d
  * (self loops included, PyG GATConv add_self_loops semantics are the caller's job).  feat (n,H,C),
  * a_src / a_dst (n,H) in float or double (is_double).  Writes out (n,H,C) = sum_j alpha_ij feat_j and
  * alpha (E,H) = softmax_j(leaky_relu(a_src[j]+a_dst[i])) with PyG's +1e-16 denominator.
+ * node_order (n, int32, may be NULL): CTA b works on node node_order[b]; a locality-preserving order (e.g. reverse
+ * Cuthill-McKee) makes concurrently running CTAs gather the same source rows, which then hit L2 instead of HBM.
  * replaces torch_geometric GATConv message passing used at ref: model/encoder.py:41-45,56-58. */
 int sdb_gat_forward(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
-                    int64_t n, int H, int C, double negative_slope, int is_double, void* out, void* alpha,
-                    void* stream);
+                    const int32_t* node_order, int64_t n, int H, int C, double negative_slope, int is_double,
+                    void* out, void* alpha, void* stream);
 /* Backward of the above.  src_rowptr / src_dst / src_eid: the same edges grouped by SOURCE node
  * (destination node and position in the by-destination order).  dlogit (E,H) is workspace.
  * Outputs grad_feat (n,H,C), grad_a_src (n,H), grad_a_dst (n,H).  Deterministic (no atomics). */
 int sdb_gat_backward(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
-                     const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, int64_t n, int H, int C,
-                     double negative_slope, int is_double, const void* alpha, const void* grad_out, void* dlogit,
-                     void* grad_feat, void* grad_a_src, void* grad_a_dst, void* stream);
+                     const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, const int32_t* node_order,
+                     int64_t n, int H, int C, double negative_slope, int is_double, const void* alpha,
+                     const void* grad_out, void* dlogit, void* grad_feat, void* grad_a_src, void* grad_a_dst,
+                     void* stream);
 
 /* k nearest OTHER points (self excluded) of every point, sorted by (distance, index); pts (n,dim) fp64, dim <= 3,
  * k <= 32 and k <= n-1.  out_idx (n,k) int32, out_dist (n,k) fp64 Euclidean distances (may be NULL).

@@ -51,9 +51,9 @@ SIGNATURES = {
     "sdb_kernel_block_f64": [c_p, c_l, c_p, c_l, c_i, c_i, c_d, c_d, c_p, c_l, c_p],
     "sdb_kernel_diag_f64": [c_p, c_p, c_l, c_i, c_i, c_d, c_p, c_p],
     "sdb_quad_form_rows_f64": [c_p, c_p, c_l, c_i, c_p, c_p],
-    "sdb_gat_forward": [c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p],
+    "sdb_gat_forward": [c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p],
     "sdb_knn_f64": [c_p, c_l, c_i, c_i, c_p, c_p, c_p],
-    "sdb_gat_backward": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    "sdb_gat_backward": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
 }
 
 _lib = None

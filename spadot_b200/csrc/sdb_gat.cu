@@ -30,13 +30,34 @@ __device__ __forceinline__ T warp_sum_t(T v) {
     return v;
 }
 
+// 16-byte vector access: 4 floats or 2 doubles per thread per load (used when C is a multiple of the width)
+template <typename T> struct Vec;
+template <> struct Vec<float> { static constexpr int W = 4; using type = float4; };
+template <> struct Vec<double> { static constexpr int W = 2; using type = double2; };
+template <typename T>
+__device__ __forceinline__ void vec_load(const T* p, T (&v)[Vec<T>::W]) {
+    const typename Vec<T>::type t = *reinterpret_cast<const typename Vec<T>::type*>(p);
+    const T* e = reinterpret_cast<const T*>(&t);
+#pragma unroll
+    for (int q = 0; q < Vec<T>::W; ++q) v[q] = e[q];
+}
+template <typename T>
+__device__ __forceinline__ void vec_store(T* p, const T (&v)[Vec<T>::W]) {
+    typename Vec<T>::type t;
+    T* e = reinterpret_cast<T*>(&t);
+#pragma unroll
+    for (int q = 0; q < Vec<T>::W; ++q) e[q] = v[q];
+    *reinterpret_cast<typename Vec<T>::type*>(p) = t;
+}
+
 // ---------------------------------------------------------------------------------------- forward
 template <typename T>
 __global__ void __launch_bounds__(128) gat_fwd_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
                                                       const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
-                                                      const int32_t* __restrict__ col, int64_t n, int H, int C, T slope,
-                                                      T* __restrict__ out, T* __restrict__ alpha) {
-    const int64_t i = blockIdx.x;
+                                                      const int32_t* __restrict__ col, const int32_t* __restrict__ order,
+                                                      int64_t n, int H, int C, T slope, T* __restrict__ out,
+                                                      T* __restrict__ alpha) {
+    const int64_t i = order ? order[blockIdx.x] : blockIdx.x;   // locality order of the CTAs (L2 reuse of gathered rows)
     const int64_t e0 = rowptr[i], e1 = rowptr[i + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // segment softmax: one warp per head (round-robin when H > 4)
@@ -65,11 +86,29 @@ __global__ void __launch_bounds__(128) gat_fwd_kernel(const T* __restrict__ feat
     __syncthreads();
     // aggregation: thread owns feature columns c, c+128, ...; each source row is read once, coalesced
     const int HC = H * C;
-    for (int c = threadIdx.x; c < HC; c += 128) {
-        const int h = c / C;
-        T acc = T(0);
-        for (int64_t e = e0; e < e1; ++e) acc += alpha[e * H + h] * feat[(int64_t)col[e] * HC + c];
-        out[i * HC + c] = acc;
+    constexpr int W = Vec<T>::W;
+    if (C % W == 0) {
+        for (int c = threadIdx.x * W; c < HC; c += 128 * W) {
+            const int h = c / C;
+            T acc[W];
+#pragma unroll
+            for (int q = 0; q < W; ++q) acc[q] = T(0);
+            for (int64_t e = e0; e < e1; ++e) {
+                const T a = alpha[e * H + h];
+                T v[W];
+                vec_load(feat + (int64_t)col[e] * HC + c, v);
+#pragma unroll
+                for (int q = 0; q < W; ++q) acc[q] += a * v[q];
+            }
+            vec_store(out + i * HC + c, acc);
+        }
+    } else {
+        for (int c = threadIdx.x; c < HC; c += 128) {
+            const int h = c / C;
+            T acc = T(0);
+            for (int64_t e = e0; e < e1; ++e) acc += alpha[e * H + h] * feat[(int64_t)col[e] * HC + c];
+            out[i * HC + c] = acc;
+        }
     }
 }
 
@@ -78,10 +117,11 @@ __global__ void __launch_bounds__(128) gat_fwd_kernel(const T* __restrict__ feat
 template <typename T>
 __global__ void __launch_bounds__(128) gat_bwd_dst_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
                                                           const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
-                                                          const int32_t* __restrict__ col, int64_t n, int H, int C, T slope,
-                                                          const T* __restrict__ alpha, const T* __restrict__ grad_out,
-                                                          T* __restrict__ dlogit, T* __restrict__ grad_a_dst) {
-    const int64_t i = blockIdx.x;
+                                                          const int32_t* __restrict__ col, const int32_t* __restrict__ order,
+                                                          int64_t n, int H, int C, T slope, const T* __restrict__ alpha,
+                                                          const T* __restrict__ grad_out, T* __restrict__ dlogit,
+                                                          T* __restrict__ grad_a_dst) {
+    const int64_t i = order ? order[blockIdx.x] : blockIdx.x;
     const int64_t e0 = rowptr[i], e1 = rowptr[i + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int HC = H * C;
@@ -93,7 +133,18 @@ __global__ void __launch_bounds__(128) gat_bwd_dst_kernel(const T* __restrict__ 
         const T* go = grad_out + i * HC + h * C;
         const T* fj = feat + (int64_t)col[e] * HC + h * C;
         T acc = T(0);
-        for (int c = lane; c < C; c += 32) acc += go[c] * fj[c];
+        constexpr int W = Vec<T>::W;
+        if (C % W == 0) {
+            for (int c = lane * W; c < C; c += 32 * W) {
+                T g[W], f[W];
+                vec_load(go + c, g);
+                vec_load(fj + c, f);
+#pragma unroll
+                for (int q = 0; q < W; ++q) acc += g[q] * f[q];
+            }
+        } else {
+            for (int c = lane; c < C; c += 32) acc += go[c] * fj[c];
+        }
         acc = warp_sum_t(acc);
         if (lane == 0) dlogit[e * H + h] = acc;
     }
@@ -120,18 +171,36 @@ __global__ void __launch_bounds__(128) gat_bwd_dst_kernel(const T* __restrict__ 
 // grad_feat[j,h,:] = sum_{e: j->i} alpha[e,h] * grad_out[i,h,:];  grad_a_src[j,h] = sum_e dlogit[e,h]
 template <typename T>
 __global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restrict__ src_rowptr, const int32_t* __restrict__ src_dst,
-                                                          const int32_t* __restrict__ src_eid, int64_t n, int H, int C,
-                                                          const T* __restrict__ alpha, const T* __restrict__ dlogit,
-                                                          const T* __restrict__ grad_out, T* __restrict__ grad_feat,
-                                                          T* __restrict__ grad_a_src) {
-    const int64_t j = blockIdx.x;
+                                                          const int32_t* __restrict__ src_eid, const int32_t* __restrict__ order,
+                                                          int64_t n, int H, int C, const T* __restrict__ alpha,
+                                                          const T* __restrict__ dlogit, const T* __restrict__ grad_out,
+                                                          T* __restrict__ grad_feat, T* __restrict__ grad_a_src) {
+    const int64_t j = order ? order[blockIdx.x] : blockIdx.x;
     const int64_t p0 = src_rowptr[j], p1 = src_rowptr[j + 1];
     const int HC = H * C;
-    for (int c = threadIdx.x; c < HC; c += 128) {
-        const int h = c / C;
-        T acc = T(0);
-        for (int64_t p = p0; p < p1; ++p) acc += alpha[(int64_t)src_eid[p] * H + h] * grad_out[(int64_t)src_dst[p] * HC + c];
-        grad_feat[j * HC + c] = acc;
+    constexpr int W = Vec<T>::W;
+    if (C % W == 0) {
+        for (int c = threadIdx.x * W; c < HC; c += 128 * W) {
+            const int h = c / C;
+            T acc[W];
+#pragma unroll
+            for (int q = 0; q < W; ++q) acc[q] = T(0);
+            for (int64_t p = p0; p < p1; ++p) {
+                const T a = alpha[(int64_t)src_eid[p] * H + h];
+                T v[W];
+                vec_load(grad_out + (int64_t)src_dst[p] * HC + c, v);
+#pragma unroll
+                for (int q = 0; q < W; ++q) acc[q] += a * v[q];
+            }
+            vec_store(grad_feat + j * HC + c, acc);
+        }
+    } else {
+        for (int c = threadIdx.x; c < HC; c += 128) {
+            const int h = c / C;
+            T acc = T(0);
+            for (int64_t p = p0; p < p1; ++p) acc += alpha[(int64_t)src_eid[p] * H + h] * grad_out[(int64_t)src_dst[p] * HC + c];
+            grad_feat[j * HC + c] = acc;
+        }
     }
     for (int h = threadIdx.x; h < H; h += 128) {
         T acc = T(0);
@@ -141,24 +210,24 @@ __global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restr
 }
 
 template <typename T>
-int gat_forward_t(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col, int64_t n, int H,
-                  int C, double slope, void* out, void* alpha, cudaStream_t st) {
-    gat_fwd_kernel<T><<<(unsigned)n, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, n, H, C, (T)slope,
-                                                  (T*)out, (T*)alpha);
+int gat_forward_t(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
+                  const int32_t* order, int64_t n, int H, int C, double slope, void* out, void* alpha, cudaStream_t st) {
+    gat_fwd_kernel<T><<<(unsigned)n, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order, n, H, C,
+                                                  (T)slope, (T*)out, (T*)alpha);
     SDB_LAUNCH_STATUS();
 }
 
 template <typename T>
 int gat_backward_t(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
-                   const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, int64_t n, int H, int C, double slope,
-                   const void* alpha, const void* grad_out, void* dlogit, void* grad_feat, void* grad_a_src, void* grad_a_dst,
-                   cudaStream_t st) {
-    gat_bwd_dst_kernel<T><<<(unsigned)n, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, n, H, C, (T)slope,
-                                                      (const T*)alpha, (const T*)grad_out, (T*)dlogit, (T*)grad_a_dst);
+                   const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, const int32_t* order, int64_t n, int H,
+                   int C, double slope, const void* alpha, const void* grad_out, void* dlogit, void* grad_feat, void* grad_a_src,
+                   void* grad_a_dst, cudaStream_t st) {
+    gat_bwd_dst_kernel<T><<<(unsigned)n, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order, n, H, C,
+                                                      (T)slope, (const T*)alpha, (const T*)grad_out, (T*)dlogit, (T*)grad_a_dst);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    gat_bwd_src_kernel<T><<<(unsigned)n, 128, 0, st>>>(src_rowptr, src_dst, src_eid, n, H, C, (const T*)alpha, (const T*)dlogit,
-                                                      (const T*)grad_out, (T*)grad_feat, (T*)grad_a_src);
+    gat_bwd_src_kernel<T><<<(unsigned)n, 128, 0, st>>>(src_rowptr, src_dst, src_eid, order, n, H, C, (const T*)alpha,
+                                                      (const T*)dlogit, (const T*)grad_out, (T*)grad_feat, (T*)grad_a_src);
     SDB_LAUNCH_STATUS();
 }
 
@@ -166,27 +235,28 @@ int gat_backward_t(const void* feat, const void* a_src, const void* a_dst, const
 
 extern "C" {
 
-int sdb_gat_forward(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col, int64_t n,
-                    int H, int C, double negative_slope, int is_double, void* out, void* alpha, void* stream) {
+int sdb_gat_forward(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
+                    const int32_t* node_order, int64_t n, int H, int C, double negative_slope, int is_double, void* out,
+                    void* alpha, void* stream) {
     SDB_CHECK_ARG(feat && a_src && a_dst && rowptr && col && out && alpha && n >= 0 && H > 0 && C > 0);
     if (n == 0) return 0;
     if (n > 2147483647LL) return SDB_E_UNSUPPORTED;
-    return is_double ? gat_forward_t<double>(feat, a_src, a_dst, rowptr, col, n, H, C, negative_slope, out, alpha, sdb_stream(stream))
-                     : gat_forward_t<float>(feat, a_src, a_dst, rowptr, col, n, H, C, negative_slope, out, alpha, sdb_stream(stream));
+    return is_double ? gat_forward_t<double>(feat, a_src, a_dst, rowptr, col, node_order, n, H, C, negative_slope, out, alpha, sdb_stream(stream))
+                     : gat_forward_t<float>(feat, a_src, a_dst, rowptr, col, node_order, n, H, C, negative_slope, out, alpha, sdb_stream(stream));
 }
 
 int sdb_gat_backward(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
-                     const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, int64_t n, int H, int C,
-                     double negative_slope, int is_double, const void* alpha, const void* grad_out, void* dlogit, void* grad_feat,
-                     void* grad_a_src, void* grad_a_dst, void* stream) {
+                     const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, const int32_t* node_order, int64_t n,
+                     int H, int C, double negative_slope, int is_double, const void* alpha, const void* grad_out, void* dlogit,
+                     void* grad_feat, void* grad_a_src, void* grad_a_dst, void* stream) {
     SDB_CHECK_ARG(feat && a_src && a_dst && rowptr && col && src_rowptr && src_dst && src_eid && alpha && grad_out && dlogit &&
                   grad_feat && grad_a_src && grad_a_dst && n >= 0 && H > 0 && C > 0);
     if (n == 0) return 0;
     if (n > 2147483647LL) return SDB_E_UNSUPPORTED;
-    return is_double ? gat_backward_t<double>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, n, H, C, negative_slope, alpha,
-                                              grad_out, dlogit, grad_feat, grad_a_src, grad_a_dst, sdb_stream(stream))
-                     : gat_backward_t<float>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, n, H, C, negative_slope, alpha,
-                                             grad_out, dlogit, grad_feat, grad_a_src, grad_a_dst, sdb_stream(stream));
+    return is_double ? gat_backward_t<double>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, node_order, n, H, C,
+                                              negative_slope, alpha, grad_out, dlogit, grad_feat, grad_a_src, grad_a_dst, sdb_stream(stream))
+                     : gat_backward_t<float>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, node_order, n, H, C,
+                                             negative_slope, alpha, grad_out, dlogit, grad_feat, grad_a_src, grad_a_dst, sdb_stream(stream));
 }
 
 }  // extern "C"

@@ -167,3 +167,39 @@ class SVGP(nn.Module):
         L_3_sum_term = -0.5 * (torch.sum(K_tilde_terms) + torch.sum(trace_terms) + torch.sum(torch.log(noise))
                                + float(b * LOG_2PI_F32) + torch.sum(precision * (y - mean_vector) ** 2))
         return L_3_sum_term, KL_term
+
+    # ------------------------------------------------------------------ all latent dimensions at once
+    def posterior_and_loss_all_dims(self, x, Y, noise):
+        """The z/2-iteration loop of SpaDOT.forward (SpaDOT/model/SpaDOT.py:57-66) as one batched evaluation.
+
+        x (b,2) coordinates of the batch, Y (b,L) and noise (b,L) the encoder means / variances of the L
+        GP latent dimensions.  Returns (mean (b,L), var (b,L), L3 (L,), KL (L,)) equal to calling
+        approximate_posterior_params(x, x, Y[:,l], noise[:,l]) + variational_loss(...) for each l: the kernel
+        blocks are shared by every l, and the L Sigma_l inverses / Choleskys run as one batched cuSOLVER call."""
+        b, L = Y.shape
+        m = self.inducing_index_points.shape[0]
+        K_mm, K_mm_inv, K_mm_log_det = self._mm()
+        K_nn = self.kernel_matrix(x, x, diag_only=True)
+        K_nm = self.kernel_matrix(x, self.inducing_index_points)
+        K_mn = K_nm.T
+        scale = self.N_train / b
+        prec = 1 / noise                                                       # (b,L)
+        sigma_l = K_mm[None] + scale * torch.matmul(K_mn[None] * prec.T[:, None, :], K_nm)     # (L,m,m)
+        sigma_l_inv = torch.linalg.inv(self._add_diagonal_jitter(sigma_l, self.jitter))
+        rhs = torch.matmul(K_mn, Y * prec)                                     # (m,L)
+        sol = torch.matmul(sigma_l_inv, rhs.T[:, :, None])[:, :, 0]            # (L,m)
+        mean = scale * torch.matmul(K_nm, sol.T)                               # (b,L)
+        var = K_nn[:, None] + torch.sum(torch.matmul(K_nm[None], sigma_l_inv - K_mm_inv[None]) * K_nm[None], dim=2).T
+        mu_hat = scale * torch.matmul(K_mm, sol.T).T                           # (L,m)
+        A_hat = torch.matmul(K_mm[None], torch.matmul(sigma_l_inv, K_mm[None]))  # (L,m,m)
+        W = torch.matmul(K_nm, K_mm_inv)                                       # (b,m)
+        mean_vector = torch.matmul(W, mu_hat.T)                                # (b,L)
+        S_chol = torch.linalg.cholesky(self._add_diagonal_jitter(A_hat, self.jitter))
+        S_log_det = 2 * torch.sum(torch.log(torch.diagonal(S_chol, dim1=1, dim2=2)), dim=1)
+        KL = 0.5 * (K_mm_log_det - S_log_det - m + torch.sum(K_mm_inv[None] * A_hat.transpose(1, 2), dim=(1, 2))
+                    + torch.sum(mu_hat * torch.matmul(mu_hat, K_mm_inv.T), dim=1))
+        K_tilde = prec * (K_nn - torch.sum(W * K_nm, dim=1))[:, None]
+        trace_terms = prec * torch.sum(torch.matmul(W[None], A_hat) * W[None], dim=2).T
+        L3 = -0.5 * (torch.sum(K_tilde, dim=0) + torch.sum(trace_terms, dim=0) + torch.sum(torch.log(noise), dim=0)
+                     + float(b * LOG_2PI_F32) + torch.sum(prec * (Y - mean_vector) ** 2, dim=0))
+        return mean, var, L3, KL

@@ -97,3 +97,24 @@ def test_gat_isolated_and_high_degree_nodes():
     mine.load_state_dict(ref.state_dict())
     x = torch.randn(n, 9, dtype=torch.float64)
     np.testing.assert_allclose(mine(x.to(dev), ei.to(dev)).detach().cpu().numpy(), ref(x, ei).detach().numpy(), rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gat_large_graph_with_locality_order_matches_oracle():
+    """n >= 20000 switches on the reverse Cuthill-McKee CTA order; results must not depend on it."""
+    from spadot_b200 import gat
+    dev = torch.device("cuda:0")
+    n = 21000
+    ei = make_graph(n, seed=4)
+    torch.manual_seed(2)
+    ref = gat_ref.GATConvRef(16, 8, heads=2).double()
+    mine = gat.GATConv(16, 8, heads=2).double().to(dev)
+    mine.load_state_dict(ref.state_dict())
+    x = torch.randn(n, 16, dtype=torch.float64)
+    xr, xm = x.clone().requires_grad_(True), x.clone().to(dev).requires_grad_(True)
+    out_r, out_m = ref(xr, ei), mine(xm, ei.to(dev))
+    assert gat.graph_for(ei.to(dev), n).order is not None
+    np.testing.assert_allclose(out_m.detach().cpu().numpy(), out_r.detach().numpy(), rtol=1e-10, atol=1e-12)
+    out_r.sum().backward()
+    out_m.sum().backward()
+    np.testing.assert_allclose(xm.grad.cpu().numpy(), xr.grad.numpy(), rtol=1e-9, atol=1e-12)

@@ -108,3 +108,32 @@ def test_svgp_chickenheart_shape_and_diag_only_scale():
     big = torch.rand(100_000, 2, dtype=torch.float64, device=dev)
     d = model.kernel_matrix(big, big, diag_only=True)
     assert d.shape == (100_000,) and float((d - 1).abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_batched_latent_dims_equal_the_per_dimension_loop():
+    from spadot_b200 import svgp
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    z = torch.rand(135, 2, generator=g, dtype=torch.float64) * 4 - 2
+    x = (torch.rand(300, 2, generator=g, dtype=torch.float64) * 4 - 2).to(dev)
+    Y = torch.randn(300, 6, generator=g, dtype=torch.float64).to(dev).requires_grad_(True)
+    NZ = (torch.rand(300, 6, generator=g, dtype=torch.float64) + 0.5).to(dev).requires_grad_(True)
+    cfg = dict(dtype=torch.float64, device=dev, kernel_type="Cauchy", kernel_scale=0.3)
+    model = svgp.SVGP(cfg, z.numpy(), N_train=747)
+    mean, var, L3, KL = model.posterior_and_loss_all_dims(x, Y, NZ)
+    (L3.sum() + KL.sum() + (mean * var).sum()).backward()
+    gY, gN = Y.grad.clone(), NZ.grad.clone()
+    Y.grad = NZ.grad = None
+    tot = 0
+    for l in range(6):
+        mean_l, var_l, mu_hat, A_hat = model.approximate_posterior_params(x, x, Y[:, l], NZ[:, l])
+        l3, kl = model.variational_loss(x, Y[:, l], NZ[:, l], mu_hat, A_hat)
+        np.testing.assert_allclose(mean[:, l].detach().cpu().numpy(), mean_l.detach().cpu().numpy(), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(var[:, l].detach().cpu().numpy(), var_l.detach().cpu().numpy(), rtol=1e-9, atol=1e-12)
+        assert float(L3[l]) == pytest.approx(float(l3), rel=1e-10)
+        assert float(KL[l]) == pytest.approx(float(kl), rel=1e-9)
+        tot = tot + l3 + kl + (mean_l * var_l).sum()
+    tot.backward()
+    np.testing.assert_allclose(gY.cpu().numpy(), Y.grad.cpu().numpy(), rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(gN.cpu().numpy(), NZ.grad.cpu().numpy(), rtol=1e-7, atol=1e-10)
