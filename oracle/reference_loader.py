@@ -53,3 +53,25 @@ def load_svgp():
     if "_spadot_ref_svgp" in sys.modules:
         return sys.modules["_spadot_ref_svgp"]
     return _load("_spadot_ref_svgp", os.path.join(_MODEL_DIR, "svgp.py"))
+
+
+def load_model():
+    """Returns the reference `SpaDOT.model.SpaDOT` module (SpaDOT/model/SpaDOT.py) importable in the build
+    container.  torch_geometric is absent, so `torch_geometric.nn.GATConv` is stubbed with the oracle's
+    plain-torch restatement (oracle/gat_ref.py; parity of that piece is unpinned) — everything else
+    (SVGPEncoder, Decoder, SVGP, the forward pass and its losses) is the unmodified reference."""
+    if "_spadot_ref_model.SpaDOT" in sys.modules:
+        return sys.modules["_spadot_ref_model.SpaDOT"]
+    from . import gat_ref
+    tg = types.ModuleType("torch_geometric")
+    tg_nn = types.ModuleType("torch_geometric.nn")
+    tg_nn.GATConv = gat_ref.GATConvRef
+    tg.nn = tg_nn
+    sys.modules.setdefault("torch_geometric", tg)
+    sys.modules.setdefault("torch_geometric.nn", tg_nn)
+    pkg = types.ModuleType("_spadot_ref_model")
+    pkg.__path__ = [_MODEL_DIR]
+    sys.modules["_spadot_ref_model"] = pkg
+    for name in ("svgp", "encoder", "decoder"):
+        _load(f"_spadot_ref_model.{name}", os.path.join(_MODEL_DIR, f"{name}.py"), "_spadot_ref_model")
+    return _load("_spadot_ref_model.SpaDOT", os.path.join(_MODEL_DIR, "SpaDOT.py"), "_spadot_ref_model")

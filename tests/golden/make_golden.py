@@ -90,7 +90,50 @@ def svgp_case(svgp_mod, name="svgp_small", seed=7):
     print(name, "written; l3", float(l3), "kl", float(kl))
 
 
-if __name__ == "__main__":
+def model_case(name="model_small", seed=5):
+    """One forward/backward of the reference SpaDOT model (GATConv stubbed, see reference_loader.load_model)
+    on a small synthetic batch with teacher-forced reparameterisation noise."""
+    import torch
+    from oracle import graph_ref
+    ref = reference_loader.load_model()
+    torch.manual_seed(seed)
+    rng = np.random.default_rng(seed)
+    n, genes, b, m = 260, 40, 96, 30
+    coords = rng.uniform(-1.5, 1.5, size=(n, 2))
+    ei = graph_ref.spatial_edge_index(coords, 6)
+    cfg = dict(input_dim=genes, z_dim=8, dtype=torch.float64, device="cpu", svgp_encoder_layers=[32, 16],
+               gat_encoder_hidden=12, gat_attention_heads=2, decoder_layers=[16, 32], kernel_type="Gaussian",
+               kernel_scale=0.1, timepoints=["t0"])
+    dl = dict(inducing_points={"t0": coords[rng.choice(n, m, replace=False)]}, N_train={"t0": n})
+    model = ref.SpaDOT(cfg, dl)
+    y = torch.from_numpy(rng.normal(size=(n, genes)))
+    x = torch.from_numpy(coords)
+    noise = [torch.from_numpy(rng.normal(size=(b, 4))) for _ in range(2)]
+    it = iter(noise)
+    orig = torch.randn_like
+    torch.randn_like = lambda t: next(it)
+    try:
+        recon, skl, gkl, align, final = model.forward(x, y, torch.from_numpy(ei), "t0", b)
+    finally:
+        torch.randn_like = orig
+    loss = 0.1 * recon - 0.7 * skl + 1e-4 * gkl + 0.1 * align
+    loss.backward()
+    out = dict(coords=coords, y=y.numpy(), edge_index=ei, inducing=dl["inducing_points"]["t0"], b=np.array(b),
+               noise0=noise[0].numpy(), noise1=noise[1].numpy(), recon=float(recon), svgp_kl=float(skl), gat_kl=float(gkl),
+               align=float(align), final=final.detach().numpy(), loss=float(loss))
+    for k, v in model.state_dict().items():
+        out["param::" + k] = v.numpy()
+    for k, p in model.named_parameters():
+        out["grad::" + k] = p.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "written; losses", float(recon), float(skl), float(gkl), float(align))
+
+
+if __name__ == "__main__" and "--model-only" in sys.argv:
+    model_case()
+
+
+if __name__ == "__main__" and "--model-only" not in sys.argv:
     assert reference_loader.available(), "reference not mounted"
     ref = reference_loader.load_ot_solvers()
     ot_case(ref, "ot_small_48x61_d6", 48, 61, 6, 11, CFG)
@@ -100,3 +143,4 @@ if __name__ == "__main__":
     wot_cfg = dict(CFG, lambda1=1.0, lambda2=50.0, epsilon=0.02)
     ot_case(ref, "ot_wotcfg_130x97_d32", 130, 97, 32, 13, wot_cfg, full_plan=False)
     svgp_case(reference_loader.load_svgp())
+    model_case()
