@@ -41,8 +41,8 @@ def check(z, model, outs, rtol, gtol):
     np.testing.assert_allclose(final.detach().cpu().numpy(), z["final"], rtol=rtol * 10, atol=1e-10)
     for name, p in model.named_parameters():
         want = z["grad::" + name]
-        scale = max(float(np.abs(want).max()), 1e-12)
-        assert float(np.abs(p.grad.cpu().numpy() - want).max()) < gtol * scale, name
+        scale = float(np.abs(want).max())        # biases in front of a BatchNorm have gradients that are rounding noise
+        assert float(np.abs(p.grad.cpu().numpy() - want).max()) < gtol * scale + 1e-13, name
 
 
 def test_model_oracle_reproduces_reference_batch(golden_dir):
