@@ -239,3 +239,27 @@ def test_reductions_of_different_width_share_scratch(ot):
         assert c4[3] == pytest.approx(np.sum(np.exp(g / 0.5) ** 2), rel=1e-12)
         assert t10[0] == pytest.approx(np.sum(np.exp(f / 0.5 + L)), rel=1e-12)
         assert t10[4] == pytest.approx(np.sum(np.exp(g / 0.5)), rel=1e-12)
+
+
+def test_analyze_pipeline_wot_conventions_chickenheart_shapes(ot):
+    """`SpaDOT analyze` on arrays: 3 adjacent pairs at ChickenHeart sizes, wot conventions (tau=10000, last growth
+    iteration).  Domain transitions must reproduce the dense oracle: tables within 1e-4, identical argmax, identical
+    dot-plot (min of row/col-normalised) argmax."""
+    from spadot_b200 import analyze
+    sizes, d = [747, 1966, 1916, 1967], 20
+    rng = np.random.default_rng(1993)
+    centres = rng.normal(0, 1.5, size=(10, d))
+    embs, labs = [], []
+    for t, n in enumerate(sizes):
+        lab = rng.integers(0, 10, n)
+        embs.append(centres[lab] + rng.normal(0, 0.5, size=(n, d)) + 0.1 * t)
+        labs.append(lab)
+    tables = analyze.ot_analysis(embs, labs, n_domains=[10] * 4)
+    cfg = dict(ot_dense.DEFAULT_OT_CONFIG, **analyze.WOT_CONFIG)
+    for t in range(3):
+        gammas = ot_dense.compute_transport_map(embs[t], embs[t + 1], cfg, return_all=True)
+        want = ot_dense.transition_table(gammas[-1], labs[t], labs[t + 1], 10, 10)
+        assert rel_max(tables[t], want) < 1e-4
+        assert np.array_equal(tables[t].argmax(1), want.argmax(1))
+        assert np.array_equal(analyze.transition_probabilities(tables[t]).argmax(1),
+                              ot_dense.plot_ot_normalisation(want).argmax(1))
