@@ -102,6 +102,12 @@ int sdb_potential_update(int64_t n, const double* L, const double* logmarg, cons
                          double eps, double alpha, double log_n_other, double c1,
                          double* pot, const double* frame, double* la_old, float* bias,
                          int* absorb_flag, int iter, double log_tau, double log_floor, void* stream);
+/* sdb_lse_finalize + sdb_potential_update fused (all outputs mandatory): combines the partials into L, updates pot,
+ * la_old, the absorb flag, and writes bias[i] (i < n only) = the bias vector of the NEXT pass over the other side. */
+int sdb_finalize_update(const float* partial, int n_splits, int64_t n, const double* norms, double c1, double* L,
+                        const double* logmarg, double eps, double alpha, double log_n_other, double* pot,
+                        const double* frame, double* la_old, float* bias, int* absorb_flag, int iter,
+                        double log_tau, double log_floor, void* stream);
 /* bias[i] = log2(e)*( pot[i]/eps - norms[i]*c1 ) for i < n (pot may be NULL = 0);
  * bias[i] = SDB_NEG_SENTINEL for n <= i < n_pad (column padding of the tensor-core pass). */
 int sdb_make_bias(int64_t n, int64_t n_pad, const double* pot, const double* norms, double eps, double c1,

@@ -28,6 +28,7 @@ SIGNATURES = {
     "sdb_lse_pass_simt": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_p, c_i, c_p, c_p],
     "sdb_lse_finalize": [c_p, c_i, c_l, c_p, c_d, c_p, c_p],
     "sdb_potential_update": [c_l, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
+    "sdb_finalize_update": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
     "sdb_make_bias": [c_l, c_l, c_p, c_p, c_d, c_d, c_p, c_p],
     "sdb_absmax_centered_f64": [c_p, c_l, c_i, c_p, c_p, c_p],
     "sdb_prep_points_split_f16": [c_p, c_l, c_i, c_p, c_i, c_p, c_l, c_i, c_p, c_p],
@@ -91,8 +92,16 @@ def check(status: int, what: str = ""):
         raise SpadotB200Error(f"{what or 'libspadot_b200'} failed: {msg} (status {status})")
 
 
+_fn_cache = {}
+
+
 def call(name: str, *args):
-    check(getattr(load(), name)(*args), name)
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(load(), name)
+    status = fn(*args)
+    if status != 0:
+        check(status, name)
 
 
 _device_ok = set()

@@ -86,6 +86,44 @@ __global__ void potential_update_kernel(int64_t n, const double* __restrict__ L,
     if (absorb_flag && (nv - fr) / eps > log_tau) atomicMax(absorb_flag, iter);
 }
 
+// finalize + potential update + next-pass bias in one launch (per-iteration launch count 9 -> 5)
+__global__ void finalize_update_kernel(const float2* __restrict__ partial, int n_splits, int64_t n, const double* __restrict__ norms,
+                                       double c1, double* __restrict__ L, const double* __restrict__ logmarg, double eps,
+                                       double alpha, double log_n_other, double* __restrict__ pot, const double* __restrict__ frame,
+                                       double* __restrict__ la_old, float* __restrict__ bias, int* __restrict__ absorb_flag, int iter,
+                                       double log_tau, double log_floor) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double M = -INFINITY;
+    for (int s = 0; s < n_splits; ++s) {
+        const float2 ps = partial[(int64_t)s * n + i];
+        if (ps.x > -1e29f && ps.y > 0.f) M = fmax(M, (double)ps.x);
+    }
+    double Li = -INFINITY;
+    if (M > -INFINITY) {
+        double S = 0.0;
+        for (int s = 0; s < n_splits; ++s) {
+            const float2 ps = partial[(int64_t)s * n + i];
+            if (ps.x > -1e29f && ps.y > 0.f) S += (double)ps.y * exp2((double)ps.x - M);
+        }
+        Li = SDB_LN2 * (M + log2(S)) - norms[i] * c1;
+    }
+    L[i] = Li;
+    const double fr = frame[i];
+    la_old[i] = (pot[i] - fr) / eps;
+    double LA = Li - log_n_other;
+    if (log_floor > -INFINITY) {
+        const double t = log_floor - fr / eps;
+        const double hi = fmax(LA, t), lo = fmin(LA, t);
+        LA = (lo == -INFINITY) ? hi : hi + log1p(exp(lo - hi));
+    }
+    const double nv = eps * alpha * (logmarg[i] - LA);
+    pot[i] = nv;
+    const double b = SDB_LOG2E * (nv / eps - norms[i] * c1);
+    bias[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
+    if ((nv - fr) / eps > log_tau) atomicMax(absorb_flag, iter);
+}
+
 __global__ void make_bias_kernel(int64_t n, int64_t n_pad, const double* __restrict__ pot, const double* __restrict__ norms,
                                  double eps, double c1, float* __restrict__ bias) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -318,6 +356,17 @@ int sdb_potential_update(int64_t n, const double* L, const double* logmarg, cons
     if (n == 0) return 0;
     potential_update_kernel<<<blocks_for(n), 256, 0, sdb_stream(stream)>>>(n, L, logmarg, norms, eps, alpha, log_n_other, c1, pot,
                                                                           frame, la_old, bias, absorb_flag, iter, log_tau, log_floor);
+    SDB_LAUNCH_STATUS();
+}
+
+int sdb_finalize_update(const float* partial, int n_splits, int64_t n, const double* norms, double c1, double* L,
+                        const double* logmarg, double eps, double alpha, double log_n_other, double* pot, const double* frame,
+                        double* la_old, float* bias, int* absorb_flag, int iter, double log_tau, double log_floor, void* stream) {
+    SDB_CHECK_ARG(partial && norms && L && logmarg && pot && frame && la_old && bias && absorb_flag && n_splits > 0 && n >= 0 && eps > 0.0);
+    if (n == 0) return 0;
+    finalize_update_kernel<<<blocks_for(n), 256, 0, sdb_stream(stream)>>>(reinterpret_cast<const float2*>(partial), n_splits, n, norms, c1, L,
+                                                                         logmarg, eps, alpha, log_n_other, pot, frame, la_old, bias,
+                                                                         absorb_flag, iter, log_tau, log_floor);
     SDB_LAUNCH_STATUS();
 }
 

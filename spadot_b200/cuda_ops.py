@@ -193,8 +193,9 @@ class CudaOps(VectorOps):
         self.X = PointSet(x64, center)
         self.Y = PointSet(y64, center)
         self.launches += 2
-        self.bias_x = torch.empty(_round_up(max(self.n, 1), 256), dtype=torch.float32, device=self.device)
-        self.bias_y = torch.empty(_round_up(max(self.m, 1), 256), dtype=torch.float32, device=self.device)
+        self.bias_x = torch.full((_round_up(max(self.n, 1), 256),), -1.0e30, dtype=torch.float32, device=self.device)
+        self.bias_y = torch.full((_round_up(max(self.m, 1), 256),), -1.0e30, dtype=torch.float32, device=self.device)
+        self._bias_key = {"x": None, "y": None}     # (potential data_ptr, eps) the bias vector was last built for
         if tc not in ("auto", "on", "off"):
             raise ValueError("tc must be 'auto', 'on' or 'off'")
         self.use_tc = tc == "on" or (tc == "auto" and self.d <= self.TC_MAX_D and self.n * self.m >= self.TC_MIN_PAIRS)
@@ -277,7 +278,38 @@ class CudaOps(VectorOps):
         """Lr_i = LSE_j[(g_j - C_ij)/eps] over all columns (natural log, fp64).  g=None means g=0."""
         self._call("sdb_make_bias", self.m, self.bias_y.numel(), _ptr(g), _ptr(self._norms(self.Y)), eps,
                    self.inv_med / eps, _ptr(self.bias_y))
+        self._bias_key["y"] = (_ptr(g), eps, self.inv_med) if g is not None else None
         return self._lse(self.X, self.Y, self.bias_y, eps, out)
+
+    def begin_solve(self):
+        self._bias_key = {"x": None, "y": None}
+
+    def fused_half_step(self, side, st, eps, alpha, it, log_tau, log_floor=NEG_INF, lse_known=False):
+        """One half-iteration with 2 launches: streamed pass (bias vector left behind by the previous half-step)
+        + sdb_finalize_update (LSE combine, potential update, tau flag, bias for the next pass).
+        side='row': g -> Lr -> f;  side='col' (single rank only): f -> Lc -> g."""
+        if side == "row":
+            P, Q, pot_in, pot, L, logmarg, frame, la, bias_in, bias_out, kin, kout, n_other = \
+                self.X, self.Y, st.g, st.f, st.Lr, st.logp, st.u, st.la_old, self.bias_y, self.bias_x, "y", "x", self.m
+        else:
+            P, Q, pot_in, pot, L, logmarg, frame, la, bias_in, bias_out, kin, kout, n_other = \
+                self.Y, self.X, st.f, st.g, st.Lc, st.logq, st.v, st.lb_old, self.bias_x, self.bias_y, "x", "y", st.N
+        c1 = self.inv_med / eps
+        key = (_ptr(pot_in), eps, self.inv_med)
+        if lse_known:
+            # L already holds the LSE at the current potentials (final-stage gap check): plain update + bias
+            self.potential_update(side, L, logmarg, eps, alpha, math.log(n_other), pot, frame, la, it, log_tau, log_floor)
+            self._call("sdb_make_bias", P.n, bias_out.numel(), _ptr(pot), _ptr(self._norms(P)), eps, c1, _ptr(bias_out))
+            self._bias_key[kout] = (_ptr(pot), eps, self.inv_med)
+            return
+        if self._bias_key[kin] != key:
+            self._call("sdb_make_bias", Q.n, bias_in.numel(), _ptr(pot_in), _ptr(self._norms(Q)), eps, c1, _ptr(bias_in))
+            self._bias_key[kin] = key
+        partial = self._lse(P, Q, bias_in, eps, finalize=False)
+        ns = partial.shape[0]
+        self._call("sdb_finalize_update", _ptr(partial), ns, P.n, _ptr(self._norms(P)), c1, _ptr(L), _ptr(logmarg), eps, alpha,
+                   math.log(n_other), _ptr(pot), _ptr(frame), _ptr(la), _ptr(bias_out), _ptr(self.flag), it, log_tau, log_floor)
+        self._bias_key[kout] = (_ptr(pot), eps, self.inv_med)
 
     def col_lse(self, f, eps, out=None):
         """Lc_j = LSE_{i local}[(f_i - C_ij)/eps] over this rank's rows."""
@@ -286,6 +318,7 @@ class CudaOps(VectorOps):
             return out.fill_(NEG_INF)
         self._call("sdb_make_bias", self.n, self.bias_x.numel(), _ptr(f), _ptr(self._norms(self.X)), eps,
                    self.inv_med / eps, _ptr(self.bias_x))
+        self._bias_key["x"] = (_ptr(f), eps, self.inv_med) if f is not None else None
         return self._lse(self.Y, self.X, self.bias_x, eps, out)
 
     # ------------------------------------------------------------------ vector updates

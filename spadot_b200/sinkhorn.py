@@ -88,6 +88,7 @@ class _State:
     """Per-solve device vectors."""
 
     def __init__(self, ops, G_local, dist: Dist):
+        getattr(ops, "begin_solve", lambda: None)()      # new potentials: cached bias vectors are stale
         self.n, self.m = ops.n, ops.m
         nt = torch.tensor([float(self.n)], dtype=torch.float64, device=ops.device)
         self.N = int(round(float(dist.sum_(nt).item())))
@@ -110,13 +111,20 @@ class _State:
 def _sweep(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_known, log_floor=NEG_INF):
     """One Sinkhorn iteration = row update + column update (ot_func.cpp:587-687) + tau bookkeeping."""
     it = ops.tick()
-    if not lr_known:
-        ops.row_lse(st.g, eps, out=st.Lr)
-    ops.potential_update("row", st.Lr, st.logp, eps, alpha1, math.log(st.m), st.f, st.u, st.la_old, it, log_tau, log_floor)
-    ops.col_lse(st.f, eps, out=st.Lc)
-    if dist.world > 1:
-        st.Lc.copy_(combine_col_lse(st.Lc, dist))
-    ops.potential_update("col", st.Lc, st.logq, eps, alpha2, math.log(st.N), st.g, st.v, st.lb_old, it, log_tau, log_floor)
+    fused = getattr(ops, "fused_half_step", None)
+    if fused is not None:
+        fused("row", st, eps, alpha1, it, log_tau, log_floor, lse_known=lr_known)
+    else:
+        if not lr_known:
+            ops.row_lse(st.g, eps, out=st.Lr)
+        ops.potential_update("row", st.Lr, st.logp, eps, alpha1, math.log(st.m), st.f, st.u, st.la_old, it, log_tau, log_floor)
+    if fused is not None and dist.world == 1:
+        fused("col", st, eps, alpha2, it, log_tau, log_floor)
+    else:
+        ops.col_lse(st.f, eps, out=st.Lc)
+        if dist.world > 1:
+            st.Lc.copy_(combine_col_lse(st.Lc, dist))
+        ops.potential_update("col", st.Lc, st.logq, eps, alpha2, math.log(st.N), st.g, st.v, st.lb_old, it, log_tau, log_floor)
     if dist.world > 1:
         dist.max_(ops.absorb_flag_tensor())
     ops.absorb(it, st.f, st.g, st.u, st.v)                        # ot_func.cpp:778-819
