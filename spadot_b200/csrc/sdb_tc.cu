@@ -487,10 +487,11 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                         cm2 = fmaxf(cm2, tv[k + 2]); cm3 = fmaxf(cm3, tv[k + 3]);
                     }
                     const float cm = fmaxf(fmaxf(cm0, cm1), fmaxf(cm2, cm3));
-                    if (cm > m_used + 64.f) {          // rare: first chunk of an item, or a much closer column shows up
-                        ssum *= sdb_ex2(m_used - cm);
-                        m_used = cm;
-                    }
+                    // branch-free lazy stabiliser: moves only when the chunk maximum exceeds it by more than 2^64
+                    // (first chunk of an item, or a much closer column shows up); otherwise the rescale is *1.
+                    const float m_new = (cm > m_used + 64.f) ? cm : m_used;
+                    ssum *= sdb_ex2(m_used - m_new);
+                    m_used = m_new;
                     if constexpr (PACKED) {
                         const uint64_t nm2 = pack2(-m_used, -m_used);
                         uint64_t acc2[CH / 2];
