@@ -133,3 +133,47 @@ def test_tc_median_sweeps_are_exact(ot, n, m, d):
     total = n * m
     assert abs(int(c1[0]) - int(c2[0])) <= max(4, total // 100000)
     assert int((h1 - h2).abs().max()) <= max(8, total // 50000)
+
+
+def test_full_size_1Mx1M_properties(ot):
+    """BASELINE.json configs[3] at full size (1M x 1M, d=32), where no CPU oracle can hold the problem:
+    (i) shift equivariance of the row pass, (ii) checksum of checksums — the LSE over all columns equals the
+    log-sum-exp of the LSEs over a 3-way column partition (run as three separate couplings), (iii) 48 random
+    rows against the fp64 oracle, (iv) one full Sinkhorn iteration keeps the potentials finite and its column
+    marginal consistent with the row marginal (total mass identity sum_i R_i = sum_j C_j)."""
+    _, sinkhorn, CudaOps = ot
+    import bench
+    n = m = 1_000_000
+    x, y = bench.synth(n, m, 32)
+    ops = CudaOps(x, y)
+    assert ops.use_tc
+    med, eps = 160.0, 0.05
+    ops.set_median(med)
+    rng = np.random.default_rng(0)
+    g_np = rng.normal(0, 0.2, m)
+    g = ops.tensor(g_np)
+    L0 = ops.row_lse(g, eps).clone()
+    L1 = ops.row_lse(g + 0.25, eps)
+    assert float((L1 - L0 - 0.25 / eps).abs().max()) < 2e-5
+    # (ii) column partition: mask out all but one third of the columns with -inf potentials
+    parts = []
+    for k in range(3):
+        gk = torch.full_like(g, float("-inf"))
+        gk[k::3] = g[k::3]
+        parts.append(ops.row_lse(gk, eps).clone())
+    combined = torch.logsumexp(torch.stack(parts), dim=0)
+    assert float((combined - L0).abs().max()) < 2e-5
+    # (iii) spot rows
+    idx = rng.integers(0, n, 48)
+    want = ot_logdomain.CostOperator(x[idx], y, median=med, block=8).row_lse(g_np / eps, eps)
+    assert np.abs(L0.cpu().numpy()[idx] - want).max() < 2e-5
+    # (iv) one iteration: mass seen from the rows equals mass seen from the columns
+    st = sinkhorn._State(ops, np.ones(n), sinkhorn.Dist(enabled=False))
+    st.u.copy_(st.f), st.v.copy_(st.g)
+    sinkhorn._sweep(ops, st, sinkhorn.Dist(enabled=False), eps, 0.1 / 0.15, 5.0 / 5.05, np.log(1000.0), False)
+    assert bool(torch.isfinite(st.f).all()) and bool(torch.isfinite(st.g).all())
+    Lr = ops.row_lse(st.g, eps)
+    Lc = ops.col_lse(st.f, eps)
+    mass_rows = float(torch.exp(st.f / eps + Lr).sum())
+    mass_cols = float(torch.exp(st.g / eps + Lc).sum())
+    assert mass_rows == pytest.approx(mass_cols, rel=1e-5)
