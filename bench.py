@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--d", type=int, default=32)
     ap.add_argument("--cpu-sample", type=int, default=8192, help="rows=cols of the dense CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the train-epoch aux measurement (N=1 only)")
     ap.add_argument("--tc", default="auto", choices=["auto", "on", "off"], help="tensor-core (tcgen05) pass")
     return ap.parse_args()
 
@@ -254,8 +255,11 @@ def gpu_main(a):
     yh = torch.from_numpy(y).pin_memory()
     e2e_steps = a.steps
 
+    ops2_holder = []
+
     def e2e_call(n_steps):
         ops2 = CudaOps(xh, yh, device=dev, tc=a.tc)  # H2D of both spot sets + point preparation
+        ops2_holder[:] = [ops2]
         ops2.set_median(median)
         st2 = sinkhorn._State(ops2, np.ones(ops2.n), dist)
         st2.u.copy_(st2.f)
@@ -338,6 +342,17 @@ def gpu_main(a):
         if world == 1 and not a.no_cpu_baseline:
             base, _ = cpu_reference_arm(a, 10, 2)
             line["cpu_baseline"] = base
+        if world == 1 and not a.no_aux:
+            # BASELINE.json's metric also names "train s/epoch": the train inner loop (SVGP + GAT) at ChickenHeart
+            # shapes, reference formulas in plain torch vs this repo's modules, both on this GPU (tools/train_epoch_bench.py)
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import train_epoch_bench
+                del ops2_holder[:]
+                torch.cuda.empty_cache()
+                line["aux_train_epoch"] = train_epoch_bench.run(dev)
+            except Exception as exc:       # the aux number must never take the headline down
+                line["aux_train_epoch"] = dict(error=repr(exc)[:200])
         print(json.dumps(line))
     if world > 1:
         td.destroy_process_group()
