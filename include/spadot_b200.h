@@ -116,6 +116,32 @@ int sdb_make_bias(int64_t n, int64_t n_pad, const double* pot, const double* nor
 int sdb_absorb(int64_t n, int64_t m, const int* absorb_flag, int iter,
                const double* f, const double* g, double* u, double* v, void* stream);
 
+/* ------------------------------------------------------------------ native sweep loop (single rank) */
+/* Everything one Sinkhorn iteration touches, so that `n_sweeps` iterations can be issued from C in one call
+ * (the reference's step1_process_double runs `iters` updates per call, ref: ot_func.cpp:690-828, :1261).
+ * All pointers are device pointers owned by the caller. */
+typedef struct sdb_sweep_desc {
+    int64_t n, m, n_total;            /* local source spots, target spots, source spots over all ranks (= n here) */
+    int32_t use_tc, dpad, dp, n_ctas; /* pass form; SIMT feature padding; tensor-core K per term; persistent grid */
+    const float* xt; int64_t ldx;     /* SIMT operands (sdb_prep_points_f64) */
+    const float* yt; int64_t ldy;
+    const void* x16; int64_t n_pad;   /* tensor-core operands (sdb_prep_points_split_f16) */
+    const void* y16; int64_t m_pad;
+    const double* norms_x; const double* norms_y;     /* norms of the representation in use */
+    const int64_t* bounds_row; const int64_t* bounds_col;   /* SIMT column splits of the row / column pass */
+    int32_t ns_row, ns_col, tps_row, tps_col;          /* number of splits; tiles per split (tensor-core form) */
+    float* partial_row; float* partial_col;            /* (ns_row, n, 2) and (ns_col, m, 2) workspaces */
+    float* bias_x; float* bias_y; int64_t m_bias;      /* bias vectors (padded to 256); padded length of bias_y */
+    double *f, *g, *u, *v, *la_old, *lb_old, *Lr, *Lc;
+    const double* logp; const double* logq;
+    int* flag;
+    double eps, inv_med, alpha1, alpha2, log_tau, log_floor, pow2_scale;   /* pow2_scale = 2^(-2*pow2_exp) */
+} sdb_sweep_desc;
+/* Issues n_sweeps x [row pass, finalize+update f, column pass, finalize+update g, absorb] on `stream`.
+ * lr_known_first != 0: Lr already holds the row LSE at the current g, the first row pass is skipped
+ * (final-stage gap check, see spadot_b200/sinkhorn.py).  Sweep i stamps the absorb flag with first_tick + i. */
+int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int first_tick, int lr_known_first, void* stream);
+
 /* ------------------------------------------------------------------ K4: stopping rules */
 /* Stage 0-4 rule (ref: ot_func.cpp:897-922).  out[0..3] =
  *   sum (a~ - old_a e^{u/eps})^2, sum a~^2, sum (b~ - old_b e^{v/eps})^2, sum b~^2

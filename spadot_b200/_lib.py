@@ -26,6 +26,7 @@ SIGNATURES = {
     "sdb_column_sums_f64": [c_p, c_l, c_i, c_p, c_p],
     "sdb_prep_points_f64": [c_p, c_l, c_i, c_p, c_p, c_l, c_i, c_p, c_p],
     "sdb_lse_pass_simt": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_p, c_i, c_p, c_p],
+    "sdb_sinkhorn_sweeps": [c_p, c_i, c_i, c_i, c_p],
     "sdb_lse_finalize": [c_p, c_i, c_l, c_p, c_d, c_p, c_p],
     "sdb_potential_update": [c_l, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
     "sdb_finalize_update": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
@@ -56,6 +57,21 @@ SIGNATURES = {
     "sdb_knn_f64": [c_p, c_l, c_i, c_i, c_p, c_p, c_p],
     "sdb_gat_backward": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
 }
+
+class SweepDesc(ctypes.Structure):
+    """struct sdb_sweep_desc of include/spadot_b200.h (field order and types must match)."""
+    _fields_ = [("n", c_l), ("m", c_l), ("n_total", c_l),
+                ("use_tc", ctypes.c_int32), ("dpad", ctypes.c_int32), ("dp", ctypes.c_int32), ("n_ctas", ctypes.c_int32),
+                ("xt", c_p), ("ldx", c_l), ("yt", c_p), ("ldy", c_l),
+                ("x16", c_p), ("n_pad", c_l), ("y16", c_p), ("m_pad", c_l),
+                ("norms_x", c_p), ("norms_y", c_p), ("bounds_row", c_p), ("bounds_col", c_p),
+                ("ns_row", ctypes.c_int32), ("ns_col", ctypes.c_int32), ("tps_row", ctypes.c_int32), ("tps_col", ctypes.c_int32),
+                ("partial_row", c_p), ("partial_col", c_p), ("bias_x", c_p), ("bias_y", c_p), ("m_bias", c_l),
+                ("f", c_p), ("g", c_p), ("u", c_p), ("v", c_p), ("la_old", c_p), ("lb_old", c_p), ("Lr", c_p), ("Lc", c_p),
+                ("logp", c_p), ("logq", c_p), ("flag", c_p),
+                ("eps", c_d), ("inv_med", c_d), ("alpha1", c_d), ("alpha2", c_d), ("log_tau", c_d), ("log_floor", c_d),
+                ("pow2_scale", c_d)]
+
 
 _lib = None
 

@@ -230,8 +230,12 @@ int launch_pairs(const PairArgs& a, const typename Epi::Params& ep, int n_splits
     if (a.n_p <= 0) return 0;
     const size_t smem = sizeof(float) * ((size_t)a.dpad * BM + 2 * (size_t)a.dpad * BN + 2 * BN);
     auto kern = pair_tile_kernel<DIRECT, Epi>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    static size_t smem_set = 0;      // per instantiation: raise the opt-in limit only when it has to grow
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        smem_set = smem;
+    }
     dim3 grid((unsigned)((a.n_p + BM - 1) / BM), (unsigned)n_splits);
     kern<<<grid, NT, smem, st>>>(a, ep);
     SDB_LAUNCH_STATUS();

@@ -1,0 +1,56 @@
+// Native sweep loop: `n_sweeps` full Sinkhorn iterations issued from C in one call.
+//
+// The reference keeps its inner loop native for the same reason (step1_process<T> runs `iters` updates per
+// call, ref: SpaDOT/utils/OT_loss/ot_func.cpp:690-828): at ChickenHeart sizes a streamed pass takes a few
+// microseconds of GPU time, so a Python-driven launch sequence (5 launches x ~13 us of interpreter + ctypes
+// per iteration) is host-bound.  This entry point issues pass -> finalize/update -> pass -> finalize/update ->
+// absorb for every iteration back to back on the caller's stream (single rank; the row-partitioned solve
+// needs a collective inside the iteration and is driven from Python).
+#include "sdb_common.cuh"
+
+extern "C" int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int first_tick, int lr_known_first, void* stream) {
+    SDB_CHECK_ARG(d && n_sweeps >= 0 && d->n > 0 && d->m > 0 && d->eps > 0.0);
+    const double c1 = d->inv_med / d->eps;
+    const double scale = 2.0 * c1 * SDB_LOG2E;
+    const double log_m = log((double)d->m), log_N = log((double)d->n_total);
+    int rc = 0;
+    auto pass = [&](bool row) -> int {
+        if (d->use_tc) {
+            return row ? sdb_lse_pass_tc(d->x16, d->n, d->n_pad, d->y16, d->m, d->m_pad, d->dp, d->bias_y, (float)(scale * d->pow2_scale),
+                                         d->tps_row, d->n_ctas, d->partial_row, stream)
+                       : sdb_lse_pass_tc(d->y16, d->m, d->m_pad, d->x16, d->n, d->n_pad, d->dp, d->bias_x, (float)(scale * d->pow2_scale),
+                                         d->tps_col, d->n_ctas, d->partial_col, stream);
+        }
+        return row ? sdb_lse_pass_simt(d->xt, d->ldx, d->n, d->yt, d->ldy, d->m, d->dpad, d->bias_y, (float)scale, d->bounds_row,
+                                       d->ns_row, d->partial_row, stream)
+                   : sdb_lse_pass_simt(d->yt, d->ldy, d->m, d->xt, d->ldx, d->n, d->dpad, d->bias_x, (float)scale, d->bounds_col,
+                                       d->ns_col, d->partial_col, stream);
+    };
+    if (!(lr_known_first && n_sweeps > 0)) {
+        // bias of the first row pass from the current g (a previous call may have used another eps)
+        rc = sdb_make_bias(d->m, d->m_bias, d->g, d->norms_y, d->eps, c1, d->bias_y, stream);
+        if (rc) return rc;
+    }
+    for (int i = 0; i < n_sweeps; ++i) {
+        const int tick = first_tick + i;
+        if (i == 0 && lr_known_first) {
+            // Lr already holds the row LSE at the current g (final-stage gap check)
+            rc = sdb_potential_update(d->n, d->Lr, d->logp, d->norms_x, d->eps, d->alpha1, log_m, c1, d->f, d->u, d->la_old, d->bias_x,
+                                      d->flag, tick, d->log_tau, d->log_floor, stream);
+        } else {
+            rc = pass(true);
+            if (rc) return rc;
+            rc = sdb_finalize_update(d->partial_row, d->ns_row, d->n, d->norms_x, c1, d->Lr, d->logp, d->eps, d->alpha1, log_m, d->f, d->u,
+                                     d->la_old, d->bias_x, d->flag, tick, d->log_tau, d->log_floor, stream);
+        }
+        if (rc) return rc;
+        rc = pass(false);
+        if (rc) return rc;
+        rc = sdb_finalize_update(d->partial_col, d->ns_col, d->m, d->norms_y, c1, d->Lc, d->logq, d->eps, d->alpha2, log_N, d->g, d->v,
+                                 d->lb_old, d->bias_y, d->flag, tick, d->log_tau, d->log_floor, stream);
+        if (rc) return rc;
+        rc = sdb_absorb(d->n, d->m, d->flag, tick, d->f, d->g, d->u, d->v, stream);
+        if (rc) return rc;
+    }
+    return 0;
+}

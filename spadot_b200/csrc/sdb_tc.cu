@@ -622,8 +622,12 @@ template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0>
 int launch_tc_v(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
     auto kern = lse_pass_tc_kernel<DP, EPI_WARPS, PACKED, POLY_EVERY>;
     constexpr int smem = TcSmem<DP>::TOTAL;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
     kern<<<n_ctas, 32 * (2 + EPI_WARPS), smem, st>>>(tmP, tmQ, a);
     SDB_LAUNCH_STATUS();
 }
@@ -632,8 +636,12 @@ template <int DP, int MODE>
 int launch_tc_sweep(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
     auto kern = lse_pass_tc_kernel<DP, 8, false, 0, MODE>;
     constexpr int smem = TcSmem<DP>::TOTAL_SWEEP;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
     kern<<<n_ctas, 32 * (2 + 8), smem, st>>>(tmP, tmQ, a);
     SDB_LAUNCH_STATUS();
 }

@@ -10,6 +10,7 @@ CPU by the test-suite, which injects an oracle-backed stand-in (tests/_numpy_ops
 """
 from __future__ import annotations
 
+import ctypes
 import math
 
 import numpy as np
@@ -172,6 +173,7 @@ class CudaOps(VectorOps):
     SIMT_MAX_D = 128
     TC_MAX_D = 64
     TC_MIN_PAIRS = 1 << 22   # below this the tensor-core pipeline cannot fill; the SIMT pass is used
+    TC_MIN_TILES = 8         # fewest 256-column tiles per (row tile, split) work item
     MAX_SPLIT_COLS = 65536   # keeps fp32 running sums < 1e-6 relative (include/spadot_b200.h)
     TARGET_CTAS = 148 * 6
 
@@ -246,7 +248,7 @@ class CudaOps(VectorOps):
         row_tiles = (n_p + 127) // 128
         col_tiles = (n_q + 255) // 256
         want = max(1, -(-4 * self.n_sm // row_tiles))                # enough items to balance a persistent grid
-        ns = min(want, max(1, col_tiles // 8))                        # ... but at least 8 tiles per item
+        ns = min(want, max(1, col_tiles // self.TC_MIN_TILES))        # ... but enough tiles per item to amortise its fill
         ns = max(ns, -(-col_tiles // (self.MAX_SPLIT_COLS // 256)))   # fp32 running-sum accuracy cap
         tps = -(-col_tiles // ns)
         return tps, -(-col_tiles // tps)
@@ -282,6 +284,44 @@ class CudaOps(VectorOps):
         return self._lse(self.X, self.Y, self.bias_y, eps, out)
 
     def begin_solve(self):
+        self._bias_key = {"x": None, "y": None}
+
+    def fused_sweeps(self, st, eps, alpha1, alpha2, log_tau, log_floor, n_sweeps, lr_known_first):
+        """n_sweeps full iterations issued by the native loop sdb_sinkhorn_sweeps (single rank)."""
+        d = _lib.SweepDesc()
+        d.n, d.m, d.n_total = self.n, self.m, st.N
+        d.use_tc = int(self.use_tc)
+        d.dpad, d.n_ctas = self.X.dpad, getattr(self, "n_sm", 0)
+        d.xt, d.ldx, d.yt, d.ldy = _ptr(self.X.xt), self.X.ld, _ptr(self.Y.xt), self.Y.ld
+        if self.use_tc:
+            d.dp = self.X.dp
+            d.x16, d.n_pad, d.y16, d.m_pad = _ptr(self.X.x16), self.X.n_pad, _ptr(self.Y.x16), self.Y.n_pad
+            d.tps_row, d.ns_row = self._tc_split_plan(self.n, self.m)
+            d.tps_col, d.ns_col = self._tc_split_plan(self.m, self.n)
+            d.pow2_scale = 2.0 ** (-2 * self.pow2_exp)
+        else:
+            b_row, d.ns_row = self._split_plan(self.n, self.m)
+            b_col, d.ns_col = self._split_plan(self.m, self.n)
+            d.bounds_row, d.bounds_col = _ptr(b_row), _ptr(b_col)
+            d.pow2_scale = 1.0
+        d.norms_x, d.norms_y = _ptr(self._norms(self.X)), _ptr(self._norms(self.Y))
+        d.partial_row, d.partial_col = _ptr(self._partial(d.ns_row, self.n)), _ptr(self._partial(d.ns_col, self.m))
+        d.bias_x, d.bias_y, d.m_bias = _ptr(self.bias_x), _ptr(self.bias_y), self.bias_y.numel()
+        d.f, d.g, d.u, d.v = _ptr(st.f), _ptr(st.g), _ptr(st.u), _ptr(st.v)
+        d.la_old, d.lb_old, d.Lr, d.Lc = _ptr(st.la_old), _ptr(st.lb_old), _ptr(st.Lr), _ptr(st.Lc)
+        d.logp, d.logq, d.flag = _ptr(st.logp), _ptr(st.logq), _ptr(self.flag)
+        d.eps, d.inv_med, d.alpha1, d.alpha2 = eps, self.inv_med, alpha1, alpha2
+        d.log_tau, d.log_floor = log_tau, log_floor
+        first = self._tick + 1
+        self._tick += n_sweeps
+        if self.n == self.m and d.ns_row == d.ns_col:
+            # both passes would share one (ns, n, 2) workspace from the cache: give the column pass its own
+            key = ("col", d.ns_col, self.m)
+            if key not in self._partials:
+                self._partials[key] = torch.empty((d.ns_col, self.m, 2), dtype=torch.float32, device=self.device)
+            d.partial_col = _ptr(self._partials[key])
+        _lib.call("sdb_sinkhorn_sweeps", ctypes.byref(d), int(n_sweeps), first, int(bool(lr_known_first)), self._stream())
+        self.launches += n_sweeps * 5 + (0 if lr_known_first else 1)
         self._bias_key = {"x": None, "y": None}
 
     def fused_half_step(self, side, st, eps, alpha, it, log_tau, log_floor=NEG_INF, lse_known=False):

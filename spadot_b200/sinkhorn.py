@@ -108,6 +108,16 @@ class _State:
         self.Lc = ops.zeros(self.m)
 
 
+def _sweeps(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_known, n_sweeps, log_floor=NEG_INF):
+    """n_sweeps iterations; one native call when the ops provide it (single rank), else a Python loop."""
+    native = getattr(ops, "fused_sweeps", None)
+    if native is not None and dist.world == 1 and n_sweeps > 0:
+        native(st, eps, alpha1, alpha2, log_tau, log_floor, n_sweeps, lr_known)
+        return
+    for i in range(n_sweeps):
+        _sweep(ops, st, dist, eps, alpha1, alpha2, log_tau, lr_known and i == 0, log_floor)
+
+
 def _sweep(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_known, log_floor=NEG_INF):
     """One Sinkhorn iteration = row update + column update (ot_func.cpp:587-687) + tau bookkeeping."""
     it = ops.tick()
@@ -155,10 +165,9 @@ def solve_duality_gap(ops, G_local, lambda1, lambda2, epsilon, batch_size=5, tol
         st.lb_old.zero_()
         sumK, lr_known, gap, n_it = None, False, math.inf, 0
         while gap > threshold:
-            for _ in range(n_inner):
-                n_it += 1
-                _sweep(ops, st, dist, eps_i, alpha1, alpha2, log_tau, lr_known)
-                lr_known = False
+            _sweeps(ops, st, dist, eps_i, alpha1, alpha2, log_tau, lr_known, n_inner)
+            n_it += n_inner
+            lr_known = False
             if final:
                 if sumK is None:
                     Lk = ops.row_lse(None, eps_i)
@@ -210,21 +219,21 @@ def solve_stablev2(ops, G_local, lambda1, lambda2, epsilon, scaling_iter=3000, t
     log_floor = math.log(1e-10)                                   # ot_solvers.py:498
     alpha1 = lambda1 / (lambda1 + eps_i)
     alpha2 = lambda2 / (lambda2 + eps_i)
-    idx = since = 0
-    for _ in range(int(scaling_iter)):
-        _sweep(ops, st, dist, eps_i, alpha1, alpha2, log_tau, False, log_floor)
-        since += 1
-        if warm and since == inner_iter_max:                      # ot_solvers.py:513-523
+    idx, done = 0, 0
+    total = int(scaling_iter)
+    while done < total:
+        chunk = min(int(inner_iter_max), total - done) if warm else total - done
+        _sweeps(ops, st, dist, eps_i, alpha1, alpha2, log_tau, False, chunk, log_floor)
+        done += chunk
+        if warm and chunk == inner_iter_max:                      # ot_solvers.py:513-523
             idx += 1
-            since = 0
             st.u.copy_(st.f)
             st.v.copy_(st.g)
             eps_i = (epsilon0 - epsilon) * math.exp(-idx) + epsilon
             alpha1 = lambda1 / (lambda1 + eps_i)
             alpha2 = lambda2 / (lambda2 + eps_i)
     # the extra iterations never absorb (ot_solvers.py:525-527)
-    for _ in range(int(extra_iter)):
-        _sweep(ops, st, dist, eps_i, alpha1, alpha2, math.inf, False, log_floor)
+    _sweeps(ops, st, dist, eps_i, alpha1, alpha2, math.inf, False, int(extra_iter), log_floor)
     ops.row_lse(st.g, eps_i, out=st.Lr)
     if info is not None:
         info.update(total_iters=int(scaling_iter) + int(extra_iter), epsilon_final=eps_i)
