@@ -316,6 +316,7 @@ def gpu_main(a):
                             peak=sfu_peak, unit="Tex2/s", frac=achieved / sfu_peak,
                             peak_source=f"{n_sm} SM x 16 MUFU lanes x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json; "
                                         "that file has no SFU entry)",
+                            frac_at_sampled_clock=(achieved / (n_sm * 16 * clk["sm_mhz"] * 1e6 / 1e12)) if clk and clk.get("sm_mhz") else None,
                             tensor_tflops=pairs * 6 * ops.X.dp / avg_pass_s / 1e12,
                             tensor_frac_of_measured_bf16=(pairs * 6 * ops.X.dp / avg_pass_s / 1e12) / float(peaks.get("bf16_tflops", 1640.6)),
                             **common)
