@@ -98,8 +98,10 @@ def compute_transport_map(a, b, config, C=None, G=None):
     if C is not None:
         from . import dense
         return dense.compute_transport_map_dense(C, config, G)
-    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
-    b = b.detach().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    # torch tensors (the train loop passes k-means centroids, utils/_train_utils.py:318) stay where they are:
+    # CUDA tensors are used in place, CPU tensors / ndarrays are uploaded once
+    a = a.detach() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach() if isinstance(b, torch.Tensor) else np.asarray(b)
     ops = CudaOps(a, b)
     dist = sinkhorn.Dist(enabled=False)
     median = sinkhorn.median_cost(ops, dist)

@@ -263,3 +263,22 @@ def test_analyze_pipeline_wot_conventions_chickenheart_shapes(ot):
         assert np.array_equal(tables[t].argmax(1), want.argmax(1))
         assert np.array_equal(analyze.transition_probabilities(tables[t]).argmax(1),
                               ot_dense.plot_ot_normalisation(want).argmax(1))
+
+
+def test_train_side_centroid_coupling_10x10(ot):
+    """utils/_train_utils.py:309-321: 10 k-means centroids per timepoint, z=20, torch tensors in, gammas[0] out."""
+    ot_solvers, _, _ = ot
+    rng = np.random.default_rng(3)
+    a, b = rng.normal(0, 1.5, (10, 20)), rng.normal(0, 1.5, (10, 20)) + 0.2
+    cfg = dict(CFG)
+    want = ot_dense.compute_transport_map(a, b, cfg)
+    got_cpu_tensor = ot_solvers.compute_transport_map(torch.from_numpy(a), torch.from_numpy(b), dict(cfg))
+    got_cuda_tensor = ot_solvers.compute_transport_map(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), dict(cfg))
+    for got in (got_cpu_tensor, got_cuda_tensor):
+        assert got.shape == (10, 10)
+        assert rel_max(got.sum(1), want.sum(1)) < MARG_RTOL
+        assert entry_rel(got, want) < ENTRY_RTOL
+    # the consumer normalises rows (utils/_train_utils.py:296-300)
+    row_norm = got_cpu_tensor / got_cpu_tensor.sum(axis=1, keepdims=True)
+    want_norm = want / want.sum(axis=1, keepdims=True)
+    assert np.abs(row_norm - want_norm).max() < 1e-5
