@@ -1,0 +1,77 @@
+"""BASELINE.json configs[2]: synthetic timepoint of 100k spots x 2000 SVGs, latent dim 32 (16 GP + 16 GAT dims),
+150 inducing points, k=30 spatial graph — SVGP+GAT training throughput of this repo's model on one GPU, float64.
+
+The reference cannot run this shape at all: _Cal_Spatial_Net builds a dense N x N adjacency (80 GB at 100k,
+utils/_utils.py:98-100), kernel_matrix(diag_only=True) builds an N x N block (model/svgp.py:43-45) and PyG's
+GATConv materialises (E,H,C) messages (3.1M x 4 x 512 fp64 = 51 GB per layer).  Prints one JSON line."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from spadot_b200 import graph, model as product  # noqa: E402
+
+
+def main():
+    dev = torch.device("cuda:0")
+    n, genes, z, m_ind, n_batches = 100_000, 2000, 32, 150, 4
+    rng = np.random.default_rng(0)
+    raw = rng.uniform(0, 20000, size=(n, 2))
+    loc = (raw - raw.mean(0)) / raw.std(0)
+    t0 = time.perf_counter()
+    ei = graph.spatial_edge_index(raw, graph.knn_cutoff(n), device=dev)
+    torch.cuda.synchronize()
+    t_graph = time.perf_counter() - t0
+    y = torch.randn(n, genes, dtype=torch.float64, device=dev).clamp_(-10, 10)
+    x = torch.from_numpy(loc).to(dev)
+    cfg = dict(input_dim=genes, z_dim=z, dtype=torch.float64, device=dev, svgp_encoder_layers=[256, 64], gat_encoder_hidden=512,
+               gat_attention_heads=4, decoder_layers=[64, 256], kernel_type="Gaussian", kernel_scale=0.1, timepoints=["t"])
+    dl = dict(inducing_points={"t": loc[rng.choice(n, m_ind, replace=False)]}, N_train={"t": n})
+    net = product.SpaDOT(cfg, dl).to(dev)
+    opt = torch.optim.AdamW(net.parameters(), lr=3e-4)
+    batches = []
+    t0 = time.perf_counter()
+    for nodes, lei, ns in graph.two_hop_batches(ei, n, batch_size=512):
+        batches.append((nodes, lei, ns))
+        if len(batches) == n_batches + 1:
+            break
+    torch.cuda.synchronize()
+    t_sample = (time.perf_counter() - t0) / len(batches)
+
+    def step(b):
+        nodes, lei, ns = b
+        recon, skl, gkl, align, _ = net.forward(x[nodes], y[nodes], lei, "t", ns)
+        loss = 0.1 * recon - 0.5 * skl + 1e-4 * gkl + 0.1 * align
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 0.3)
+        opt.step()
+        return float(loss)
+
+    step(batches[0])                                   # warm-up (cuBLAS/cuSOLVER handles, graph caches)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    losses = [step(b) for b in batches[1:]]
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / n_batches
+    sub_nodes = int(np.mean([b[0].numel() for b in batches[1:]]))
+    sub_edges = int(np.mean([b[1].shape[1] for b in batches[1:]]))
+    # full-timepoint inference (all_latent_samples) without n x n temporaries
+    net.eval()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    lat = net.all_latent_samples(loc, y, ei, "t")
+    torch.cuda.synchronize()
+    t_inf = time.perf_counter() - t0
+    print(json.dumps(dict(workload=f"SYN-T one timepoint: {n} spots x {genes} genes, z={z}, {m_ind} inducing, k=30, fp64",
+                          graph_build_s=t_graph, sample_batch_s=t_sample, subgraph_nodes=sub_nodes, subgraph_edges=sub_edges,
+                          train_step_s=dt, seeds_per_s=512 / dt, losses=losses, all_latent_samples_s=t_inf,
+                          latent_shape=list(lat.shape), peak_mem_gb=torch.cuda.max_memory_allocated() / 1e9)))
+
+
+if __name__ == "__main__":
+    main()
