@@ -239,7 +239,7 @@ struct TcArgs {
     unsigned long long cap;
 };
 
-template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, int MODE = MODE_LSE>
+template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, int MODE = MODE_LSE, bool PIPE = false>
 __global__ void __launch_bounds__(32 * (2 + EPI_WARPS), 1)
 lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, TcArgs a) {
     using S = TcSmem<DP>;
@@ -450,6 +450,74 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             const int t0 = sp * a.tiles_per_split;
             const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
             float m_used = SDB_NEG_SENTINEL, ssum = 0.f;
+            if constexpr (PIPE) {
+                // Software-pipelined form: the FP32 stage of chunk c+1 (t = scale*d + bias, chunk maximum) and the SFU
+                // stage of chunk c (ex2, sum) sit in one basic block with no dependence between them, so the scheduler
+                // interleaves FMA-pipe and MUFU work of the same warp instead of running them as alternating phases.
+                for (int t = t0; t < t1; ++t, ++tile_ctr) {
+                    const int acc = tile_ctr & 1;
+                    const int bs = tile_ctr % BIAS_STAGES;
+                    mbar_wait(b_full + bs, (tile_ctr / BIAS_STAGES) & 1);
+                    mbar_wait(t_full + acc, (tile_ctr >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t bias_s = bias_base + bs * TILE_N * 4;
+                    const uint32_t tbase = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TILE_N + part * COLS;
+                    uint32_t d[2][CH];
+                    uint64_t tv2[2][CH / 2];
+                    float cmv[2];
+                    auto stage_a = [&](int c) {            // FP32 stage: packed fma + chunk maximum
+#pragma unroll
+                        for (int k4 = 0; k4 < CH / 4; ++k4) {
+                            const float4 b = lds128(bias_s + (c * CH + k4 * 4) * 4);
+                            tv2[c & 1][k4 * 2 + 0] = ffma2(scale2, pack2(__uint_as_float(d[c & 1][k4 * 4 + 0]), __uint_as_float(d[c & 1][k4 * 4 + 1])), pack2(b.x, b.y));
+                            tv2[c & 1][k4 * 2 + 1] = ffma2(scale2, pack2(__uint_as_float(d[c & 1][k4 * 4 + 2]), __uint_as_float(d[c & 1][k4 * 4 + 3])), pack2(b.z, b.w));
+                        }
+                        float m0 = SDB_NEG_SENTINEL, m1 = SDB_NEG_SENTINEL, m2 = SDB_NEG_SENTINEL, m3 = SDB_NEG_SENTINEL;
+#pragma unroll
+                        for (int k = 0; k < CH / 2; k += 2) {
+                            float a0, a1, a2, a3;
+                            unpack2(tv2[c & 1][k], a0, a1);
+                            unpack2(tv2[c & 1][k + 1], a2, a3);
+                            m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1); m2 = fmaxf(m2, a2); m3 = fmaxf(m3, a3);
+                        }
+                        cmv[c & 1] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    };
+                    tmem_ld<CH>(tbase, d[0]);
+                    tmem_ld_wait();
+                    tmem_ld<CH>(tbase + CH, d[1]);
+                    stage_a(0);
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const float cm = cmv[c & 1];
+                        const float m_new = (cm > m_used + 64.f) ? cm : m_used;
+                        ssum *= sdb_ex2(m_used - m_new);
+                        m_used = m_new;
+                        const uint64_t nm2 = pack2(-m_used, -m_used);
+                        if (c + 1 < NCH) {
+                            tmem_ld_wait();                                   // chunk c+1 has landed in d[(c+1)&1]
+                            if (c + 2 < NCH) tmem_ld<CH>(tbase + (c + 2) * CH, d[c & 1]);   // d[c&1] was consumed by stage_a(c)
+                            stage_a(c + 1);
+                        }
+                        uint64_t acc2[CH / 2];
+#pragma unroll
+                        for (int k = 0; k < CH / 2; ++k) {                     // SFU stage of chunk c
+                            float a0, a1;
+                            unpack2(fadd2(tv2[c & 1][k], nm2), a0, a1);
+                            acc2[k] = pack2(sdb_ex2(a0), sdb_ex2(a1));
+                        }
+#pragma unroll
+                        for (int w = CH / 4; w > 0; w >>= 1)
+#pragma unroll
+                            for (int k = 0; k < w; ++k) acc2[k] = fadd2(acc2[k], acc2[k + w]);
+                        float e0, e1;
+                        unpack2(acc2[0], e0, e1);
+                        ssum += e0 + e1;
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(t_empty + acc); mbar_arrive(b_empty + bs); }
+                }
+            } else {
             for (int t = t0; t < t1; ++t, ++tile_ctr) {
                 const int acc = tile_ctr & 1;
                 const int bs = tile_ctr % BIAS_STAGES;
@@ -526,6 +594,7 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) { mbar_arrive(t_empty + acc); mbar_arrive(b_empty + bs); }
+            }
             }
             // merge the column slices' row statistics and emit one (max, sum) per row
             if (part > 0) sMerge[(part - 1) * TILE_M + row_in_tile] = make_float2(m_used, ssum);
@@ -618,9 +687,9 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows_pad, int dp, int b
     return r == CUDA_SUCCESS ? 0 : SDB_E_DRIVER;
 }
 
-template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0>
+template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, bool PIPE = false>
 int launch_tc_v(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
-    auto kern = lse_pass_tc_kernel<DP, EPI_WARPS, PACKED, POLY_EVERY>;
+    auto kern = lse_pass_tc_kernel<DP, EPI_WARPS, PACKED, POLY_EVERY, MODE_LSE, PIPE>;
     constexpr int smem = TcSmem<DP>::TOTAL;
     static bool attr_set = false;
     if (!attr_set) {
@@ -647,13 +716,14 @@ int launch_tc_sweep(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs
 }
 
 // Tuning variant (development knob SDB_TC_VARIANT): 0 scalar epilogue, 1 packed f32x2 (all exponentials on the SFU),
-// 2/3/4 packed with every 2nd/3rd/4th pair of exponentials evaluated by the FMA-pipe polynomial.
+// 2/3/4 packed with every 2nd/3rd/4th pair of exponentials evaluated by the FMA-pipe polynomial,
+// 5 packed + software-pipelined (FP32 stage of chunk c+1 interleaved with the SFU stage of chunk c).
 int tc_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SDB_TC_VARIANT");
-        v = e ? atoi(e) : 1;
-        if (v < 0 || v > 4) v = 1;
+        v = e ? atoi(e) : 5;
+        if (v < 0 || v > 5) v = 5;
     }
     return v;
 }
@@ -665,6 +735,7 @@ int launch_tc(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, i
         case 2: return launch_tc_v<DP, 8, true, 2>(tmP, tmQ, a, n_ctas, st);
         case 3: return launch_tc_v<DP, 8, true, 3>(tmP, tmQ, a, n_ctas, st);
         case 4: return launch_tc_v<DP, 8, true, 4>(tmP, tmQ, a, n_ctas, st);
+        case 5: return launch_tc_v<DP, 8, true, 0, true>(tmP, tmQ, a, n_ctas, st);
         default: return launch_tc_v<DP, 8, true>(tmP, tmQ, a, n_ctas, st);
     }
 }
