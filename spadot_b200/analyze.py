@@ -33,17 +33,46 @@ def transport_between(X0, X1, config=None, growth_rates=None, dist=None):
     return cp, growth
 
 
-def ot_analysis(embeddings, labels, config=None, n_domains=None):
+def label_codes(labels):
+    """Domain labels -> (integer codes, sorted names).  The reference keys populations by the strings
+    '<timepoint>_<kmeans label>' and wot orders them lexicographically (_analyze_utils.py:128-136)."""
+    names, codes = np.unique(np.asarray(labels).astype(str), return_inverse=True)
+    return codes.astype(np.int64), list(names)
+
+
+def ot_analysis(embeddings, labels, config=None, n_domains=None, out_dir=None, ids=None, prefix=""):
     """Transition tables between the domains of adjacent timepoints (_analyze_utils.py:128-138).
 
-    embeddings: list of (N_t, d) latent arrays in timepoint order; labels: list of integer domain labels.
-    Returns a list of (k_t, k_{t+1}) float64 arrays, table[a, b] = sum of transported mass from domain a to b."""
-    tables = []
+    embeddings: list of (N_t, d) latent arrays in timepoint order; labels: list of domain labels (integers, or
+    anything `label_codes` can order).  Returns a list of (k_t, k_{t+1}) float64 arrays, table[a, b] = transported
+    mass from domain a to domain b.  With `out_dir`, also writes what wot leaves on disk in array form:
+    `OT_g.txt` (TSV: id, g0..gK = learned growth per growth iteration, as examples/ChickenHeart_output/OT_g.txt) and
+    `<prefix>transition_table_<t>_<t+1>.npz` (table, row / column domain names)."""
+    import os
+    tables, growth_rows = [], []
+    coded = []
+    for lab in labels:
+        lab = np.asarray(lab)
+        coded.append((lab.astype(np.int64), [str(v) for v in range(int(lab.max()) + 1)]) if np.issubdtype(lab.dtype, np.integer)
+                     else label_codes(lab))
     for t in range(len(embeddings) - 1):
-        cp, _ = transport_between(embeddings[t], embeddings[t + 1], config)
-        k0 = (n_domains[t] if n_domains else None)
-        k1 = (n_domains[t + 1] if n_domains else None)
-        tables.append(cp.transition_table(labels[t], labels[t + 1], k0, k1).cpu().numpy())
+        cp, growth = transport_between(embeddings[t], embeddings[t + 1], config)
+        k0 = n_domains[t] if n_domains else len(coded[t][1])
+        k1 = n_domains[t + 1] if n_domains else len(coded[t + 1][1])
+        tables.append(cp.transition_table(coded[t][0], coded[t + 1][0], k0, k1).cpu().numpy())
+        growth_rows.append(np.stack(growth, axis=1))
+        if out_dir is not None:
+            os.makedirs(out_dir, exist_ok=True)
+            np.savez(os.path.join(out_dir, f"{prefix}transition_table_{t}_{t + 1}.npz"), table=tables[-1],
+                     rows=np.array(coded[t][1]), cols=np.array(coded[t + 1][1]))
+    if out_dir is not None and growth_rows:
+        G = np.concatenate(growth_rows, axis=0)
+        names = np.concatenate([np.asarray(ids[t]).astype(str) if ids is not None else
+                                np.array([f"t{t}_{i}" for i in range(len(embeddings[t]))]) for t in range(len(embeddings) - 1)])
+        with open(os.path.join(out_dir, "OT_g.txt"), "w") as fh:
+            fh.write("id\t" + "\t".join(f"g{k}" for k in range(G.shape[1])) + "\n")
+            for name, row in zip(names, G):
+                fh.write(name + "\t" + "\t".join(repr(float(v)) for v in row) + "\n")
     return tables
 
 

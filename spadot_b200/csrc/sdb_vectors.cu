@@ -417,7 +417,7 @@ int sdb_row_mass(int64_t n, const double* f, const double* Lr, double eps, doubl
 
 int sdb_plan_dense_f64(const double* x, const double* y, int64_t n, int64_t m, int d, const double* f, const double* g,
                        double inv_med, double eps, double inv_m, double* plan, void* stream) {
-    SDB_CHECK_ARG(x && y && f && g && plan && d > 0 && d <= 1024);
+    SDB_CHECK_ARG(x && y && f && g && plan && d > 0 && d <= 400);   // 2*32*(d+1) doubles of shared memory
     if (n == 0 || m == 0) return 0;
     dim3 grid((unsigned)((m + 31) / 32), (unsigned)((n + 31) / 32));
     if (grid.y > 65535) return SDB_E_UNSUPPORTED;

@@ -282,3 +282,18 @@ def test_train_side_centroid_coupling_10x10(ot):
     row_norm = got_cpu_tensor / got_cpu_tensor.sum(axis=1, keepdims=True)
     want_norm = want / want.sum(axis=1, keepdims=True)
     assert np.abs(row_norm - want_norm).max() < 1e-5
+
+
+def test_analyze_writes_growth_and_tables(ot, tmp_path):
+    from spadot_b200 import analyze
+    rng = np.random.default_rng(0)
+    embs = [rng.normal(0, 1, (150, 8)), rng.normal(0, 1, (170, 8)) + 0.1, rng.normal(0, 1, (160, 8)) + 0.2]
+    labs = [np.array([f"D{t}_{k}" for k in rng.integers(0, 4, e.shape[0])]) for t, e in enumerate(embs)]
+    tables = analyze.ot_analysis(embs, labs, out_dir=str(tmp_path), prefix="run_")
+    assert len(tables) == 2 and tables[0].shape == (4, 4)
+    g = np.loadtxt(tmp_path / "OT_g.txt", skiprows=1, usecols=(1, 2, 3, 4))
+    assert g.shape == (150 + 170, 4) and np.all(g[:, 0] == 1.0) and np.all(g > 0)
+    z = np.load(tmp_path / "run_transition_table_0_1.npz")
+    assert list(z["rows"]) == ["D0_0", "D0_1", "D0_2", "D0_3"] and np.allclose(z["table"], tables[0])
+    # growth column k+1 = row sums of the plan of growth iteration k (ot_solvers.py:116); the table sums to the last one
+    assert tables[0].sum() == pytest.approx(g[:150, 3].sum(), rel=1e-6)
