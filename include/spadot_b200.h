@@ -270,6 +270,20 @@ int sdb_gat_backward(const void* feat, const void* a_src, const void* a_dst, con
  * replaces sklearn NearestNeighbors in _Cal_Spatial_Net (ref: utils/_utils.py:65-69). */
 int sdb_knn_f64(const double* pts, int64_t n, int dim, int k, int32_t* out_idx, double* out_dist, void* stream);
 
+/* ------------------------------------------------------------------ K7: k-means Lloyd iterations */
+/* One Lloyd E-step (+ accumulation for the M-step): labels[i] <- argmin_j |c_j|^2 - 2 x_i.c_j (first minimum on ties),
+ * *changed set to 1 when any label moved; with sums (k,d) / counts (k) non-NULL (zeroed by the caller) the per-cluster
+ * coordinate sums and sizes are accumulated.  X (n,d), centers (k,d) row-major fp64; k <= 64, k*d <= 4096.
+ * replaces sklearn.cluster.KMeans' lloyd_iter behind ref: utils/_train_utils.py:255-269, utils/_analyze_utils.py:10-39. */
+int sdb_kmeans_assign(const double* X, const double* centers, int64_t n, int d, int k, int32_t* labels, int* changed,
+                      double* sums, double* counts, void* stream);
+/* centers_new = sums / counts (empty clusters keep their centre); *shift_sq = sum |centers_new - centers_old|^2. */
+int sdb_kmeans_update(const double* sums, const double* counts, const double* centers_old, double* centers_new, int d,
+                      int k, double* shift_sq, void* stream);
+/* out1[0] = sum_i |x_i - c_{labels[i]}|^2 (direct differences); scratch as for the other reductions. */
+int sdb_kmeans_inertia(const double* X, const double* centers, const int32_t* labels, int64_t n, int d, double* out1,
+                       void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,9 @@ SIGNATURES = {
     "sdb_kernel_diag_f64": [c_p, c_p, c_l, c_i, c_i, c_d, c_p, c_p],
     "sdb_quad_form_rows_f64": [c_p, c_p, c_l, c_i, c_p, c_p],
     "sdb_gat_forward": [c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p],
+    "sdb_kmeans_assign": [c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
+    "sdb_kmeans_update": [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p],
+    "sdb_kmeans_inertia": [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p],
     "sdb_knn_f64": [c_p, c_l, c_i, c_i, c_p, c_p, c_p],
     "sdb_gat_backward": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
 }

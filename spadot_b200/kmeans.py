@@ -1,0 +1,116 @@
+"""Drop-in for the `sklearn.cluster.KMeans(n_clusters, random_state, n_init=10)` calls of SpaDOT
+(utils/_train_utils.py:255-269 every epoch, utils/_analyze_utils.py:10-39,42-105 in analyze).
+
+The procedure is sklearn's, step for step, so the same `random_state` gives the same clustering:
+centre the data, `tol * mean(var)`, then for each of the `n_init` runs draw the k-means++ seeds from ONE
+RandomState stream (sklearn's own `kmeans_plusplus`, a few k x n distance evaluations on the host), run
+Lloyd's iterations to strict label convergence or a squared centre shift below the tolerance, keep the run
+with the smallest inertia.  Lloyd's iterations — the part that scales with n x k x iterations x n_init — run on
+the device (csrc/sdb_kmeans.cu: fused assignment + per-cluster accumulation, centre update, inertia).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from sklearn.cluster import kmeans_plusplus
+from sklearn.utils import check_random_state
+from sklearn.utils.extmath import row_norms
+
+from . import _lib
+
+
+def _same_clustering(l1, l2, k):
+    """sklearn's _is_same_clustering: every label of l1 maps to a single label of l2."""
+    pairs = np.unique(l1.astype(np.int64) * k + l2.astype(np.int64))
+    return pairs.size == np.unique(l1).size
+
+
+class KMeans:
+    def __init__(self, n_clusters=8, *, n_init=10, max_iter=300, tol=1e-4, random_state=None, device=None):
+        self.n_clusters, self.n_init, self.max_iter, self.tol, self.random_state = n_clusters, n_init, max_iter, tol, random_state
+        self.device = device
+
+    # ------------------------------------------------------------------ one Lloyd run on the device
+    def _lloyd(self, Xd, X_host, centers_init, tol):
+        n, d = Xd.shape
+        k = self.n_clusters
+        dev = Xd.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        centers = torch.from_numpy(np.ascontiguousarray(centers_init)).to(dev)
+        centers_new = torch.empty_like(centers)
+        labels = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        work = torch.zeros(k * d + k + 2, dtype=torch.float64, device=dev)     # sums | counts | shift | (pad)
+        sums, counts, shift = work[:k * d], work[k * d:k * d + k], work[k * d + k:k * d + k + 1]
+        changed = torch.zeros(1, dtype=torch.int32, device=dev)
+        strict, n_iter = False, 0
+        for it in range(self.max_iter):
+            n_iter = it + 1
+            work.zero_()
+            changed.zero_()
+            _lib.call("sdb_kmeans_assign", Xd.data_ptr(), centers.data_ptr(), n, d, k, labels.data_ptr(), changed.data_ptr(),
+                      sums.data_ptr(), counts.data_ptr(), st)
+            cnt = counts.cpu().numpy()
+            if (cnt == 0).any():
+                self._relocate_empty(X_host, labels, centers, sums, counts, cnt)
+            _lib.call("sdb_kmeans_update", sums.data_ptr(), counts.data_ptr(), centers.data_ptr(), centers_new.data_ptr(), d, k,
+                      shift.data_ptr(), st)
+            centers, centers_new = centers_new, centers
+            if int(changed.item()) == 0:
+                strict = True
+                break
+            if float(shift.item()) <= tol:
+                break
+        if not strict:
+            # rerun the E-step so that the labels match the final centres (sklearn does the same)
+            changed.zero_()
+            _lib.call("sdb_kmeans_assign", Xd.data_ptr(), centers.data_ptr(), n, d, k, labels.data_ptr(), changed.data_ptr(), 0, 0, st)
+        scratch = torch.zeros(10 * 1024 + 2, dtype=torch.float64, device=dev)
+        out = torch.zeros(1, dtype=torch.float64, device=dev)
+        _lib.call("sdb_kmeans_inertia", Xd.data_ptr(), centers.data_ptr(), labels.data_ptr(), n, d, out.data_ptr(), scratch.data_ptr(), st)
+        return labels.cpu().numpy().astype(np.int32), float(out.item()), centers.cpu().numpy(), n_iter
+
+    @staticmethod
+    def _relocate_empty(X, labels, centers, sums, counts, cnt):
+        """sklearn's _relocate_empty_clusters_dense: an empty cluster takes the sample farthest from its centre."""
+        lab = labels.cpu().numpy()
+        c_old = centers.cpu().numpy()
+        s = sums.cpu().numpy().reshape(c_old.shape).copy()
+        w = cnt.copy()
+        empty = np.where(w == 0)[0]
+        dist = ((X - c_old[lab]) ** 2).sum(axis=1)
+        far = np.argpartition(dist, -empty.size)[:-empty.size - 1:-1]
+        for new_id, far_idx in zip(empty, far):
+            old_id = lab[far_idx]
+            s[old_id] -= X[far_idx]
+            s[new_id] = X[far_idx]
+            w[new_id] = 1.0
+            w[old_id] -= 1.0
+        sums.copy_(torch.from_numpy(s.reshape(-1)).to(sums.device))
+        counts.copy_(torch.from_numpy(w).to(counts.device))
+
+    # ------------------------------------------------------------------ sklearn surface
+    def fit(self, X, y=None):
+        _lib.require_device()
+        X = np.array(X, dtype=np.float64, order="C", copy=True)
+        n, d = X.shape
+        if n < self.n_clusters:
+            raise ValueError(f"n_samples={n} should be >= n_clusters={self.n_clusters}.")
+        tol = float(np.mean(np.var(X, axis=0)) * self.tol)
+        rs = check_random_state(self.random_state)
+        mean = X.mean(axis=0)
+        X -= mean
+        x_sq = row_norms(X, squared=True)
+        dev = torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
+        Xd = torch.from_numpy(X).to(dev)
+        best = None
+        for _ in range(self.n_init):
+            centers_init, _ = kmeans_plusplus(X, self.n_clusters, x_squared_norms=x_sq, random_state=rs)
+            labels, inertia, centers, n_iter = self._lloyd(Xd, X, centers_init, tol)
+            if best is None or (inertia < best[1] and not _same_clustering(labels, best[0], self.n_clusters)):
+                best = (labels, inertia, centers, n_iter)
+        self.labels_, self.inertia_, centers, self.n_iter_ = best
+        self.cluster_centers_ = centers + mean
+        return self
+
+    def fit_predict(self, X, y=None):
+        return self.fit(X).labels_
