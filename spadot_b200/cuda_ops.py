@@ -104,8 +104,12 @@ class VectorOps:
                          log_floor=NEG_INF):
         """side='row' updates f (local rows), side='col' updates g; see sdb_potential_update."""
         self._call("sdb_potential_update", pot.numel(), _ptr(L), _ptr(logmarg), _ptr(self._side_norms(side, pot)), eps,
-                   alpha, log_n_other, self._c1(eps), _ptr(pot), _ptr(frame), _ptr(la_old), 0, _ptr(self.flag), it,
-                   log_tau, log_floor)
+                   alpha, log_n_other, self._c1(eps), _ptr(pot), _ptr(frame), _ptr(la_old), self._bias_out(side, pot, eps),
+                   _ptr(self.flag), it, log_tau, log_floor)
+
+    def _bias_out(self, side, pot, eps):
+        """Device pointer of the fp32 bias vector the update should refresh for the next pass (0 = none)."""
+        return 0
 
     def absorb_flag_tensor(self):
         return self.flag
@@ -339,8 +343,6 @@ class CudaOps(VectorOps):
         if lse_known:
             # L already holds the LSE at the current potentials (final-stage gap check): plain update + bias
             self.potential_update(side, L, logmarg, eps, alpha, math.log(n_other), pot, frame, la, it, log_tau, log_floor)
-            self._call("sdb_make_bias", P.n, bias_out.numel(), _ptr(pot), _ptr(self._norms(P)), eps, c1, _ptr(bias_out))
-            self._bias_key[kout] = (_ptr(pot), eps, self.inv_med)
             return
         if self._bias_key[kin] != key:
             self._call("sdb_make_bias", Q.n, bias_in.numel(), _ptr(pot_in), _ptr(self._norms(Q)), eps, c1, _ptr(bias_in))
@@ -367,6 +369,13 @@ class CudaOps(VectorOps):
 
     def _c1(self, eps):
         return self.inv_med / eps
+
+    def _bias_out(self, side, pot, eps):
+        # the potential changes in place: the cached bias vector of that side must follow it (the cache is keyed by
+        # pointer, so a stale entry would otherwise be reused by the next pass)
+        k, bias = ("x", self.bias_x) if side == "row" else ("y", self.bias_y)
+        self._bias_key[k] = (_ptr(pot), eps, self.inv_med)
+        return _ptr(bias)
 
     def plan_dense(self, f, g, eps):
         plan = torch.empty((self.n, self.m), dtype=torch.float64, device=self.device)

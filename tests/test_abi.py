@@ -69,3 +69,50 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{fn} imports oracle"
                 assert "_numpy_ops" not in src or fn == "cuda_ops.py" and "tests/_numpy_ops.py" in src
+
+
+# ------------------------------------------------------------------ libot_b200.so: the reference's own ABI
+def libot_header_functions():
+    text = open(os.path.join(ROOT, "include", "libot_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|void|float|double)\s+(\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("void", "") else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+REFERENCE_EXPORTS = {        # nm -D of the libot.so the reference ships (SpaDOT/utils/OT_loss/libot.so), with parameter counts
+    "dummy_float": 14, "dummy_double": 14, "primal_float": 14, "primal_double": 14, "dual_float": 14, "dual_double": 14,
+    "compute_duality_gap_float": 14, "compute_duality_gap_double": 14, "update_k_float": 8, "update_k_double": 8,
+    "update_R_float": 6, "update_R_double": 6, "step1_process_double": 23, "update_process_double": 28,
+}
+
+
+def test_libot_drop_in_exports_the_reference_symbols():
+    """libot_b200.so loads without a GPU and exports the fourteen symbols of the reference's libot.so with the
+    parameter counts of ot_func.cpp:938-1373; the header declares exactly those (+ three identification helpers)."""
+    from spadot_b200 import ot_func
+    funcs = libot_header_functions()
+    for name, n_args in REFERENCE_EXPORTS.items():
+        assert funcs.get(name) == n_args, (name, funcs.get(name), n_args)
+        fn = getattr(ot_func.lib, name)
+        assert len(fn.argtypes) == n_args, name
+    extra = set(funcs) - set(REFERENCE_EXPORTS)
+    assert extra == {"libot_b200_device_check", "libot_b200_version", "libot_b200_counters"}, extra
+    for name in extra:
+        assert hasattr(ot_func.lib, name)
+    assert ot_func.lib.libot_b200_version() == 100
+    assert ot_func.lib.dummy_double.restype is not None
+    # the wrapper module mirrors the reference's ot_func.py function names (ot_solvers.py:10 imports these)
+    for name in ("dummy_c", "primal_c", "dual_c", "compute_duality_gap_c", "update_K_c", "update_R_c", "step1_process_c",
+                 "update_process_c"):
+        assert callable(getattr(ot_func, name))
+
+
+def test_libot_drop_in_reports_missing_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from spadot_b200 import ot_func
+    assert ot_func.lib.libot_b200_device_check() != 0      # compute entry points abort the process in this state

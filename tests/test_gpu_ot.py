@@ -297,3 +297,60 @@ def test_analyze_writes_growth_and_tables(ot, tmp_path):
     assert list(z["rows"]) == ["D0_0", "D0_1", "D0_2", "D0_3"] and np.allclose(z["table"], tables[0])
     # growth column k+1 = row sums of the plan of growth iteration k (ot_solvers.py:116); the table sums to the last one
     assert tables[0].sum() == pytest.approx(g[:150, 3].sum(), rel=1e-6)
+
+
+class _LoopbackDist:
+    """The multi-rank code path on one GPU: a 2-rank group whose other rank owns no rows (its partial
+    column LSE is -inf, its sums are 0), so every collective is the identity."""
+
+    def __new__(cls, sinkhorn):
+        class Loop(sinkhorn.Dist):
+            def __init__(self):
+                super().__init__(enabled=False)
+                self.world = 2
+
+            def sum_(self, t):
+                self.collectives += 1
+                return t
+
+            def max_(self, t):
+                self.collectives += 1
+                return t
+
+            def gather_cat(self, t):
+                return t
+        return Loop()
+
+
+@pytest.mark.parametrize("n,m,d,tc", [(1500, 1300, 20, "off"), (2600, 2100, 32, "on")])
+def test_multi_rank_code_path_matches_native_loop(ot, n, m, d, tc):
+    """Regression: the per-iteration Python loop used for world > 1 (row pass fused, column pass + all-reduce +
+    potential update) must walk the same iterates as the native single-rank loop — same iterations per epsilon
+    stage, same potentials.  (A stale cached bias vector once froze g inside a stage on this path only.)"""
+    ot_solvers, sinkhorn, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, d, seed=n)
+    G = np.exp(np.random.default_rng(1).normal(0, 0.3, n))
+    cfg = dict(CFG)
+    cp1 = ot_solvers.solve_coupling(a, b, cfg, G=G, ops=CudaOps(a, b, tc=tc), dist=sinkhorn.Dist(enabled=False))
+    loop = _LoopbackDist(sinkhorn)
+    cp2 = ot_solvers.solve_coupling(a, b, cfg, G=G, ops=CudaOps(a, b, tc=tc), dist=loop)
+    assert loop.collectives > 0
+    assert cp1.median == cp2.median
+    assert cp1.info["iters_per_stage"] == cp2.info["iters_per_stage"], (cp1.info, cp2.info)
+    assert float((cp1.f - cp2.f).abs().max()) < 1e-6
+    assert float((cp1.g - cp2.g).abs().max()) < 1e-6
+
+
+def test_two_gpu_row_partition_matches_single_gpu():
+    """tests/dist_gpu_check.py under torchrun (NCCL) when the box has >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dist_gpu_check.py")],
+                       capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("dist check") == 2, r.stdout

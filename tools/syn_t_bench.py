@@ -16,9 +16,18 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from spadot_b200 import graph, model as product  # noqa: E402
 
 
-def main():
+def main(argv=None):
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=100_000)
+    ap.add_argument("--genes", type=int, default=2000)
+    ap.add_argument("--z", type=int, default=32)
+    ap.add_argument("--inducing", type=int, default=150)
+    ap.add_argument("--batches", type=int, default=4)
+    ap.add_argument("--name", default="SYN-T")
+    a = ap.parse_args(argv)
     dev = torch.device("cuda:0")
-    n, genes, z, m_ind, n_batches = 100_000, 2000, 32, 150, 4
+    n, genes, z, m_ind, n_batches = a.n, a.genes, a.z, a.inducing, a.batches
     rng = np.random.default_rng(0)
     raw = rng.uniform(0, 20000, size=(n, 2))
     loc = (raw - raw.mean(0)) / raw.std(0)
@@ -67,7 +76,7 @@ def main():
     lat = net.all_latent_samples(loc, y, ei, "t")
     torch.cuda.synchronize()
     t_inf = time.perf_counter() - t0
-    print(json.dumps(dict(workload=f"SYN-T one timepoint: {n} spots x {genes} genes, z={z}, {m_ind} inducing, k=30, fp64",
+    print(json.dumps(dict(workload=f"{a.name} one timepoint: {n} spots x {genes} genes, z={z}, {m_ind} inducing, k=30, fp64",
                           graph_build_s=t_graph, sample_batch_s=t_sample, subgraph_nodes=sub_nodes, subgraph_edges=sub_edges,
                           train_step_s=dt, seeds_per_s=512 / dt, losses=losses, all_latent_samples_s=t_inf,
                           latent_shape=list(lat.shape), peak_mem_gb=torch.cuda.max_memory_allocated() / 1e9)))
