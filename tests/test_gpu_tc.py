@@ -177,3 +177,38 @@ def test_full_size_1Mx1M_properties(ot):
     mass_rows = float(torch.exp(st.f / eps + Lr).sum())
     mass_cols = float(torch.exp(st.g / eps + Lc).sum())
     assert mass_rows == pytest.approx(mass_cols, rel=1e-5)
+
+
+@pytest.mark.timeout(600)
+def test_parity_8192x8192_three_way(ot):
+    """SURVEY 8d's largest parity shape: the streamed tensor-core solve, libot_b200.so (the reference's dense ABI on
+    the device) and the reference's own ot_func.cpp compiled unmodified (oracle/_ref), same inputs, d = 32.
+    Tolerances are the north star's: marginals 1e-5 relative, plan entries rtol 1e-4, transition table 1e-4 with the
+    same argmax; the two dense fp64 paths must agree to 1e-9."""
+    from oracle import ref_lib
+    from spadot_b200 import ot_func
+    if not ref_lib.available():
+        pytest.skip("oracle/_ref/libot_ref.so (the compiled reference) is not present")
+    ot_solvers, sinkhorn, CudaOps = ot
+    n = m = 8192
+    a, b, la, lb = ot_dense.synthetic_embeddings(n, m, 32, seed=8192)
+    Cn, med = ot_dense.median_normalised_cost(a, b)
+    kw = dict(lambda1=CFG["lambda1"], lambda2=CFG["lambda2"], epsilon=CFG["epsilon"], tau=CFG["tau"],
+              batch_size=CFG["batch_size"], tolerance=CFG["tolerance"], epsilon0=CFG["epsilon0"])
+    want = ref_lib.duality_gap_solve(Cn, np.ones(n), **kw)
+    dense_dev = ref_lib.duality_gap_solve(Cn, np.ones(n), L=ref_lib.bind(ot_func.LIB_PATH), **kw)
+    big = want > 1e-8 * want.max()
+    assert (np.abs(dense_dev - want)[big] / want[big]).max() < 1e-9
+    del dense_dev
+    ops = CudaOps(a, b)
+    assert ops.use_tc
+    cp = ot_solvers.solve_coupling(a, b, CFG, ops=ops)
+    assert cp.median == med
+    got = cp.plan().cpu().numpy()
+    assert np.abs(got.sum(1) - want.sum(1)).max() / want.sum(1).max() < 1e-5
+    assert np.abs(got.sum(0) - want.sum(0)).max() / want.sum(0).max() < 1e-5
+    assert (np.abs(got - want)[big] / want[big]).max() < 1e-4
+    tab = cp.transition_table(la, lb, 10, 10).cpu().numpy()
+    tab_ref = ot_dense.transition_table(want, la, lb, 10, 10)
+    assert np.abs(tab - tab_ref).max() / tab_ref.max() < 1e-4
+    assert np.array_equal(tab.argmax(1), tab_ref.argmax(1))
