@@ -9,9 +9,10 @@
  *     pointer; matrices are (m, n) with `int m, int n` trailing; scalars by value;
  *   - buffers documented "in/out" are mutated in place exactly where the reference mutates them;
  *   - no handles, no contexts, no error codes besides the reference's own (-1 from step1_process,
- *     NaN gap); calls are serialised by one process-wide mutex; device buffers are allocated and
- *     freed inside each call (the reference mallocs / frees its temporaries per call as well), so
- *     nothing but three counters survives between calls;
+ *     NaN gap); calls are serialised by one process-wide mutex; between calls the library keeps
+ *     three counters and a pool of the device blocks the last calls used (cudaMalloc/cudaFree of
+ *     matrix-sized blocks cost more than the PCIe copies; libot_b200_release() or the environment
+ *     variable LIBOT_B200_POOL=0 returns to allocate-per-call) — never any problem data;
  *   - there is NO CPU fallback: without a usable sm_100 device every entry point prints a message
  *     to stderr and aborts the process (the ABI has no error channel to report it through).
  *
@@ -94,6 +95,8 @@ double update_process_double(double* R, double* a, double* b, double* old_a, dou
 /* Not part of the reference ABI: library/device identification for tests (0 = a usable sm_100 device is present). */
 int libot_b200_device_check(void);
 int libot_b200_version(void);
+/* Frees every pooled device block. */
+void libot_b200_release(void);
 /* Cumulative counters since load: kernels launched, bytes uploaded, bytes downloaded (for the bench's accounting). */
 void libot_b200_counters(long long* launches, long long* h2d_bytes, long long* d2h_bytes);
 

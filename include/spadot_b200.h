@@ -141,6 +141,14 @@ typedef struct sdb_sweep_desc {
  * lr_known_first != 0: Lr already holds the row LSE at the current g, the first row pass is skipped
  * (final-stage gap check, see spadot_b200/sinkhorn.py).  Sweep i stamps the absorb flag with first_tick + i. */
 int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int first_tick, int lr_known_first, void* stream);
+/* The same n_sweeps iterations in ONE cooperative launch (SIMT form only, use_tc == 0): CTAs walk the (slab, split)
+ * items of each pass and meet at a grid barrier between pass and update, so a ChickenHeart-sized iteration costs four
+ * barriers instead of five launches.  barrier2: two zero-initialised unsigned ints owned by the caller (reusable across
+ * calls).  Grid = d->n_ctas CTAs (capped by co-residency; 0 = one per work item); the caller sizes the column splits
+ * for it.  Same tile and update code as sdb_sinkhorn_sweeps; the partials of a row are combined by a warp instead of a
+ * thread, so iterates agree to fp64 rounding of that sum. */
+int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_sweeps, int first_tick, int lr_known_first,
+                                   unsigned int* barrier2, void* stream);
 
 /* ------------------------------------------------------------------ K4: stopping rules */
 /* Stage 0-4 rule (ref: ot_func.cpp:897-922).  out[0..3] =

@@ -27,6 +27,7 @@ SIGNATURES = {
     "sdb_prep_points_f64": [c_p, c_l, c_i, c_p, c_p, c_l, c_i, c_p, c_p],
     "sdb_lse_pass_simt": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_p, c_i, c_p, c_p],
     "sdb_sinkhorn_sweeps": [c_p, c_i, c_i, c_i, c_p],
+    "sdb_sinkhorn_sweeps_persistent": [c_p, c_i, c_i, c_i, c_p, c_p],
     "sdb_lse_finalize": [c_p, c_i, c_l, c_p, c_d, c_p, c_p],
     "sdb_potential_update": [c_l, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
     "sdb_finalize_update": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],

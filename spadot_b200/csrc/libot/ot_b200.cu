@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -28,6 +29,40 @@ namespace {
 std::mutex g_mu;
 long long g_launches = 0, g_h2d = 0, g_d2h = 0;
 int g_device_ok = -1;
+
+// LIBOT_B200_TRACE=1: one stderr line per entry point with its wall time split (development aid; adds syncs).
+bool tracing() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("LIBOT_B200_TRACE"); on = (e && *e && *e != '0') ? 1 : 0; }
+    return on == 1;
+}
+struct Trace {
+    const char* name;
+    std::chrono::steady_clock::time_point t0, last;
+    double h2d = 0, d2h = 0, compute = 0, alloc = 0;
+    explicit Trace(const char* n) : name(n), t0(std::chrono::steady_clock::now()), last(t0) {}
+    double lap() {
+        auto now = std::chrono::steady_clock::now();
+        double ms = std::chrono::duration<double, std::milli>(now - last).count();
+        last = now;
+        return ms;
+    }
+    ~Trace() {
+        if (!tracing()) return;
+        double total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "libot_b200 %-22s total %9.3f ms  alloc %8.3f  h2d %8.3f  compute %8.3f  d2h %8.3f\n", name, total, alloc, h2d,
+                compute, d2h);
+    }
+};
+Trace* g_trace = nullptr;
+struct TraceScope {
+    Trace t;
+    explicit TraceScope(const char* n) : t(n) { g_trace = &t; }
+    ~TraceScope() { g_trace = nullptr; }
+};
+void trace_compute_done() {
+    if (tracing() && g_trace) { cudaDeviceSynchronize(); g_trace->compute += g_trace->lap(); }
+}
 
 [[noreturn]] void die(const char* what, cudaError_t e) {
     fprintf(stderr, "libot_b200: %s failed: %s. This library runs on a B200 (sm_100a) only and has no CPU fallback.\n", what,
@@ -56,27 +91,75 @@ void require_device() {
     }
 }
 
+// Device memory pool.  cudaMalloc / cudaFree of matrix-sized blocks cost 1-150 ms each on the GPU box (measured with
+// LIBOT_B200_TRACE: more than the PCIe copies they serve), so freed blocks are kept and handed out again: a request
+// takes the smallest pooled block of at least its size and at most twice its size.  The pool only ever holds what
+// one call had live at once; libot_b200_release() (or LIBOT_B200_POOL=0) gives the memory back.
+struct PoolBlock { void* p; size_t bytes; };
+std::vector<PoolBlock> g_pool;
+bool pooling() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("LIBOT_B200_POOL"); on = (e && *e == '0') ? 0 : 1; }
+    return on == 1;
+}
+void* pool_acquire(size_t bytes, size_t* got) {
+    int best = -1;
+    for (int i = 0; i < (int)g_pool.size(); ++i)
+        if (g_pool[i].bytes >= bytes && g_pool[i].bytes <= 2 * bytes + 4096 && (best < 0 || g_pool[i].bytes < g_pool[best].bytes)) best = i;
+    if (best >= 0) {
+        PoolBlock b = g_pool[best];
+        g_pool.erase(g_pool.begin() + best);
+        *got = b.bytes;
+        return b.p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation && !g_pool.empty()) {          // make room and retry once
+        cudaGetLastError();
+        for (auto& b : g_pool) cudaFree(b.p);
+        g_pool.clear();
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) die("cudaMalloc", e);
+    *got = bytes;
+    return p;
+}
+void pool_release(void* p, size_t bytes) {
+    if (!p) return;
+    if (pooling()) g_pool.push_back({p, bytes});
+    else cudaFree(p);
+}
+void pool_clear() {
+    for (auto& b : g_pool) cudaFree(b.p);
+    g_pool.clear();
+}
+
 // Device buffer living for one call (the reference mallocs / frees its temporaries per call as well).
 template <typename T>
 struct Buf {
     T* d = nullptr;
-    size_t n = 0;
+    size_t n = 0, cap_bytes = 0;
     Buf() {}
     explicit Buf(size_t count) { alloc(count); }
     Buf(const Buf&) = delete;
     Buf& operator=(const Buf&) = delete;
-    ~Buf() { if (d) cudaFree(d); }
+    ~Buf() { pool_release(d, cap_bytes); }
     void alloc(size_t count) {
         n = count;
-        CK(cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(T)));
+        if (tracing() && g_trace) g_trace->lap();
+        d = static_cast<T*>(pool_acquire(std::max<size_t>(count, 1) * sizeof(T), &cap_bytes));
+        if (tracing() && g_trace) g_trace->alloc += g_trace->lap();
     }
     void up(const T* h) {
         if (n) CK(cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice));
         g_h2d += (long long)(n * sizeof(T));
+        if (tracing() && g_trace) g_trace->h2d += g_trace->lap();
     }
     void down(T* h) const {
+        if (tracing() && g_trace) { cudaDeviceSynchronize(); g_trace->compute += g_trace->lap(); }
         if (n) CK(cudaMemcpy(h, d, n * sizeof(T), cudaMemcpyDeviceToHost));
         g_d2h += (long long)(n * sizeof(T));
+        if (tracing() && g_trace) g_trace->d2h += g_trace->lap();
     }
     void zero() { CK(cudaMemset(d, 0, std::max<size_t>(n, 1) * sizeof(T))); }
 };
@@ -410,6 +493,7 @@ template <typename T>
 GapParts<T> gap_from_host(const T* C, const T* K, const T* R, const T* dx, const T* dy, const T* p, const T* q, const T* a,
                           const T* b, T eps, T lambda1, T lambda2, int m, int n) {
     std::lock_guard<std::mutex> lock(g_mu);
+    TraceScope ts("primal/dual/gap");
     require_device();
     const size_t mn = (size_t)m * (size_t)n;
     Buf<T> dC, dK, dR, ddx, ddy, dp, dq, da, db;
@@ -424,6 +508,7 @@ GapParts<T> gap_from_host(const T* C, const T* K, const T* R, const T* dx, const
 template <typename T>
 void update_k_host(T* K, T* K_, const T* C, const T* u, const T* v, T eps, int m, int n) {
     std::lock_guard<std::mutex> lock(g_mu);
+    TraceScope ts("update_k");
     require_device();
     if (m <= 0 || n <= 0) return;
     const size_t mn = (size_t)m * (size_t)n;
@@ -438,6 +523,7 @@ void update_k_host(T* K, T* K_, const T* C, const T* u, const T* v, T eps, int m
 template <typename T>
 void update_R_host(T* R, const T* K, const T* a, const T* b, int m, int n) {
     std::lock_guard<std::mutex> lock(g_mu);
+    TraceScope ts("update_R");
     require_device();
     if (m <= 0 || n <= 0) return;
     const size_t mn = (size_t)m * (size_t)n;
@@ -522,6 +608,11 @@ int libot_b200_device_check(void) {
     return device_check();
 }
 
+void libot_b200_release(void) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    pool_clear();
+}
+
 void libot_b200_counters(long long* launches, long long* h2d_bytes, long long* d2h_bytes) {
     std::lock_guard<std::mutex> lock(g_mu);
     if (launches) *launches = g_launches;
@@ -573,6 +664,7 @@ int step1_process_double(double* a, double* b, double* old_a, double* old_b, dou
                          double* p, double* q, double* u, double* v, int cur_iter, int max_iter, int iters, double tau,
                          double lambda1, double lambda2, double alpha1, double alpha2, double epsilon, int m, int n) {
     std::lock_guard<std::mutex> lock(g_mu);
+    TraceScope ts("step1_process");
     require_device();
     if (m <= 0 || n <= 0 || iters <= 0) return cur_iter;
     Solve s(K, C, a, b, old_a, old_b, dx, dy, p, q, u, v, m, n);
@@ -587,6 +679,7 @@ double update_process_double(double* R, double* a, double* b, double* old_a, dou
                              double lambda1, double lambda2, double alpha1, double alpha2, int cur_iter, int max_iter, int m,
                              int n) {
     std::lock_guard<std::mutex> lock(g_mu);
+    TraceScope ts("update_process");
     require_device();
     double gap = 1e100;                                                                           // ot_func.cpp:861
     if (m <= 0 || n <= 0) return gap;

@@ -85,3 +85,69 @@ static inline int sdb_reduce_grid(int64_t n) {
     if (b > SDB_REDUCE_BLOCKS) b = SDB_REDUCE_BLOCKS;
     return (int)b;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// One row of the Sinkhorn potential update, shared by the vector kernels (sdb_vectors.cu) and the persistent
+// small-problem kernel (sdb_pairs.cu).  No __restrict__ / read-only loads here: inside the persistent kernel these
+// buffers are rewritten by other CTAs between grid barriers.
+__device__ __forceinline__ double sdb_combine_partials(const float2* partial, int n_splits, int64_t n, int64_t i, double norm_c1) {
+    double M = -INFINITY;
+    for (int s = 0; s < n_splits; ++s) {
+        const float2 ps = __ldcg(partial + (int64_t)s * n + i);      // L2: written by other CTAs (possibly of this very kernel)
+        if (ps.x > -1e29f && ps.y > 0.f) M = fmax(M, (double)ps.x);
+    }
+    if (!(M > -INFINITY)) return -INFINITY;
+    double S = 0.0;
+    for (int s = 0; s < n_splits; ++s) {
+        const float2 ps = __ldcg(partial + (int64_t)s * n + i);
+        if (ps.x > -1e29f && ps.y > 0.f) S += (double)ps.y * exp2((double)ps.x - M);
+    }
+    return SDB_LN2 * (M + log2(S)) - norm_c1;
+}
+
+// The same combination by one warp per row: lanes take splits lane, lane+32, ... so all partials of a row are in
+// flight at once (one L2 round trip instead of 2*n_splits dependent ones); every lane returns the result.
+__device__ __forceinline__ double sdb_combine_partials_warp(const float2* partial, int n_splits, int64_t n, int64_t i, double norm_c1) {
+    const int lane = threadIdx.x & 31;
+    // pass 1: the row maximum (exact in fp32: the partial maxima are floats), loads of all splits in flight at once
+    float2 first = make_float2(SDB_NEG_SENTINEL, 0.f);
+    float mx = -INFINITY;
+    for (int s = lane; s < n_splits; s += 32) {
+        const float2 ps = __ldcg(partial + (int64_t)s * n + i);
+        if (s == lane) first = ps;
+        if (ps.x > -1e29f && ps.y > 0.f) mx = fmaxf(mx, ps.x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (!(mx > -INFINITY)) return -INFINITY;
+    // pass 2: one fp64 exp2 per (lane, split) against the common maximum, then a plain fp64 warp sum
+    const double M = (double)mx;
+    double S = 0.0;
+    for (int s = lane; s < n_splits; s += 32) {
+        const float2 ps = (s == lane) ? first : __ldcg(partial + (int64_t)s * n + i);
+        if (ps.x > -1e29f && ps.y > 0.f) S += (double)ps.y * exp2((double)ps.x - M);
+    }
+    S = sdb_warp_sum(S);
+    return SDB_LN2 * (M + log2(S)) - norm_c1;
+}
+
+// pot_i <- eps*alpha*(logmarg_i - LA_i) with la_old, tau flag and next-pass bias (see sdb_potential_update in the header)
+__device__ __forceinline__ void sdb_update_row(int64_t i, double Li, double logmarg_i, double norm_i, double eps, double alpha,
+                                               double log_n_other, double c1, double* pot, const double* frame, double* la_old,
+                                               float* bias, int* absorb_flag, int iter, double log_tau, double log_floor) {
+    const double fr = frame ? frame[i] : 0.0;
+    if (la_old) la_old[i] = (pot[i] - fr) / eps;
+    double LA = Li - log_n_other;
+    if (log_floor > -INFINITY) {   // K(b dy) + 1e-10 of ot_solvers.py:501-502 in total potentials
+        const double t = log_floor - fr / eps;
+        const double hi = fmax(LA, t), lo = fmin(LA, t);
+        LA = (lo == -INFINITY) ? hi : hi + log1p(exp(lo - hi));
+    }
+    const double nv = eps * alpha * (logmarg_i - LA);
+    pot[i] = nv;
+    if (bias) {
+        const double b = SDB_LOG2E * (nv / eps - norm_i * c1);
+        bias[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;  // NaN -> sentinel too
+    }
+    if (absorb_flag && (nv - fr) / eps > log_tau) atomicMax(absorb_flag, iter);
+}

@@ -35,17 +35,17 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 // --------------------------------------------------------------------------------------------
+// One work item = (64-row slab, column split).  Used by the one-item-per-CTA kernel below and by the persistent
+// small-problem kernel, whose CTAs walk many items per pass.
 template <bool DIRECT, class Epi>
-__global__ void __launch_bounds__(NT) pair_tile_kernel(PairArgs a, typename Epi::Params ep) {
-    extern __shared__ __align__(16) float smem[];
+__device__ __forceinline__ void pair_tile_item(const PairArgs& a, const typename Epi::Params& ep, int row_tile, int split, float* smem) {
     const int dpad = a.dpad;
     float* Ps = smem;                       // [dpad][BM]
     float* Qs = Ps + dpad * BM;             // [2][dpad][BN]
     float* Bs = Qs + 2 * dpad * BN;         // [2][BN]
 
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int64_t row0 = (int64_t)blockIdx.x * BM;
-    const int split = blockIdx.y;
+    const int64_t row0 = (int64_t)row_tile * BM;
     const int64_t c0 = a.split_bounds[split], c1 = a.split_bounds[split + 1];
     const int64_t j_begin = c0 & ~int64_t(3);
     const int n_tiles = (c1 > c0) ? (int)((c1 - j_begin + BN - 1) / BN) : 0;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(NT) pair_tile_kernel(PairArgs a, typename Epi:
         if (tid < BN) {
             int64_t j = j0 + tid;
             float b = SDB_NEG_SENTINEL;
-            if (j >= c0 && j < c1) b = a.bias ? a.bias[j] : 0.f;
+            if (j >= c0 && j < c1) b = a.bias ? __ldcg(a.bias + j) : 0.f;    // L2: rewritten between passes
             Bs[buf * BN + tid] = b;
         }
     };
@@ -113,6 +113,12 @@ __global__ void __launch_bounds__(NT) pair_tile_kernel(PairArgs a, typename Epi:
     }
     cp_async_wait<0>();
     epi.finish(tx);
+}
+
+template <bool DIRECT, class Epi>
+__global__ void __launch_bounds__(NT) pair_tile_kernel(PairArgs a, typename Epi::Params ep) {
+    extern __shared__ __align__(16) float smem[];
+    pair_tile_item<DIRECT, Epi>(a, ep, (int)blockIdx.x, (int)blockIdx.y, smem);
 }
 
 // -------------------------------------------------------------------------------------------- LSE
@@ -241,7 +247,164 @@ int launch_pairs(const PairArgs& a, const typename Epi::Params& ep, int n_splits
     SDB_LAUNCH_STATUS();
 }
 
+// -------------------------------------------------------------------------------------------- persistent sweeps
+// Small problems (ChickenHeart timepoints: ~2000 x 2000 spots) are latency-bound: five launches of a few
+// microseconds of work each per iteration.  This kernel runs `n_sweeps` whole iterations in ONE cooperative launch:
+//   row pass over (slab, split) items -> grid barrier -> combine + update f -> grid barrier ->
+//   column pass -> grid barrier -> combine + update g -> grid barrier -> absorb (u <- f, v <- g if tau was exceeded)
+// Buffers that change inside the kernel (potentials, bias vectors, partials, the flag) are read with plain loads or
+// cp.async.cg (L2), never through the read-only path; the grid barrier's fences order them.
+struct PersistArgs {
+    PairArgs row, col;                 // row pass: P = x, Q = y, bias = bias_y;  column pass: P = y, Q = x, bias = bias_x
+    int ns_row, ns_col;
+    float scale;
+    float2* partial_row; float2* partial_col;
+    const double* norms_x; const double* norms_y;
+    float* bias_x; float* bias_y;
+    double *f, *g, *u, *v, *la_old, *lb_old, *Lr, *Lc;
+    const double* logp; const double* logq;
+    int* flag;
+    double eps, c1, alpha1, alpha2, log_m, log_N, log_tau, log_floor;
+    int n_sweeps, first_tick, lr_known_first;
+    unsigned int* barrier;             // [2]: arrival counter, generation (zero-initialised once by the host)
+};
+
+// Grid barrier (all CTAs are co-resident: cooperative launch).  One acq_rel atomic per CTA on the arrival counter;
+// the last arriver resets it and releases the next generation, the others poll the generation with acquire loads.
+// Release/acquire at gpu scope (instead of two membar.sc) orders every thread's earlier writes before, and every
+// later read after, the barrier: the bar.sync pair extends that from thread 0 to the whole CTA.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int arrived;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(bar) : "memory");
+        if (arrived == gridDim.x - 1) {
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
+        } else {
+            unsigned int g;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(bar + 1) : "memory");
+            } while (g == gen);
+        }
+    }
+    gen += 1u;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT) sinkhorn_persistent_kernel(PersistArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    unsigned int gen = *reinterpret_cast<volatile unsigned int*>(a.barrier + 1);
+    const int64_t n = a.row.n_p, m = a.col.n_p;
+    const int row_tiles = (int)((n + BM - 1) / BM), col_tiles = (int)((m + BM - 1) / BM);
+    const int64_t gtid = (int64_t)blockIdx.x * NT + threadIdx.x, gsize = (int64_t)gridDim.x * NT;
+    const int64_t gwarp = gtid >> 5, n_warps = gsize >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int sweep = 0; sweep < a.n_sweeps; ++sweep) {
+        const int tick = a.first_tick + sweep;
+        const bool skip_row_pass = (sweep == 0 && a.lr_known_first);
+        if (!skip_row_pass) {
+            LseEpi::Params ep{a.scale, a.partial_row};
+            for (int item = blockIdx.x; item < row_tiles * a.ns_row; item += gridDim.x) {
+                pair_tile_item<false, LseEpi>(a.row, ep, item % row_tiles, item / row_tiles, smem);
+                __syncthreads();
+            }
+            grid_barrier(a.barrier, gen);
+        }
+        for (int64_t i = gwarp; i < n; i += n_warps) {               // one warp per row: lanes over the splits
+            double Li;
+            if (skip_row_pass) Li = a.Lr[i];
+            else Li = sdb_combine_partials_warp(a.partial_row, a.ns_row, n, i, a.norms_x[i] * a.c1);
+            if (lane == 0) {
+                a.Lr[i] = Li;
+                sdb_update_row(i, Li, a.logp[i], a.norms_x[i], a.eps, a.alpha1, a.log_m, a.c1, a.f, a.u, a.la_old, a.bias_x, a.flag,
+                               tick, a.log_tau, a.log_floor);
+            }
+        }
+        grid_barrier(a.barrier, gen);
+        {
+            LseEpi::Params ep{a.scale, a.partial_col};
+            for (int item = blockIdx.x; item < col_tiles * a.ns_col; item += gridDim.x) {
+                pair_tile_item<false, LseEpi>(a.col, ep, item % col_tiles, item / col_tiles, smem);
+                __syncthreads();
+            }
+        }
+        grid_barrier(a.barrier, gen);
+        for (int64_t j = gwarp; j < m; j += n_warps) {
+            const double Lj = sdb_combine_partials_warp(a.partial_col, a.ns_col, m, j, a.norms_y[j] * a.c1);
+            if (lane == 0) {
+                a.Lc[j] = Lj;
+                sdb_update_row(j, Lj, a.logq[j], a.norms_y[j], a.eps, a.alpha2, a.log_N, a.c1, a.g, a.v, a.lb_old, a.bias_y, a.flag,
+                               tick, a.log_tau, a.log_floor);
+            }
+        }
+        grid_barrier(a.barrier, gen);
+        if (*reinterpret_cast<volatile int*>(a.flag) == tick) {          // ot_func.cpp:792-819 in total potentials
+            for (int64_t i = gtid; i < n; i += gsize) a.u[i] = a.f[i];
+            for (int64_t j = gtid; j < m; j += gsize) a.v[j] = a.g[j];
+        }
+        // u, v are next written/read by the same warps' lane 0 / these threads only after later barriers
+    }
+}
+
 }  // namespace
+
+extern "C" int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_sweeps, int first_tick, int lr_known_first,
+                                              unsigned int* barrier2, void* stream) {
+    SDB_CHECK_ARG(d && barrier2 && n_sweeps >= 0 && d->n > 0 && d->m > 0 && d->eps > 0.0);
+    if (d->use_tc) return SDB_E_UNSUPPORTED;
+    if (d->dpad <= 0 || d->dpad > MAX_DPAD || (d->dpad & 3)) return SDB_E_UNSUPPORTED;
+    SDB_CHECK_ARG(d->xt && d->yt && d->bounds_row && d->bounds_col && d->partial_row && d->partial_col && d->bias_x && d->bias_y);
+    SDB_CHECK_ARG(d->f && d->g && d->u && d->v && d->la_old && d->lb_old && d->Lr && d->Lc && d->logp && d->logq && d->flag);
+    SDB_CHECK_ARG(d->ns_row > 0 && d->ns_col > 0 && !(d->ldx & 3) && !(d->ldy & 3));
+    if (n_sweeps == 0) return 0;
+    const double c1 = d->inv_med / d->eps;
+    PersistArgs a;
+    a.row = PairArgs{d->xt, d->ldx, d->n, d->yt, d->ldy, d->m, d->dpad, d->bias_y, d->bounds_row};
+    a.col = PairArgs{d->yt, d->ldy, d->m, d->xt, d->ldx, d->n, d->dpad, d->bias_x, d->bounds_col};
+    a.ns_row = d->ns_row; a.ns_col = d->ns_col;
+    a.scale = (float)(2.0 * c1 * SDB_LOG2E);
+    a.partial_row = reinterpret_cast<float2*>(d->partial_row); a.partial_col = reinterpret_cast<float2*>(d->partial_col);
+    a.norms_x = d->norms_x; a.norms_y = d->norms_y; a.bias_x = d->bias_x; a.bias_y = d->bias_y;
+    a.f = d->f; a.g = d->g; a.u = d->u; a.v = d->v; a.la_old = d->la_old; a.lb_old = d->lb_old; a.Lr = d->Lr; a.Lc = d->Lc;
+    a.logp = d->logp; a.logq = d->logq; a.flag = d->flag;
+    a.eps = d->eps; a.c1 = c1; a.alpha1 = d->alpha1; a.alpha2 = d->alpha2;
+    a.log_m = log((double)d->m); a.log_N = log((double)d->n_total); a.log_tau = d->log_tau; a.log_floor = d->log_floor;
+    a.n_sweeps = n_sweeps; a.first_tick = first_tick; a.lr_known_first = lr_known_first;
+    a.barrier = barrier2;
+    cudaStream_t st = sdb_stream(stream);
+    if (!lr_known_first) {       // bias of the first row pass from the current g (a previous call may have used another eps)
+        int rc = sdb_make_bias(d->m, d->m_bias, d->g, d->norms_y, d->eps, c1, d->bias_y, stream);
+        if (rc) return rc;
+    }
+    const size_t smem = sizeof(float) * ((size_t)d->dpad * BM + 2 * (size_t)d->dpad * BN + 2 * BN);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(sinkhorn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        smem_set = smem;
+    }
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return (int)e;
+    }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_persistent_kernel, NT, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) return SDB_E_UNSUPPORTED;
+    // grid: the caller's choice (d->n_ctas, it sized the splits for it), capped by what can be co-resident
+    const int64_t row_items = ((d->n + BM - 1) / BM) * d->ns_row, col_items = ((d->m + BM - 1) / BM) * d->ns_col;
+    int64_t want = d->n_ctas > 0 ? d->n_ctas : (row_items > col_items ? row_items : col_items);
+    const int64_t cap = (int64_t)n_sm * per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    void* params[] = {&a};
+    e = cudaLaunchCooperativeKernel((const void*)sinkhorn_persistent_kernel, dim3((unsigned)grid), dim3(NT), params, smem, st);
+    return (int)e;
+}
 
 extern "C" int sdb_lse_pass_simt(const float* pt, int64_t ldp, int64_t n_p, const float* qt, int64_t ldq, int64_t n_q,
                                  int dpad, const float* bias, float scale, const int64_t* split_bounds, int n_splits,

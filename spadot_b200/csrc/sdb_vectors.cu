@@ -69,21 +69,8 @@ __global__ void potential_update_kernel(int64_t n, const double* __restrict__ L,
                                         int iter, double log_tau, double log_floor) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double fr = frame ? frame[i] : 0.0;
-    if (la_old) la_old[i] = (pot[i] - fr) / eps;
-    double LA = L[i] - log_n_other;
-    if (log_floor > -INFINITY) {   // K(b dy) + 1e-10 of ot_solvers.py:501-502 in total potentials
-        const double t = log_floor - fr / eps;
-        const double hi = fmax(LA, t), lo = fmin(LA, t);
-        LA = (lo == -INFINITY) ? hi : hi + log1p(exp(lo - hi));
-    }
-    const double nv = eps * alpha * (logmarg[i] - LA);
-    pot[i] = nv;
-    if (bias) {
-        double b = SDB_LOG2E * (nv / eps - norms[i] * c1);
-        bias[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;  // NaN -> sentinel too
-    }
-    if (absorb_flag && (nv - fr) / eps > log_tau) atomicMax(absorb_flag, iter);
+    sdb_update_row(i, L[i], logmarg[i], norms[i], eps, alpha, log_n_other, c1, pot, frame, la_old, bias, absorb_flag, iter, log_tau,
+                   log_floor);
 }
 
 // finalize + potential update + next-pass bias in one launch (per-iteration launch count 9 -> 5)
@@ -94,34 +81,10 @@ __global__ void finalize_update_kernel(const float2* __restrict__ partial, int n
                                        double log_tau, double log_floor) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double M = -INFINITY;
-    for (int s = 0; s < n_splits; ++s) {
-        const float2 ps = partial[(int64_t)s * n + i];
-        if (ps.x > -1e29f && ps.y > 0.f) M = fmax(M, (double)ps.x);
-    }
-    double Li = -INFINITY;
-    if (M > -INFINITY) {
-        double S = 0.0;
-        for (int s = 0; s < n_splits; ++s) {
-            const float2 ps = partial[(int64_t)s * n + i];
-            if (ps.x > -1e29f && ps.y > 0.f) S += (double)ps.y * exp2((double)ps.x - M);
-        }
-        Li = SDB_LN2 * (M + log2(S)) - norms[i] * c1;
-    }
+    const double Li = sdb_combine_partials(partial, n_splits, n, i, norms[i] * c1);
     L[i] = Li;
-    const double fr = frame[i];
-    la_old[i] = (pot[i] - fr) / eps;
-    double LA = Li - log_n_other;
-    if (log_floor > -INFINITY) {
-        const double t = log_floor - fr / eps;
-        const double hi = fmax(LA, t), lo = fmin(LA, t);
-        LA = (lo == -INFINITY) ? hi : hi + log1p(exp(lo - hi));
-    }
-    const double nv = eps * alpha * (logmarg[i] - LA);
-    pot[i] = nv;
-    const double b = SDB_LOG2E * (nv / eps - norms[i] * c1);
-    bias[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
-    if ((nv - fr) / eps > log_tau) atomicMax(absorb_flag, iter);
+    sdb_update_row(i, Li, logmarg[i], norms[i], eps, alpha, log_n_other, c1, pot, frame, la_old, bias, absorb_flag, iter, log_tau,
+                   log_floor);
 }
 
 __global__ void make_bias_kernel(int64_t n, int64_t n_pad, const double* __restrict__ pot, const double* __restrict__ norms,

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -120,16 +121,16 @@ class VectorOps:
     def stage_criterion(self, f, u, la_old, g, v, lb_old, eps):
         self._call("sdb_stage_criterion", f.numel(), g.numel(), _ptr(f), _ptr(u), _ptr(la_old), _ptr(g), _ptr(v),
                    _ptr(lb_old), eps, _ptr(self.out10), _ptr(self.scratch))
-        return self.out10[:4].clone()
+        return self.out10[:4]        # read back (synchronously) by the caller before the next reduction overwrites it
 
     def gap_terms(self, f, Lr, logp, g, Lc, logq, eps, lam1, lam2, dx, dy):
         self._call("sdb_gap_terms", f.numel(), g.numel(), _ptr(f), _ptr(Lr), _ptr(logp), _ptr(g), _ptr(Lc), _ptr(logq),
                    eps, lam1, lam2, dx, dy, _ptr(self.out10), _ptr(self.scratch))
-        return self.out10.clone()
+        return self.out10
 
     def sum_exp(self, L):
         self._call("sdb_sum_exp", L.numel(), _ptr(L), 0, 0.0, _ptr(self.out10), _ptr(self.scratch))
-        return self.out10[:1].clone()
+        return self.out10[:1]
 
     def row_mass(self, f, Lr, eps):
         out = torch.empty_like(f)
@@ -180,6 +181,8 @@ class CudaOps(VectorOps):
     TC_MIN_TILES = 8         # fewest 256-column tiles per (row tile, split) work item
     MAX_SPLIT_COLS = 65536   # keeps fp32 running sums < 1e-6 relative (include/spadot_b200.h)
     TARGET_CTAS = 148 * 6
+    PERSISTENT_MAX_PAIRS = 1 << 24   # SIMT problems up to this many pairs run their sweeps in one cooperative launch
+    PERSISTENT_CTAS_PER_SM = int(os.environ.get("SDB_PERSISTENT_CTAS_PER_SM", "2"))
 
     def __init__(self, x_local, y, device=None, tc="auto"):
         self._init_vectors(device)
@@ -221,6 +224,8 @@ class CudaOps(VectorOps):
         self._splits = {}
         self._partials = {}
         self.inv_med = 1.0
+        self.persistent = os.environ.get("SDB_PERSISTENT", "1") != "0"      # development knob (A/B against the launch loop)
+        self._barrier = None
 
     # ------------------------------------------------------------------ plumbing
     def set_median(self, median: float):
@@ -232,14 +237,28 @@ class CudaOps(VectorOps):
             row_tiles = max(1, (n_p + 63) // 64)
             want = max(1, -(-self.TARGET_CTAS // row_tiles))
             lo = max(1, -(-n_q // self.MAX_SPLIT_COLS))
-            hi = max(1, n_q // 256)
+            tiles = max(1, -(-n_q // 64))
+            hi = max(1, n_q // 256) if n_q >= 4096 else tiles      # small problems: down to one 64-column tile per item
             ns = int(min(max(want, lo), max(hi, lo), 65535))
-            bounds = torch.tensor([(n_q * s) // ns for s in range(ns + 1)], dtype=torch.int64, device=self.device)
+            # split boundaries on 64-column tile boundaries: no item streams a mostly masked tile
+            bounds = torch.tensor([min(n_q, 64 * ((tiles * s) // ns)) for s in range(ns)] + [n_q], dtype=torch.int64,
+                                  device=self.device)
             self._splits[key] = (bounds, ns)
         return self._splits[key]
 
-    def _partial(self, ns, n_p):
-        key = (ns, n_p)
+    def _persist_plan(self, n_p, n_q, grid):
+        key = ("persist", n_p, n_q, grid)
+        if key not in self._splits:
+            row_tiles = max(1, (n_p + 63) // 64)
+            tiles = max(1, -(-n_q // 64))
+            ns = max(min(max(1, grid // row_tiles), tiles), -(-n_q // self.MAX_SPLIT_COLS))
+            bounds = torch.tensor([min(n_q, 64 * ((tiles * s) // ns)) for s in range(ns)] + [n_q], dtype=torch.int64,
+                                  device=self.device)
+            self._splits[key] = (bounds, ns)
+        return self._splits[key]
+
+    def _partial(self, ns, n_p, tag=None):
+        key = (ns, n_p) if tag is None else (tag, ns, n_p)
         if key not in self._partials:
             self._partials[key] = torch.empty((ns, n_p, 2), dtype=torch.float32, device=self.device)
         return self._partials[key]
@@ -324,8 +343,24 @@ class CudaOps(VectorOps):
             if key not in self._partials:
                 self._partials[key] = torch.empty((d.ns_col, self.m, 2), dtype=torch.float32, device=self.device)
             d.partial_col = _ptr(self._partials[key])
-        _lib.call("sdb_sinkhorn_sweeps", ctypes.byref(d), int(n_sweeps), first, int(bool(lr_known_first)), self._stream())
-        self.launches += n_sweeps * 5 + (0 if lr_known_first else 1)
+        if not self.use_tc and self.persistent and self.n * self.m <= self.PERSISTENT_MAX_PAIRS:
+            # small problem: all n_sweeps iterations in one cooperative launch (grid barriers instead of launches);
+            # column splits sized so that one pass is about one work item per CTA
+            if self._barrier is None:
+                self._barrier = torch.zeros(2, dtype=torch.int32, device=self.device)
+                self._n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+            d.n_ctas = self._n_sm * self.PERSISTENT_CTAS_PER_SM
+            b_row, d.ns_row = self._persist_plan(self.n, self.m, d.n_ctas)
+            b_col, d.ns_col = self._persist_plan(self.m, self.n, d.n_ctas)
+            d.bounds_row, d.bounds_col = _ptr(b_row), _ptr(b_col)
+            d.partial_row = _ptr(self._partial(d.ns_row, self.n, "prow"))
+            d.partial_col = _ptr(self._partial(d.ns_col, self.m, "pcol"))
+            _lib.call("sdb_sinkhorn_sweeps_persistent", ctypes.byref(d), int(n_sweeps), first, int(bool(lr_known_first)),
+                      _ptr(self._barrier), self._stream())
+            self.launches += 1 + (0 if lr_known_first else 1)
+        else:
+            _lib.call("sdb_sinkhorn_sweeps", ctypes.byref(d), int(n_sweeps), first, int(bool(lr_known_first)), self._stream())
+            self.launches += n_sweeps * 5 + (0 if lr_known_first else 1)
         self._bias_key = {"x": None, "y": None}
 
     def fused_half_step(self, side, st, eps, alpha, it, log_tau, log_floor=NEG_INF, lse_known=False):

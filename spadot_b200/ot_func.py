@@ -60,6 +60,8 @@ lib.libot_b200_device_check.restype = _I
 lib.libot_b200_version.restype = _I
 lib.libot_b200_counters.argtypes = [ctypes.POINTER(ctypes.c_longlong)] * 3
 lib.libot_b200_counters.restype = None
+lib.libot_b200_release.argtypes = []
+lib.libot_b200_release.restype = None
 
 
 def counters():
@@ -67,6 +69,11 @@ def counters():
     v = [ctypes.c_longlong(0) for _ in range(3)]
     lib.libot_b200_counters(*[ctypes.byref(x) for x in v])
     return tuple(int(x.value) for x in v)
+
+
+def release():
+    """Return the library's pooled device memory to the driver."""
+    lib.libot_b200_release()
 
 
 def _gap_like(name, C, K, R, dx, dy, p, q, a, b, epsilon, lambda1, lambda2, use_float):

@@ -15,7 +15,6 @@ plus the streamed entry point the reference has no equivalent of:
 """
 from __future__ import annotations
 
-from copy import deepcopy
 
 import numpy as np
 import torch
@@ -89,6 +88,26 @@ def solve_coupling(a, b, config, G=None, solver="duality_gap", median=None, ops=
     return Coupling(ops, st, eps, median, info, dist)
 
 
+class _PlanDownload:
+    """Device -> pinned host copy of a dense plan on a side stream; `result()` waits for it and returns the ndarray
+    (a view of the pinned buffer, owned by the returned array)."""
+
+    def __init__(self, plan_dev):
+        self.dev = plan_dev
+        self.host = torch.empty(plan_dev.shape, dtype=plan_dev.dtype, pin_memory=True)
+        cur = torch.cuda.current_stream(plan_dev.device)
+        self.stream = torch.cuda.Stream(plan_dev.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self.host.copy_(plan_dev, non_blocking=True)
+        self.done = self.stream.record_event()
+
+    def result(self):
+        self.done.synchronize()
+        self.dev = None
+        return self.host.numpy()
+
+
 def compute_transport_map(a, b, config, C=None, G=None):
     """ot_solvers.py:95-121: cost = sqeuclidean / median, `growth_iters` solves with
     G <- gamma.sum(axis=1), returns gammas[0] as an (N, M) float64 ndarray.
@@ -111,9 +130,9 @@ def compute_transport_map(a, b, config, C=None, G=None):
         config["G"] = row_sums                                    # ot_solvers.py:113-117
         cp = solve_coupling(a, b, config, G=row_sums, median=median, ops=ops, dist=dist)
         if first is None:
-            first = cp.plan().cpu().numpy()
+            first = _PlanDownload(cp.plan())     # gammas[0]: its device->host copy overlaps the remaining growth solves
         row_sums = cp.row_mass().cpu().numpy()
-    return deepcopy(first)
+    return first.result()
 
 
 def optimal_transport_duality_gap(C, G, lambda1, lambda2, epsilon, batch_size, tolerance, tau, epsilon0, max_iter,

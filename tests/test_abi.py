@@ -91,7 +91,7 @@ REFERENCE_EXPORTS = {        # nm -D of the libot.so the reference ships (SpaDOT
 
 def test_libot_drop_in_exports_the_reference_symbols():
     """libot_b200.so loads without a GPU and exports the fourteen symbols of the reference's libot.so with the
-    parameter counts of ot_func.cpp:938-1373; the header declares exactly those (+ three identification helpers)."""
+    parameter counts of ot_func.cpp:938-1373; the header declares exactly those (+ four housekeeping helpers)."""
     from spadot_b200 import ot_func
     funcs = libot_header_functions()
     for name, n_args in REFERENCE_EXPORTS.items():
@@ -99,7 +99,7 @@ def test_libot_drop_in_exports_the_reference_symbols():
         fn = getattr(ot_func.lib, name)
         assert len(fn.argtypes) == n_args, name
     extra = set(funcs) - set(REFERENCE_EXPORTS)
-    assert extra == {"libot_b200_device_check", "libot_b200_version", "libot_b200_counters"}, extra
+    assert extra == {"libot_b200_device_check", "libot_b200_version", "libot_b200_counters", "libot_b200_release"}, extra
     for name in extra:
         assert hasattr(ot_func.lib, name)
     assert ot_func.lib.libot_b200_version() == 100

@@ -203,7 +203,7 @@ def test_parity_8192x8192_three_way(ot):
     ops = CudaOps(a, b)
     assert ops.use_tc
     cp = ot_solvers.solve_coupling(a, b, CFG, ops=ops)
-    assert cp.median == med
+    assert cp.median == pytest.approx(med, rel=1e-13)      # exact order statistic; the oracle's cdist may differ in the last bit
     got = cp.plan().cpu().numpy()
     assert np.abs(got.sum(1) - want.sum(1)).max() / want.sum(1).max() < 1e-5
     assert np.abs(got.sum(0) - want.sum(0)).max() / want.sum(0).max() < 1e-5
