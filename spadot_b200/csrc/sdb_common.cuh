@@ -13,6 +13,31 @@
 
 static inline cudaStream_t sdb_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch (PDL).  Inside sdb_sinkhorn_sweeps the kernels of one iteration are launched with
+// the programmatic-stream-serialization attribute: each kernel signals `launch_dependents` as soon as it is set up
+// and executes `griddepcontrol.wait` before it touches anything its predecessor writes, so launch latency, barrier /
+// TMEM set-up and the first operand tiles of a pass overlap the tail of the previous kernel.  Every kernel of the
+// chain waits in every thread, which makes completion transitive along the stream.  Outside that loop sdb_pdl is 0,
+// launches are ordinary and both instructions are no-ops.
+extern thread_local int sdb_pdl;
+__device__ __forceinline__ void sdb_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void sdb_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t sdb_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = sdb_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float sdb_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

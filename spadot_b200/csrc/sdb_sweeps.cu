@@ -8,12 +8,29 @@
 // needs a collective inside the iteration and is driven from Python).
 #include "sdb_common.cuh"
 
+#include <cstdlib>
+
+thread_local int sdb_pdl = 0;
+
+namespace {
+bool pdl_enabled() {                 // development knob: SDB_PDL=0 launches the loop's kernels without overlap
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("SDB_PDL"); on = (e && *e == '0') ? 0 : 1; }
+    return on == 1;
+}
+struct PdlScope {
+    explicit PdlScope(bool on) { sdb_pdl = on ? 1 : 0; }
+    ~PdlScope() { sdb_pdl = 0; }
+};
+}  // namespace
+
 extern "C" int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int first_tick, int lr_known_first, void* stream) {
     SDB_CHECK_ARG(d && n_sweeps >= 0 && d->n > 0 && d->m > 0 && d->eps > 0.0);
     const double c1 = d->inv_med / d->eps;
     const double scale = 2.0 * c1 * SDB_LOG2E;
     const double log_m = log((double)d->m), log_N = log((double)d->n_total);
     int rc = 0;
+    PdlScope pdl(pdl_enabled() && d->use_tc);      // the SIMT pass kernel is not part of the PDL chain
     auto pass = [&](bool row) -> int {
         if (d->use_tc) {
             return row ? sdb_lse_pass_tc(d->x16, d->n, d->n_pad, d->y16, d->m, d->m_pad, d->dp, d->bias_y, (float)(scale * d->pow2_scale),

@@ -283,6 +283,9 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    // PDL (sdb_common.cuh): the next kernel of the stream may be scheduled from here on; this kernel's operand tiles
+    // and MMAs do not depend on its predecessor, only the bias vector and the output buffer do (waits below).
+    sdb_launch_dependents();
 
     const int n_items = a.n_row_tiles * a.n_splits;
 
@@ -307,6 +310,7 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                     tma_load_2d(dst + S::B_BYTES, &tmQ, full + s, DP, t * TILE_N);
                     const int bs = tile_ctr % BIAS_STAGES;
                     mbar_wait(b_empty + bs, ((tile_ctr / BIAS_STAGES) & 1) ^ 1);
+                    if (tile_ctr == 0) sdb_grid_dependency_wait();     // the bias was written by the previous kernel
                     mbar_expect_tx(b_full + bs, TILE_N * 4);
                     bulk_load_1d(sBias + bs * TILE_N, a.bias + (size_t)t * TILE_N, TILE_N * 4, b_full + bs);
                 }
@@ -363,6 +367,7 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         constexpr int COLS = TILE_N / PARTS;         // columns per warp per tile
         constexpr int CH = (EPI_WARPS == 8) ? 32 : 16;
         constexpr int NCH = COLS / CH;
+        sdb_grid_dependency_wait();        // before anything is written to global memory (partials, histograms)
         const int ew = warp - 2;
         const int part = ew >> 2;
         const int quad = warp & 3;                   // TMEM lane quadrant accessible to this warp
@@ -701,8 +706,7 @@ int launch_tc_v(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a,
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    kern<<<n_ctas, 32 * (2 + EPI_WARPS), smem, st>>>(tmP, tmQ, a);
-    SDB_LAUNCH_STATUS();
+    return (int)sdb_launch(kern, dim3(n_ctas), dim3(32 * (2 + EPI_WARPS)), smem, st, tmP, tmQ, a);
 }
 
 template <int DP, int MODE>

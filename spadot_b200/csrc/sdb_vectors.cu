@@ -67,6 +67,8 @@ __global__ void potential_update_kernel(int64_t n, const double* __restrict__ L,
                                         double c1, double* __restrict__ pot, const double* __restrict__ frame,
                                         double* __restrict__ la_old, float* __restrict__ bias, int* __restrict__ absorb_flag,
                                         int iter, double log_tau, double log_floor) {
+    sdb_launch_dependents();
+    sdb_grid_dependency_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     sdb_update_row(i, L[i], logmarg[i], norms[i], eps, alpha, log_n_other, c1, pot, frame, la_old, bias, absorb_flag, iter, log_tau,
@@ -79,6 +81,8 @@ __global__ void finalize_update_kernel(const float2* __restrict__ partial, int n
                                        double alpha, double log_n_other, double* __restrict__ pot, const double* __restrict__ frame,
                                        double* __restrict__ la_old, float* __restrict__ bias, int* __restrict__ absorb_flag, int iter,
                                        double log_tau, double log_floor) {
+    sdb_launch_dependents();
+    sdb_grid_dependency_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double Li = sdb_combine_partials(partial, n_splits, n, i, norms[i] * c1);
@@ -89,6 +93,8 @@ __global__ void finalize_update_kernel(const float2* __restrict__ partial, int n
 
 __global__ void make_bias_kernel(int64_t n, int64_t n_pad, const double* __restrict__ pot, const double* __restrict__ norms,
                                  double eps, double c1, float* __restrict__ bias) {
+    sdb_launch_dependents();
+    sdb_grid_dependency_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pad) return;
     if (i >= n) { bias[i] = SDB_NEG_SENTINEL; return; }
@@ -99,6 +105,8 @@ __global__ void make_bias_kernel(int64_t n, int64_t n_pad, const double* __restr
 
 __global__ void absorb_kernel(int64_t n, int64_t m, const int* __restrict__ flag, int iter, const double* __restrict__ f,
                               const double* __restrict__ g, double* __restrict__ u, double* __restrict__ v) {
+    sdb_launch_dependents();
+    sdb_grid_dependency_wait();
     if (*flag != iter) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) u[i] = f[i];
@@ -317,9 +325,8 @@ int sdb_potential_update(int64_t n, const double* L, const double* logmarg, cons
                          int* absorb_flag, int iter, double log_tau, double log_floor, void* stream) {
     SDB_CHECK_ARG(L && logmarg && norms && pot && n >= 0 && eps > 0.0);
     if (n == 0) return 0;
-    potential_update_kernel<<<blocks_for(n), 256, 0, sdb_stream(stream)>>>(n, L, logmarg, norms, eps, alpha, log_n_other, c1, pot,
-                                                                          frame, la_old, bias, absorb_flag, iter, log_tau, log_floor);
-    SDB_LAUNCH_STATUS();
+    return (int)sdb_launch(potential_update_kernel, dim3(blocks_for(n)), dim3(256), 0, sdb_stream(stream), n, L, logmarg, norms, eps,
+                           alpha, log_n_other, c1, pot, frame, la_old, bias, absorb_flag, iter, log_tau, log_floor);
 }
 
 int sdb_finalize_update(const float* partial, int n_splits, int64_t n, const double* norms, double c1, double* L,
@@ -327,18 +334,17 @@ int sdb_finalize_update(const float* partial, int n_splits, int64_t n, const dou
                         double* la_old, float* bias, int* absorb_flag, int iter, double log_tau, double log_floor, void* stream) {
     SDB_CHECK_ARG(partial && norms && L && logmarg && pot && frame && la_old && bias && absorb_flag && n_splits > 0 && n >= 0 && eps > 0.0);
     if (n == 0) return 0;
-    finalize_update_kernel<<<blocks_for(n), 256, 0, sdb_stream(stream)>>>(reinterpret_cast<const float2*>(partial), n_splits, n, norms, c1, L,
-                                                                         logmarg, eps, alpha, log_n_other, pot, frame, la_old, bias,
-                                                                         absorb_flag, iter, log_tau, log_floor);
-    SDB_LAUNCH_STATUS();
+    return (int)sdb_launch(finalize_update_kernel, dim3(blocks_for(n)), dim3(256), 0, sdb_stream(stream),
+                           reinterpret_cast<const float2*>(partial), n_splits, n, norms, c1, L, logmarg, eps, alpha, log_n_other, pot,
+                           frame, la_old, bias, absorb_flag, iter, log_tau, log_floor);
 }
 
 int sdb_make_bias(int64_t n, int64_t n_pad, const double* pot, const double* norms, double eps, double c1, float* bias,
                   void* stream) {
     SDB_CHECK_ARG(norms && bias && n >= 0 && n_pad >= n && eps > 0.0);
     if (n_pad == 0) return 0;
-    make_bias_kernel<<<blocks_for(n_pad), 256, 0, sdb_stream(stream)>>>(n, n_pad, pot, norms, eps, c1, bias);
-    SDB_LAUNCH_STATUS();
+    return (int)sdb_launch(make_bias_kernel, dim3(blocks_for(n_pad)), dim3(256), 0, sdb_stream(stream), n, n_pad, pot, norms, eps, c1,
+                           bias);
 }
 
 int sdb_absorb(int64_t n, int64_t m, const int* absorb_flag, int iter, const double* f, const double* g, double* u, double* v,
@@ -346,8 +352,7 @@ int sdb_absorb(int64_t n, int64_t m, const int* absorb_flag, int iter, const dou
     SDB_CHECK_ARG(absorb_flag && f && g && u && v);
     const int64_t mx = n > m ? n : m;
     if (mx == 0) return 0;
-    absorb_kernel<<<blocks_for(mx), 256, 0, sdb_stream(stream)>>>(n, m, absorb_flag, iter, f, g, u, v);
-    SDB_LAUNCH_STATUS();
+    return (int)sdb_launch(absorb_kernel, dim3(blocks_for(mx)), dim3(256), 0, sdb_stream(stream), n, m, absorb_flag, iter, f, g, u, v);
 }
 
 int sdb_stage_criterion(int64_t n, int64_t m, const double* f, const double* u, const double* la_old, const double* g,
