@@ -180,17 +180,20 @@ struct TcSmem {
     static constexpr int STAGES = (DP == 64) ? 2 : 4;
     static constexpr int A_BYTES = TILE_M * DP * 2;     // one of (hi, lo)
     static constexpr int B_BYTES = TILE_N * DP * 2;
-    static constexpr int OFF_A = 0;                                     // [2][A_BYTES]
-    static constexpr int OFF_B = OFF_A + 2 * A_BYTES;                   // [STAGES][2][B_BYTES]
+    static constexpr int A_STAGES = (DP == 64) ? 1 : 2;                 // row-tile operand double buffer: the next item's rows
+                                                                        // load while the current item's last tiles still multiply
+    static constexpr int OFF_A = 0;                                     // [A_STAGES][2][A_BYTES]
+    static constexpr int OFF_B = OFF_A + A_STAGES * 2 * A_BYTES;        // [STAGES][2][B_BYTES]
     static constexpr int OFF_BIAS = OFF_B + STAGES * 2 * B_BYTES;       // [BIAS_STAGES][TILE_N] float
     static constexpr int OFF_MERGE = OFF_BIAS + BIAS_STAGES * TILE_N * 4;  // [3][TILE_M] float2
     static constexpr int OFF_BAR = OFF_MERGE + 3 * TILE_M * 8;          // barriers
-    static constexpr int N_BARS = 2 * STAGES + 2 + 4 + 2 * BIAS_STAGES;
+    static constexpr int N_BARS = 2 * STAGES + 2 * A_STAGES + 4 + 2 * BIAS_STAGES;
     static constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
     static constexpr int OFF_HIST = OFF_TMEM + 16;                      // [SWEEP_BINS] uint32 (median sweeps only)
     static constexpr int TOTAL = OFF_HIST + 1024;                       // + alignment slack (LSE pass)
     static constexpr int OFF_SDIST = OFF_HIST + SWEEP_BINS * 4;        // [32][256] float (histogram sweep only)
     static constexpr int TOTAL_SWEEP = OFF_SDIST + 32 * 256 * 4 + 1024;
+    static_assert(TOTAL_SWEEP <= 227 * 1024, "shared-memory budget of one CTA");
 };
 
 // Rare paths of the median sweeps, kept out of line so the hot loop stays small (an inlined fp64 loop per
@@ -255,9 +258,9 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
     uint64_t* full = bars;                      // [STAGES]
     uint64_t* empty = full + STAGES;            // [STAGES]
-    uint64_t* a_full = empty + STAGES;
-    uint64_t* a_empty = a_full + 1;
-    uint64_t* t_full = a_empty + 1;             // [2]
+    uint64_t* a_full = empty + STAGES;          // [A_STAGES]
+    uint64_t* a_empty = a_full + S::A_STAGES;   // [A_STAGES]
+    uint64_t* t_full = a_empty + S::A_STAGES;   // [2]
     uint64_t* t_empty = t_full + 2;             // [2]
     uint64_t* b_full = t_empty + 2;             // [BIAS_STAGES]
     uint64_t* b_empty = b_full + BIAS_STAGES;   // [BIAS_STAGES]
@@ -267,8 +270,7 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
-        mbar_init(a_full, 1);
-        mbar_init(a_empty, 1);
+        for (int i = 0; i < S::A_STAGES; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(t_full + i, 1); mbar_init(t_empty + i, N_EPI_WARPS); }
         for (int i = 0; i < BIAS_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, N_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -297,10 +299,12 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 const int rt = item % a.n_row_tiles, sp = item / a.n_row_tiles;
                 const int t0 = sp * a.tiles_per_split;
                 const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
-                mbar_wait(a_empty, (item_ctr & 1) ^ 1);
-                mbar_expect_tx(a_full, 2 * S::A_BYTES);
-                tma_load_2d(sA, &tmP, a_full, 0, rt * TILE_M);
-                tma_load_2d(sA + S::A_BYTES, &tmP, a_full, DP, rt * TILE_M);
+                const int as = item_ctr % S::A_STAGES;
+                uint8_t* sAs = sA + (size_t)as * 2 * S::A_BYTES;
+                mbar_wait(a_empty + as, ((item_ctr / S::A_STAGES) & 1) ^ 1);
+                mbar_expect_tx(a_full + as, 2 * S::A_BYTES);
+                tma_load_2d(sAs, &tmP, a_full + as, 0, rt * TILE_M);
+                tma_load_2d(sAs + S::A_BYTES, &tmP, a_full + as, DP, rt * TILE_M);
                 for (int t = t0; t < t1; ++t, ++tile_ctr) {
                     const int s = tile_ctr % STAGES;
                     mbar_wait(empty + s, ((tile_ctr / STAGES) & 1) ^ 1);
@@ -321,13 +325,14 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         // instruction descriptor: D=f32 (bit 4), A=B=f16 K-major, N>>3 at [17,23), M>>4 at [24,29)
         constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
         uint32_t tile_ctr = 0, item_ctr = 0;
-        const uint64_t dAh = make_desc<DP>(smem_u32(sA));
-        const uint64_t dAl = make_desc<DP>(smem_u32(sA + S::A_BYTES));
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
             const int sp = item / a.n_row_tiles;
             const int t0 = sp * a.tiles_per_split;
             const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
-            mbar_wait(a_full, item_ctr & 1);
+            const int as = item_ctr % S::A_STAGES;
+            const uint64_t dAh = make_desc<DP>(smem_u32(sA + (size_t)as * 2 * S::A_BYTES));
+            const uint64_t dAl = make_desc<DP>(smem_u32(sA + (size_t)as * 2 * S::A_BYTES + S::A_BYTES));
+            mbar_wait(a_full + as, (item_ctr / S::A_STAGES) & 1);
             for (int t = t0; t < t1; ++t, ++tile_ctr) {
                 const int s = tile_ctr % STAGES;
                 const int acc = tile_ctr & 1;
@@ -351,7 +356,7 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                     for (int k = 0; k < KSTEPS; ++k) umma_f16(d_tmem, dAh + 2 * k, dBh + 2 * k, idesc, 1);
                     umma_commit(empty + s);
                     umma_commit(t_full + acc);
-                    if (t == t1 - 1) umma_commit(a_empty);
+                    if (t == t1 - 1) umma_commit(a_empty + as);
                 }
                 __syncwarp();
             }

@@ -178,7 +178,7 @@ class CudaOps(VectorOps):
     SIMT_MAX_D = 128
     TC_MAX_D = 64
     TC_MIN_PAIRS = 1 << 22   # below this the tensor-core pipeline cannot fill; the SIMT pass is used
-    TC_MIN_TILES = 8         # fewest 256-column tiles per (row tile, split) work item
+    TC_ITEM_OVERHEAD_TILES = float(os.environ.get("SDB_TC_ITEM_OVERHEAD", "2.0"))   # item switch cost in tile-times (split planner)
     MAX_SPLIT_COLS = 65536   # keeps fp32 running sums < 1e-6 relative (include/spadot_b200.h)
     TARGET_CTAS = 148 * 6
     PERSISTENT_MAX_PAIRS = 1 << 24   # SIMT problems up to this many pairs run their sweeps in one cooperative launch
@@ -268,13 +268,23 @@ class CudaOps(VectorOps):
         return P.norms16 if self.use_tc else P.norms
 
     def _tc_split_plan(self, n_p, n_q):
-        row_tiles = (n_p + 127) // 128
-        col_tiles = (n_q + 255) // 256
-        want = max(1, -(-4 * self.n_sm // row_tiles))                # enough items to balance a persistent grid
-        ns = min(want, max(1, col_tiles // self.TC_MIN_TILES))        # ... but enough tiles per item to amortise its fill
-        ns = max(ns, -(-col_tiles // (self.MAX_SPLIT_COLS // 256)))   # fp32 running-sum accuracy cap
-        tps = -(-col_tiles // ns)
-        return tps, -(-col_tiles // tps)
+        """(tiles per split, number of splits) of one tensor-core pass.  Work items (128-row tile, split) are dealt
+        round-robin to the persistent CTAs, so the pass lasts  ceil(items / CTAs) * (tiles per item + per-item overhead):
+        pick the split length that minimises it (ties: longer items).  Splits never exceed MAX_SPLIT_COLS columns
+        (fp32 running-sum accuracy)."""
+        key = ("tc", n_p, n_q)
+        if key not in self._splits:
+            row_tiles = (n_p + 127) // 128
+            col_tiles = (n_q + 255) // 256
+            best = None
+            for tps in range(1, min(col_tiles, self.MAX_SPLIT_COLS // 256) + 1):
+                ns = -(-col_tiles // tps)
+                rounds = -(-(row_tiles * ns) // self.n_sm)
+                cost = rounds * (tps + self.TC_ITEM_OVERHEAD_TILES)
+                if best is None or cost <= best[0]:
+                    best = (cost, tps, ns)
+            self._splits[key] = (best[1], best[2])
+        return self._splits[key]
 
     def _lse(self, P: PointSet, Q: PointSet, bias, eps, out=None, bounds=None, ns=None, finalize=True, simt=False):
         c1 = self.inv_med / eps

@@ -18,9 +18,9 @@ def t_pass(ops, g, reps=20):
 for n in (1024, 2048, 4096, 8192, 16384, 32768, 65536):
     x, y = bench.synth(n, n, 32)
     out = [f"n={n}"]
-    for tc, mint in (("off", 8), ("on", 8), ("on", 4), ("on", 2), ("on", 1)):
-        CudaOps.TC_MIN_TILES = mint
+    for tc, mint in (("off", 1.0), ("on", 0.5), ("on", 1.0), ("on", 2.0), ("on", 4.0)):
+        CudaOps.TC_ITEM_OVERHEAD_TILES = mint          # split planner's per-item overhead, in tile-times
         ops = CudaOps(x, y, tc=tc); ops.set_median(160.0)
         g = ops.zeros(n)
-        out.append(f"tc={tc}/min{mint}: {t_pass(ops, g):8.1f} us")
+        out.append(f"tc={tc}/over{mint}: {t_pass(ops, g):8.1f} us")
     print("  ".join(out), flush=True)
