@@ -354,3 +354,25 @@ def test_two_gpu_row_partition_matches_single_gpu():
                        capture_output=True, text=True, timeout=280)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("dist check") == 2, r.stdout
+
+
+@pytest.mark.parametrize("n,m,d", [(1, 1, 3), (1, 700, 2), (65, 63, 5), (130, 4000, 7), (1966, 1916, 20), (300, 411, 70)])
+def test_persistent_sweeps_match_launch_loop(ot, n, m, d):
+    """sdb_sinkhorn_sweeps_persistent (one cooperative launch per batch of iterations) walks the same iterates as the
+    five-launches-per-iteration loop: same iterations per stage, potentials equal to fp64 rounding of the LSE combine."""
+    ot_solvers, sinkhorn, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, d, seed=n + m)
+    G = np.exp(np.random.default_rng(2).normal(0, 0.3, n))
+    out = []
+    for persistent in (True, False):
+        ops = CudaOps(a, b, tc="off")
+        ops.persistent = persistent
+        l0 = ops.launches
+        cp = ot_solvers.solve_coupling(a, b, dict(CFG), G=G, ops=ops, dist=sinkhorn.Dist(enabled=False))
+        out.append((cp, ops.launches - l0))
+    (cp1, l1), (cp2, l2) = out
+    assert l1 < l2 / 2, (l1, l2)                       # the persistent path really ran (far fewer launches)
+    assert cp1.info["iters_per_stage"] == cp2.info["iters_per_stage"]
+    assert float((cp1.f - cp2.f).abs().max()) < 1e-7
+    assert float((cp1.g - cp2.g).abs().max()) < 1e-7
+    assert abs(cp1.info["gap"]) <= 1e-8
