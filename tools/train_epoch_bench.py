@@ -63,7 +63,7 @@ def epoch(model, opt, data, beta1=0.5):
     return torch.stack(trace).cpu().numpy()
 
 
-def run(dev=None, with_reference=True):
+def run(dev=None, with_reference=True, with_cpu=True):
     dev = dev or torch.device("cuda:0")
     torch.manual_seed(0)
     data = make_data(dev)
@@ -94,7 +94,46 @@ def run(dev=None, with_reference=True):
         res.update(speedup_second_epoch=out["reference"]["second_epoch_s"] / out["spadot_b200"]["second_epoch_s"],
                    loss_trace_max_rel_diff=float(rel.max()))
     res.update(loss_first=float(traces["spadot_b200"][0]), loss_last=float(traces["spadot_b200"][-1]))
+    if with_cpu:
+        res["host_cpu_sample"] = cpu_sample(data, mine, dev)
     return res
+
+
+def cpu_sample(data, mine, dev, tp="D4"):
+    """BASELINE's "train s/epoch ... vs host CPU", on a bounded sample: ONE optimiser step (fwd + bwd + clip + AdamW) of
+    the first mini-batch of the smallest timepoint, reference formulas in torch on the host cores vs this repo's modules
+    on the GPU, same weights."""
+    d = data[tp]
+    nodes, lei, ns = d["batches"][0]
+    cpu = torch.device("cpu")
+    cfg = dict(input_dim=GENES, z_dim=20, dtype=torch.float64, device=cpu, svgp_encoder_layers=[256, 64], gat_encoder_hidden=512,
+               gat_attention_heads=4, decoder_layers=[64, 256], kernel_type="Gaussian", kernel_scale=0.1, timepoints=[tp])
+    ref = model_ref.SpaDOTRef(cfg, dict(inducing_points={tp: d["inducing"]}, N_train={tp: d["n"]}))
+    ref.load_state_dict({k: v.cpu() for k, v in mine.state_dict().items() if k in ref.state_dict()}, strict=False)
+    x_c, y_c, e_c = d["loc"][nodes].cpu(), d["y"][nodes].cpu(), lei.cpu()
+
+    def one_step(model, x, y, e):
+        opt = torch.optim.AdamW(model.parameters(), lr=3e-4)
+        recon, skl, gkl, align, _ = model.forward(x, y, e, tp, ns)
+        loss = 0.1 * recon - 0.5 * skl + 1e-4 * gkl + 0.1 * align
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.3)
+        opt.step()
+        return float(loss)
+
+    t0 = time.perf_counter()
+    one_step(ref, x_c, y_c, e_c)
+    t_cpu = time.perf_counter() - t0
+    one_step(mine, d["loc"][nodes], d["y"][nodes], lei)         # warm
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    one_step(mine, d["loc"][nodes], d["y"][nodes], lei)
+    torch.cuda.synchronize()
+    t_gpu = time.perf_counter() - t0
+    return dict(sample=f"one optimiser step, timepoint {tp} ({d['n']} spots, {len(d['inducing'])} inducing points), {ns} seeds, "
+                       f"sub-graph of {int(nodes.numel())} nodes, fp64", reference_cpu_s=t_cpu, cpu_threads=torch.get_num_threads(),
+                spadot_b200_gpu_s=t_gpu, ratio=t_cpu / t_gpu)
 
 
 if __name__ == "__main__":
