@@ -19,6 +19,8 @@
 
 #include "sdb_common.cuh"
 
+#include <type_traits>
+
 namespace {
 
 constexpr int TILE_M = 128;          // rows per CTA item (UMMA M)
@@ -242,7 +244,7 @@ struct TcArgs {
     unsigned long long cap;
 };
 
-template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, int MODE = MODE_LSE, bool PIPE = false>
+template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, int MODE = MODE_LSE, bool PIPE = false, bool XTILE = false>
 __global__ void __launch_bounds__(32 * (2 + EPI_WARPS), 1)
 lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, TcArgs a) {
     using S = TcSmem<DP>;
@@ -464,7 +466,118 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             const int t0 = sp * a.tiles_per_split;
             const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
             float m_used = SDB_NEG_SENTINEL, ssum = 0.f;
-            if constexpr (PIPE) {
+            if constexpr (XTILE) {
+                // Cross-tile software pipeline.  Same chunk pipeline as PIPE, but it does not drain at tile boundaries: the
+                // first two tcgen05.ld of tile t+1 and the FP32 stage of its first chunk are issued inside the last two
+                // chunks of tile t, and tile t's accumulator is released as soon as its last TMEM read has landed.  In
+                // the PIPE form both warps of a sub-partition hit the boundary together (same barrier) and the SFU
+                // idles for one TMEM round trip + one FP32 stage per tile (~13 % of the tile).
+                static_assert(NCH == 4, "the cross-tile pipeline is written for four chunks per tile");
+                uint32_t d[2][CH];
+                uint64_t tv2[2][CH / 2];
+                float cmv[2];
+                auto stage_a = [&](int c, uint32_t bias_s) {            // FP32 stage: packed fma + chunk maximum
+#pragma unroll
+                    for (int k4 = 0; k4 < CH / 4; ++k4) {
+                        const float4 b = lds128(bias_s + (c * CH + k4 * 4) * 4);
+                        tv2[c & 1][k4 * 2 + 0] = ffma2(scale2, pack2(__uint_as_float(d[c & 1][k4 * 4 + 0]), __uint_as_float(d[c & 1][k4 * 4 + 1])), pack2(b.x, b.y));
+                        tv2[c & 1][k4 * 2 + 1] = ffma2(scale2, pack2(__uint_as_float(d[c & 1][k4 * 4 + 2]), __uint_as_float(d[c & 1][k4 * 4 + 3])), pack2(b.z, b.w));
+                    }
+                    float m0 = SDB_NEG_SENTINEL, m1 = SDB_NEG_SENTINEL, m2 = SDB_NEG_SENTINEL, m3 = SDB_NEG_SENTINEL;
+#pragma unroll
+                    for (int k = 0; k < CH / 2; k += 2) {
+                        float a0, a1, a2, a3;
+                        unpack2(tv2[c & 1][k], a0, a1);
+                        unpack2(tv2[c & 1][k + 1], a2, a3);
+                        m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1); m2 = fmaxf(m2, a2); m3 = fmaxf(m3, a3);
+                    }
+                    cmv[c & 1] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                };
+                auto stabilise = [&](int c) {                           // branch-free lazy stabiliser (see PIPE)
+                    const float cm = cmv[c & 1];
+                    const float m_new = (cm > m_used + 64.f) ? cm : m_used;
+                    ssum *= sdb_ex2(m_used - m_new);
+                    m_used = m_new;
+                };
+                auto sfu_stage = [&](int c) {                           // SFU stage of chunk c
+                    const uint64_t nm2 = pack2(-m_used, -m_used);
+                    uint64_t acc2[CH / 2];
+#pragma unroll
+                    for (int k = 0; k < CH / 2; ++k) {
+                        float a0, a1;
+                        unpack2(fadd2(tv2[c & 1][k], nm2), a0, a1);
+                        acc2[k] = pack2(sdb_ex2(a0), sdb_ex2(a1));
+                    }
+#pragma unroll
+                    for (int w = CH / 4; w > 0; w >>= 1)
+#pragma unroll
+                        for (int k = 0; k < w; ++k) acc2[k] = fadd2(acc2[k], acc2[k + w]);
+                    float e0, e1;
+                    unpack2(acc2[0], e0, e1);
+                    ssum += e0 + e1;
+                };
+                auto tile_tbase = [&](uint32_t ctr) { return tmem_base + ((uint32_t)(quad * 32) << 16) + (ctr & 1) * TILE_N + part * COLS; };
+                auto tile_bias = [&](uint32_t ctr) { return bias_base + (ctr % BIAS_STAGES) * TILE_N * 4; };
+                // item prologue: first tile's first two loads and its first FP32 stage
+                mbar_wait(b_full + tile_ctr % BIAS_STAGES, (tile_ctr / BIAS_STAGES) & 1);
+                mbar_wait(t_full + (tile_ctr & 1), (tile_ctr >> 1) & 1);
+                tc_fence_after();
+                tmem_ld<CH>(tile_tbase(tile_ctr), d[0]);
+                tmem_ld_wait();
+                tmem_ld<CH>(tile_tbase(tile_ctr) + CH, d[1]);
+                stage_a(0, tile_bias(tile_ctr));
+                // one tile; HAS_NEXT is a compile-time flag so that the steady-state body has no data-dependent branches
+                // (a branch around the next tile's FP32 stage would put it in another basic block than the SFU stage it
+                // is meant to overlap)
+                auto tile_body = [&](auto has_next_c) {
+                    constexpr bool HAS_NEXT = decltype(has_next_c)::value;
+                    const int acc = tile_ctr & 1;
+                    const int bs = tile_ctr % BIAS_STAGES;
+                    const uint32_t bias_s = tile_bias(tile_ctr);
+                    const uint32_t tbase = tile_tbase(tile_ctr);
+                    const uint32_t nctr = tile_ctr + 1;
+                    // chunk 0
+                    stabilise(0);
+                    tmem_ld_wait();                                   // chunk 1 landed in d[1]
+                    tmem_ld<CH>(tbase + 2 * CH, d[0]);
+                    stage_a(1, bias_s);
+                    sfu_stage(0);
+                    // chunk 1
+                    stabilise(1);
+                    tmem_ld_wait();                                   // chunk 2 landed in d[0]
+                    tmem_ld<CH>(tbase + 3 * CH, d[1]);
+                    stage_a(2, bias_s);
+                    sfu_stage(1);
+                    // the next tile's accumulator and bias (long finished: the MMA runs a whole tile ahead)
+                    if constexpr (HAS_NEXT) {
+                        mbar_wait(b_full + nctr % BIAS_STAGES, (nctr / BIAS_STAGES) & 1);
+                        mbar_wait(t_full + (nctr & 1), (nctr >> 1) & 1);
+                        tc_fence_after();
+                    }
+                    // chunk 2
+                    stabilise(2);
+                    tmem_ld_wait();                                   // chunk 3 landed in d[1]: this accumulator is drained
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty + acc);
+                    if constexpr (HAS_NEXT) tmem_ld<CH>(tile_tbase(nctr), d[0]);
+                    stage_a(3, bias_s);
+                    sfu_stage(2);
+                    // chunk 3
+                    stabilise(3);
+                    if constexpr (HAS_NEXT) {
+                        tmem_ld_wait();                               // next tile's chunk 0 landed in d[0]
+                        tmem_ld<CH>(tile_tbase(nctr) + CH, d[1]);
+                        stage_a(0, tile_bias(nctr));
+                    }
+                    sfu_stage(3);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(b_empty + bs);
+                    ++tile_ctr;
+                };
+                for (int t = t0; t < t1 - 1; ++t) tile_body(std::true_type{});
+                tile_body(std::false_type{});
+            } else if constexpr (PIPE) {
                 // Software-pipelined form: the FP32 stage of chunk c+1 (t = scale*d + bias, chunk maximum) and the SFU
                 // stage of chunk c (ex2, sum) sit in one basic block with no dependence between them, so the scheduler
                 // interleaves FMA-pipe and MUFU work of the same warp instead of running them as alternating phases.
@@ -701,9 +814,9 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows_pad, int dp, int b
     return r == CUDA_SUCCESS ? 0 : SDB_E_DRIVER;
 }
 
-template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, bool PIPE = false>
+template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, bool PIPE = false, bool XTILE = false>
 int launch_tc_v(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
-    auto kern = lse_pass_tc_kernel<DP, EPI_WARPS, PACKED, POLY_EVERY, MODE_LSE, PIPE>;
+    auto kern = lse_pass_tc_kernel<DP, EPI_WARPS, PACKED, POLY_EVERY, MODE_LSE, PIPE, XTILE>;
     constexpr int smem = TcSmem<DP>::TOTAL;
     static bool attr_set = false;
     if (!attr_set) {
@@ -730,13 +843,14 @@ int launch_tc_sweep(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs
 
 // Tuning variant (development knob SDB_TC_VARIANT): 0 scalar epilogue, 1 packed f32x2 (all exponentials on the SFU),
 // 2/3/4 packed with every 2nd/3rd/4th pair of exponentials evaluated by the FMA-pipe polynomial,
-// 5 packed + software-pipelined (FP32 stage of chunk c+1 interleaved with the SFU stage of chunk c).
+// 5 packed + software-pipelined (FP32 stage of chunk c+1 interleaved with the SFU stage of chunk c),
+// 6 the same pipeline carried across tile boundaries.
 int tc_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("SDB_TC_VARIANT");
         v = e ? atoi(e) : 5;
-        if (v < 0 || v > 5) v = 5;
+        if (v < 0 || v > 6) v = 5;
     }
     return v;
 }
@@ -749,6 +863,7 @@ int launch_tc(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, i
         case 3: return launch_tc_v<DP, 8, true, 3>(tmP, tmQ, a, n_ctas, st);
         case 4: return launch_tc_v<DP, 8, true, 4>(tmP, tmQ, a, n_ctas, st);
         case 5: return launch_tc_v<DP, 8, true, 0, true>(tmP, tmQ, a, n_ctas, st);
+        case 6: return launch_tc_v<DP, 8, true, 0, true, true>(tmP, tmQ, a, n_ctas, st);
         default: return launch_tc_v<DP, 8, true>(tmP, tmQ, a, n_ctas, st);
     }
 }
