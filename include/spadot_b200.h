@@ -143,7 +143,7 @@ typedef struct sdb_sweep_desc {
 int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int first_tick, int lr_known_first, void* stream);
 /* The same n_sweeps iterations in ONE cooperative launch (SIMT form only, use_tc == 0): CTAs walk the (slab, split)
  * items of each pass and meet at a grid barrier between pass and update, so a ChickenHeart-sized iteration costs four
- * barriers instead of five launches.  barrier2: two zero-initialised unsigned ints owned by the caller (reusable across
+ * barriers instead of five launches.  barrier2: two unsigned ints owned by the caller (zeroed by every call, reusable across
  * calls).  Grid = d->n_ctas CTAs (capped by co-residency; 0 = one per work item); the caller sizes the column splits
  * for it.  Same tile and update code as sdb_sinkhorn_sweeps; the partials of a row are combined by a warp instead of a
  * thread, so iterates agree to fp64 rounding of that sum. */

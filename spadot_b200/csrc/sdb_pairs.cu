@@ -401,6 +401,9 @@ extern "C" int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_swe
     const int64_t cap = (int64_t)n_sm * per_sm;
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
+    // a launch that died inside a barrier must not poison the next one: start every launch from a clean counter pair
+    e = cudaMemsetAsync(barrier2, 0, 2 * sizeof(unsigned int), st);
+    if (e != cudaSuccess) return (int)e;
     void* params[] = {&a};
     e = cudaLaunchCooperativeKernel((const void*)sinkhorn_persistent_kernel, dim3((unsigned)grid), dim3(NT), params, smem, st);
     return (int)e;
