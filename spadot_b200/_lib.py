@@ -58,6 +58,7 @@ SIGNATURES = {
     "sdb_kmeans_assign": [c_p, c_p, c_l, c_i, c_i, c_p, c_p, c_p, c_p, c_p],
     "sdb_kmeans_update": [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p],
     "sdb_kmeans_inertia": [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p],
+    "sdb_kmeans_lloyd_runs": [c_p, c_l, c_i, c_i, c_p, c_i, c_i, c_d, c_p, c_p, c_p, c_p, c_p, c_p],
     "sdb_knn_f64": [c_p, c_l, c_i, c_i, c_p, c_p, c_p],
     "sdb_gat_backward": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
 }

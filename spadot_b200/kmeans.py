@@ -6,7 +6,9 @@ centre the data, `tol * mean(var)`, then for each of the `n_init` runs draw the 
 RandomState stream (sklearn's own `kmeans_plusplus`, a few k x n distance evaluations on the host), run
 Lloyd's iterations to strict label convergence or a squared centre shift below the tolerance, keep the run
 with the smallest inertia.  Lloyd's iterations — the part that scales with n x k x iterations x n_init — run on
-the device (csrc/sdb_kmeans.cu: fused assignment + per-cluster accumulation, centre update, inertia).
+the device (csrc/sdb_kmeans.cu): for the sizes SpaDOT meets every epoch all n_init restarts are ONE launch, one CTA per
+restart running its whole loop on chip; larger problems use per-iteration kernels (fused assignment + per-cluster
+accumulation, centre update, inertia) driven from the host.
 """
 from __future__ import annotations
 
@@ -69,6 +71,26 @@ class KMeans:
         _lib.call("sdb_kmeans_inertia", Xd.data_ptr(), centers.data_ptr(), labels.data_ptr(), n, d, out.data_ptr(), scratch.data_ptr(), st)
         return labels.cpu().numpy().astype(np.int32), float(out.item()), centers.cpu().numpy(), n_iter
 
+    FUSED_MAX_ELEMS = 1 << 21     # n*d up to which all restarts run as one launch, one CTA per restart
+
+    def _lloyd_fused(self, Xd, inits, tol):
+        """All restarts in one launch (sdb_kmeans_lloyd_runs); None for a restart that has to be redone on the host path."""
+        n, d = Xd.shape
+        k, r = self.n_clusters, len(inits)
+        dev = Xd.device
+        c0 = torch.from_numpy(np.ascontiguousarray(np.stack(inits))).to(dev)
+        labels = torch.empty((r, n), dtype=torch.int32, device=dev)
+        centers = torch.empty((r, k, d), dtype=torch.float64, device=dev)
+        inertia = torch.empty(r, dtype=torch.float64, device=dev)
+        meta = torch.empty((2, r), dtype=torch.int32, device=dev)
+        _lib.call("sdb_kmeans_lloyd_runs", Xd.data_ptr(), n, d, k, c0.data_ptr(), r, int(self.max_iter), float(tol),
+                  labels.data_ptr(), centers.data_ptr(), inertia.data_ptr(), meta[0].data_ptr(), meta[1].data_ptr(),
+                  torch.cuda.current_stream(dev).cuda_stream)
+        meta_h = meta.cpu().numpy()
+        labels_h, centers_h, inertia_h = labels.cpu().numpy(), centers.cpu().numpy(), inertia.cpu().numpy()
+        return [(labels_h[i].astype(np.int32), float(inertia_h[i]), centers_h[i], int(meta_h[0, i])) if meta_h[1, i] == 0 else None
+                for i in range(r)]
+
     @staticmethod
     def _relocate_empty(X, labels, centers, sums, counts, cnt):
         """sklearn's _relocate_empty_clusters_dense: an empty cluster takes the sample farthest from its centre."""
@@ -102,10 +124,15 @@ class KMeans:
         x_sq = row_norms(X, squared=True)
         dev = torch.device(self.device) if self.device is not None else torch.device("cuda", torch.cuda.current_device())
         Xd = torch.from_numpy(X).to(dev)
+        # Lloyd's iterations draw no random numbers, so seeding every restart first consumes the RandomState stream
+        # exactly as sklearn's seed / run / seed / run order does
+        inits = [kmeans_plusplus(X, self.n_clusters, x_squared_norms=x_sq, random_state=rs)[0] for _ in range(self.n_init)]
+        runs = self._lloyd_fused(Xd, inits, tol) if n * d <= self.FUSED_MAX_ELEMS else [None] * self.n_init
         best = None
-        for _ in range(self.n_init):
-            centers_init, _ = kmeans_plusplus(X, self.n_clusters, x_squared_norms=x_sq, random_state=rs)
-            labels, inertia, centers, n_iter = self._lloyd(Xd, X, centers_init, tol)
+        for centers_init, run in zip(inits, runs):
+            # a fused run that met an empty cluster (or a problem too large for one CTA per run) goes through the
+            # host-driven iterations, which implement sklearn's relocation
+            labels, inertia, centers, n_iter = run if run is not None else self._lloyd(Xd, X, centers_init, tol)
             if best is None or (inertia < best[1] and not _same_clustering(labels, best[0], self.n_clusters)):
                 best = (labels, inertia, centers, n_iter)
         self.labels_, self.inertia_, centers, self.n_iter_ = best

@@ -263,9 +263,17 @@ def median_cost(ops, dist: Dist | None = None, n_samples=1 << 22, n_bins=4096, s
        differences; 4. radix-select the two middle order statistics among those candidates.
     Sweeps classify with fp32 distances of the centred points; brackets are widened by REL_MARGIN so the
     classification can never disagree with the exact fp64 value about membership of the true median."""
+    import time
     dist = dist or Dist(enabled=False)
     REL_MARGIN = 1e-5     # >= 4x the worst-case relative error of the fp32 / fp16-split distances
     n, m = ops.n, ops.m
+    phases, t_last = {}, time.perf_counter()
+
+    def mark(name):      # host wall-clock between points that synchronise anyway (reported through `info`)
+        nonlocal t_last
+        now = time.perf_counter()
+        phases[name] = phases.get(name, 0.0) + now - t_last
+        t_last = now
     N = int(round(float(dist.sum_(torch.tensor([float(n)], dtype=torch.float64, device=ops.device)).item())))
     total = N * m
     k_lo, k_hi = (total - 1) // 2, total // 2
@@ -279,18 +287,23 @@ def median_cost(ops, dist: Dist | None = None, n_samples=1 << 22, n_bins=4096, s
         n_local = int(counts[1].item())
         if n_local > cap:
             return None, below, n_local
+        mark("collect_sweep")
         allc = dist.gather_cat(cand[:n_local].contiguous())
+        mark("gather")
         return allc, below, int(allc.numel())
 
     lo, hi = 0.0, math.inf
     expect = None
     if total > small_limit:
         ns = int(max(1024, min(n_samples, total // 16) // dist.world))
-        gen = torch.Generator(device="cpu").manual_seed(seed + 7919 * dist.rank)
-        ii = torch.randint(0, max(n, 1), (ns,), generator=gen)
-        jj = torch.randint(0, m, (ns,), generator=gen)
+        # the sample only brackets the median (the result is exact whatever it is): draw it where the points live
+        sdev = ops.device if getattr(ops.device, "type", "cpu") == "cuda" else "cpu"
+        gen = torch.Generator(device=sdev).manual_seed(seed + 7919 * dist.rank)
+        ii = torch.randint(0, max(n, 1), (ns,), generator=gen, device=sdev)
+        jj = torch.randint(0, m, (ns,), generator=gen, device=sdev)
         samp = torch.sort(dist.gather_cat(ops.pair_distances(ii, jj)))[0] if n > 0 else torch.zeros(0, dtype=torch.float64)
         S = int(samp.numel())
+        mark("sample")
         width = 6.0 * 0.5 / math.sqrt(S)
         lo = float(samp[max(0, int((0.5 - width) * S))].item()) * (1 - REL_MARGIN)
         hi = float(samp[min(S - 1, int((0.5 + width) * S))].item()) * (1 + REL_MARGIN)
@@ -299,6 +312,7 @@ def median_cost(ops, dist: Dist | None = None, n_samples=1 << 22, n_bins=4096, s
             hist, counts = ops.cost_histogram(float(np.float32(lo)), float(np.float32(hi)), n_bins)
             hist = dist.sum_(hist).cpu().numpy()
             below = int(dist.sum_(counts[:1].clone()).item())
+            mark("hist_sweep")
             csum = below + np.cumsum(hist)
             if below <= k_lo and csum[-1] > k_hi:
                 b_lo = int(np.searchsorted(csum, k_lo, side="right"))
@@ -331,6 +345,7 @@ def median_cost(ops, dist: Dist | None = None, n_samples=1 << 22, n_bins=4096, s
         cap = int(min(total, 1 << 28))
     v_lo = _select_rank(ops, cand, n_cand, k_lo - below)
     v_hi = v_lo if k_hi == k_lo else _select_rank(ops, cand, n_cand, k_hi - below)
+    mark("select")
     if info is not None:
-        info.update(sweeps=sweeps, candidates=n_cand, below=below)
+        info.update(sweeps=sweeps, candidates=n_cand, below=below, phases_s=phases)
     return 0.5 * (v_lo + v_hi)

@@ -43,3 +43,20 @@ def test_duplicate_points_trigger_empty_cluster_relocation():
     want = SkKMeans(n_clusters=6, random_state=0, n_init=3).fit(X)
     assert len(set(got.labels_)) == 6
     assert got.inertia_ == pytest.approx(want.inertia_, rel=1e-8)
+
+
+@pytest.mark.parametrize("n,d,k,seed", [(747, 20, 10, 1), (2500, 20, 15, 6), (64, 3, 5, 9)])
+def test_one_launch_restarts_match_host_driven_iterations(n, d, k, seed):
+    """sdb_kmeans_lloyd_runs (all n_init restarts in one launch, whole Lloyd loop on chip) against the per-iteration
+    kernels driven from the host and against sklearn: same labels, inertia and iteration count."""
+    from spadot_b200.kmeans import KMeans
+    X = latent(n, d, 8, seed, sd=0.8)
+    fused = KMeans(n_clusters=k, random_state=1993, n_init=10).fit(X)
+    host = KMeans(n_clusters=k, random_state=1993, n_init=10)
+    host.FUSED_MAX_ELEMS = 0
+    host.fit(X)
+    want = SkKMeans(n_clusters=k, random_state=1993, n_init=10).fit(X)
+    assert np.array_equal(fused.labels_, host.labels_) and np.array_equal(fused.labels_, want.labels_)
+    assert fused.inertia_ == pytest.approx(host.inertia_, rel=1e-12)
+    assert fused.inertia_ == pytest.approx(want.inertia_, rel=1e-10)
+    assert fused.n_iter_ == host.n_iter_ == want.n_iter_
