@@ -253,7 +253,7 @@ def _select_rank(ops, cand, n_cand, k):
     return float(np.array([prefix], dtype=np.uint64).view(np.float64)[0])
 
 
-def median_cost(ops, dist: Dist | None = None, n_samples=1 << 22, n_bins=4096, seed=0, small_limit=1 << 22,
+def median_cost(ops, dist: Dist | None = None, n_samples=1 << 24, n_bins=4096, seed=0, small_limit=1 << 22,
                 info: dict | None = None):
     """Exact np.median of all N*M squared distances (ot_solvers.py:103) without materialising them.
 
