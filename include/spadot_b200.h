@@ -294,7 +294,7 @@ int sdb_kmeans_inertia(const double* X, const double* centers, const int32_t* la
 /* n_runs complete Lloyd runs in ONE launch, one CTA per run (the n_init restarts of a fit; ref: sklearn's
  * _kmeans_single_lloyd behind utils/_train_utils.py:262-266).  centers_init: (n_runs, k, d).  Outputs per run: labels (n),
  * centres (k, d), inertia, iterations, status (0 = done, 1 = met an empty cluster: redo that run with the host-driven
- * kernels above, which implement sklearn's relocation).  Meant for n*d up to a few million (one SM streams X from L2). */
+ * kernels above, which implement sklearn's relocation).  Meant for n*d up to about half a million (one SM streams X from L2). */
 int sdb_kmeans_lloyd_runs(const double* X, int64_t n, int d, int k, const double* centers_init, int n_runs, int max_iter,
                           double tol, int32_t* labels_out, double* centers_out, double* inertia_out, int32_t* n_iter_out,
                           int32_t* status_out, void* stream);

@@ -71,7 +71,7 @@ class KMeans:
         _lib.call("sdb_kmeans_inertia", Xd.data_ptr(), centers.data_ptr(), labels.data_ptr(), n, d, out.data_ptr(), scratch.data_ptr(), st)
         return labels.cpu().numpy().astype(np.int32), float(out.item()), centers.cpu().numpy(), n_iter
 
-    FUSED_MAX_ELEMS = 1 << 21     # n*d up to which all restarts run as one launch, one CTA per restart
+    FUSED_MAX_ELEMS = 1 << 19     # n*d up to which all restarts run as one launch, one CTA per restart (measured crossover: 20k x 20 faster, 30k x 20 slower)
 
     def _lloyd_fused(self, Xd, inits, tol):
         """All restarts in one launch (sdb_kmeans_lloyd_runs); None for a restart that has to be redone on the host path."""
