@@ -609,6 +609,7 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                             tv2[c & 1][k4 * 2 + 0] = ffma2(scale2, pack2(__uint_as_float(d[c & 1][k4 * 4 + 0]), __uint_as_float(d[c & 1][k4 * 4 + 1])), pack2(b.x, b.y));
                             tv2[c & 1][k4 * 2 + 1] = ffma2(scale2, pack2(__uint_as_float(d[c & 1][k4 * 4 + 2]), __uint_as_float(d[c & 1][k4 * 4 + 3])), pack2(b.z, b.w));
                         }
+#ifndef SDB_EXPERIMENT_NOMAX
                         float m0 = SDB_NEG_SENTINEL, m1 = SDB_NEG_SENTINEL, m2 = SDB_NEG_SENTINEL, m3 = SDB_NEG_SENTINEL;
 #pragma unroll
                         for (int k = 0; k < CH / 2; k += 2) {
@@ -618,6 +619,7 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                             m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1); m2 = fmaxf(m2, a2); m3 = fmaxf(m3, a3);
                         }
                         cmv[c & 1] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+#endif
                     };
                     tmem_ld<CH>(tbase, d[0]);
                     tmem_ld_wait();
@@ -625,10 +627,12 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                     stage_a(0);
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
+#ifndef SDB_EXPERIMENT_NOMAX
                         const float cm = cmv[c & 1];
                         const float m_new = (cm > m_used + 64.f) ? cm : m_used;
                         ssum *= sdb_ex2(m_used - m_new);
                         m_used = m_new;
+#endif
                         const uint64_t nm2 = pack2(-m_used, -m_used);
                         if (c + 1 < NCH) {
                             tmem_ld_wait();                                   // chunk c+1 has landed in d[(c+1)&1]
