@@ -89,6 +89,23 @@ int sdb_lse_pass_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q
  *      = LSE_j[(g_j - C_ij)/eps]; -inf when every partial is empty. */
 int sdb_lse_finalize(const float* partial, int n_splits, int64_t n, const double* norms,
                      double c1, double* L, void* stream);
+/* Predicted stabiliser.  A pass may take, per row, an upper bound m_i of its largest exponent (row_m) instead of tracking the
+ * running maximum (one max tree + stabiliser update per 32-column chunk: ~16 % of the epilogue's instructions, and the
+ * epilogue is issue-bound): the partials then hold (m_i, sum_j 2^(t_ij - m_i)).  The *_pred finalizers below write the
+ * prediction for the NEXT pass over the same rows, m_next[i] = M + log2 S + 1 (an upper bound of this pass's largest
+ * exponent), and OR 1 into *bad_flag unless 2^-60 < S < 2^100 (no term overflowed, the dominant terms were not flushed to
+ * zero); a caller that passed row_m must check the flag and, if it is set, redo the pass with tracking (row_m = NULL).
+ * m_next / bad_flag may be NULL; with both NULL the *_pred entry points are the plain ones. */
+int sdb_lse_finalize_pred(const float* partial, int n_splits, int64_t n, const double* norms, double c1, double* L,
+                          float* m_next, int* bad_flag, void* stream);
+int sdb_finalize_update_pred(const float* partial, int n_splits, int64_t n, const double* norms, double c1, double* L,
+                             const double* logmarg, double eps, double alpha, double log_n_other, double* pot,
+                             const double* frame, double* la_old, float* bias, int* absorb_flag, int iter,
+                             double log_tau, double log_floor, float* m_next, int* bad_flag, void* stream);
+/* sdb_lse_pass_tc with the predicted stabiliser: row_m[i] for i < n_p (NULL = track the maximum, i.e. sdb_lse_pass_tc). */
+int sdb_lse_pass_tc_pred(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad,
+                         int dp, const float* bias_padded, float scale, int tiles_per_split, int n_ctas,
+                         const float* row_m, float* partial, void* stream);
 
 /* Potential update of one side (ref: ot_func.cpp:610-668 in total potentials):
  *   la_old[i] = (pot[i] - frame[i]) / eps                       (log of the reference's old_a)
@@ -136,6 +153,12 @@ typedef struct sdb_sweep_desc {
     const double* logp; const double* logq;
     int* flag;
     double eps, inv_med, alpha1, alpha2, log_tau, log_floor, pow2_scale;   /* pow2_scale = 2^(-2*pow2_exp) */
+    /* predicted stabiliser (tensor-core form; see sdb_lse_pass_tc_pred): per-row predictions of the row / column pass,
+     * written by every finalize when non-NULL; sweep i uses them in its row pass if i >= pred_from_row and in its column
+     * pass if i >= pred_from_col.  The caller checks *bad_flag after the call and redoes the batch with pred_from_* past
+     * n_sweeps if it is set. */
+    float* m_x; float* m_y; int* bad_flag;
+    int32_t pred_from_row, pred_from_col;
 } sdb_sweep_desc;
 /* Issues n_sweeps x [row pass, finalize+update f, column pass, finalize+update g, absorb] on `stream`.
  * lr_known_first != 0: Lr already holds the row LSE at the current g, the first row pass is skipped

@@ -29,6 +29,9 @@ SIGNATURES = {
     "sdb_sinkhorn_sweeps": [c_p, c_i, c_i, c_i, c_p],
     "sdb_sinkhorn_sweeps_persistent": [c_p, c_i, c_i, c_i, c_p, c_p],
     "sdb_lse_finalize": [c_p, c_i, c_l, c_p, c_d, c_p, c_p],
+    "sdb_lse_finalize_pred": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_p, c_p],
+    "sdb_finalize_update_pred": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p, c_p, c_p],
+    "sdb_lse_pass_tc_pred": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_i, c_i, c_p, c_p, c_p],
     "sdb_potential_update": [c_l, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
     "sdb_finalize_update": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
     "sdb_make_bias": [c_l, c_l, c_p, c_p, c_d, c_d, c_p, c_p],
@@ -75,7 +78,8 @@ class SweepDesc(ctypes.Structure):
                 ("f", c_p), ("g", c_p), ("u", c_p), ("v", c_p), ("la_old", c_p), ("lb_old", c_p), ("Lr", c_p), ("Lc", c_p),
                 ("logp", c_p), ("logq", c_p), ("flag", c_p),
                 ("eps", c_d), ("inv_med", c_d), ("alpha1", c_d), ("alpha2", c_d), ("log_tau", c_d), ("log_floor", c_d),
-                ("pow2_scale", c_d)]
+                ("pow2_scale", c_d),
+                ("m_x", c_p), ("m_y", c_p), ("bad_flag", c_p), ("pred_from_row", ctypes.c_int32), ("pred_from_col", ctypes.c_int32)]
 
 
 _lib = None

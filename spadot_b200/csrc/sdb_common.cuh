@@ -115,18 +115,38 @@ static inline int sdb_reduce_grid(int64_t n) {
 // One row of the Sinkhorn potential update, shared by the vector kernels (sdb_vectors.cu) and the persistent
 // small-problem kernel (sdb_pairs.cu).  No __restrict__ / read-only loads here: inside the persistent kernel these
 // buffers are rewritten by other CTAs between grid barriers.
-__device__ __forceinline__ double sdb_combine_partials(const float2* partial, int n_splits, int64_t n, int64_t i, double norm_c1) {
+// Predicted stabiliser: a pass may be given, per row, an upper bound m_i of its largest exponent
+// instead of tracking the running maximum; the partials then carry (m_i, sum 2^(t - m_i)).  After combining, the
+// prediction for the NEXT pass over the same rows is  M + log2 S + 1  (>= this pass's largest exponent), and the pass was
+// sound iff  2^-60 < S < 2^100: no term overflowed and the dominant terms were not flushed to zero.
+#define SDB_PRED_S_MIN 8.673617379884035e-19     /* 2^-60  */
+#define SDB_PRED_S_MAX 1.2676506002282294e30     /* 2^100 */
+__device__ __forceinline__ void sdb_prediction_out(double M, double S, int64_t i, float* m_next, int* bad_flag) {
+    if (m_next) m_next[i] = (M > -INFINITY && S > 0.0) ? (float)(M + log2(S)) + 1.0f : 0.0f;
+    if (bad_flag && M > -INFINITY && !(S > SDB_PRED_S_MIN && S < SDB_PRED_S_MAX)) atomicOr(bad_flag, 1);
+}
+
+__device__ __forceinline__ double sdb_combine_partials(const float2* partial, int n_splits, int64_t n, int64_t i, double norm_c1,
+                                                       float* m_next = nullptr, int* bad_flag = nullptr) {
     double M = -INFINITY;
     for (int s = 0; s < n_splits; ++s) {
         const float2 ps = __ldcg(partial + (int64_t)s * n + i);      // L2: written by other CTAs (possibly of this very kernel)
         if (ps.x > -1e29f && ps.y > 0.f) M = fmax(M, (double)ps.x);
     }
-    if (!(M > -INFINITY)) return -INFINITY;
+    if (!(M > -INFINITY)) {
+        // nothing valid: either every column is masked, or (predicted pass) every term was flushed to zero
+        bool any = false;
+        for (int s = 0; s < n_splits; ++s) any |= (__ldcg(partial + (int64_t)s * n + i).x > -1e29f);
+        if (m_next) m_next[i] = 0.0f;
+        if (bad_flag && any) atomicOr(bad_flag, 1);
+        return -INFINITY;
+    }
     double S = 0.0;
     for (int s = 0; s < n_splits; ++s) {
         const float2 ps = __ldcg(partial + (int64_t)s * n + i);
         if (ps.x > -1e29f && ps.y > 0.f) S += (double)ps.y * exp2((double)ps.x - M);
     }
+    sdb_prediction_out(M, S, i, m_next, bad_flag);
     return SDB_LN2 * (M + log2(S)) - norm_c1;
 }
 

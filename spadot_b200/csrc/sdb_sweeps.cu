@@ -31,18 +31,21 @@ extern "C" int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int fi
     const double log_m = log((double)d->m), log_N = log((double)d->n_total);
     int rc = 0;
     PdlScope pdl(pdl_enabled() && d->use_tc);      // the SIMT pass kernel is not part of the PDL chain
-    auto pass = [&](bool row) -> int {
+    auto pass = [&](bool row, bool predicted) -> int {
         if (d->use_tc) {
-            return row ? sdb_lse_pass_tc(d->x16, d->n, d->n_pad, d->y16, d->m, d->m_pad, d->dp, d->bias_y, (float)(scale * d->pow2_scale),
-                                         d->tps_row, d->n_ctas, d->partial_row, stream)
-                       : sdb_lse_pass_tc(d->y16, d->m, d->m_pad, d->x16, d->n, d->n_pad, d->dp, d->bias_x, (float)(scale * d->pow2_scale),
-                                         d->tps_col, d->n_ctas, d->partial_col, stream);
+            return row ? sdb_lse_pass_tc_pred(d->x16, d->n, d->n_pad, d->y16, d->m, d->m_pad, d->dp, d->bias_y,
+                                              (float)(scale * d->pow2_scale), d->tps_row, d->n_ctas, predicted ? d->m_x : nullptr,
+                                              d->partial_row, stream)
+                       : sdb_lse_pass_tc_pred(d->y16, d->m, d->m_pad, d->x16, d->n, d->n_pad, d->dp, d->bias_x,
+                                              (float)(scale * d->pow2_scale), d->tps_col, d->n_ctas, predicted ? d->m_y : nullptr,
+                                              d->partial_col, stream);
         }
         return row ? sdb_lse_pass_simt(d->xt, d->ldx, d->n, d->yt, d->ldy, d->m, d->dpad, d->bias_y, (float)scale, d->bounds_row,
                                        d->ns_row, d->partial_row, stream)
                    : sdb_lse_pass_simt(d->yt, d->ldy, d->m, d->xt, d->ldx, d->n, d->dpad, d->bias_x, (float)scale, d->bounds_col,
                                        d->ns_col, d->partial_col, stream);
     };
+    const bool pred = d->use_tc && d->m_x && d->m_y && d->bad_flag;
     if (!(lr_known_first && n_sweeps > 0)) {
         // bias of the first row pass from the current g (a previous call may have used another eps)
         rc = sdb_make_bias(d->m, d->m_bias, d->g, d->norms_y, d->eps, c1, d->bias_y, stream);
@@ -55,16 +58,18 @@ extern "C" int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int fi
             rc = sdb_potential_update(d->n, d->Lr, d->logp, d->norms_x, d->eps, d->alpha1, log_m, c1, d->f, d->u, d->la_old, d->bias_x,
                                       d->flag, tick, d->log_tau, d->log_floor, stream);
         } else {
-            rc = pass(true);
+            rc = pass(true, pred && i >= d->pred_from_row);
             if (rc) return rc;
-            rc = sdb_finalize_update(d->partial_row, d->ns_row, d->n, d->norms_x, c1, d->Lr, d->logp, d->eps, d->alpha1, log_m, d->f, d->u,
-                                     d->la_old, d->bias_x, d->flag, tick, d->log_tau, d->log_floor, stream);
+            rc = sdb_finalize_update_pred(d->partial_row, d->ns_row, d->n, d->norms_x, c1, d->Lr, d->logp, d->eps, d->alpha1, log_m, d->f,
+                                          d->u, d->la_old, d->bias_x, d->flag, tick, d->log_tau, d->log_floor, pred ? d->m_x : nullptr,
+                                          pred ? d->bad_flag : nullptr, stream);
         }
         if (rc) return rc;
-        rc = pass(false);
+        rc = pass(false, pred && i >= d->pred_from_col);
         if (rc) return rc;
-        rc = sdb_finalize_update(d->partial_col, d->ns_col, d->m, d->norms_y, c1, d->Lc, d->logq, d->eps, d->alpha2, log_N, d->g, d->v,
-                                 d->lb_old, d->bias_y, d->flag, tick, d->log_tau, d->log_floor, stream);
+        rc = sdb_finalize_update_pred(d->partial_col, d->ns_col, d->m, d->norms_y, c1, d->Lc, d->logq, d->eps, d->alpha2, log_N, d->g,
+                                      d->v, d->lb_old, d->bias_y, d->flag, tick, d->log_tau, d->log_floor, pred ? d->m_y : nullptr,
+                                      pred ? d->bad_flag : nullptr, stream);
         if (rc) return rc;
         rc = sdb_absorb(d->n, d->m, d->flag, tick, d->f, d->g, d->u, d->v, stream);
         if (rc) return rc;

@@ -226,6 +226,7 @@ __device__ __noinline__ void sweep_collect_rare(uint32_t mask, const double* xi,
 
 struct TcArgs {
     const float* bias;       // padded to a multiple of TILE_N with SDB_NEG_SENTINEL
+    const float* row_m;      // predicted stabiliser per row (FIXED_M kernels), else unused
     float scale;
     int64_t n_p;
     int n_row_tiles, n_col_tiles, tiles_per_split, n_splits;
@@ -244,7 +245,8 @@ struct TcArgs {
     unsigned long long cap;
 };
 
-template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, int MODE = MODE_LSE, bool PIPE = false, bool XTILE = false>
+template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, int MODE = MODE_LSE, bool PIPE = false, bool XTILE = false,
+          bool FIXED_M = false>
 __global__ void __launch_bounds__(32 * (2 + EPI_WARPS), 1)
 lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, TcArgs a) {
     using S = TcSmem<DP>;
@@ -476,6 +478,11 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             const int t0 = sp * a.tiles_per_split;
             const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
             float m_used = SDB_NEG_SENTINEL, ssum = 0.f;
+            if constexpr (FIXED_M) {
+                // predicted stabiliser: an upper bound of this row's largest exponent, supplied by the caller
+                const int64_t prow = (int64_t)rt * TILE_M + row_in_tile;
+                m_used = prow < a.n_p ? __ldg(a.row_m + prow) : 0.f;
+            }
             if constexpr (XTILE) {
                 // Cross-tile software pipeline.  Same chunk pipeline as PIPE, but it does not drain at tile boundaries: the
                 // first two tcgen05.ld of tile t+1 and the FP32 stage of its first chunk are issued inside the last two
@@ -609,17 +616,17 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                             tv2[c & 1][k4 * 2 + 0] = ffma2(scale2, pack2(__uint_as_float(d[c & 1][k4 * 4 + 0]), __uint_as_float(d[c & 1][k4 * 4 + 1])), pack2(b.x, b.y));
                             tv2[c & 1][k4 * 2 + 1] = ffma2(scale2, pack2(__uint_as_float(d[c & 1][k4 * 4 + 2]), __uint_as_float(d[c & 1][k4 * 4 + 3])), pack2(b.z, b.w));
                         }
-#ifndef SDB_EXPERIMENT_NOMAX
-                        float m0 = SDB_NEG_SENTINEL, m1 = SDB_NEG_SENTINEL, m2 = SDB_NEG_SENTINEL, m3 = SDB_NEG_SENTINEL;
+                        if constexpr (!FIXED_M) {
+                            float m0 = SDB_NEG_SENTINEL, m1 = SDB_NEG_SENTINEL, m2 = SDB_NEG_SENTINEL, m3 = SDB_NEG_SENTINEL;
 #pragma unroll
-                        for (int k = 0; k < CH / 2; k += 2) {
-                            float a0, a1, a2, a3;
-                            unpack2(tv2[c & 1][k], a0, a1);
-                            unpack2(tv2[c & 1][k + 1], a2, a3);
-                            m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1); m2 = fmaxf(m2, a2); m3 = fmaxf(m3, a3);
+                            for (int k = 0; k < CH / 2; k += 2) {
+                                float a0, a1, a2, a3;
+                                unpack2(tv2[c & 1][k], a0, a1);
+                                unpack2(tv2[c & 1][k + 1], a2, a3);
+                                m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1); m2 = fmaxf(m2, a2); m3 = fmaxf(m3, a3);
+                            }
+                            cmv[c & 1] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                         }
-                        cmv[c & 1] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-#endif
                     };
                     tmem_ld<CH>(tbase, d[0]);
                     tmem_ld_wait();
@@ -627,12 +634,12 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                     stage_a(0);
 #pragma unroll
                     for (int c = 0; c < NCH; ++c) {
-#ifndef SDB_EXPERIMENT_NOMAX
-                        const float cm = cmv[c & 1];
-                        const float m_new = (cm > m_used + 64.f) ? cm : m_used;
-                        ssum *= sdb_ex2(m_used - m_new);
-                        m_used = m_new;
-#endif
+                        if constexpr (!FIXED_M) {
+                            const float cm = cmv[c & 1];
+                            const float m_new = (cm > m_used + 64.f) ? cm : m_used;
+                            ssum *= sdb_ex2(m_used - m_new);
+                            m_used = m_new;
+                        }
                         const uint64_t nm2 = pack2(-m_used, -m_used);
                         if (c + 1 < NCH) {
                             tmem_ld_wait();                                   // chunk c+1 has landed in d[(c+1)&1]
@@ -828,9 +835,9 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows_pad, int dp, int b
     return r == CUDA_SUCCESS ? 0 : SDB_E_DRIVER;
 }
 
-template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, bool PIPE = false, bool XTILE = false>
+template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, bool PIPE = false, bool XTILE = false, bool FIXED_M = false>
 int launch_tc_v(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
-    auto kern = lse_pass_tc_kernel<DP, EPI_WARPS, PACKED, POLY_EVERY, MODE_LSE, PIPE, XTILE>;
+    auto kern = lse_pass_tc_kernel<DP, EPI_WARPS, PACKED, POLY_EVERY, MODE_LSE, PIPE, XTILE, FIXED_M>;
     constexpr int smem = TcSmem<DP>::TOTAL;
     static bool attr_set = false;
     if (!attr_set) {
@@ -871,6 +878,7 @@ int tc_variant() {
 
 template <int DP>
 int launch_tc(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
+    if (a.row_m != nullptr) return launch_tc_v<DP, 8, true, 0, true, false, true>(tmP, tmQ, a, n_ctas, st);   // predicted stabiliser
     switch (tc_variant()) {
         case 0: return launch_tc_v<DP, 8, false>(tmP, tmQ, a, n_ctas, st);
         case 2: return launch_tc_v<DP, 8, true, 2>(tmP, tmQ, a, n_ctas, st);
@@ -906,6 +914,13 @@ int sdb_prep_points_split_f16(const double* x, int64_t n, int d, const double* c
 
 int sdb_lse_pass_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad, int dp,
                     const float* bias_padded, float scale, int tiles_per_split, int n_ctas, float* partial, void* stream) {
+    return sdb_lse_pass_tc_pred(p16, n_p, n_p_pad, q16, n_q, n_q_pad, dp, bias_padded, scale, tiles_per_split, n_ctas, nullptr, partial,
+                                stream);
+}
+
+int sdb_lse_pass_tc_pred(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad, int dp,
+                         const float* bias_padded, float scale, int tiles_per_split, int n_ctas, const float* row_m, float* partial,
+                         void* stream) {
     SDB_CHECK_ARG(p16 && q16 && bias_padded && partial && n_p > 0 && n_q > 0 && tiles_per_split > 0 && n_ctas > 0);
     SDB_CHECK_ARG((n_p_pad % TILE_N) == 0 && (n_q_pad % TILE_N) == 0 && n_p_pad >= n_p && n_q_pad >= n_q);
     SDB_CHECK_ARG(((uintptr_t)p16 % 128) == 0 && ((uintptr_t)q16 % 128) == 0 && ((uintptr_t)bias_padded % 16) == 0);
@@ -917,6 +932,7 @@ int sdb_lse_pass_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q
     if (rc) return rc;
     TcArgs a{};
     a.bias = bias_padded;
+    a.row_m = row_m;
     a.scale = scale;
     a.n_p = n_p;
     a.n_row_tiles = (int)((n_p + TILE_M - 1) / TILE_M);

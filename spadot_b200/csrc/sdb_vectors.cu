@@ -45,21 +45,12 @@ __global__ void prep_points_kernel(const double* __restrict__ x, int64_t n, int 
 
 // ------------------------------------------------------------------------------------ LSE combine + updates
 __global__ void lse_finalize_kernel(const float2* __restrict__ partial, int n_splits, int64_t n,
-                                    const double* __restrict__ norms, double c1, double* __restrict__ L) {
+                                    const double* __restrict__ norms, double c1, double* __restrict__ L, float* m_next, int* bad_flag) {
+    sdb_launch_dependents();
+    sdb_grid_dependency_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double M = -INFINITY;
-    for (int s = 0; s < n_splits; ++s) {
-        const float2 ps = partial[(int64_t)s * n + i];
-        if (ps.x > -1e29f && ps.y > 0.f) M = fmax(M, (double)ps.x);
-    }
-    if (M == -INFINITY) { L[i] = -INFINITY; return; }
-    double S = 0.0;
-    for (int s = 0; s < n_splits; ++s) {
-        const float2 ps = partial[(int64_t)s * n + i];
-        if (ps.x > -1e29f && ps.y > 0.f) S += (double)ps.y * exp2((double)ps.x - M);
-    }
-    L[i] = SDB_LN2 * (M + log2(S)) - norms[i] * c1;
+    L[i] = sdb_combine_partials(partial, n_splits, n, i, norms[i] * c1, m_next, bad_flag);
 }
 
 __global__ void potential_update_kernel(int64_t n, const double* __restrict__ L, const double* __restrict__ logmarg,
@@ -80,12 +71,12 @@ __global__ void finalize_update_kernel(const float2* __restrict__ partial, int n
                                        double c1, double* __restrict__ L, const double* __restrict__ logmarg, double eps,
                                        double alpha, double log_n_other, double* __restrict__ pot, const double* __restrict__ frame,
                                        double* __restrict__ la_old, float* __restrict__ bias, int* __restrict__ absorb_flag, int iter,
-                                       double log_tau, double log_floor) {
+                                       double log_tau, double log_floor, float* m_next, int* bad_flag) {
     sdb_launch_dependents();
     sdb_grid_dependency_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double Li = sdb_combine_partials(partial, n_splits, n, i, norms[i] * c1);
+    const double Li = sdb_combine_partials(partial, n_splits, n, i, norms[i] * c1, m_next, bad_flag);
     L[i] = Li;
     sdb_update_row(i, Li, logmarg[i], norms[i], eps, alpha, log_n_other, c1, pot, frame, la_old, bias, absorb_flag, iter, log_tau,
                    log_floor);
@@ -316,8 +307,15 @@ int sdb_prep_points_f64(const double* x, int64_t n, int d, const double* center,
 int sdb_lse_finalize(const float* partial, int n_splits, int64_t n, const double* norms, double c1, double* L, void* stream) {
     SDB_CHECK_ARG(partial && norms && L && n_splits > 0 && n >= 0);
     if (n == 0) return 0;
-    lse_finalize_kernel<<<blocks_for(n), 256, 0, sdb_stream(stream)>>>(reinterpret_cast<const float2*>(partial), n_splits, n, norms, c1, L);
-    SDB_LAUNCH_STATUS();
+    return sdb_lse_finalize_pred(partial, n_splits, n, norms, c1, L, nullptr, nullptr, stream);
+}
+
+int sdb_lse_finalize_pred(const float* partial, int n_splits, int64_t n, const double* norms, double c1, double* L, float* m_next,
+                          int* bad_flag, void* stream) {
+    SDB_CHECK_ARG(partial && norms && L && n_splits > 0 && n >= 0);
+    if (n == 0) return 0;
+    return (int)sdb_launch(lse_finalize_kernel, dim3(blocks_for(n)), dim3(256), 0, sdb_stream(stream),
+                           reinterpret_cast<const float2*>(partial), n_splits, n, norms, c1, L, m_next, bad_flag);
 }
 
 int sdb_potential_update(int64_t n, const double* L, const double* logmarg, const double* norms, double eps, double alpha,
@@ -334,9 +332,19 @@ int sdb_finalize_update(const float* partial, int n_splits, int64_t n, const dou
                         double* la_old, float* bias, int* absorb_flag, int iter, double log_tau, double log_floor, void* stream) {
     SDB_CHECK_ARG(partial && norms && L && logmarg && pot && frame && la_old && bias && absorb_flag && n_splits > 0 && n >= 0 && eps > 0.0);
     if (n == 0) return 0;
+    return sdb_finalize_update_pred(partial, n_splits, n, norms, c1, L, logmarg, eps, alpha, log_n_other, pot, frame, la_old, bias,
+                                    absorb_flag, iter, log_tau, log_floor, nullptr, nullptr, stream);
+}
+
+int sdb_finalize_update_pred(const float* partial, int n_splits, int64_t n, const double* norms, double c1, double* L,
+                             const double* logmarg, double eps, double alpha, double log_n_other, double* pot, const double* frame,
+                             double* la_old, float* bias, int* absorb_flag, int iter, double log_tau, double log_floor, float* m_next,
+                             int* bad_flag, void* stream) {
+    SDB_CHECK_ARG(partial && norms && L && logmarg && pot && frame && la_old && bias && absorb_flag && n_splits > 0 && n >= 0 && eps > 0.0);
+    if (n == 0) return 0;
     return (int)sdb_launch(finalize_update_kernel, dim3(blocks_for(n)), dim3(256), 0, sdb_stream(stream),
                            reinterpret_cast<const float2*>(partial), n_splits, n, norms, c1, L, logmarg, eps, alpha, log_n_other, pot,
-                           frame, la_old, bias, absorb_flag, iter, log_tau, log_floor);
+                           frame, la_old, bias, absorb_flag, iter, log_tau, log_floor, m_next, bad_flag);
 }
 
 int sdb_make_bias(int64_t n, int64_t n_pad, const double* pot, const double* norms, double eps, double c1, float* bias,

@@ -181,6 +181,8 @@ class CudaOps(VectorOps):
     TC_ITEM_OVERHEAD_TILES = float(os.environ.get("SDB_TC_ITEM_OVERHEAD", "2.0"))   # item switch cost in tile-times (split planner)
     MAX_SPLIT_COLS = 65536   # keeps fp32 running sums < 1e-6 relative (include/spadot_b200.h)
     TARGET_CTAS = 148 * 6
+    PREDICT = os.environ.get("SDB_PREDICTED_MAX", "1") != "0"   # predicted stabiliser in the tensor-core pass (see _Pred)
+    PREDICT_MIN_PAIRS = 1 << 28      # below this a batch of sweeps is too short for the verification read-back to pay
     PERSISTENT_MAX_PAIRS = 1 << 24   # SIMT problems up to this many pairs run their sweeps in one cooperative launch
     PERSISTENT_CTAS_PER_SM = int(os.environ.get("SDB_PERSISTENT_CTAS_PER_SM", "2"))
 
@@ -226,6 +228,7 @@ class CudaOps(VectorOps):
         self.inv_med = 1.0
         self.persistent = os.environ.get("SDB_PERSISTENT", "1") != "0"      # development knob (A/B against the launch loop)
         self._barrier = None
+        self._pred = None
 
     # ------------------------------------------------------------------ plumbing
     def set_median(self, median: float):
@@ -263,6 +266,62 @@ class CudaOps(VectorOps):
             self._partials[key] = torch.empty((ns, n_p, 2), dtype=torch.float32, device=self.device)
         return self._partials[key]
 
+    # ------------------------------------------------------------------ predicted stabiliser
+    # The tensor-core epilogue is issue-bound and ~16 % of its instructions track the running row maximum.  A pass over
+    # rows that were swept one iteration ago can instead be told an upper bound of each row's largest exponent (the
+    # previous pass's LSE in log2 units, + 1): the finalize kernel verifies that the sums stayed inside [2^-60, 2^100] and
+    # raises `bad` otherwise, in which case the caller restores its snapshot of the potentials and redoes the work with the
+    # tracking kernel (and predictions stay off for the rest of that solve).  Predictions are only used when the last
+    # pass over the same side ran with the same (eps, median): the first iteration of every epsilon stage tracks.
+    class _Pred:
+        def __init__(self, ops):
+            self.m = {"x": torch.zeros(max(ops.n, 1), dtype=torch.float32, device=ops.device),
+                      "y": torch.zeros(max(ops.m, 1), dtype=torch.float32, device=ops.device)}
+            self.bad = torch.zeros(1, dtype=torch.int32, device=ops.device)
+            self.fresh = {"x": None, "y": None}
+            self.ok = True          # False after a misprediction, until the next solve
+            self.used = False       # a predicted pass is in flight and not yet verified
+
+    def _pred_state(self):
+        if not (self.use_tc and self.PREDICT and self.n * self.m >= self.PREDICT_MIN_PAIRS):
+            return None
+        if self._pred is None:
+            self._pred = CudaOps._Pred(self)
+        return self._pred if self._pred.ok else None
+
+    def predicting(self):
+        """True when sweeps may use predictions, i.e. the caller should hold a snapshot for `settle` to fall back on."""
+        return self._pred_state() is not None
+
+    def snapshot(self, st):
+        vec = (st.f, st.g, st.u, st.v, st.la_old, st.lb_old, st.Lr, st.Lc)
+        return [t.clone() for t in vec], self.flag.clone(), self._tick
+
+    def restore(self, st, snap):
+        vec = (st.f, st.g, st.u, st.v, st.la_old, st.lb_old, st.Lr, st.Lc)
+        for t, c in zip(vec, snap[0]):
+            t.copy_(c)
+        self.flag.copy_(snap[1])
+        self._tick = snap[2]
+        self._bias_key = {"x": None, "y": None}
+
+    def settle(self, dist=None):
+        """Verify the predicted passes issued since the last call (one small synchronising read-back).  False means a
+        prediction was out of range: the results since the caller's snapshot are invalid and predictions are now off."""
+        ps = self._pred
+        if ps is None or not ps.used:
+            return True
+        ps.used = False
+        flag = ps.bad
+        if dist is not None and dist.world > 1:
+            flag = dist.max_(flag)
+        if int(flag.item()) == 0:
+            return True
+        ps.bad.zero_()
+        ps.ok = False
+        ps.fresh = {"x": None, "y": None}
+        return False
+
     # ------------------------------------------------------------------ K3 passes
     def _norms(self, P: PointSet):
         return P.norms16 if self.use_tc else P.norms
@@ -286,14 +345,15 @@ class CudaOps(VectorOps):
             self._splits[key] = (best[1], best[2])
         return self._splits[key]
 
-    def _lse(self, P: PointSet, Q: PointSet, bias, eps, out=None, bounds=None, ns=None, finalize=True, simt=False):
+    def _lse(self, P: PointSet, Q: PointSet, bias, eps, out=None, bounds=None, ns=None, finalize=True, simt=False, row_m=None,
+             m_next=None, bad=None):
         c1 = self.inv_med / eps
         scale = 2.0 * c1 * math.log2(math.e)
         if self.use_tc and not simt:
             tps, ns = self._tc_split_plan(P.n, Q.n)
             partial = self._partial(ns, P.n)
-            self._call("sdb_lse_pass_tc", _ptr(P.x16), P.n, P.n_pad, _ptr(Q.x16), Q.n, Q.n_pad, P.dp, _ptr(bias),
-                       scale * 2.0 ** (-2 * self.pow2_exp), tps, self.n_sm, _ptr(partial))
+            self._call("sdb_lse_pass_tc_pred", _ptr(P.x16), P.n, P.n_pad, _ptr(Q.x16), Q.n, Q.n_pad, P.dp, _ptr(bias),
+                       scale * 2.0 ** (-2 * self.pow2_exp), tps, self.n_sm, _ptr(row_m), _ptr(partial))
             norms = P.norms16
         else:
             if bounds is None:
@@ -306,18 +366,37 @@ class CudaOps(VectorOps):
             return partial
         if out is None:
             out = torch.empty(P.n, dtype=torch.float64, device=self.device)
-        self._call("sdb_lse_finalize", _ptr(partial), ns, P.n, _ptr(norms), c1, _ptr(out))
+        self._call("sdb_lse_finalize_pred", _ptr(partial), ns, P.n, _ptr(norms), c1, _ptr(out), _ptr(m_next), _ptr(bad))
         return out
 
-    def row_lse(self, g, eps, out=None):
-        """Lr_i = LSE_j[(g_j - C_ij)/eps] over all columns (natural log, fp64).  g=None means g=0."""
+    def _pred_args(self, side_key, eps, allow):
+        """(row_m, m_next, bad) tensors for a pass over the rows of side `side_key`, and bookkeeping of freshness."""
+        ps = self._pred_state() if allow else None
+        if ps is None:
+            return None, None, None
+        key = (eps, self.inv_med)
+        use = ps.fresh[side_key] == key
+        ps.fresh[side_key] = key
+        ps.used = ps.used or use
+        return (ps.m[side_key] if use else None), ps.m[side_key], ps.bad
+
+    def row_lse(self, g, eps, out=None, predict=False):
+        """Lr_i = LSE_j[(g_j - C_ij)/eps] over all columns (natural log, fp64).  g=None means g=0.
+        predict=True (the solver's own potential only): may use / refresh the predicted stabiliser; the caller must
+        `settle()` before trusting the result."""
         self._call("sdb_make_bias", self.m, self.bias_y.numel(), _ptr(g), _ptr(self._norms(self.Y)), eps,
                    self.inv_med / eps, _ptr(self.bias_y))
         self._bias_key["y"] = (_ptr(g), eps, self.inv_med) if g is not None else None
-        return self._lse(self.X, self.Y, self.bias_y, eps, out)
+        row_m, m_next, bad = self._pred_args("x", eps, predict and g is not None)
+        return self._lse(self.X, self.Y, self.bias_y, eps, out, row_m=row_m, m_next=m_next, bad=bad)
 
     def begin_solve(self):
         self._bias_key = {"x": None, "y": None}
+        if self._pred is not None:          # new potentials: old predictions mean nothing; a new solve may predict again
+            self._pred.fresh = {"x": None, "y": None}
+            self._pred.ok = True
+            self._pred.used = False
+            self._pred.bad.zero_()
 
     def fused_sweeps(self, st, eps, alpha1, alpha2, log_tau, log_floor, n_sweeps, lr_known_first):
         """n_sweeps full iterations issued by the native loop sdb_sinkhorn_sweeps (single rank)."""
@@ -345,6 +424,16 @@ class CudaOps(VectorOps):
         d.logp, d.logq, d.flag = _ptr(st.logp), _ptr(st.logq), _ptr(self.flag)
         d.eps, d.inv_med, d.alpha1, d.alpha2 = eps, self.inv_med, alpha1, alpha2
         d.log_tau, d.log_floor = log_tau, log_floor
+        ps = self._pred_state()
+        if ps is not None:
+            key = (eps, self.inv_med)
+            d.m_x, d.m_y, d.bad_flag = _ptr(ps.m["x"]), _ptr(ps.m["y"]), _ptr(ps.bad)
+            d.pred_from_row = 0 if ps.fresh["x"] == key else (2 if lr_known_first else 1)
+            d.pred_from_col = 0 if ps.fresh["y"] == key else 1
+            if n_sweeps > (1 if lr_known_first else 0):
+                ps.fresh["x"] = key
+            ps.fresh["y"] = key
+            ps.used = ps.used or d.pred_from_row < n_sweeps or d.pred_from_col < n_sweeps
         first = self._tick + 1
         self._tick += n_sweeps
         if self.n == self.m and d.ns_row == d.ns_col:
@@ -392,21 +481,24 @@ class CudaOps(VectorOps):
         if self._bias_key[kin] != key:
             self._call("sdb_make_bias", Q.n, bias_in.numel(), _ptr(pot_in), _ptr(self._norms(Q)), eps, c1, _ptr(bias_in))
             self._bias_key[kin] = key
-        partial = self._lse(P, Q, bias_in, eps, finalize=False)
+        row_m, m_next, bad = self._pred_args("x" if side == "row" else "y", eps, True)
+        partial = self._lse(P, Q, bias_in, eps, finalize=False, row_m=row_m)
         ns = partial.shape[0]
-        self._call("sdb_finalize_update", _ptr(partial), ns, P.n, _ptr(self._norms(P)), c1, _ptr(L), _ptr(logmarg), eps, alpha,
-                   math.log(n_other), _ptr(pot), _ptr(frame), _ptr(la), _ptr(bias_out), _ptr(self.flag), it, log_tau, log_floor)
+        self._call("sdb_finalize_update_pred", _ptr(partial), ns, P.n, _ptr(self._norms(P)), c1, _ptr(L), _ptr(logmarg), eps, alpha,
+                   math.log(n_other), _ptr(pot), _ptr(frame), _ptr(la), _ptr(bias_out), _ptr(self.flag), it, log_tau, log_floor,
+                   _ptr(m_next), _ptr(bad))
         self._bias_key[kout] = (_ptr(pot), eps, self.inv_med)
 
-    def col_lse(self, f, eps, out=None):
-        """Lc_j = LSE_{i local}[(f_i - C_ij)/eps] over this rank's rows."""
+    def col_lse(self, f, eps, out=None, predict=False):
+        """Lc_j = LSE_{i local}[(f_i - C_ij)/eps] over this rank's rows (predict: see row_lse)."""
         if self.n == 0:
             out = torch.empty(self.m, dtype=torch.float64, device=self.device) if out is None else out
             return out.fill_(NEG_INF)
         self._call("sdb_make_bias", self.n, self.bias_x.numel(), _ptr(f), _ptr(self._norms(self.X)), eps,
                    self.inv_med / eps, _ptr(self.bias_x))
         self._bias_key["x"] = (_ptr(f), eps, self.inv_med) if f is not None else None
-        return self._lse(self.Y, self.X, self.bias_x, eps, out)
+        row_m, m_next, bad = self._pred_args("y", eps, predict and f is not None)
+        return self._lse(self.Y, self.X, self.bias_x, eps, out, row_m=row_m, m_next=m_next, bad=bad)
 
     # ------------------------------------------------------------------ vector updates
     def _side_norms(self, side, pot):

@@ -108,17 +108,46 @@ class _State:
         self.Lc = ops.zeros(self.m)
 
 
+def _predicting(ops):
+    """The device ops may run passes with a predicted stabiliser (cuda_ops.CudaOps._Pred): work issued since a snapshot
+    must then be verified with ops.settle() and redone from the snapshot if a prediction was out of range."""
+    fn = getattr(ops, "predicting", None)
+    return fn is not None and fn()
+
+
+def _checked(ops, dist: Dist, fn):
+    """Run fn() (passes that only write their own output); redo it once with tracking if a prediction failed."""
+    out = fn()
+    settle = getattr(ops, "settle", None)
+    if settle is not None and not settle(dist):
+        out = fn()
+    return out
+
+
 def _sweeps(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_known, n_sweeps, log_floor=NEG_INF):
     """n_sweeps iterations; one native call when the ops provide it (single rank), else a Python loop."""
     native = getattr(ops, "fused_sweeps", None)
     if native is not None and dist.world == 1 and n_sweeps > 0:
+        snap = ops.snapshot(st) if _predicting(ops) else None
         native(st, eps, alpha1, alpha2, log_tau, log_floor, n_sweeps, lr_known)
+        if snap is not None and not ops.settle(dist):
+            ops.restore(st, snap)                                 # predictions are off now: this batch tracks
+            native(st, eps, alpha1, alpha2, log_tau, log_floor, n_sweeps, lr_known)
         return
     for i in range(n_sweeps):
         _sweep(ops, st, dist, eps, alpha1, alpha2, log_tau, lr_known and i == 0, log_floor)
 
 
 def _sweep(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_known, log_floor=NEG_INF):
+    """One Sinkhorn iteration, verified: see _sweep_body."""
+    snap = ops.snapshot(st) if _predicting(ops) else None
+    _sweep_body(ops, st, dist, eps, alpha1, alpha2, log_tau, lr_known, log_floor)
+    if snap is not None and not ops.settle(dist):
+        ops.restore(st, snap)
+        _sweep_body(ops, st, dist, eps, alpha1, alpha2, log_tau, lr_known, log_floor)
+
+
+def _sweep_body(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_known, log_floor=NEG_INF):
     """One Sinkhorn iteration = row update + column update (ot_func.cpp:587-687) + tau bookkeeping."""
     it = ops.tick()
     fused = getattr(ops, "fused_half_step", None)
@@ -131,7 +160,10 @@ def _sweep(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_known, 
     if fused is not None and dist.world == 1:
         fused("col", st, eps, alpha2, it, log_tau, log_floor)
     else:
-        ops.col_lse(st.f, eps, out=st.Lc)
+        if _predicting(ops):
+            ops.col_lse(st.f, eps, out=st.Lc, predict=True)       # verified by the settle() of _sweep
+        else:
+            ops.col_lse(st.f, eps, out=st.Lc)
         if dist.world > 1:
             st.Lc.copy_(combine_col_lse(st.Lc, dist))
         ops.potential_update("col", st.Lc, st.logq, eps, alpha2, math.log(st.N), st.g, st.v, st.lb_old, it, log_tau, log_floor)
@@ -172,7 +204,10 @@ def solve_duality_gap(ops, G_local, lambda1, lambda2, epsilon, batch_size=5, tol
                 if sumK is None:
                     Lk = ops.row_lse(None, eps_i)
                     sumK = float(dist.sum_(ops.sum_exp(Lk)).item())
-                ops.row_lse(st.g, eps_i, out=st.Lr)               # also the next iteration's row pass
+                if _predicting(ops):                              # also the next iteration's row pass
+                    _checked(ops, dist, lambda: ops.row_lse(st.g, eps_i, out=st.Lr, predict=True))
+                else:
+                    ops.row_lse(st.g, eps_i, out=st.Lr)
                 lr_known = True
                 t = ops.gap_terms(st.f, st.Lr, st.logp, st.g, st.Lc, st.logq, eps_i, lambda1, lambda2,
                                   1.0 / st.N, 1.0 / st.m)

@@ -26,6 +26,7 @@ def main():
         r0, r1 = (n * rank) // world, (n * (rank + 1)) // world
         dist = sinkhorn.Dist()
         ops = CudaOps(a[r0:r1], b, tc=tc)
+        ops.PREDICT_MIN_PAIRS = 0          # predicted stabiliser on (tensor-core case): its flag rides on an all-reduce
         cp = ot_solvers.solve_coupling(a[r0:r1], b, cfg, G=G[r0:r1], ops=ops, dist=dist)
         tab = cp.transition_table(la[r0:r1], lb, 10, 10).cpu().numpy()
         # single-GPU run of the same problem on every rank
@@ -41,7 +42,8 @@ def main():
         assert df < 1e-6 and dg < 1e-6 and dt < 1e-6, (df, dg, dt)
         if rank == 0:
             print(f"dist check {n}x{m} d={d} tc={tc}: world={world} |df|={df:.2e} |dg|={dg:.2e} table rel={dt:.2e} "
-                  f"iters={cp.info['iters_per_stage']} collectives={dist.collectives}", flush=True)
+                  f"iters={cp.info['iters_per_stage']} collectives={dist.collectives} "
+                  f"predicted={ops._pred is not None and ops._pred.ok}", flush=True)
     td.destroy_process_group()
 
 

@@ -333,7 +333,10 @@ def test_multi_rank_code_path_matches_native_loop(ot, n, m, d, tc):
     cfg = dict(CFG)
     cp1 = ot_solvers.solve_coupling(a, b, cfg, G=G, ops=CudaOps(a, b, tc=tc), dist=sinkhorn.Dist(enabled=False))
     loop = _LoopbackDist(sinkhorn)
-    cp2 = ot_solvers.solve_coupling(a, b, cfg, G=G, ops=CudaOps(a, b, tc=tc), dist=loop)
+    ops2 = CudaOps(a, b, tc=tc)
+    ops2.PREDICT_MIN_PAIRS = 0                          # the predicted stabiliser rides along on the tensor-core case
+    cp2 = ot_solvers.solve_coupling(a, b, cfg, G=G, ops=ops2, dist=loop)
+    assert (ops2._pred is not None and ops2._pred.ok) == (tc == "on")
     assert loop.collectives > 0
     assert cp1.median == cp2.median
     assert cp1.info["iters_per_stage"] == cp2.info["iters_per_stage"], (cp1.info, cp2.info)

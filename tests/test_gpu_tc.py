@@ -212,3 +212,70 @@ def test_parity_8192x8192_three_way(ot):
     tab_ref = ot_dense.transition_table(want, la, lb, 10, 10)
     assert np.abs(tab - tab_ref).max() / tab_ref.max() < 1e-4
     assert np.array_equal(tab.argmax(1), tab_ref.argmax(1))
+
+
+def _six_sweeps(sinkhorn, ops, n, dist, corrupt=None):
+    """3 + 3 sweeps at the final-stage parameters through the public driver; optional tampering in between."""
+    st = sinkhorn._State(ops, np.ones(n), dist)
+    st.u.copy_(st.f)
+    st.v.copy_(st.g)
+    args = (0.05, 0.1 / 0.15, 5.0 / 5.05, float(np.log(1000.0)))
+    sinkhorn._sweeps(ops, st, dist, *args, False, 3)
+    if corrupt is not None:
+        corrupt(ops)
+    sinkhorn._sweeps(ops, st, dist, *args, False, 3)
+    torch.cuda.synchronize()
+    return st
+
+
+@pytest.mark.parametrize("loop", ["native", "python"])
+def test_predicted_stabiliser_matches_tracking_and_falls_back(ot, loop):
+    """Predicted stabiliser of the tensor-core pass (sdb_lse_pass_tc_pred): same potentials as the tracking kernel; a
+    prediction tampered with between two batches is caught by the finalize check, the batch is redone from the snapshot
+    with tracking, and the result is still the tracking result."""
+    _, sinkhorn, CudaOps = ot
+    n, m = 3000, 2600
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, 32, seed=5)
+    dist = sinkhorn.Dist(enabled=False)
+
+    def make(predict):
+        ops = CudaOps(a, b, tc="on")
+        ops.set_median(160.0)
+        ops.PREDICT, ops.PREDICT_MIN_PAIRS = predict, 0
+        if loop == "python":
+            ops.fused_sweeps = None                      # the per-iteration path used for world > 1 and by bench.py
+        return ops
+
+    ref = _six_sweeps(sinkhorn, make(False), n, dist)
+    ops = make(True)
+    got = _six_sweeps(sinkhorn, ops, n, dist)
+    assert ops._pred is not None and ops._pred.ok and ops._pred.fresh["x"] is not None      # predictions really ran
+    assert float((got.f - ref.f).abs().max()) < 2e-6 and float((got.g - ref.g).abs().max()) < 2e-6
+
+    def tamper(o):
+        o._pred.m["x"] += 400.0                           # every term of the next row pass underflows
+    ops2 = make(True)
+    got2 = _six_sweeps(sinkhorn, ops2, n, dist, corrupt=tamper)
+    assert ops2._pred.ok is False                         # the misprediction was detected ...
+    assert float((got2.f - ref.f).abs().max()) < 2e-6 and float((got2.g - ref.g).abs().max()) < 2e-6   # ... and repaired
+
+    def tamper_low(o):
+        o._pred.m["y"] -= 400.0                           # terms of the next column pass overflow
+    ops3 = make(True)
+    got3 = _six_sweeps(sinkhorn, ops3, n, dist, corrupt=tamper_low)
+    assert ops3._pred.ok is False
+    assert float((got3.f - ref.f).abs().max()) < 2e-6 and float((got3.g - ref.g).abs().max()) < 2e-6
+
+
+def test_predicted_stabiliser_full_solve_same_iterations(ot):
+    ot_solvers, sinkhorn, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(2600, 2100, 20, seed=9)
+    out = []
+    for predict in (False, True):
+        ops = CudaOps(a, b, tc="on")
+        ops.PREDICT, ops.PREDICT_MIN_PAIRS = predict, 0
+        out.append(ot_solvers.solve_coupling(a, b, dict(CFG), ops=ops, dist=sinkhorn.Dist(enabled=False)))
+    cp0, cp1 = out
+    assert cp1.ops._pred is not None and cp1.ops._pred.ok
+    assert cp0.info["iters_per_stage"] == cp1.info["iters_per_stage"]
+    assert float((cp0.f - cp1.f).abs().max()) < 2e-6 and float((cp0.g - cp1.g).abs().max()) < 2e-6
