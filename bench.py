@@ -312,7 +312,8 @@ def gpu_main(a):
             # and ~4 fp32 instructions, so the binding pipe is the SFU.
             sfu_peak = n_sm * 16 * sm_max * 1e6 / 1e12
             achieved = pairs / avg_pass_s / 1e12
-            roofline = dict(bound="sfu", kernel="lse_pass_tc_kernel<%d> (sdb_lse_pass_tc)" % ops.X.dp, achieved=achieved,
+            entry = "sdb_lse_pass_tc_pred, predicted stabiliser" if ops.predicting() else "sdb_lse_pass_tc"
+            roofline = dict(bound="sfu", kernel="lse_pass_tc_kernel<%d> (%s)" % (ops.X.dp, entry), achieved=achieved,
                             peak=sfu_peak, unit="Tex2/s", frac=achieved / sfu_peak,
                             peak_source=f"{n_sm} SM x 16 MUFU lanes x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json; "
                                         "that file has no SFU entry)",
