@@ -229,6 +229,7 @@ class CudaOps(VectorOps):
         self.persistent = os.environ.get("SDB_PERSISTENT", "1") != "0"      # development knob (A/B against the launch loop)
         self._barrier = None
         self._pred = None
+        self._pred_allowed = False          # set per solve by begin_solve()
 
     # ------------------------------------------------------------------ plumbing
     def set_median(self, median: float):
@@ -283,7 +284,7 @@ class CudaOps(VectorOps):
             self.used = False       # a predicted pass is in flight and not yet verified
 
     def _pred_state(self):
-        if not (self.use_tc and self.PREDICT and self.n * self.m >= self.PREDICT_MIN_PAIRS):
+        if not self._pred_allowed:
             return None
         if self._pred is None:
             self._pred = CudaOps._Pred(self)
@@ -390,8 +391,13 @@ class CudaOps(VectorOps):
         row_m, m_next, bad = self._pred_args("x", eps, predict and g is not None)
         return self._lse(self.X, self.Y, self.bias_y, eps, out, row_m=row_m, m_next=m_next, bad=bad)
 
-    def begin_solve(self):
+    def begin_solve(self, dist=None):
         self._bias_key = {"x": None, "y": None}
+        # whether this solve may predict is decided once and identically on every rank (settle() is collective)
+        ok = bool(self.use_tc and self.PREDICT and self.n * self.m >= self.PREDICT_MIN_PAIRS)
+        if dist is not None and dist.world > 1:
+            ok = bool(int(dist.min_(torch.tensor([int(ok)], dtype=torch.int32, device=self.device)).item()))
+        self._pred_allowed = ok
         if self._pred is not None:          # new potentials: old predictions mean nothing; a new solve may predict again
             self._pred.fresh = {"x": None, "y": None}
             self._pred.ok = True

@@ -58,6 +58,12 @@ class Dist:
             self.collectives += 1
         return t
 
+    def min_(self, t):
+        if self.world > 1:
+            self.td.all_reduce(t, op=self.td.ReduceOp.MIN, group=self.group)
+            self.collectives += 1
+        return t
+
     def gather_cat(self, t):
         """Concatenate variable-length 1-D tensors from all ranks (used by the median only)."""
         if self.world == 1:
@@ -88,7 +94,9 @@ class _State:
     """Per-solve device vectors."""
 
     def __init__(self, ops, G_local, dist: Dist):
-        getattr(ops, "begin_solve", lambda: None)()      # new potentials: cached bias vectors are stale
+        begin = getattr(ops, "begin_solve", None)          # new potentials: cached bias vectors / predictions are stale
+        if begin is not None:
+            begin(dist)
         self.n, self.m = ops.n, ops.m
         nt = torch.tensor([float(self.n)], dtype=torch.float64, device=ops.device)
         self.N = int(round(float(dist.sum_(nt).item())))
