@@ -1,5 +1,6 @@
+"""Exact streamed median (K5) against the size of its bracketing sample: total time, candidates, phase split."""
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
 from spadot_b200 import sinkhorn
