@@ -142,8 +142,14 @@ def _sweeps(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_known,
             ops.restore(st, snap)                                 # predictions are off now: this batch tracks
             native(st, eps, alpha1, alpha2, log_tau, log_floor, n_sweeps, lr_known)
         return
+    # per-iteration path (row-partitioned solve, or ops without a native loop): one snapshot / verification per batch
+    snap = ops.snapshot(st) if _predicting(ops) and n_sweeps > 0 else None
     for i in range(n_sweeps):
-        _sweep(ops, st, dist, eps, alpha1, alpha2, log_tau, lr_known and i == 0, log_floor)
+        _sweep_body(ops, st, dist, eps, alpha1, alpha2, log_tau, lr_known and i == 0, log_floor)
+    if snap is not None and not ops.settle(dist):
+        ops.restore(st, snap)
+        for i in range(n_sweeps):
+            _sweep_body(ops, st, dist, eps, alpha1, alpha2, log_tau, lr_known and i == 0, log_floor)
 
 
 def _sweep(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_known, log_floor=NEG_INF):
