@@ -17,7 +17,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, plans
 
 NEG_INF = float("-inf")
 
@@ -238,26 +238,16 @@ class CudaOps(VectorOps):
     def _split_plan(self, n_p, n_q):
         key = (n_p, n_q)
         if key not in self._splits:
-            row_tiles = max(1, (n_p + 63) // 64)
-            want = max(1, -(-self.TARGET_CTAS // row_tiles))
-            lo = max(1, -(-n_q // self.MAX_SPLIT_COLS))
-            tiles = max(1, -(-n_q // 64))
-            hi = max(1, n_q // 256) if n_q >= 4096 else tiles      # small problems: down to one 64-column tile per item
-            ns = int(min(max(want, lo), max(hi, lo), 65535))
-            # split boundaries on 64-column tile boundaries: no item streams a mostly masked tile
-            bounds = torch.tensor([min(n_q, 64 * ((tiles * s) // ns)) for s in range(ns)] + [n_q], dtype=torch.int64,
-                                  device=self.device)
+            ns = plans.simt_splits(n_p, n_q, self.TARGET_CTAS, self.MAX_SPLIT_COLS)
+            bounds = torch.tensor(plans.aligned_bounds(n_q, ns), dtype=torch.int64, device=self.device)
             self._splits[key] = (bounds, ns)
         return self._splits[key]
 
     def _persist_plan(self, n_p, n_q, grid):
         key = ("persist", n_p, n_q, grid)
         if key not in self._splits:
-            row_tiles = max(1, (n_p + 63) // 64)
-            tiles = max(1, -(-n_q // 64))
-            ns = max(min(max(1, grid // row_tiles), tiles), -(-n_q // self.MAX_SPLIT_COLS))
-            bounds = torch.tensor([min(n_q, 64 * ((tiles * s) // ns)) for s in range(ns)] + [n_q], dtype=torch.int64,
-                                  device=self.device)
+            ns = plans.persistent_splits(n_p, n_q, grid, self.MAX_SPLIT_COLS)
+            bounds = torch.tensor(plans.aligned_bounds(n_q, ns), dtype=torch.int64, device=self.device)
             self._splits[key] = (bounds, ns)
         return self._splits[key]
 
@@ -328,22 +318,10 @@ class CudaOps(VectorOps):
         return P.norms16 if self.use_tc else P.norms
 
     def _tc_split_plan(self, n_p, n_q):
-        """(tiles per split, number of splits) of one tensor-core pass.  Work items (128-row tile, split) are dealt
-        round-robin to the persistent CTAs, so the pass lasts  ceil(items / CTAs) * (tiles per item + per-item overhead):
-        pick the split length that minimises it (ties: longer items).  Splits never exceed MAX_SPLIT_COLS columns
-        (fp32 running-sum accuracy)."""
+        """(tiles per split, number of splits) of one tensor-core pass, see plans.tc_split_plan."""
         key = ("tc", n_p, n_q)
         if key not in self._splits:
-            row_tiles = (n_p + 127) // 128
-            col_tiles = (n_q + 255) // 256
-            best = None
-            for tps in range(1, min(col_tiles, self.MAX_SPLIT_COLS // 256) + 1):
-                ns = -(-col_tiles // tps)
-                rounds = -(-(row_tiles * ns) // self.n_sm)
-                cost = rounds * (tps + self.TC_ITEM_OVERHEAD_TILES)
-                if best is None or cost <= best[0]:
-                    best = (cost, tps, ns)
-            self._splits[key] = (best[1], best[2])
+            self._splits[key] = plans.tc_split_plan(n_p, n_q, self.n_sm, self.MAX_SPLIT_COLS, self.TC_ITEM_OVERHEAD_TILES)
         return self._splits[key]
 
     def _lse(self, P: PointSet, Q: PointSet, bias, eps, out=None, bounds=None, ns=None, finalize=True, simt=False, row_m=None,
