@@ -115,3 +115,69 @@ def test_row_partitioned_solve_world2_gloo():
     np.testing.assert_allclose(plan2, want2, rtol=1e-9, atol=1e-300)
     np.testing.assert_allclose(out[0]["tab"], ot_dense.transition_table(want, la, lb, 10, 10), rtol=1e-9)
     np.testing.assert_allclose(out[0]["tab"], out[1]["tab"], rtol=1e-14)
+
+
+class _FaultyPredictingOps(NumpyOps):
+    """NumpyOps that claims to predict, corrupts the potentials of its `fail_at`-th verified batch and reports it through
+    settle(): the drivers must restore their snapshot and redo exactly that work (the protocol of CudaOps._Pred)."""
+
+    def __init__(self, x, y, fail_at):
+        super().__init__(x, y)
+        self.fail_at, self.batches, self.pending_fault, self.ok = fail_at, 0, False, True
+        self.redone = 0
+
+    def begin_solve(self, dist=None):
+        self.batches, self.pending_fault, self.ok = 0, False, True
+
+    def predicting(self):
+        return self.ok
+
+    def snapshot(self, st):
+        self.batches += 1
+        if self.batches == self.fail_at:
+            self.pending_fault = True
+        vec = (st.f, st.g, st.u, st.v, st.la_old, st.lb_old, st.Lr, st.Lc)
+        return [t.clone() for t in vec], self.flag.clone(), self._tick
+
+    def restore(self, st, snap):
+        vec = (st.f, st.g, st.u, st.v, st.la_old, st.lb_old, st.Lr, st.Lc)
+        for t, c in zip(vec, snap[0]):
+            t.copy_(c)
+        self.flag.copy_(snap[1])
+        self._tick = snap[2]
+        self.redone += 1
+
+    def potential_update(self, side, L, *args, **kw):
+        if self.pending_fault and self.ok:
+            L = L + 3.0                                   # a mispredicted pass: garbage LSE for this batch
+        return super().potential_update(side, L, *args, **kw)
+
+    def row_lse(self, g, eps, out=None, predict=False):
+        return super().row_lse(g, eps, out)
+
+    def col_lse(self, f, eps, out=None, predict=False):
+        return super().col_lse(f, eps, out)
+
+    def settle(self, dist=None):
+        if self.pending_fault and self.ok:
+            self.pending_fault, self.ok = False, False   # detected: predictions off for the rest of the solve
+            return False
+        return True
+
+
+@pytest.mark.parametrize("fail_at", [1, 4, 17])
+def test_mispredicted_batch_is_redone_from_the_snapshot(fail_at):
+    a, b, _, _ = ot_dense.synthetic_embeddings(60, 50, 5, seed=4)
+    Cn, med = ot_dense.median_normalised_cost(a, b)
+    ref_ops = NumpyOps(a, b)
+    ref_ops.set_median(med)
+    info_ref = {}
+    st_ref, _ = sinkhorn.solve_duality_gap(ref_ops, np.ones(60), info=info_ref, **CFG)
+    ops = _FaultyPredictingOps(a, b, fail_at)
+    ops.set_median(med)
+    info = {}
+    st, _ = sinkhorn.solve_duality_gap(ops, np.ones(60), info=info, **CFG)
+    assert ops.redone == 1 and ops.ok is False
+    assert info["iters_per_stage"] == info_ref["iters_per_stage"]
+    np.testing.assert_allclose(st.f.numpy(), st_ref.f.numpy(), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(st.g.numpy(), st_ref.g.numpy(), rtol=0, atol=1e-12)
