@@ -29,7 +29,7 @@ default_config = {                      # ot_solvers.py:19-36
 }
 
 _SOLVER_KEYS = ("lambda1", "lambda2", "epsilon", "batch_size", "tolerance", "tau", "epsilon0", "max_iter",
-                "scaling_iter", "extra_iter", "inner_iter_max")
+                "scaling_iter", "extra_iter", "inner_iter_max", "profiling")
 
 
 class Coupling:

@@ -186,8 +186,42 @@ def _sweep_body(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_kn
     ops.absorb(it, st.f, st.g, st.u, st.v)                        # ot_func.cpp:778-819
 
 
+class _StageTrace:
+    """The reference's `profiling` switch (config.yaml:56; ot_solvers.py:244-245,437-444): one printed line per epsilon
+    stage with wall time (after a device synchronisation) and iterations, plus an NVTX range per stage for nsys/ncu."""
+
+    def __init__(self, ops, enabled):
+        self.on = bool(enabled)
+        self.cuda = self.on and getattr(getattr(ops, "device", None), "type", "cpu") == "cuda"
+        self.t0 = 0.0
+
+    def _sync(self):
+        if self.cuda:
+            torch.cuda.synchronize()
+
+    def begin(self, e, eps):
+        if not self.on:
+            return
+        import time
+        print("Compute for epsilon scaling {} (epsilon = {:.6g})".format(e, eps))       # ot_solvers.py:245
+        if self.cuda:
+            torch.cuda.nvtx.range_push(f"sinkhorn stage {e} eps={eps:.4g}")
+        self._sync()
+        self.t0 = time.perf_counter()
+
+    def end(self, e, n_it, gap):
+        if not self.on:
+            return
+        import time
+        self._sync()
+        if self.cuda:
+            torch.cuda.nvtx.range_pop()
+        print("  stage {}: {} iterations, {:.3f} ms, criterion {:.3e}".format(e, n_it, 1e3 * (time.perf_counter() - self.t0), gap))
+
+
 def solve_duality_gap(ops, G_local, lambda1, lambda2, epsilon, batch_size=5, tolerance=1e-8, tau=1000.0,
-                      epsilon0=1.0, max_iter=1e7, dist: Dist | None = None, info: dict | None = None, **ignored):
+                      epsilon0=1.0, max_iter=1e7, dist: Dist | None = None, info: dict | None = None, profiling=False,
+                      **ignored):
     """optimal_transport_duality_gap (ot_solvers.py:164-449) on the device.
 
     Returns the state (potentials f,g on the device, row LSE at the final g) and the final epsilon.
@@ -198,10 +232,12 @@ def solve_duality_gap(ops, G_local, lambda1, lambda2, epsilon, batch_size=5, tol
     eps_i = epsilon0 * scale_factor
     log_tau = math.log(tau)
     iters, total, gap = [], 0, math.inf
+    trace = _StageTrace(ops, profiling and dist.rank == 0)
     for e in range(EPSILON_SCALINGS + 1):
         st.u.copy_(st.f)                                          # absorb, ot_solvers.py:249-252
         st.v.copy_(st.g)
         eps_i = eps_i / scale_factor
+        trace.begin(e, eps_i)
         alpha1 = lambda1 / (lambda1 + eps_i)
         alpha2 = lambda2 / (lambda2 + eps_i)
         final = e == EPSILON_SCALINGS
@@ -248,6 +284,7 @@ def solve_duality_gap(ops, G_local, lambda1, lambda2, epsilon, batch_size=5, tol
                 break
         iters.append(n_it)
         total += n_it
+        trace.end(e, n_it, gap)
     if math.isnan(gap):
         raise RuntimeError("Overflow encountered in duality gap computation, please report this incident")
     if not lr_known:

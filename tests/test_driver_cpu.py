@@ -181,3 +181,18 @@ def test_mispredicted_batch_is_redone_from_the_snapshot(fail_at):
     assert info["iters_per_stage"] == info_ref["iters_per_stage"]
     np.testing.assert_allclose(st.f.numpy(), st_ref.f.numpy(), rtol=0, atol=1e-12)
     np.testing.assert_allclose(st.g.numpy(), st_ref.g.numpy(), rtol=0, atol=1e-12)
+
+
+def test_profiling_flag_prints_one_trace_line_per_stage(capsys):
+    """config.yaml's ot_config.profiling (ot_solvers.py:244-245): per-stage trace, results unchanged."""
+    a, b, _, _ = ot_dense.synthetic_embeddings(40, 30, 4, seed=1)
+    _, med = ot_dense.median_normalised_cost(a, b)
+    ops = NumpyOps(a, b)
+    ops.set_median(med)
+    info = {}
+    sinkhorn.solve_duality_gap(ops, np.ones(40), info=info, **dict(CFG, profiling=True))
+    out = capsys.readouterr().out
+    assert out.count("Compute for epsilon scaling") == 6
+    assert out.count("iterations,") == 6 and "stage 5: %d iterations" % info["iters_per_stage"][5] in out
+    sinkhorn.solve_duality_gap(ops, np.ones(40), **CFG)
+    assert capsys.readouterr().out == ""
