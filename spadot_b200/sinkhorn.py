@@ -232,6 +232,7 @@ def solve_duality_gap(ops, G_local, lambda1, lambda2, epsilon, batch_size=5, tol
     eps_i = epsilon0 * scale_factor
     log_tau = math.log(tau)
     iters, total, gap = [], 0, math.inf
+    hit_max_iter = False
     trace = _StageTrace(ops, profiling and dist.rank == 0)
     for e in range(EPSILON_SCALINGS + 1):
         st.u.copy_(st.f)                                          # absorb, ot_solvers.py:249-252
@@ -281,6 +282,11 @@ def solve_duality_gap(ops, G_local, lambda1, lambda2, epsilon, batch_size=5, tol
                 if math.isnan(gap):
                     break        # `while (nan > threshold)` is false in the reference as well
             if n_it >= max_iter:
+                # the reference announces this and gives up on the stage (ot_solvers.py:339-341, ot_func.cpp:821-824);
+                # like its native path the iteration budget is per stage (current_iter is passed as 0, ot_solvers.py:288)
+                import warnings
+                warnings.warn("Reached max_iter with duality gap still above threshold. Returning", RuntimeWarning, stacklevel=2)
+                hit_max_iter = True
                 break
         iters.append(n_it)
         total += n_it
@@ -290,7 +296,7 @@ def solve_duality_gap(ops, G_local, lambda1, lambda2, epsilon, batch_size=5, tol
     if not lr_known:
         ops.row_lse(st.g, eps_i, out=st.Lr)
     if info is not None:
-        info.update(iters_per_stage=iters, total_iters=total, gap=float(gap), epsilon_final=eps_i)
+        info.update(iters_per_stage=iters, total_iters=total, gap=float(gap), epsilon_final=eps_i, max_iter_reached=hit_max_iter)
     return st, eps_i
 
 

@@ -196,3 +196,15 @@ def test_profiling_flag_prints_one_trace_line_per_stage(capsys):
     assert out.count("iterations,") == 6 and "stage 5: %d iterations" % info["iters_per_stage"][5] in out
     sinkhorn.solve_duality_gap(ops, np.ones(40), **CFG)
     assert capsys.readouterr().out == ""
+
+
+def test_max_iter_warns_and_returns_like_the_reference():
+    a, b, _, _ = ot_dense.synthetic_embeddings(30, 25, 4, seed=2)
+    _, med = ot_dense.median_normalised_cost(a, b)
+    ops = NumpyOps(a, b)
+    ops.set_median(med)
+    info = {}
+    with pytest.warns(RuntimeWarning, match="Reached max_iter with duality gap still above threshold"):
+        st, _ = sinkhorn.solve_duality_gap(ops, np.ones(30), info=info, **dict(CFG, max_iter=5))
+    assert info["max_iter_reached"] and info["iters_per_stage"] == [5] * 6       # the budget is per stage (ot_solvers.py:288)
+    assert torch.isfinite(st.f).all() and torch.isfinite(st.g).all()
