@@ -92,8 +92,13 @@ class _PlanDownload:
     """Device -> pinned host copy of a dense plan on a side stream; `result()` waits for it and returns the ndarray
     (a view of the pinned buffer, owned by the returned array)."""
 
+    PINNED_MAX_BYTES = 1 << 28       # beyond this, page-locking the buffer costs more than it hides: plain copy at the end
+
     def __init__(self, plan_dev):
         self.dev = plan_dev
+        self.done = None
+        if plan_dev.numel() * plan_dev.element_size() > self.PINNED_MAX_BYTES:
+            return
         self.host = torch.empty(plan_dev.shape, dtype=plan_dev.dtype, pin_memory=True)
         cur = torch.cuda.current_stream(plan_dev.device)
         self.stream = torch.cuda.Stream(plan_dev.device)
@@ -103,6 +108,10 @@ class _PlanDownload:
         self.done = self.stream.record_event()
 
     def result(self):
+        if self.done is None:
+            out = self.dev.cpu().numpy()
+            self.dev = None
+            return out
         self.done.synchronize()
         self.dev = None
         return self.host.numpy()
