@@ -76,6 +76,12 @@ int sdb_absmax_centered_f64(const double* x, int64_t n, int d, const double* cen
  * norms[i] = sum_k ((hi+lo) * 2^-pow2_exp)^2 in fp64.  dp in {16,32,64} >= d; rows [n, n_pad) are zero; n_pad % 256 == 0. */
 int sdb_prep_points_split_f16(const double* x, int64_t n, int d, const double* center, int pow2_exp,
                               void* out16, int64_t n_pad, int dp, double* norms, void* stream);
+/* The same with an arbitrary positive prescale q instead of 2^pow2_exp: v = (x-center)*q, norms of (hi+lo)/q.  The streamed
+ * solver folds the whole exponent scale into the points, q^2 * S = 2*c1*log2(e) with S a power of two, so that the `scale`
+ * argument of sdb_lse_pass_tc is exactly representable in fp32 (an fp32-rounded scale is a 2^-24 relative error common to
+ * every term of every row: a systematic bias of the plan that grows like 1/eps). */
+int sdb_prep_points_split_f16_scaled(const double* x, int64_t n, int d, const double* center, double prescale,
+                                     void* out16, int64_t n_pad, int dp, double* norms, void* stream);
 /* Same contract as sdb_lse_pass_simt with scale already multiplied by 2^(-2*pow2_exp); splits are
  * runs of `tiles_per_split` 256-column tiles: n_splits = ceil(ceil(n_q/256)/tiles_per_split) and
  * partial holds n_splits*n_p (max,sum) pairs.  bias_padded has n_q_pad entries (see sdb_make_bias).
@@ -321,6 +327,14 @@ int sdb_kmeans_inertia(const double* X, const double* centers, const int32_t* la
 int sdb_kmeans_lloyd_runs(const double* X, int64_t n, int d, int k, const double* centers_init, int n_runs, int max_iter,
                           double tol, int32_t* labels_out, double* centers_out, double* inertia_out, int32_t* n_iter_out,
                           int32_t* status_out, void* stream);
+
+/* ------------------------------------------------------------------ pipe micro-benchmarks (roofline denominators) */
+/* One launch of n_ctas x 512 threads running `iters` rounds of independent chains of one instruction kind:
+ * kind 0 = MUFU.EX2 (ex2.approx.ftz.f32), 1 = FFMA, 2 = FFMA2 (fma.rn.f32x2), 3 = the epilogue's mix per two pairs
+ * (FFMA2, FADD2, 2 x MUFU.EX2, FADD2; counted in ex2).  *ops_out_host (HOST pointer, may be NULL) receives the number of
+ * operations of that kind the launch executes (ex2 evaluations, or FMAs = 2 flop each); the caller times the launch.
+ * `out` needs n_ctas*512 floats and is never written.  SURVEY.md 8(d): "to be confirmed by a micro-benchmark on the box". */
+int sdb_pipe_peak(int kind, int n_ctas, int iters, float* out, double* ops_out_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,7 @@ SIGNATURES = {
     "sdb_make_bias": [c_l, c_l, c_p, c_p, c_d, c_d, c_p, c_p],
     "sdb_absmax_centered_f64": [c_p, c_l, c_i, c_p, c_p, c_p],
     "sdb_prep_points_split_f16": [c_p, c_l, c_i, c_p, c_i, c_p, c_l, c_i, c_p, c_p],
+    "sdb_prep_points_split_f16_scaled": [c_p, c_l, c_i, c_p, c_d, c_p, c_l, c_i, c_p, c_p],
     "sdb_lse_pass_tc": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_i, c_i, c_p, c_p],
     "sdb_absorb": [c_l, c_l, c_p, c_i, c_p, c_p, c_p, c_p, c_p],
     "sdb_stage_criterion": [c_l, c_l, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_p, c_p, c_p],
@@ -63,6 +64,7 @@ SIGNATURES = {
     "sdb_kmeans_inertia": [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p],
     "sdb_kmeans_lloyd_runs": [c_p, c_l, c_i, c_i, c_p, c_i, c_i, c_d, c_p, c_p, c_p, c_p, c_p, c_p],
     "sdb_knn_f64": [c_p, c_l, c_i, c_i, c_p, c_p, c_p],
+    "sdb_pipe_peak": [c_i, c_i, c_i, c_p, c_p, c_p],
     "sdb_gat_backward": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
 }
 

@@ -905,9 +905,14 @@ int sdb_absmax_centered_f64(const double* x, int64_t n, int d, const double* cen
 
 int sdb_prep_points_split_f16(const double* x, int64_t n, int d, const double* center, int pow2_exp, void* out16, int64_t n_pad,
                               int dp, double* norms, void* stream) {
+    return sdb_prep_points_split_f16_scaled(x, n, d, center, ldexp(1.0, pow2_exp), out16, n_pad, dp, norms, stream);
+}
+
+int sdb_prep_points_split_f16_scaled(const double* x, int64_t n, int d, const double* center, double prescale, void* out16,
+                                     int64_t n_pad, int dp, double* norms, void* stream) {
     SDB_CHECK_ARG(x && center && out16 && norms && d > 0 && dp >= d && (dp == 16 || dp == 32 || dp == 64) && n_pad >= n &&
-                  (n_pad % TILE_N) == 0);
-    prep_split_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, sdb_stream(stream)>>>(x, n, d, center, ldexp(1.0, pow2_exp),
+                  (n_pad % TILE_N) == 0 && prescale > 0.0);
+    prep_split_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, sdb_stream(stream)>>>(x, n, d, center, prescale,
                                                                                        reinterpret_cast<__half*>(out16), n_pad, dp, norms);
     SDB_LAUNCH_STATUS();
 }

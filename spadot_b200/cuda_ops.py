@@ -47,15 +47,17 @@ class PointSet:
                   _ptr(self.norms), st)
         self.x16 = None          # fp16 hi/lo split for the tensor-core pass (built on demand)
 
-    def build_split(self, center, pow2_exp):
-        """fp16 hi/lo split [n_pad][2*dp] (+ fp64 norms of the represented points) for sdb_lse_pass_tc."""
-        self.dp = 16 if self.d <= 16 else 32 if self.d <= 32 else 64
-        self.n_pad = _round_up(max(self.n, 1), 256)
-        self.x16 = torch.empty((self.n_pad, 2 * self.dp), dtype=torch.float16, device=self.x64.device)
-        self.norms16 = torch.empty(self.n, dtype=torch.float64, device=self.x64.device)
+    def build_split(self, center, prescale):
+        """fp16 hi/lo split [n_pad][2*dp] of (x - center) * prescale (+ fp64 norms of the represented points) for
+        sdb_lse_pass_tc.  Rebuilt in place when the prescale changes (CudaOps._prep)."""
+        if self.x16 is None:
+            self.dp = 16 if self.d <= 16 else 32 if self.d <= 32 else 64
+            self.n_pad = _round_up(max(self.n, 1), 256)
+            self.x16 = torch.empty((self.n_pad, 2 * self.dp), dtype=torch.float16, device=self.x64.device)
+            self.norms16 = torch.empty(self.n, dtype=torch.float64, device=self.x64.device)
         st = torch.cuda.current_stream(self.x64.device).cuda_stream
-        _lib.call("sdb_prep_points_split_f16", _ptr(self.x64), self.n, self.d, _ptr(center), pow2_exp, _ptr(self.x16),
-                  self.n_pad, self.dp, _ptr(self.norms16), st)
+        _lib.call("sdb_prep_points_split_f16_scaled", _ptr(self.x64), self.n, self.d, _ptr(center), float(prescale),
+                  _ptr(self.x16), self.n_pad, self.dp, _ptr(self.norms16), st)
 
 
 class VectorOps:
@@ -216,13 +218,10 @@ class CudaOps(VectorOps):
             amax = torch.zeros(1, dtype=torch.float64, device=self.device)
             self._call("sdb_absmax_centered_f64", _ptr(x64), self.n, self.d, _ptr(center), _ptr(amax))
             self._call("sdb_absmax_centered_f64", _ptr(y64), self.m, self.d, _ptr(center), _ptr(amax))
-            amax = float(amax.item())
-            # scale so that the largest |coordinate| lands in [2^13, 2^14): fp16 hi+lo then carries 22 bits
-            self.pow2_exp = 14 - (math.frexp(amax)[1] if amax > 0 else 0)
-            self.X.build_split(center, self.pow2_exp)
-            self.Y.build_split(center, self.pow2_exp)
-            self.launches += 2
+            self.amax = float(amax.item())
             self.n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+            self._split_key = None
+            self._build_splits(None)
         self._splits = {}
         self._partials = {}
         self.inv_med = 1.0
@@ -234,6 +233,49 @@ class CudaOps(VectorOps):
     # ------------------------------------------------------------------ plumbing
     def set_median(self, median: float):
         self.inv_med = 1.0 / float(median)
+
+    # Exact exponent scale.  A pass evaluates 2^(bias_j + S * (x^.y^)) with x^ = (x - centre) * q split into fp16 hi + lo.
+    # q^2 * S = 2*c1*log2(e) * (1 + TC_TRUNC_COMP), c1 = 1/(median*eps), and S is a POWER OF TWO: the only fp32 constant that
+    # multiplies the accumulator is then exact.  (With q a fixed power of two, S was an arbitrary real rounded to fp32: a
+    # relative error of up to 2^-24 = 6e-8 common to every term.  Dominant terms have S*(x^.y^) ~ 2*c1*|x|^2*log2(e), ~30
+    # at eps = 0.05 but ~150 at eps = 0.01 for BASELINE's mixture, so that one rounding alone biased every LSE by up to
+    # 6e-6 — and through the fixed point every plan entry by the same relative amount.)
+    # TC_TRUNC_COMP compensates the tensor core's accumulate: tcgen05.mma adds each K=16 step into its fp32 accumulator with
+    # truncation toward zero, i.e. a mean error of -1/2 ulp per step at the magnitude of the running sum.  The hi.hi chain
+    # (issued last, the cross chains are 2^-11 of it) has ks = dp/16 steps with running sums ~ (j/ks) of the dot product D:
+    # mean error -1/2 * sum_j (j/ks) * E[ulp/x] * D = -(ks+1)/4 * 0.7213 * 2^-23 * D for log-uniform mantissas
+    # (tools/tc_precision.py measures the residual bias), which the prescale gives back.  What is left is the random part,
+    # +-1/2 ulp per step and pair, which averages out over the columns of a sum.
+    TC_TRUNC_COMP_PER_KSTEP = float(os.environ.get("SDB_TC_TRUNC_COMP", "1.0"))
+
+    def _trunc_comp(self):
+        ks = self.X.dp // 16
+        return self.TC_TRUNC_COMP_PER_KSTEP * (ks + 1) / 4.0 * 0.7213 * 2.0 ** -23
+
+    def _build_splits(self, eps):
+        """(Re)build the fp16 hi/lo splits for the exponent scale of `eps` (None: plain power-of-two prescale, used by the
+        median sweeps before any eps is known).  Largest |coordinate| * q stays in [2^12.5, 2^13.5): hi + lo carry 22 bits."""
+        e = math.frexp(self.amax)[1] if self.amax > 0 else 0
+        q0 = 2.0 ** (13 - e)                                  # amax * q0 in [2^12, 2^13)
+        if eps is None:
+            key, q, S = None, 2.0 * q0, None
+        else:
+            T = 2.0 * (self.inv_med / eps) * math.log2(math.e) * (1.0 + self._trunc_comp())
+            k = round(math.log2(T / (2.0 * q0 * q0)) - 0.5)  # S = 2^k, q = sqrt(T/S) in [q0*sqrt2, 2*q0*sqrt2)
+            S = 2.0 ** k
+            q = math.sqrt(T / S)
+            key = (eps, self.inv_med)
+        self.X.build_split(self.center, q)
+        self.Y.build_split(self.center, q)
+        self.launches += 2
+        self.prescale, self.tc_scale, self._split_key = q, S, key
+        self._nx32 = None
+        self._bias_key = {"x": None, "y": None}
+
+    def _prep(self, eps):
+        """Called by every operation that takes eps, before anything derived from the split points (norms, bias) is used."""
+        if self.use_tc and self._split_key != (eps, self.inv_med):
+            self._build_splits(eps)
 
     def _split_plan(self, n_p, n_q):
         key = (n_p, n_q)
@@ -329,10 +371,11 @@ class CudaOps(VectorOps):
         c1 = self.inv_med / eps
         scale = 2.0 * c1 * math.log2(math.e)
         if self.use_tc and not simt:
+            assert self._split_key == (eps, self.inv_med), "CudaOps._prep(eps) must run before a tensor-core pass"
             tps, ns = self._tc_split_plan(P.n, Q.n)
             partial = self._partial(ns, P.n)
             self._call("sdb_lse_pass_tc_pred", _ptr(P.x16), P.n, P.n_pad, _ptr(Q.x16), Q.n, Q.n_pad, P.dp, _ptr(bias),
-                       scale * 2.0 ** (-2 * self.pow2_exp), tps, self.n_sm, _ptr(row_m), _ptr(partial))
+                       self.tc_scale, tps, self.n_sm, _ptr(row_m), _ptr(partial))
             norms = P.norms16
         else:
             if bounds is None:
@@ -363,6 +406,7 @@ class CudaOps(VectorOps):
         """Lr_i = LSE_j[(g_j - C_ij)/eps] over all columns (natural log, fp64).  g=None means g=0.
         predict=True (the solver's own potential only): may use / refresh the predicted stabiliser; the caller must
         `settle()` before trusting the result."""
+        self._prep(eps)
         self._call("sdb_make_bias", self.m, self.bias_y.numel(), _ptr(g), _ptr(self._norms(self.Y)), eps,
                    self.inv_med / eps, _ptr(self.bias_y))
         self._bias_key["y"] = (_ptr(g), eps, self.inv_med) if g is not None else None
@@ -384,6 +428,7 @@ class CudaOps(VectorOps):
 
     def fused_sweeps(self, st, eps, alpha1, alpha2, log_tau, log_floor, n_sweeps, lr_known_first):
         """n_sweeps full iterations issued by the native loop sdb_sinkhorn_sweeps (single rank)."""
+        self._prep(eps)
         d = _lib.SweepDesc()
         d.n, d.m, d.n_total = self.n, self.m, st.N
         d.use_tc = int(self.use_tc)
@@ -394,7 +439,8 @@ class CudaOps(VectorOps):
             d.x16, d.n_pad, d.y16, d.m_pad = _ptr(self.X.x16), self.X.n_pad, _ptr(self.Y.x16), self.Y.n_pad
             d.tps_row, d.ns_row = self._tc_split_plan(self.n, self.m)
             d.tps_col, d.ns_col = self._tc_split_plan(self.m, self.n)
-            d.pow2_scale = 2.0 ** (-2 * self.pow2_exp)
+            # the native loop multiplies 2*c1*log2(e) by this factor and rounds to fp32: exactly the power of two S
+            d.pow2_scale = self.tc_scale / (2.0 * (self.inv_med / eps) * math.log2(math.e))
         else:
             b_row, d.ns_row = self._split_plan(self.n, self.m)
             b_col, d.ns_col = self._split_plan(self.m, self.n)
@@ -456,6 +502,7 @@ class CudaOps(VectorOps):
         else:
             P, Q, pot_in, pot, L, logmarg, frame, la, bias_in, bias_out, kin, kout, n_other = \
                 self.Y, self.X, st.f, st.g, st.Lc, st.logq, st.v, st.lb_old, self.bias_x, self.bias_y, "x", "y", st.N
+        self._prep(eps)
         c1 = self.inv_med / eps
         key = (_ptr(pot_in), eps, self.inv_med)
         if lse_known:
@@ -478,6 +525,7 @@ class CudaOps(VectorOps):
         if self.n == 0:
             out = torch.empty(self.m, dtype=torch.float64, device=self.device) if out is None else out
             return out.fill_(NEG_INF)
+        self._prep(eps)
         self._call("sdb_make_bias", self.n, self.bias_x.numel(), _ptr(f), _ptr(self._norms(self.X)), eps,
                    self.inv_med / eps, _ptr(self.bias_x))
         self._bias_key["x"] = (_ptr(f), eps, self.inv_med) if f is not None else None
@@ -490,6 +538,10 @@ class CudaOps(VectorOps):
 
     def _c1(self, eps):
         return self.inv_med / eps
+
+    def potential_update(self, side, L, logmarg, eps, *args, **kw):
+        self._prep(eps)
+        return super().potential_update(side, L, logmarg, eps, *args, **kw)
 
     def _bias_out(self, side, pot, eps):
         # the potential changes in place: the cached bias vector of that side must follow it (the cache is keyed by
@@ -528,7 +580,7 @@ class CudaOps(VectorOps):
             nx, ny = self._sweep_norms()
             tps, _ = self._tc_split_plan(self.n, self.m)
             self._call("sdb_cost_histogram_tc", _ptr(self.X.x16), self.n, self.X.n_pad, _ptr(self.Y.x16), self.m, self.Y.n_pad,
-                       self.X.dp, _ptr(nx), _ptr(ny), -2.0 * 2.0 ** (-2 * self.pow2_exp), tps, self.n_sm, lo, hi, n_bins,
+                       self.X.dp, _ptr(nx), _ptr(ny), -2.0 / (self.prescale * self.prescale), tps, self.n_sm, lo, hi, n_bins,
                        _ptr(hist), _ptr(counts))
             return hist, counts
         bounds, ns = self._split_plan(self.n, self.m)
@@ -543,7 +595,7 @@ class CudaOps(VectorOps):
             nx, ny = self._sweep_norms()
             tps, _ = self._tc_split_plan(self.n, self.m)
             self._call("sdb_cost_collect_tc", _ptr(self.X.x16), self.n, self.X.n_pad, _ptr(self.Y.x16), self.m, self.Y.n_pad,
-                       self.X.dp, _ptr(nx), _ptr(ny), -2.0 * 2.0 ** (-2 * self.pow2_exp), tps, self.n_sm, lo, hi,
+                       self.X.dp, _ptr(nx), _ptr(ny), -2.0 / (self.prescale * self.prescale), tps, self.n_sm, lo, hi,
                        _ptr(self.X.x64), _ptr(self.Y.x64), self.d, _ptr(cand), cap, _ptr(counts))
             return cand, counts
         bounds, ns = self._split_plan(self.n, self.m)

@@ -56,11 +56,15 @@ _GRAPH_CACHE: dict = {}
 
 def graph_for(edge_index, num_nodes, add_self_loops=True):
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, num_nodes, add_self_loops, str(edge_index.device))
-    g = _GRAPH_CACHE.get(key)
-    if g is None:
-        if len(_GRAPH_CACHE) > 64:
-            _GRAPH_CACHE.clear()
-        g = _GRAPH_CACHE[key] = CsrGraph(edge_index, num_nodes, add_self_loops)
+    hit = _GRAPH_CACHE.get(key)
+    # the entry keeps the edge_index tensor alive, so its address cannot be recycled by the caching allocator for another
+    # batch's edges while the entry exists; a hit must be the very same tensor object
+    if hit is not None and hit[0] is edge_index:
+        return hit[1]
+    if len(_GRAPH_CACHE) > 64:
+        _GRAPH_CACHE.clear()
+    g = CsrGraph(edge_index, num_nodes, add_self_loops)
+    _GRAPH_CACHE[key] = (edge_index, g)
     return g
 
 

@@ -7,8 +7,8 @@ adjacency and without torch_geometric.
   (by source, then target).
 * `knn_cutoff(n)` = `min(30, 6 * round(n / 1000))`  (utils/_train_utils.py:69).
 * `two_hop_batches(...)` stands in for `NeighborLoader(num_neighbors=[f, f], batch_size, input_nodes=None)`
-  (utils/_train_utils.py:80-85) for the case the reference always runs in (fan-out >= every in-degree, no
-  shuffling): seeds first, then newly reached nodes; edges = every edge into a seed or into a 1-hop node.
+  (utils/_train_utils.py:80-85, `subgraph_type="induced"`, no shuffling): seeds first, then newly reached nodes;
+  edges = the induced sub-graph of the sampled nodes (see `two_hop_batches` for the fan-out deviation).
 """
 from __future__ import annotations
 
@@ -63,22 +63,30 @@ class InNeighbours:
 
 
 def two_hop_batches(edge_index, num_nodes, batch_size=512, num_hops=2):
-    """Yields (node_ids, local_edge_index, n_seeds): seeds are node_ids[:n_seeds] in sequential order."""
+    """Yields (node_ids, local_edge_index, n_seeds): seeds are node_ids[:n_seeds] in sequential order.
+
+    Node set = seeds, then the nodes newly reached by each hop over incoming edges; edge set = the INDUCED sub-graph,
+    i.e. every edge of the full graph whose source and target were both sampled (`subgraph_type="induced"`,
+    utils/_train_utils.py:80-85) — the encoder has three GAT layers over a 2-hop batch, so the 2-hop nodes must
+    aggregate from their sampled in-neighbours and not only from their self loop.
+    Known deviation: the reference's fan-out is max(30, 6*round(N/1000)) per hop; a node whose in-degree (self loop
+    included) exceeds it is randomly sub-sampled there (PyG's C++ RNG, not reproducible), here every in-neighbour is
+    taken.  With k <= 12 (N < 2500, all ChickenHeart timepoints) in-degrees stay far below 30."""
     nb = InNeighbours(edge_index, num_nodes)
     dev = edge_index.device
+    local = torch.full((num_nodes,), -1, dtype=torch.long, device=dev)     # one map, reset per batch where touched
     for s0 in range(0, num_nodes, batch_size):
         seeds = torch.arange(s0, min(num_nodes, s0 + batch_size), device=dev)
         nodes, frontier = seeds, seeds
-        local = torch.full((num_nodes,), -1, dtype=torch.long, device=dev)
         local[seeds] = torch.arange(seeds.numel(), device=dev)
-        es, et = [], []
         for _ in range(num_hops):
-            s, t = nb.edges_into(frontier)
-            es.append(s)
-            et.append(t)
+            s, _t = nb.edges_into(frontier)
             new = torch.unique(s[local[s] < 0])
             local[new] = torch.arange(nodes.numel(), nodes.numel() + new.numel(), device=dev)
             nodes = torch.cat([nodes, new])
             frontier = new
-        s, t = torch.cat(es), torch.cat(et)
-        yield nodes, torch.stack([local[s], local[t]]), int(seeds.numel())
+        s, t = nb.edges_into(nodes)
+        keep = local[s] >= 0
+        lei = torch.stack([local[s[keep]], local[t[keep]]])
+        local[nodes] = -1
+        yield nodes, lei, int(seeds.numel())

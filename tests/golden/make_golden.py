@@ -129,6 +129,38 @@ def model_case(name="model_small", seed=5):
     print(name, "written; losses", float(recon), float(skl), float(gkl), float(align))
 
 
+def visium_like_coords(n, seed, jitter=0.35):
+    """Hexagonal lattice in pixel units (100 px pitch) with sub-pixel registration jitter, cropped to n spots: the
+    geometry of a Visium capture area (ChickenHeart).  The jitter breaks the exact distance ties of an ideal lattice,
+    as real full-resolution pixel coordinates do."""
+    rng = np.random.default_rng(seed)
+    side = int(np.ceil(np.sqrt(n))) + 2
+    pts = np.array([[i + 0.5 * (j % 2), j * np.sqrt(3) / 2] for j in range(side) for i in range(side)]) * 100.0
+    keep = np.sort(rng.permutation(pts.shape[0])[:n])          # tissue does not cover the whole lattice
+    return pts[keep] + rng.normal(0.0, jitter, size=(n, 2))
+
+
+def graph_case(name, n, seed, kind):
+    """edge_index of the reference's own `_Cal_Spatial_Net` + dense_to_sparse (utils/_utils.py:52-100,
+    utils/_train_utils.py:69-72) at ChickenHeart sizes; the edge counts printed by the reference must be those of
+    examples/ChickenHeart.ipynb:221-230 (4482 @ 747 spots, 23592 @ 1966 spots)."""
+    k = int(min(30, 6 * round(n / 1000)))                       # utils/_train_utils.py:69
+    coords = visium_like_coords(n, seed) if kind == "visium" else np.random.default_rng(seed).uniform(0, 6000, size=(n, 2))
+    ei, log = reference_loader.reference_edge_index(coords, k)
+    n_edges = int(log.split("The graph contains ")[1].split(" edges")[0])
+    assert n_edges == n * k and ei.shape[1] == n * (k + 1)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), coords=coords, edge_index=ei.astype(np.int32), k=np.array(k),
+                        printed_edges=np.array(n_edges))
+    print(name, "written;", log.strip().splitlines()[1])
+
+
+if __name__ == "__main__" and "--graph-only" in sys.argv:
+    graph_case("graph_visium_747", 747, 21, "visium")
+    graph_case("graph_visium_1966", 1966, 22, "visium")
+    graph_case("graph_uniform_1916", 1916, 23, "uniform")
+    sys.exit(0)
+
+
 if __name__ == "__main__" and "--model-only" in sys.argv:
     model_case()
 
@@ -144,3 +176,6 @@ if __name__ == "__main__" and "--model-only" not in sys.argv:
     ot_case(ref, "ot_wotcfg_130x97_d32", 130, 97, 32, 13, wot_cfg, full_plan=False)
     svgp_case(reference_loader.load_svgp())
     model_case()
+    graph_case("graph_visium_747", 747, 21, "visium")
+    graph_case("graph_visium_1966", 1966, 22, "visium")
+    graph_case("graph_uniform_1916", 1916, 23, "uniform")

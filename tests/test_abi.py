@@ -116,3 +116,25 @@ def test_libot_drop_in_reports_missing_device():
         pytest.skip("CUDA present")
     from spadot_b200 import ot_func
     assert ot_func.lib.libot_b200_device_check() != 0      # compute entry points abort the process in this state
+
+
+def test_reference_ctypes_layer_binds_libot_b200_unmodified():
+    """The reference's own ot_func.py (SpaDOT/utils/OT_loss/ot_func.py:8-315) executed with `LoadLibrary` resolving to
+    libot_b200.so: every `lib.<name>.argtypes = ...` statement of the reference must find its symbol, and the reference's
+    ot_solvers.py must import on top of it.  No compute call is made (no GPU here); tests/test_gpu_libot.py runs the
+    reference's solver through this binding on the device."""
+    import sys
+    from oracle import reference_loader
+    if not (reference_loader.available() or reference_loader.compiled_available()):
+        pytest.skip("neither /root/reference nor oracle/_ref/pyref is present")
+    from spadot_b200 import ot_func
+    mod = reference_loader.load_ot_solvers(lib_path=ot_func.LIB_PATH, tag="_spadot_ref_abi")
+    ref_ot_func = sys.modules["_spadot_ref_abi.ot_func"]
+    assert os.path.realpath(ref_ot_func.lib._name) == os.path.realpath(ot_func.LIB_PATH)
+    for name in ("dummy", "primal", "dual", "compute_duality_gap", "update_k", "update_R"):
+        for sfx in ("float", "double"):
+            assert getattr(ref_ot_func.lib, f"{name}_{sfx}").argtypes is not None
+    assert len(ref_ot_func.lib.update_process_double.argtypes) == 26      # the reference's own (short) declaration
+    for fn in ("update_K_c", "update_R_c", "step1_process_c", "update_process_c", "compute_duality_gap_c"):
+        assert callable(getattr(ref_ot_func, fn))
+    assert callable(mod.optimal_transport_duality_gap) and callable(mod.compute_transport_map)

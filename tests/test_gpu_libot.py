@@ -194,3 +194,46 @@ def test_reference_driver_module_runs_on_the_drop_in(libs):
         close(x, y, 1e-9)
     launches, h2d, d2h = ot_func.counters()
     assert launches > 0 and h2d > 0 and d2h > 0
+
+
+# ------------------------------------------------------------------ the UNMODIFIED reference driver on the drop-in
+def _reference_driver_on(lib_path, tag):
+    from oracle import reference_loader
+    if not (reference_loader.available() or reference_loader.compiled_available()):
+        pytest.skip("neither /root/reference nor oracle/_ref/pyref (its byte-compiled driver) is present")
+    return reference_loader.load_ot_solvers(lib_path=lib_path, tag=tag)
+
+
+@pytest.mark.parametrize("name", ["ot_small_48x61_d6", "ot_growth_90x70_d20", "ot_medium_300x411_d20", "ot_wotcfg_130x97_d32"])
+def test_unmodified_reference_solver_text_runs_on_libot_b200(libs, golden_dir, name):
+    """INTEGRATION.md section 5, executed: the reference's own ot_func.py + ot_solvers.py (source where /root/reference is
+    mounted, else the byte-compiled copies of oracle/_ref/pyref), with NOTHING changed but the library that
+    `ctypes.cdll.LoadLibrary` (ot_func.py:10) resolves — libot_b200.so instead of libot.so.  Its
+    `optimal_transport_duality_gap(use_C=True)` (ot_solvers.py:164-449, native loop :283-290) and `compute_transport_map`
+    (:95-121) must reproduce the golden vectors that the same text produced on the reference's shipped libot.so."""
+    import contextlib
+    import io
+    ot_func, _, _ = libs
+    ref = _reference_driver_on(ot_func.LIB_PATH, "_spadot_ref_on_b200")
+    bound = os.path.realpath(__import__("sys").modules["_spadot_ref_on_b200.ot_func"].lib._name)
+    assert bound == os.path.realpath(ot_func.LIB_PATH)
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    cfg = {k: float(v) for k, v in zip(z["cfg_keys"], z["cfg_vals"])}
+    for k in ("growth_iters", "batch_size", "scaling_iter", "inner_iter_max", "extra_iter"):
+        cfg[k] = int(cfg[k])
+    cfg.update(use_C=True, use_Py=False, profiling=False)
+    a, b, G = z["a"], z["b"], z["G"]
+    C = ot_dense.sqeuclidean(a, b)
+    Cn = C / z["median"]
+    launches0 = ot_func.counters()[0]
+    with contextlib.redirect_stdout(io.StringIO()):
+        plan = ref.optimal_transport_duality_gap(C=Cn.copy(), G=G.copy(), **cfg)
+        gamma0 = ref.compute_transport_map(a, b, dict(cfg), G=G.copy())
+    assert ot_func.counters()[0] > launches0            # the device library did the work
+    np.testing.assert_allclose(plan.sum(1), z["gap_row_sums"], rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(plan.sum(0), z["gap_col_sums"], rtol=1e-9, atol=1e-300)
+    if "plan_gap" in z:
+        np.testing.assert_allclose(plan, z["plan_gap"], rtol=1e-8, atol=1e-300)
+    else:
+        np.testing.assert_allclose(plan[z["sample_i"], z["sample_j"]], z["plan_gap_samples"], rtol=1e-8, atol=1e-300)
+    np.testing.assert_allclose(gamma0, plan, rtol=1e-9, atol=1e-300)       # gammas[0] of the growth loop, ot_solvers.py:121
