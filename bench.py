@@ -7,13 +7,20 @@ dim 32; BASELINE.json configs[3]) at the final-stage regularisation eps=0.05, la
 potential updates + tau bookkeeping, i.e. 2*N*M kernel evaluations.
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path (oracle/_ref)
+  python bench.py --impl reference --steps K --warmup W    # the reference's own CPU path
 
 N > 1: launched by torchrun, one rank per GPU; source spots (rows) are partitioned across ranks,
-target spots are replicated, the column pass is followed by the all-reduce pair of
-spadot_b200.sinkhorn.combine_col_lse.  Total work is fixed => "scaling": "strong".
+target spots are replicated, the column pass is followed by ONE all-reduce (sum) of the M-vector of
+partial sums against a shift every rank already holds.  Total work is fixed => "scaling": "strong".
+
+Reference arm: the reference's UNMODIFIED solver text (`compute_transport_map` ->
+`optimal_transport_duality_gap`, SpaDOT/utils/OT_loss/ot_solvers.py:95-449) imported from /root/reference
+where mounted, else from its byte-compiled copy in oracle/_ref/pyref, on a dense sample that fits host
+memory, rescaled by N*M; BLAS threads are set explicitly (torchrun exports OMP_NUM_THREADS=1).
 """
 import argparse
+import contextlib
+import io
 import json
 import math
 import os
@@ -40,9 +47,11 @@ def parse():
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--m", type=int, default=1_000_000)
     ap.add_argument("--d", type=int, default=32)
-    ap.add_argument("--cpu-sample", type=int, default=8192, help="rows=cols of the dense CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=None,
+                    help="rows=cols of the dense CPU sample (default 8192 for --impl reference, 4096 for the cpu_baseline leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the train-epoch aux measurement (N=1 only)")
+    ap.add_argument("--no-full-solve", action="store_true", help="skip the end-to-end full solve (e2e falls back to fixed steps)")
     ap.add_argument("--tc", default="auto", choices=["auto", "on", "off"], help="tensor-core (tcgen05) pass")
     return ap.parse_args()
 
@@ -60,68 +69,93 @@ def synth(n, m, d, seed=1993):
     return x, y
 
 
+def ot_config():
+    return dict(growth_iters=1, epsilon=EPS, epsilon0=1.0, lambda1=LAM1, lambda2=LAM2, tau=TAU, scaling_iter=3000,
+                inner_iter_max=50, tolerance=1e-8, max_iter=1e7, batch_size=5, extra_iter=1000, use_Py=False, use_C=True,
+                profiling=False)
+
+
 # ----------------------------------------------------------------------------------------- CPU arms
-def cpu_reference_arm(a, steps, warmup):
-    """Times the reference's native inner loop (step1_process_double, ot_func.cpp:690-828, compiled
-    unmodified into oracle/_ref) — or the oracle port when that library is absent — on a dense sample
-    and rescales to the full workload's pair count (t_iter is proportional to N*M)."""
-    from oracle import ot_dense, ref_lib
-    s = a.cpu_sample
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+@contextlib.contextmanager
+def blas_threads(n):
+    """Set the BLAS / OpenMP pools to n threads whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 for
+    nproc > 1, which silently cut round 1's multi-rank reference runs to one thread) and report what is really used."""
+    used = {"threads": 1, "how": "threadpoolctl unavailable: library defaults"}
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        with threadpool_limits(limits=n):
+            pools = [p for p in threadpool_info() if p.get("user_api") in ("blas", "openmp")]
+            blas = [p["num_threads"] for p in pools if p.get("user_api") == "blas"]
+            used["threads"] = int(max(blas)) if blas else int(max([p["num_threads"] for p in pools] or [1]))
+            used["how"] = "threadpoolctl.threadpool_limits(%d); pools %s" % (n, [(p.get("internal_api"), p["num_threads"]) for p in pools])
+            yield used
+    except ImportError:
+        yield used
+
+
+def cpu_reference_arm(a, sample):
+    """One full stock solve of the reference on a dense s x s sample of the workload (cost matrix + median + six
+    epsilon stages to 1e-8, everything timed), per leg:
+      (i)  use_C=True  — SpaDOT's default config: libot's native loop, single-threaded by construction;
+      (ii) use_C=False, use_Py=True — the numpy/BLAS text, which is what wot runs in `SpaDOT analyze`.
+    Iterations of that very solve are counted by the oracle port on the same inputs (identical counts are a tested
+    property, tests/test_oracle_golden.py); value = iterations / wall time of the fastest leg, rescaled by N*M."""
+    from oracle import ot_dense, reference_loader
+    s = int(sample)
     x, y = synth(s, s, a.d)
-    t0 = time.perf_counter()
-    C, _ = ot_dense.median_normalised_cost(x, y)
-    K = np.exp(-C / EPS)
-    build_s = time.perf_counter() - t0
-    I = J = s
-    dx, dy = np.ones(I) / I, np.ones(J) / J
-    p, q = np.ones(I), np.ones(J)
-    u, v = np.zeros(I), np.zeros(J)
-    av, bv = np.ones(I), np.ones(J)
-    oa, ob = av.copy(), bv.copy()
-    a1, a2 = LAM1 / (LAM1 + EPS), LAM2 / (LAM2 + EPS)
+    cfg = ot_config()
     scale = (float(s) * float(s)) / (float(a.n) * float(a.m))
-    results = []
-
-    def timed(run):
-        run(warmup)
+    legs = []
+    with blas_threads(host_threads()) as used:
         t0 = time.perf_counter()
-        run(steps)
-        return time.perf_counter() - t0
-
-    if ref_lib.available():
-        # (i) the reference's native inner loop, compiled unmodified: single-threaded by construction
-        def run_native(k):
-            ref_lib.step1(av, bv, oa, ob, K, C, dx, dy, p, q, u, v, 0, 10 ** 7, k, TAU, LAM1, LAM2, a1, a2, EPS)
-        results.append(("reference", 1, "libot_ref.so step1_process_double (ot_func.cpp:690-828, 1 thread)", timed(run_native)))
-
-    # (ii) the numpy twin of the same update (ot_solvers.py:311-316) = what wot runs in `SpaDOT analyze`; BLAS threads
-    state = dict(a=np.ones(I), b=np.ones(J))
-
-    def run_numpy(k):
-        for _ in range(k):
-            state["a"] = (p / (K @ (state["b"] * dy))) ** a1 * np.exp(-u / (LAM1 + EPS))
-            state["b"] = (q / (K.T @ (state["a"] * dx))) ** a2 * np.exp(-v / (LAM2 + EPS))
-    results.append(("reference" if not ref_lib.available() else "port", os.cpu_count() or 1,
-                    "numpy K.dot / K.T.dot path (ot_solvers.py:311-316, BLAS threads)", timed(run_numpy)))
-    kind, cores, what, dt = min(results, key=lambda r: r[3])
-    it_per_s_sample = steps / dt
-    others = "; ".join(f"{w}: {steps / t:.2f} iter/s" for _, _, w, t in results)
-    return dict(value=it_per_s_sample * scale, unit=UNIT, cores=cores, kind=kind,
-                sample=f"dense fp64 {s}x{s} d={a.d} (K,C resident; {build_s:.1f}s to build, untimed), fastest of [{others}] "
-                       f"at sample size ({steps} iterations), rescaled by N*M ratio {scale:.3e} to the full workload"), dt / steps
+        Cn, _ = ot_dense.median_normalised_cost(x, y)
+        info = {}
+        ot_dense.duality_gap_solve(Cn, np.ones(s), info=info, **{k: cfg[k] for k in
+                                   ("lambda1", "lambda2", "epsilon", "batch_size", "tolerance", "tau", "epsilon0", "max_iter")})
+        port_s = time.perf_counter() - t0
+        del Cn
+        iters = int(info["total_iters"])
+        legs.append(("port", used["threads"], "oracle/ot_dense.py (numpy restatement, BLAS threads)", port_s))
+        have_ref = reference_loader.available() or reference_loader.compiled_available()
+        if have_ref:
+            ref = reference_loader.load_ot_solvers()
+            src = "source under /root/reference" if reference_loader.available() else "byte-compiled oracle/_ref/pyref + oracle/_ref/libot_ref.so"
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref.compute_transport_map(*synth(256, 256, a.d), dict(cfg))                  # untimed warm-up (imports, page-in)
+            for label, use_C, use_Py, thr in (("use_C=True: native libot loop, 1 thread by construction", True, False, 1),
+                                              ("use_C=False,use_Py=True: numpy/BLAS text (= wot's solver)", False, True, used["threads"])):
+                t0 = time.perf_counter()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    ref.compute_transport_map(x, y, dict(cfg, use_C=use_C, use_Py=use_Py))
+                legs.append(("reference", thr, f"reference compute_transport_map ({src}; {label})", time.perf_counter() - t0))
+            legs = legs[1:]          # the port only counted the iterations
+        kind, cores, what, dt = min(legs, key=lambda r: r[3])
+        others = "; ".join(f"{w}: {iters / t:.3f} iter/s in {t:.1f}s on {c} thread(s)" for _, c, w, t in legs)
+        return dict(value=iters / dt * scale, unit=UNIT, cores=cores, kind=kind,
+                    sample=f"ONE stock solve of a dense fp64 {s}x{s} d={a.d} sample (sqeuclidean cost + median + 6 eps stages to 1e-8 = "
+                           f"{iters} Sinkhorn iterations, all timed); legs at sample size: [{others}]; fastest rescaled by the N*M ratio "
+                           f"{scale:.3e} to the full workload; host threads available {host_threads()}, BLAS: {used['how']}",
+                    iterations=iters, sample_seconds=dt), dt / iters
 
 
 def reference_main(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, ms = cpu_reference_arm(a, a.steps, a.warmup)
+    s = a.cpu_sample or 8192
+    base, sec_per_iter = cpu_reference_arm(a, s)
+    scale = (float(s) ** 2) / (float(a.n) * float(a.m))
     line = dict(metric=METRIC, value=base["value"], unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
-                ms_per_step=ms * 1e3 / ((float(a.cpu_sample) ** 2) / (float(a.n) * float(a.m))),
-                higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
-                impl="reference", config=dict(workload=workload_name(a)), cpu_baseline=base,
-                e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
-                gpu_launches=0)
+                ms_per_step=sec_per_iter * 1e3 / scale, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+                data="synthetic", impl="reference", config=dict(workload=workload_name(a)), cpu_baseline=base,
+                e2e=dict(value=base["value"], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line))
 
 
@@ -170,7 +204,7 @@ class ClockSampler:
 def gpu_main(a):
     import torch
     import torch.distributed as td
-    from spadot_b200 import sinkhorn
+    from spadot_b200 import ot_solvers, sinkhorn
     from spadot_b200.cuda_ops import CudaOps
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -187,7 +221,7 @@ def gpu_main(a):
     x_all, y = synth(a.n, a.m, a.d)
     x = np.ascontiguousarray(x_all[r0:r1])
     del x_all
-    # fixed normalisation: E|x-y|^2 for this mixture (the exact median is K5's job, untimed here)
+    # fixed normalisation: E|x-y|^2 for this mixture (the exact median is K5's job; it is inside the full-solve e2e)
     median = float(2 * a.d * (1.5 ** 2 + 0.5 ** 2))
 
     def barrier():
@@ -241,6 +275,7 @@ def gpu_main(a):
     barrier()
     t_wall1 = time.perf_counter()
     timed_lse.on = False
+    collectives_per_step = (dist.collectives - coll0) / a.steps if world > 1 else 0      # read before anything else runs
     elapsed = torch.tensor([ev0.elapsed_time(ev1) / 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         td.all_reduce(elapsed, op=td.ReduceOp.MAX)
@@ -248,78 +283,123 @@ def gpu_main(a):
     launches = ops.launches - launches0
     pass_ms = [e0.elapsed_time(e1) for e0, e1 in pass_events]
     clk = clocks.stop(t_wall0, t_wall1) if clocks else None
+    ops._call = orig_call
     finite = bool(torch.isfinite(st.f).all().item() and torch.isfinite(st.g).all().item())
 
-    # ---- e2e: host buffers in, potentials out, through the public API, copies inside the timed region
+    # ---- parity of the timed iterates (every N runs the same W+K iterations from the same inputs: the SCALE lines must
+    # carry equal checksums, and the row LSE at the final g is checked against the fp64 oracle on 32 rows of rank 0)
+    f_sum = float(dist.sum_(st.f.sum().reshape(1).clone()).item())
+    f_abs = float(dist.sum_(st.f.abs().sum().reshape(1).clone()).item())
+    g_sum, g_abs = float(st.g.sum().item()), float(st.g.abs().sum().item())
+    Lr_dev = ops.row_lse(st.g, EPS)
+    parity = dict(f_checksum=f_sum, f_abs_checksum=f_abs, g_checksum=g_sum, g_abs_checksum=g_abs, iterations=a.warmup + a.steps)
+    if rank == 0:
+        from oracle import ot_logdomain                       # the checker, never the thing measured
+        idx = np.random.default_rng(7).integers(0, ops.n, 32)
+        g_host = st.g.cpu().numpy()
+        want = ot_logdomain.CostOperator(x[idx], y, median=median, block=8).row_lse(g_host / EPS, EPS)
+        got = Lr_dev.cpu().numpy()[idx]
+        f_host = st.f.cpu().numpy()[idx]
+        parity.update(rows_checked=32, lse_max_abs_err=float(np.abs(got - want).max()), lse_mean_err=float((got - want).mean()),
+                      checker="oracle/ot_logdomain.py fp64 row LSE at the final g", f_rows_sample=[float(v) for v in f_host[:4]])
+
+    # ---- e2e (i): the public call a user makes — host buffers in, potentials on the host out; exact median + six
+    # epsilon stages to 1e-8; host<->device copies inside the timed region.  BASELINE's "OT wall-time at N x M".
     xh = torch.from_numpy(x).pin_memory()
     yh = torch.from_numpy(y).pin_memory()
-    e2e_steps = a.steps
+    del ops, st
+    torch.cuda.empty_cache()
+    cfg = ot_config()
+    full = None
+    if not a.no_full_solve:
+        ws = max(2048, min(20000, a.n // 8))
+        cpw = ot_solvers.solve_coupling(x[:max(1, ws // world)], y[:ws], cfg, dist=dist, device=dev)    # untimed warm-up (first-use costs)
+        del cpw
+        barrier()
+        t0 = time.perf_counter()
+        cp = ot_solvers.solve_coupling(xh, yh, cfg, dist=dist, device=dev)
+        f_host, g_host2 = cp.f.cpu(), (cp.g.cpu() if rank == 0 else None)
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(tt, op=td.ReduceOp.MAX)
+        full = dict(seconds=float(tt.item()), iterations=int(cp.info["total_iters"]), iters_per_stage=cp.info["iters_per_stage"],
+                    gap=cp.info["gap"], median=cp.median, median_sweeps=cp.info.get("sweeps"),
+                    h2d=(xh.numel() + yh.numel()) * 8, d2h=f_host.numel() * 8 + (g_host2.numel() * 8 if g_host2 is not None else 0))
+        del cp
+        torch.cuda.empty_cache()
 
-    ops2_holder = []
-
-    def e2e_call(n_steps):
+    # ---- e2e (ii): fixed number of iterations from host buffers (same work per step as the timed region above)
+    def e2e_fixed(n_steps):
         ops2 = CudaOps(xh, yh, device=dev, tc=a.tc)  # H2D of both spot sets + point preparation
-        ops2_holder[:] = [ops2]
         ops2.set_median(median)
         st2 = sinkhorn._State(ops2, np.ones(ops2.n), dist)
         st2.u.copy_(st2.f)
         st2.v.copy_(st2.g)
         sinkhorn._sweeps(ops2, st2, dist, EPS, a1, a2, log_tau, False, n_steps)   # native loop when single-rank
-        return st2.f.cpu(), (st2.g.cpu() if rank == 0 else None)      # D2H of the result
+        out = st2.f.cpu(), (st2.g.cpu() if rank == 0 else None)      # D2H of the result
+        return out + (ops2,)
 
-    e2e_call(1)                                      # warm-up call (allocator growth, first-use costs), untimed
+    e2e_fixed(1)                                     # warm-up call (allocator growth, first-use costs), untimed
     barrier()
     t0 = time.perf_counter()
-    f_host, g_host = e2e_call(e2e_steps)
+    f2, g2, ops2 = e2e_fixed(a.steps)
     barrier()
     e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         td.all_reduce(e2e_t, op=td.ReduceOp.MAX)
     e2e_t = float(e2e_t.item())
     h2d = (xh.numel() + yh.numel()) * 8
-    d2h = f_host.numel() * 8 + (g_host.numel() * 8 if g_host is not None else 0)
+    d2h = f2.numel() * 8 + (g2.numel() * 8 if g2 is not None else 0)
+    fixed = dict(value=a.steps / e2e_t, unit=UNIT, steps=a.steps, seconds=e2e_t, h2d_bytes_per_step=h2d / a.steps,
+                 d2h_bytes_per_step=d2h / a.steps, api="CudaOps(host x, host y) + sinkhorn sweeps + potentials to host")
 
     if rank == 0:
-        import json as _json
         peaks = {}
         try:
-            peaks = _json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
         # algorithmic work of one pass launch on this rank: n_p*n_q pair evaluations,
         # each (2*dpad + 8) fp32 flop in the SIMT form and one ex2.
-        n_loc = ops.n
+        n_loc, use_tc = ops2.n, bool(ops2.use_tc)
         pairs = float(n_loc) * float(a.m)
-        flop_per_pair = 2 * ops.X.dpad + 8
+        flop_per_pair = 2 * ops2.X.dpad + 8
         avg_pass_s = (sum(pass_ms) / len(pass_ms)) / 1e3 if pass_ms else float("nan")
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         traffic = None
         try:
-            tj = _json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            key = f"lse_pass_{'tc' if ops.use_tc else 'simt'} n={a.n} m={a.m} d={a.d} world={world}"
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            key = f"lse_pass_{'tc' if ops2.use_tc else 'simt'} n={a.n} m={a.m} d={a.d} world={world}"
             traffic = tj.get(key, {}).get("dram_bytes_per_launch")
         except Exception:
             pass
-        common = dict(traffic=traffic, traffic_source="ncu --set full, profiles/r1_traffic.json" if traffic else None,
-                      algorithmic_hbm_bytes_per_launch=(n_loc + a.m) * (ops.X.dpad + 2) * 4,
+        measured = None
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import pipe_peaks
+            del ops2
+            torch.cuda.empty_cache()
+            measured = pipe_peaks.measure(dev)
+        except Exception as exc:
+            measured = dict(error=repr(exc)[:200])
+        common = dict(traffic=traffic, traffic_source="ncu --set full, profiles/r2_traffic.json" if traffic else None,
+                      algorithmic_hbm_bytes_per_launch=(n_loc + a.m) * (32 * 4 + 4) if a.d <= 32 else None,
                       pass_ms_avg=avg_pass_s * 1e3, pass_launches=len(pass_ms),
-                      share_of_step=(sum(pass_ms) / 1e3) / elapsed,
-                      hbm_gbs_algorithmic=((n_loc + a.m) * (ops.X.dpad + 2) * 4) / avg_pass_s / 1e9,
-                      pairs_per_launch=pairs)
-        if ops.use_tc:
+                      share_of_step=(sum(pass_ms) / 1e3) / elapsed, pairs_per_launch=pairs, measured_pipe_peaks=measured)
+        if use_tc:
             # tensor-core form: the dot product runs on tcgen05; what is left per pair is one ex2 (SFU, 16/clk/SM)
             # and ~4 fp32 instructions, so the binding pipe is the SFU.
-            sfu_peak = n_sm * 16 * sm_max * 1e6 / 1e12
+            sfu_nominal = n_sm * 16 * sm_max * 1e6 / 1e12
             achieved = pairs / avg_pass_s / 1e12
-            entry = "sdb_lse_pass_tc_pred, predicted stabiliser" if ops.predicting() else "sdb_lse_pass_tc"
-            roofline = dict(bound="sfu", kernel="lse_pass_tc_kernel<%d> (%s)" % (ops.X.dp, entry), achieved=achieved,
-                            peak=sfu_peak, unit="Tex2/s", frac=achieved / sfu_peak,
-                            peak_source=f"{n_sm} SM x 16 MUFU lanes x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json; "
-                                        "that file has no SFU entry)",
+            sfu_measured = measured.get("mufu_ex2", {}).get("value") if isinstance(measured, dict) else None
+            roofline = dict(bound="sfu", kernel="lse_pass_tc_kernel (sdb_lse_pass_tc_pred)", achieved=achieved,
+                            peak=sfu_nominal, unit="Tex2/s", frac=achieved / sfu_nominal,
+                            peak_source=f"nominal: {n_sm} SM x 16 MUFU lanes x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json, which has "
+                                        "no SFU entry); measured beside it by the MUFU.EX2 micro-benchmark of this run (sdb_pipe_peak)",
+                            peak_measured=sfu_measured, frac_of_measured=(achieved / sfu_measured) if sfu_measured else None,
                             frac_at_sampled_clock=(achieved / (n_sm * 16 * clk["sm_mhz"] * 1e6 / 1e12)) if clk and clk.get("sm_mhz") else None,
-                            tensor_tflops=pairs * 6 * ops.X.dp / avg_pass_s / 1e12,
-                            tensor_frac_of_measured_bf16=(pairs * 6 * ops.X.dp / avg_pass_s / 1e12) / float(peaks.get("bf16_tflops", 1640.6)),
                             **common)
         else:
             fp32_peak = n_sm * 128 * 2 * sm_max * 1e6 / 1e12
@@ -329,19 +409,25 @@ def gpu_main(a):
                             peak_source=f"{n_sm} SM x 128 FMA x 2 x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json; "
                                         "that file has no fp32 entry)",
                             ex2_per_s=pairs / avg_pass_s, **common)
+        if full is not None:
+            e2e = dict(value=full["iterations"] / full["seconds"], unit=UNIT, h2d_bytes_per_step=full["h2d"] / full["iterations"],
+                       d2h_bytes_per_step=full["d2h"] / full["iterations"], steps=full["iterations"], seconds=full["seconds"],
+                       api="spadot_b200.ot_solvers.solve_coupling(host x, host y, config): exact median (K5) + six eps stages to "
+                           "tolerance 1e-8, potentials copied back to the host", iters_per_stage=full["iters_per_stage"],
+                       gap=full["gap"], median=full["median"], median_sweeps=full["median_sweeps"], fixed_steps=fixed)
+        else:
+            e2e = dict(fixed)
         line = dict(metric=METRIC, value=a.steps / elapsed, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,
                     ms_per_step=elapsed * 1e3 / a.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
-                    dtype="f16x2-split tensor tiles + f32 epilogue / f64 vectors" if ops.use_tc else "f32 tiles / f64 vectors", data="synthetic", impl="spadot_b200",
+                    dtype="f16x2-split tensor tiles + f32 epilogue / f64 vectors" if use_tc else "f32 tiles / f64 vectors", data="synthetic", impl="spadot_b200",
                     config=dict(workload=workload_name(a), rows_per_rank=n_loc, parallelism=f"row-partition x{world}",
                                 l2_policy="inputs per pass (>=136 MB at 1M) exceed reuse; potentials rewritten every step",
-                                median="analytic (K5 exact median untimed)", finite=finite,
-                                collectives_per_step=(dist.collectives - coll0) / a.steps if world > 1 else 0),
-                    e2e=dict(value=e2e_steps / e2e_t, unit=UNIT, h2d_bytes_per_step=h2d / e2e_steps,
-                             d2h_bytes_per_step=d2h / e2e_steps, steps=e2e_steps, seconds=e2e_t,
-                             api="CudaOps(host x, host y) + sinkhorn sweeps + potentials to host"),
+                                median="analytic in the timed steps (K5 exact median is inside e2e)", finite=finite,
+                                collectives_per_step=collectives_per_step),
+                    e2e=e2e, e2e_full_solve_s=full["seconds"] if full else None, parity=parity,
                     gpu_launches=launches, clocks=clk, roofline=roofline)
         if world == 1 and not a.no_cpu_baseline:
-            base, _ = cpu_reference_arm(a, 10, 2)
+            base, _ = cpu_reference_arm(a, a.cpu_sample or 4096)
             line["cpu_baseline"] = base
         if world == 1 and not a.no_aux:
             # BASELINE.json's metric also names "train s/epoch": the train inner loop (SVGP + GAT) at ChickenHeart
@@ -349,7 +435,6 @@ def gpu_main(a):
             try:
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import train_epoch_bench
-                del ops2_holder[:]
                 torch.cuda.empty_cache()
                 line["aux_train_epoch"] = train_epoch_bench.run(dev)
             except Exception as exc:       # the aux number must never take the headline down

@@ -60,11 +60,12 @@ int sdb_prep_points_f64(const double* x, int64_t n, int d, const double* center,
 /* partial[(s*n_p + i)*2 + {0,1}] = (max, sum) of 2^(bias_j + scale*x_i.y_j - max) over the
  * columns j in [split_bounds[s], split_bounds[s+1]) (device array of n_splits+1 entries; keep
  * each split <= 65536 columns so the fp32 running sums stay below 1e-6 relative error).
- * dpad <= 128, dpad % 4 == 0.  Grid = ceil(n_p/64) x n_splits CTAs of 256 threads.
+ * dpad <= 128, dpad % 4 == 0.  Grid = ceil(n_p/64) x n_splits CTAs of 256 threads.  `scale` is a double: the kernel applies
+ * it as an fp32 (hi, lo) pair, t = fma(hi, d, fma(lo, d, bias)), so its rounding is not a bias common to every term.
  * replaces: gemv/gemtv + update_k of ref: utils/OT_loss/ot_func.cpp:43-249,547-568. */
 int sdb_lse_pass_simt(const float* pt, int64_t ldp, int64_t n_p,
                       const float* qt, int64_t ldq, int64_t n_q, int dpad,
-                      const float* bias, float scale,
+                      const float* bias, double scale,
                       const int64_t* split_bounds, int n_splits,
                       float* partial, void* stream);
 

@@ -25,7 +25,7 @@ SIGNATURES = {
     "sdb_device_check": [],
     "sdb_column_sums_f64": [c_p, c_l, c_i, c_p, c_p],
     "sdb_prep_points_f64": [c_p, c_l, c_i, c_p, c_p, c_l, c_i, c_p, c_p],
-    "sdb_lse_pass_simt": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_p, c_i, c_p, c_p],
+    "sdb_lse_pass_simt": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_d, c_p, c_i, c_p, c_p],
     "sdb_sinkhorn_sweeps": [c_p, c_i, c_i, c_i, c_p],
     "sdb_sinkhorn_sweeps_persistent": [c_p, c_i, c_i, c_i, c_p, c_p],
     "sdb_lse_finalize": [c_p, c_i, c_l, c_p, c_d, c_p, c_p],

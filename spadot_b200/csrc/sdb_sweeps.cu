@@ -40,9 +40,9 @@ extern "C" int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int fi
                                               (float)(scale * d->pow2_scale), d->tps_col, d->n_ctas, predicted ? d->m_y : nullptr,
                                               d->partial_col, stream);
         }
-        return row ? sdb_lse_pass_simt(d->xt, d->ldx, d->n, d->yt, d->ldy, d->m, d->dpad, d->bias_y, (float)scale, d->bounds_row,
+        return row ? sdb_lse_pass_simt(d->xt, d->ldx, d->n, d->yt, d->ldy, d->m, d->dpad, d->bias_y, scale, d->bounds_row,
                                        d->ns_row, d->partial_row, stream)
-                   : sdb_lse_pass_simt(d->yt, d->ldy, d->m, d->xt, d->ldx, d->n, d->dpad, d->bias_x, (float)scale, d->bounds_col,
+                   : sdb_lse_pass_simt(d->yt, d->ldy, d->m, d->xt, d->ldx, d->n, d->dpad, d->bias_x, scale, d->bounds_col,
                                        d->ns_col, d->partial_col, stream);
     };
     const bool pred = d->use_tc && d->m_x && d->m_y && d->bad_flag;

@@ -53,18 +53,40 @@ SWEEP = [(eps, l1, l2, 3000, 2600) for eps in (0.01, 0.02, 0.1) for (l1, l2) in 
         [(eps, 50.0, 50.0, 1000, 900) for eps in (0.01, 0.02, 0.1)]
 
 
+_ORACLE_CACHE = {}
+
+
+def _oracle(eps, lam1, lam2, n, m):
+    key = (eps, lam1, lam2, n, m)
+    if key not in _ORACLE_CACHE:
+        _ORACLE_CACHE.clear()                                      # one dense plan at a time
+        a, b, la, lb = ot_dense.synthetic_embeddings(n, m, 32, seed=17)
+        cfg = dict(CFG, epsilon=eps, lambda1=lam1, lambda2=lam2)
+        Cn, _ = ot_dense.median_normalised_cost(a, b)
+        info_ref = {}
+        want = ot_dense.duality_gap_solve(Cn, np.ones(n), info=info_ref, **cfg)
+        _ORACLE_CACHE[key] = (a, b, la, lb, cfg, want, info_ref)
+    return _ORACLE_CACHE[key]
+
+
+@pytest.mark.parametrize("tc", ["on", "off"])
 @pytest.mark.parametrize("eps,lam1,lam2,n,m", SWEEP)
-def test_tc_full_solve_at_sweep_extremes(ot, eps, lam1, lam2, n, m):
+def test_full_solve_at_sweep_extremes(ot, eps, lam1, lam2, n, m, tc):
+    """tc="on": the tcgen05 pass (what 250k x 250k runs); tc="off": the SIMT pass (what oracle-sized problems run by
+    default).  Measured in round 2 (profiles/r2_sweep_parity.jsonl): marginals <= 6e-6, entries <= 2.2e-5 at eps = 0.01."""
     ot_solvers, sinkhorn, CudaOps = ot
-    a, b, la, lb = ot_dense.synthetic_embeddings(n, m, 32, seed=17)
-    cfg = dict(CFG, epsilon=eps, lambda1=lam1, lambda2=lam2)
-    Cn, med = ot_dense.median_normalised_cost(a, b)
-    info_ref = {}
-    want = ot_dense.duality_gap_solve(Cn, np.ones(n), info=info_ref, **cfg)
-    ops = CudaOps(a, b, tc="on")
+    a, b, la, lb, cfg, want, info_ref = _oracle(eps, lam1, lam2, n, m)
+    ops = CudaOps(a, b, tc=tc)
     cp = ot_solvers.solve_coupling(a, b, cfg, ops=ops, dist=sinkhorn.Dist(enabled=False))
     got = cp.plan().cpu().numpy()
-    assert cp.info["iters_per_stage"] == info_ref["iters_per_stage"]
+    if lam1 < 50.0:
+        assert cp.info["iters_per_stage"] == info_ref["iters_per_stage"]
+    else:
+        # near-balanced corner: thousands of iterations per stage on a plateau where the change per iteration (the
+        # reference's stage criterion, ot_func.cpp:897-922) is of the order of fp32 noise: the stopping batch moves by
+        # a fraction of a percent (fp64 libraries with different summation orders do the same), the plan does not
+        for it, ref in zip(cp.info["iters_per_stage"], info_ref["iters_per_stage"]):
+            assert abs(it - ref) <= max(5, 0.01 * ref)
     assert np.abs(got.sum(1) - want.sum(1)).max() / want.sum(1).max() < 1e-5
     assert np.abs(got.sum(0) - want.sum(0)).max() / want.sum(0).max() < 1e-5
     big = want > 1e-8 * want.max()
