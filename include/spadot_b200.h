@@ -57,7 +57,9 @@ int sdb_prep_points_f64(const double* x, int64_t n, int d, const double* center,
                         float* xt, int64_t ld, int dpad, double* norms, void* stream);
 
 /* ------------------------------------------------------------------ K3: streamed LSE pass (SIMT fp32) */
-/* partial[(s*n_p + i)*2 + {0,1}] = (max, sum) of 2^(bias_j + scale*x_i.y_j - max) over the
+/* DIRECT-DIFFERENCE form: partial[(s*n_p + i)*2 + {0,1}] = (max, sum) of 2^(bias_j + scale*|x_i - y_j|^2 - max), with
+ * scale = -c1*log2(e) and bias_j = log2(e)*g_j/eps — i.e. pass an all-zero `norms` vector to sdb_make_bias,
+ * sdb_lse_finalize* and sdb_potential_update on this path (the squared norms live inside |x_i - y_j|^2).  Over the
  * columns j in [split_bounds[s], split_bounds[s+1]) (device array of n_splits+1 entries; keep
  * each split <= 65536 columns so the fp32 running sums stay below 1e-6 relative error).
  * dpad <= 128, dpad % 4 == 0.  Grid = ceil(n_p/64) x n_splits CTAs of 256 threads.  `scale` is a double: the kernel applies
@@ -109,6 +111,22 @@ int sdb_finalize_update_pred(const float* partial, int n_splits, int64_t n, cons
                              const double* logmarg, double eps, double alpha, double log_n_other, double* pot,
                              const double* frame, double* la_old, float* bias, int* absorb_flag, int iter,
                              double log_tau, double log_floor, float* m_next, int* bad_flag, void* stream);
+/* Row-partitioned solve, column step with ONE collective.  Every rank runs its column pass against the SAME
+ * per-column shift (row_m of sdb_lse_pass_tc_pred = the previous combined column LSE in log2 units + 1, kept in `shift`), so
+ * the per-rank sums are addable:
+ *   sdb_partial_sums_f64:     sums[j] = sum over splits of partial.sum * 2^(partial.max - shift[j])  (j < n), and two riders
+ *                             sums[n] = (*absorb_flag == iter), sums[n+1] = (*bad_flag != 0)   [n+2 doubles]
+ *   caller:                   all-reduce(SUM) of the n+2 doubles (NCCL)
+ *   sdb_update_from_sums_f64: L[j] = ln2*(shift[j] + log2 sums[j]) - norms[j]*c1, then exactly sdb_potential_update on it,
+ *                             shift[j] <- shift[j] + log2 sums[j] + 1 for the next iteration, *bad_flag |= 1 unless
+ *                             2^-60 < sums[j] < 2^100 or if sums[n+1] > 0, atomicMax(absorb_flag, iter) if sums[n] > 0.
+ * Identical inputs on every rank => identical g, bias, shift and flags on every rank without further exchange. */
+int sdb_partial_sums_f64(const float* partial, int n_splits, int64_t n, const float* shift, double* sums, const int* absorb_flag,
+                         int iter, const int* bad_flag, void* stream);
+int sdb_update_from_sums_f64(const double* sums, float* shift, int64_t n, const double* norms, double c1, double* L,
+                             const double* logmarg, double eps, double alpha, double log_n_other, double* pot, const double* frame,
+                             double* la_old, float* bias, int* absorb_flag, int iter, double log_tau, double log_floor, int* bad_flag,
+                             void* stream);
 /* sdb_lse_pass_tc with the predicted stabiliser: row_m[i] for i < n_p (NULL = track the maximum, i.e. sdb_lse_pass_tc). */
 int sdb_lse_pass_tc_pred(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad,
                          int dp, const float* bias_padded, float scale, int tiles_per_split, int n_ctas,

@@ -30,14 +30,14 @@ def available() -> bool:
 
 
 def compiled_available() -> bool:
-    """oracle/_ref/pyref/*.pyc: the reference's ot_func.py / ot_solvers.py byte-compiled UNMODIFIED by oracle/Makefile
+    """oracle/_ref/pyref/*.pycode: the reference's ot_func.py / ot_solvers.py byte-compiled UNMODIFIED by oracle/Makefile
     (`make pyref`, build container only).  Like oracle/_ref/libot_ref.so they are git-ignored build outputs that travel
     to the GPU box, where /root/reference does not exist."""
-    return all(os.path.exists(os.path.join(_PYREF, f)) for f in ("ot_func.pyc", "ot_solvers.pyc"))
+    return all(os.path.exists(os.path.join(_PYREF, f)) for f in ("ot_func.pycode", "ot_solvers.pycode"))
 
 
 def _load(name, path, package=None):
-    if path.endswith(".pyc"):
+    if path.endswith(".pycode"):
         from importlib.machinery import SourcelessFileLoader
         spec = importlib.util.spec_from_loader(name, SourcelessFileLoader(name, path))
     else:
@@ -63,7 +63,7 @@ def load_ot_solvers(lib_path=None, tag=None):
     if available():
         d, ext = _OT_DIR, ".py"
     elif compiled_available():
-        d, ext = _PYREF, ".pyc"
+        d, ext = _PYREF, ".pycode"        # (not *.pyc: snapshot tools drop that extension)
         if lib_path is None:
             lib_path = os.path.join(os.path.dirname(_PYREF), "libot_ref.so")    # the reference's ot_func.cpp, compiled
     else:

@@ -31,6 +31,8 @@ SIGNATURES = {
     "sdb_lse_finalize": [c_p, c_i, c_l, c_p, c_d, c_p, c_p],
     "sdb_lse_finalize_pred": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_p, c_p],
     "sdb_finalize_update_pred": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p, c_p, c_p],
+    "sdb_partial_sums_f64": [c_p, c_i, c_l, c_p, c_p, c_p, c_i, c_p, c_p],
+    "sdb_update_from_sums_f64": [c_p, c_p, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p, c_p],
     "sdb_lse_pass_tc_pred": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_i, c_i, c_p, c_p, c_p],
     "sdb_potential_update": [c_l, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
     "sdb_finalize_update": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],

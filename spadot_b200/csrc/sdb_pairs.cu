@@ -123,7 +123,11 @@ __global__ void __launch_bounds__(NT) pair_tile_kernel(PairArgs a, typename Epi:
 
 // -------------------------------------------------------------------------------------------- LSE
 struct LseEpi {
-    // scale = scale_hi + scale_lo: the exponent scale 2*c1*log2(e) as an fp32 pair.  A single fp32 rounds it by up to 2^-24
+    // The SIMT pass works on direct differences, acc = |x_i - y_j|^2 (like scipy's cdist behind ref: ot_solvers.py:102): no
+    // |x|^2 + |y|^2 - 2 x.y cancellation, so the fp32 rounding of the tile math is relative to the COST of a pair, not to
+    // |x||y| (at eps = 0.01 the dot-product form put 1.3e-5 on the marginals, the direct form 1e-6; the inner loop pays one
+    // extra FADD per feature, which the latency-bound problems this path serves do not notice).
+    // scale = scale_hi + scale_lo: the exponent scale -c1*log2(e) as an fp32 pair.  A single fp32 rounds it by up to 2^-24
     // relative, and that error is common to every term of every row: dominant terms have scale*x.y ~ 150 at eps = 0.01, i.e.
     // an LSE bias of up to 9e-6 that goes one-to-one into the plan (measured: marginals off by 1.3e-5 at eps = 0.01).
     struct Params { float scale, scale_lo; float2* partial; };
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_persistent_kernel(PersistArgs a) 
         if (!skip_row_pass) {
             LseEpi::Params ep{a.scale, a.scale_lo, a.partial_row};
             for (int item = blockIdx.x; item < row_tiles * a.ns_row; item += gridDim.x) {
-                pair_tile_item<false, LseEpi>(a.row, ep, item % row_tiles, item / row_tiles, smem);
+                pair_tile_item<true, LseEpi>(a.row, ep, item % row_tiles, item / row_tiles, smem);
                 __syncthreads();
             }
             grid_barrier(a.barrier, gen);
@@ -328,7 +332,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_persistent_kernel(PersistArgs a) 
         {
             LseEpi::Params ep{a.scale, a.scale_lo, a.partial_col};
             for (int item = blockIdx.x; item < col_tiles * a.ns_col; item += gridDim.x) {
-                pair_tile_item<false, LseEpi>(a.col, ep, item % col_tiles, item / col_tiles, smem);
+                pair_tile_item<true, LseEpi>(a.col, ep, item % col_tiles, item / col_tiles, smem);
                 __syncthreads();
             }
         }
@@ -366,8 +370,8 @@ extern "C" int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_swe
     a.row = PairArgs{d->xt, d->ldx, d->n, d->yt, d->ldy, d->m, d->dpad, d->bias_y, d->bounds_row};
     a.col = PairArgs{d->yt, d->ldy, d->m, d->xt, d->ldx, d->n, d->dpad, d->bias_x, d->bounds_col};
     a.ns_row = d->ns_row; a.ns_col = d->ns_col;
-    a.scale = (float)(2.0 * c1 * SDB_LOG2E);
-    a.scale_lo = (float)(2.0 * c1 * SDB_LOG2E - (double)a.scale);
+    a.scale = (float)(-c1 * SDB_LOG2E);                      // direct-difference form: t = bias_j - c1*log2(e)*|x_i - y_j|^2
+    a.scale_lo = (float)(-c1 * SDB_LOG2E - (double)a.scale);
     a.partial_row = reinterpret_cast<float2*>(d->partial_row); a.partial_col = reinterpret_cast<float2*>(d->partial_col);
     a.norms_x = d->norms_x; a.norms_y = d->norms_y; a.bias_x = d->bias_x; a.bias_y = d->bias_y;
     a.f = d->f; a.g = d->g; a.u = d->u; a.v = d->v; a.la_old = d->la_old; a.lb_old = d->lb_old; a.Lr = d->Lr; a.Lc = d->Lc;
@@ -420,7 +424,7 @@ extern "C" int sdb_lse_pass_simt(const float* pt, int64_t ldp, int64_t n_p, cons
     PairArgs a{pt, ldp, n_p, qt, ldq, n_q, dpad, bias, split_bounds};
     const float s_hi = (float)scale;
     LseEpi::Params ep{s_hi, (float)(scale - (double)s_hi), reinterpret_cast<float2*>(partial)};
-    return launch_pairs<false, LseEpi>(a, ep, n_splits, sdb_stream(stream));
+    return launch_pairs<true, LseEpi>(a, ep, n_splits, sdb_stream(stream));
 }
 
 extern "C" int sdb_cost_histogram(const float* pt, int64_t ldp, int64_t n_p, const float* qt, int64_t ldq, int64_t n_q,

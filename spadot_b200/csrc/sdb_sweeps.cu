@@ -27,7 +27,8 @@ struct PdlScope {
 extern "C" int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int first_tick, int lr_known_first, void* stream) {
     SDB_CHECK_ARG(d && n_sweeps >= 0 && d->n > 0 && d->m > 0 && d->eps > 0.0);
     const double c1 = d->inv_med / d->eps;
-    const double scale = 2.0 * c1 * SDB_LOG2E;
+    const double scale = 2.0 * c1 * SDB_LOG2E;      // tensor-core form: exponent = bias_j + scale * x_i.y_j (norms inside the bias)
+    const double scale_direct = -c1 * SDB_LOG2E;    // SIMT form: exponent = bias_j + scale_direct * |x_i - y_j|^2 (norm vectors are zero)
     const double log_m = log((double)d->m), log_N = log((double)d->n_total);
     int rc = 0;
     PdlScope pdl(pdl_enabled() && d->use_tc);      // the SIMT pass kernel is not part of the PDL chain
@@ -40,9 +41,9 @@ extern "C" int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int fi
                                               (float)(scale * d->pow2_scale), d->tps_col, d->n_ctas, predicted ? d->m_y : nullptr,
                                               d->partial_col, stream);
         }
-        return row ? sdb_lse_pass_simt(d->xt, d->ldx, d->n, d->yt, d->ldy, d->m, d->dpad, d->bias_y, scale, d->bounds_row,
+        return row ? sdb_lse_pass_simt(d->xt, d->ldx, d->n, d->yt, d->ldy, d->m, d->dpad, d->bias_y, scale_direct, d->bounds_row,
                                        d->ns_row, d->partial_row, stream)
-                   : sdb_lse_pass_simt(d->yt, d->ldy, d->m, d->xt, d->ldx, d->n, d->dpad, d->bias_x, scale, d->bounds_col,
+                   : sdb_lse_pass_simt(d->yt, d->ldy, d->m, d->xt, d->ldx, d->n, d->dpad, d->bias_x, scale_direct, d->bounds_col,
                                        d->ns_col, d->partial_col, stream);
     };
     const bool pred = d->use_tc && d->m_x && d->m_y && d->bad_flag;

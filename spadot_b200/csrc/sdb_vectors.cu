@@ -82,6 +82,59 @@ __global__ void finalize_update_kernel(const float2* __restrict__ partial, int n
                    log_floor);
 }
 
+// ---- row-partitioned solve: the column step with ONE collective ("a shift s_j known identically on all ranks")
+// Every rank sweeps its rows against the same per-column shift (the previous combined column LSE in log2 units, + 1: the
+// predicted stabiliser), so the per-rank sums are directly addable: sums[j] = sum_s partial_s(j).sum * 2^(partial_s(j).max - shift[j]).
+// Two more slots ride in the same all-reduce(SUM): sums[n] = 1 if this rank's row update exceeded tau in iteration `iter`
+// (ref: ot_func.cpp:778-790), sums[n+1] = 1 if one of this rank's predicted passes was out of range.
+__global__ void partial_sums_kernel(const float2* __restrict__ partial, int n_splits, int64_t n, const float* __restrict__ shift,
+                                    double* __restrict__ sums, const int* __restrict__ absorb_flag, int iter,
+                                    const int* __restrict__ bad_flag) {
+    sdb_launch_dependents();
+    sdb_grid_dependency_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        sums[n] = (absorb_flag && *absorb_flag == iter) ? 1.0 : 0.0;
+        sums[n + 1] = (bad_flag && *bad_flag != 0) ? 1.0 : 0.0;
+    }
+    if (i >= n) return;
+    const double sh = (double)shift[i];
+    double S = 0.0;
+    for (int s = 0; s < n_splits; ++s) {
+        const float2 ps = __ldcg(partial + (int64_t)s * n + i);
+        if (ps.x > -1e29f && ps.y > 0.f) S += (double)ps.y * exp2((double)ps.x - sh);
+    }
+    sums[i] = S;
+}
+
+// After the all-reduce: LSE from the combined sums, potential update, next-pass bias, next shift, verification — the same on
+// every rank, because every rank holds the same sums.
+__global__ void update_from_sums_kernel(const double* __restrict__ sums, float* shift, int64_t n, const double* __restrict__ norms,
+                                        double c1, double* __restrict__ L, const double* __restrict__ logmarg, double eps, double alpha,
+                                        double log_n_other, double* __restrict__ pot, const double* __restrict__ frame,
+                                        double* __restrict__ la_old, float* __restrict__ bias, int* __restrict__ absorb_flag, int iter,
+                                        double log_tau, double log_floor, int* bad_flag) {
+    sdb_launch_dependents();
+    sdb_grid_dependency_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        if (sums[n] > 0.0) atomicMax(absorb_flag, iter);
+        if (bad_flag && sums[n + 1] > 0.0) atomicOr(bad_flag, 1);
+    }
+    if (i >= n) return;
+    const double S = sums[i], M = (double)shift[i];
+    double Li = -INFINITY;
+    if (S > 0.0 && S < INFINITY) {
+        Li = SDB_LN2 * (M + log2(S)) - norms[i] * c1;
+        sdb_prediction_out(M, S, i, shift, bad_flag);             // shift[i] <- M + log2 S + 1; range check of the combined sum
+    } else if (bad_flag) {
+        atomicOr(bad_flag, 1);                                    // every term flushed, or an overflow: redo with tracking
+    }
+    L[i] = Li;
+    sdb_update_row(i, Li, logmarg[i], norms[i], eps, alpha, log_n_other, c1, pot, frame, la_old, bias, absorb_flag, iter, log_tau,
+                   log_floor);
+}
+
 __global__ void make_bias_kernel(int64_t n, int64_t n_pad, const double* __restrict__ pot, const double* __restrict__ norms,
                                  double eps, double c1, float* __restrict__ bias) {
     sdb_launch_dependents();
@@ -334,6 +387,22 @@ int sdb_finalize_update(const float* partial, int n_splits, int64_t n, const dou
     if (n == 0) return 0;
     return sdb_finalize_update_pred(partial, n_splits, n, norms, c1, L, logmarg, eps, alpha, log_n_other, pot, frame, la_old, bias,
                                     absorb_flag, iter, log_tau, log_floor, nullptr, nullptr, stream);
+}
+
+int sdb_partial_sums_f64(const float* partial, int n_splits, int64_t n, const float* shift, double* sums, const int* absorb_flag,
+                         int iter, const int* bad_flag, void* stream) {
+    SDB_CHECK_ARG(partial && shift && sums && n_splits > 0 && n >= 0);
+    return (int)sdb_launch(partial_sums_kernel, dim3(blocks_for(n > 0 ? n : 1)), dim3(256), 0, sdb_stream(stream),
+                           reinterpret_cast<const float2*>(partial), n_splits, n, shift, sums, absorb_flag, iter, bad_flag);
+}
+
+int sdb_update_from_sums_f64(const double* sums, float* shift, int64_t n, const double* norms, double c1, double* L,
+                             const double* logmarg, double eps, double alpha, double log_n_other, double* pot, const double* frame,
+                             double* la_old, float* bias, int* absorb_flag, int iter, double log_tau, double log_floor, int* bad_flag,
+                             void* stream) {
+    SDB_CHECK_ARG(sums && shift && norms && L && logmarg && pot && frame && la_old && bias && absorb_flag && n > 0 && eps > 0.0);
+    return (int)sdb_launch(update_from_sums_kernel, dim3(blocks_for(n)), dim3(256), 0, sdb_stream(stream), sums, shift, n, norms, c1, L,
+                           logmarg, eps, alpha, log_n_other, pot, frame, la_old, bias, absorb_flag, iter, log_tau, log_floor, bad_flag);
 }
 
 int sdb_finalize_update_pred(const float* partial, int n_splits, int64_t n, const double* norms, double c1, double* L,

@@ -41,10 +41,12 @@ class PointSet:
         self.dpad = _round_up(self.d, 4)
         self.ld = _round_up(self.n, 64) + 64
         self.xt = torch.empty((self.dpad, self.ld), dtype=torch.float32, device=x64.device)
-        self.norms = torch.empty(self.n, dtype=torch.float64, device=x64.device)
+        self.norms_sq = torch.empty(self.n, dtype=torch.float64, device=x64.device)     # |x_i|^2 of the fp32 copy
+        # the SIMT pass evaluates |x_i - y_j|^2 by direct differences: its bias / finalize kernels take zero norms
+        self.norms = torch.zeros(self.n, dtype=torch.float64, device=x64.device)
         st = torch.cuda.current_stream(x64.device).cuda_stream
         _lib.call("sdb_prep_points_f64", _ptr(x64), self.n, self.d, _ptr(center), _ptr(self.xt), self.ld, self.dpad,
-                  _ptr(self.norms), st)
+                  _ptr(self.norms_sq), st)
         self.x16 = None          # fp16 hi/lo split for the tensor-core pass (built on demand)
 
     def build_split(self, center, prescale):
@@ -314,6 +316,8 @@ class CudaOps(VectorOps):
             self.fresh = {"x": None, "y": None}
             self.ok = True          # False after a misprediction, until the next solve
             self.used = False       # a predicted pass is in flight and not yet verified
+            self.common_y = None    # (eps, inv_med) for which m["y"] is the rank-independent column shift (multi-rank solve)
+            self.unmerged = False   # a predicted pass ran whose `bad` flag other ranks have not seen yet
 
     def _pred_state(self):
         if not self._pred_allowed:
@@ -346,13 +350,17 @@ class CudaOps(VectorOps):
             return True
         ps.used = False
         flag = ps.bad
-        if dist is not None and dist.world > 1:
+        if dist is not None and dist.world > 1 and ps.unmerged:
+            # only when a predicted pass ran since the last merged column step (whose all-reduce carries the flag): the
+            # host-side `unmerged` is the same on every rank, so every rank takes this branch or none does
             flag = dist.max_(flag)
+        ps.unmerged = False
         if int(flag.item()) == 0:
             return True
         ps.bad.zero_()
         ps.ok = False
         ps.fresh = {"x": None, "y": None}
+        ps.common_y = None
         return False
 
     # ------------------------------------------------------------------ K3 passes
@@ -381,7 +389,7 @@ class CudaOps(VectorOps):
             if bounds is None:
                 bounds, ns = self._split_plan(P.n, Q.n)
             partial = self._partial(ns, P.n)
-            self._call("sdb_lse_pass_simt", _ptr(P.xt), P.ld, P.n, _ptr(Q.xt), Q.ld, Q.n, P.dpad, _ptr(bias), scale,
+            self._call("sdb_lse_pass_simt", _ptr(P.xt), P.ld, P.n, _ptr(Q.xt), Q.ld, Q.n, P.dpad, _ptr(bias), -0.5 * scale,
                        _ptr(bounds), ns, _ptr(partial))
             norms = P.norms
         if not finalize:
@@ -400,6 +408,7 @@ class CudaOps(VectorOps):
         use = ps.fresh[side_key] == key
         ps.fresh[side_key] = key
         ps.used = ps.used or use
+        ps.unmerged = ps.unmerged or use
         return (ps.m[side_key] if use else None), ps.m[side_key], ps.bad
 
     def row_lse(self, g, eps, out=None, predict=False):
@@ -424,6 +433,8 @@ class CudaOps(VectorOps):
             self._pred.fresh = {"x": None, "y": None}
             self._pred.ok = True
             self._pred.used = False
+            self._pred.common_y = None
+            self._pred.unmerged = False
             self._pred.bad.zero_()
 
     def fused_sweeps(self, st, eps, alpha1, alpha2, log_tau, log_floor, n_sweeps, lr_known_first):
@@ -531,6 +542,53 @@ class CudaOps(VectorOps):
         self._bias_key["x"] = (_ptr(f), eps, self.inv_med) if f is not None else None
         row_m, m_next, bad = self._pred_args("y", eps, predict and f is not None)
         return self._lse(self.Y, self.X, self.bias_x, eps, out, row_m=row_m, m_next=m_next, bad=bad)
+
+    # ------------------------------------------------------------------ row-partitioned column step with one collective
+    # (driver: sinkhorn._sweep_body; kernels: sdb_partial_sums_f64 / sdb_update_from_sums_f64, see include/spadot_b200.h)
+    def col_shift_ready(self, eps):
+        """True when every rank holds the same per-column shift for (eps, median): the column pass can then run against it
+        and the per-rank sums are combined by ONE all-reduce(SUM).  Same answer on every rank by construction."""
+        ps = self._pred_state()
+        return ps is not None and ps.common_y == (eps, self.inv_med)
+
+    def seed_col_shift(self, st, eps):
+        """After a column step combined the long way (max + sum all-reduces): shift_j = combined LSE_j in log2 units + 1."""
+        ps = self._pred_state()
+        if ps is None:
+            return
+        self._prep(eps)
+        t = (st.Lc + self._norms(self.Y) * (self.inv_med / eps)) * math.log2(math.e) + 1.0
+        ps.m["y"].copy_(torch.where(torch.isfinite(t), t, torch.zeros_like(t)))
+        ps.fresh["y"] = ps.common_y = (eps, self.inv_med)
+
+    def col_partial_sums(self, st, eps, it):
+        """This rank's column sums against the common shift, + the tau and verification riders: (M + 2) doubles."""
+        self._prep(eps)
+        ps = self._pred
+        if getattr(self, "_sum_vec", None) is None:
+            self._sum_vec = torch.zeros(self.m + 2, dtype=torch.float64, device=self.device)
+        vec = self._sum_vec
+        if self.n == 0:
+            return vec.zero_()
+        key = (_ptr(st.f), eps, self.inv_med)
+        if self._bias_key["x"] != key:
+            self._call("sdb_make_bias", self.n, self.bias_x.numel(), _ptr(st.f), _ptr(self._norms(self.X)), eps, self.inv_med / eps,
+                       _ptr(self.bias_x))
+            self._bias_key["x"] = key
+        partial = self._lse(self.Y, self.X, self.bias_x, eps, finalize=False, row_m=ps.m["y"])
+        self._call("sdb_partial_sums_f64", _ptr(partial), partial.shape[0], self.m, _ptr(ps.m["y"]), _ptr(vec), _ptr(self.flag), it,
+                   _ptr(ps.bad))
+        ps.used = True
+        return vec
+
+    def col_update_from_sums(self, vec, st, eps, alpha2, it, log_tau, log_floor=NEG_INF):
+        ps = self._pred
+        self._call("sdb_update_from_sums_f64", _ptr(vec), _ptr(ps.m["y"]), self.m, _ptr(self._norms(self.Y)), self.inv_med / eps,
+                   _ptr(st.Lc), _ptr(st.logq), eps, alpha2, math.log(st.N), _ptr(st.g), _ptr(st.v), _ptr(st.lb_old), _ptr(self.bias_y),
+                   _ptr(self.flag), it, log_tau, log_floor, _ptr(ps.bad))
+        self._bias_key["y"] = (_ptr(st.g), eps, self.inv_med)
+        ps.used = True
+        ps.unmerged = False          # the all-reduce carried every rank's flag: `bad` is now the same everywhere
 
     # ------------------------------------------------------------------ vector updates
     def _side_norms(self, side, pot):

@@ -9,9 +9,11 @@ total potentials  f = u + eps*log a,  g = v + eps*log b  (SURVEY.md §3.3):
 
 Each LSE is one streamed device pass that recomputes cost tiles from the embeddings, so
 nothing of size N x M exists unless the caller asks for the dense plan.  Rows (source
-spots) may be partitioned across ranks: the row pass is local, the column pass produces a
-per-rank partial LSE over M columns that is combined with two small all-reduces
-(max, then sum) — the only data-path collectives.
+spots) may be partitioned across ranks: the row pass is local, the column pass produces
+per-rank partial sums over M columns against a shift every rank already holds (the previous
+combined column LSE), combined with ONE all-reduce(SUM) per iteration that also carries the
+tau and verification flags; only the first iteration of an epsilon stage, which has no such
+shift yet, combines with max-then-sum — the only data-path collectives.
 
 The drivers are written against the `ops` interface of cuda_ops.CudaOps.
 """
@@ -171,17 +173,29 @@ def _sweep_body(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_kn
         if not lr_known:
             ops.row_lse(st.g, eps, out=st.Lr)
         ops.potential_update("row", st.Lr, st.logp, eps, alpha1, math.log(st.m), st.f, st.u, st.la_old, it, log_tau, log_floor)
+    merged = False
+    ready = getattr(ops, "col_shift_ready", None) if dist.world > 1 else None
     if fused is not None and dist.world == 1:
         fused("col", st, eps, alpha2, it, log_tau, log_floor)
+    elif ready is not None and ready(eps):
+        # every rank holds the same per-column shift (the previous combined LSE): per-rank sums are addable, ONE collective;
+        # the tau flag of the row update and the verification flag of the predicted passes ride in two extra slots
+        vec = ops.col_partial_sums(st, eps, it)
+        dist.sum_(vec)
+        ops.col_update_from_sums(vec, st, eps, alpha2, it, log_tau, log_floor)
+        merged = True
     else:
-        if _predicting(ops):
+        seed = getattr(ops, "seed_col_shift", None) if dist.world > 1 else None
+        if _predicting(ops) and seed is None:
             ops.col_lse(st.f, eps, out=st.Lc, predict=True)       # verified by the settle() of _sweep
         else:
             ops.col_lse(st.f, eps, out=st.Lc)
         if dist.world > 1:
-            st.Lc.copy_(combine_col_lse(st.Lc, dist))
+            st.Lc.copy_(combine_col_lse(st.Lc, dist))             # first iteration of a stage: max, then sum
         ops.potential_update("col", st.Lc, st.logq, eps, alpha2, math.log(st.N), st.g, st.v, st.lb_old, it, log_tau, log_floor)
-    if dist.world > 1:
+        if seed is not None:
+            seed(st, eps)
+    if dist.world > 1 and not merged:
         dist.max_(ops.absorb_flag_tensor())
     ops.absorb(it, st.f, st.g, st.u, st.v)                        # ot_func.cpp:778-819
 

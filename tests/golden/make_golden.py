@@ -129,6 +129,77 @@ def model_case(name="model_small", seed=5):
     print(name, "written; losses", float(recon), float(skl), float(gkl), float(align))
 
 
+TRAIN_CFG = dict(z_dim=8, svgp_encoder_layers=[32, 16], gat_encoder_hidden=12, gat_attention_heads=2, decoder_layers=[16, 32],
+                 kernel_type="Gaussian", kernel_scale=0.1, lr=3e-4, lambda1=0.1, beta1=1.0, beta2=1e-4, omiga1=0.1, maxiter=100)
+
+
+def train_problem(seed=9, sizes=(300, 260), genes=40, m=28, batch=64):
+    """Two small timepoints: standardised coordinates, expression, reference-built kNN graph, induced 2-hop batches."""
+    from oracle import graph_ref
+    rng = np.random.default_rng(seed)
+    tps = {}
+    for t, n in enumerate(sizes):
+        raw = rng.uniform(0, 3000, size=(n, 2))
+        loc = (raw - raw.mean(0)) / raw.std(0)                    # StandardScaler per timepoint, _train_utils.py:133-138
+        ei = graph_ref.spatial_edge_index(raw, 6)
+        batches = [(nodes, lei, ns) for nodes, lei, ns in graph_ref.two_hop_batches_ref(ei, n, batch)]
+        tps[f"t{t}"] = dict(loc=loc, y=rng.normal(size=(n, genes)), edge_index=ei, inducing=loc[rng.choice(n, m, replace=False)],
+                            batches=batches, n=n)
+    return tps
+
+
+def train_run(model, tps, epochs, noise_seed, device="cpu"):
+    """The optimiser loop of train_SpaDOT (utils/_train_utils.py:155-236) before the k-means / OT regularisers switch on:
+    AdamW(lr), elbo = lambda1*Recon - beta1(epoch)*SVGP_KL + beta2*GAT_KL + omiga1*alignment, clip_grad_norm_ 0.3, fixed
+    timepoint order; reparameterisation noise drawn from one seeded CPU generator (teacher-forced across devices)."""
+    from oracle import graph_ref
+    gen = torch.Generator().manual_seed(noise_seed)
+    noise = lambda t: torch.randn(t.shape, dtype=t.dtype, generator=gen).to(t.device)       # noqa: E731
+    opt = torch.optim.AdamW(filter(lambda p: p.requires_grad, model.parameters()), lr=TRAIN_CFG["lr"])
+    beta1s = graph_ref.beta_cycle_linear(TRAIN_CFG["maxiter"], stop=TRAIN_CFG["beta1"])
+    model.train()
+    trace = []
+    orig = torch.randn_like
+    torch.randn_like = noise
+    if hasattr(model, "noise_fn"):
+        model.noise_fn = noise
+    try:
+        for epoch in range(epochs):
+            for tp, d in tps.items():
+                x_all, y_all = torch.as_tensor(d["loc"], device=device), torch.as_tensor(d["y"], device=device)
+                for nodes, lei, ns in d["batches"]:
+                    nodes_t, lei_t = torch.as_tensor(nodes, device=device), torch.as_tensor(lei, device=device)
+                    recon, skl, gkl, align, _ = model.forward(x_all[nodes_t], y_all[nodes_t], lei_t, tp, ns)
+                    elbo = TRAIN_CFG["lambda1"] * recon - beta1s[epoch] * skl + TRAIN_CFG["beta2"] * gkl + TRAIN_CFG["omiga1"] * align
+                    opt.zero_grad()
+                    elbo.backward()
+                    torch.nn.utils.clip_grad_norm_(model.parameters(), 0.3)
+                    opt.step()
+                    trace.append([float(elbo), float(recon), float(skl), float(gkl), float(align)])
+    finally:
+        torch.randn_like = orig
+    return np.array(trace)
+
+
+def train_case(name="train_trace_small", seed=9, epochs=3):
+    """30 optimiser steps of the reference's OWN model class (GATConv stubbed, see reference_loader.load_model) in the
+    reference's training loop: the loss trace north_star asks to reproduce "within 1e-3 relative with the same seed"."""
+    ref = reference_loader.load_model()
+    tps = train_problem(seed)
+    torch.manual_seed(seed)
+    cfg = dict(input_dim=40, dtype=torch.float64, device="cpu", timepoints=list(tps), **{k: TRAIN_CFG[k] for k in
+               ("z_dim", "svgp_encoder_layers", "gat_encoder_hidden", "gat_attention_heads", "decoder_layers", "kernel_type", "kernel_scale")})
+    dl = dict(inducing_points={tp: d["inducing"] for tp, d in tps.items()}, N_train={tp: d["n"] for tp, d in tps.items()})
+    model = ref.SpaDOT(cfg, dl)
+    out = {"param::" + k: v.clone().numpy() for k, v in model.state_dict().items()}
+    trace = train_run(model, tps, epochs, noise_seed=seed + 1)
+    out.update(trace=trace, epochs=np.array(epochs), seed=np.array(seed))
+    for k, v in model.state_dict().items():
+        out["final::" + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "written;", len(trace), "steps; elbo", trace[0, 0], "->", trace[-1, 0])
+
+
 def visium_like_coords(n, seed, jitter=0.35):
     """Hexagonal lattice in pixel units (100 px pitch) with sub-pixel registration jitter, cropped to n spots: the
     geometry of a Visium capture area (ChickenHeart).  The jitter breaks the exact distance ties of an ideal lattice,
@@ -154,10 +225,16 @@ def graph_case(name, n, seed, kind):
     print(name, "written;", log.strip().splitlines()[1])
 
 
+if __name__ == "__main__" and "--train-only" in sys.argv:
+    train_case()
+    sys.exit(0)
+
+
 if __name__ == "__main__" and "--graph-only" in sys.argv:
     graph_case("graph_visium_747", 747, 21, "visium")
     graph_case("graph_visium_1966", 1966, 22, "visium")
     graph_case("graph_uniform_1916", 1916, 23, "uniform")
+    train_case()
     sys.exit(0)
 
 

@@ -70,14 +70,46 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, a, b, G, la, lb, out):
+class _CommonShiftOps(NumpyOps):
+    """NumpyOps + the one-collective column step of the row-partitioned solve (CudaOps.col_shift_ready /
+    col_partial_sums / col_update_from_sums / seed_col_shift), restated in fp64 numpy: every rank sums
+    exp(local LSE - shift) against the same shift (the previous combined LSE + 1), one all-reduce(SUM) of M + 2 doubles
+    carries the sums, the tau flag of the row update and the verification flag."""
+
+    def __init__(self, x, y):
+        super().__init__(x, y)
+        self.shift, self.shift_key, self.merged_steps = None, None, 0
+
+    def col_shift_ready(self, eps):
+        return self.shift_key == (eps, self.inv_med)
+
+    def seed_col_shift(self, st, eps):
+        self.shift = torch.where(torch.isfinite(st.Lc), st.Lc + 1.0, torch.zeros_like(st.Lc))
+        self.shift_key = (eps, self.inv_med)
+
+    def col_partial_sums(self, st, eps, it):
+        vec = torch.zeros(self.m + 2, dtype=torch.float64)
+        vec[:self.m] = torch.exp(self.col_lse(st.f, eps) - self.shift)
+        vec[self.m] = 1.0 if int(self.flag[0]) == it else 0.0
+        return vec
+
+    def col_update_from_sums(self, vec, st, eps, alpha2, it, log_tau, log_floor=float("-inf")):
+        if float(vec[self.m]) > 0:
+            self.flag[0] = max(int(self.flag[0]), it)
+        st.Lc.copy_(self.shift + torch.log(vec[:self.m]))
+        self.shift = torch.where(torch.isfinite(st.Lc), st.Lc + 1.0, torch.zeros_like(st.Lc))
+        self.potential_update("col", st.Lc, st.logq, eps, alpha2, float(np.log(st.N)), st.g, st.v, st.lb_old, it, log_tau, log_floor)
+        self.merged_steps += 1
+
+
+def _worker(rank, world, port, a, b, G, la, lb, out, ops_cls=NumpyOps):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     td.init_process_group("gloo", rank=rank, world_size=world)
     try:
         n = a.shape[0]
         r0, r1 = (n * rank) // world, (n * (rank + 1)) // world
         dist = sinkhorn.Dist()
-        ops = NumpyOps(a[r0:r1], b)
+        ops = ops_cls(a[r0:r1], b)
         med = sinkhorn.median_cost(ops, dist, small_limit=0, n_samples=2048, n_bins=64)
         ops.set_median(med)
         info = {}
@@ -86,7 +118,8 @@ def _worker(rank, world, port, a, b, G, la, lb, out):
         tab = dist.sum_(ops.transition_table(st.f, st.g, eps, la[r0:r1], lb, 10, 10)).numpy()
         st2, eps2 = sinkhorn.solve_stablev2(ops, G[r0:r1], dist=dist, **dict(CFG, scaling_iter=120, extra_iter=30))
         out[rank] = dict(med=med, rows=(r0, r1), plan=plan_rows, iters=info["iters_per_stage"], tab=tab,
-                         plan2=ops.plan_dense(st2.f, st2.g, eps2).numpy(), collectives=dist.collectives)
+                         plan2=ops.plan_dense(st2.f, st2.g, eps2).numpy(), collectives=dist.collectives,
+                         merged_steps=getattr(ops, "merged_steps", 0))
     finally:
         td.destroy_process_group()
 
@@ -115,6 +148,33 @@ def test_row_partitioned_solve_world2_gloo():
     np.testing.assert_allclose(plan2, want2, rtol=1e-9, atol=1e-300)
     np.testing.assert_allclose(out[0]["tab"], ot_dense.transition_table(want, la, lb, 10, 10), rtol=1e-9)
     np.testing.assert_allclose(out[0]["tab"], out[1]["tab"], rtol=1e-14)
+
+
+def test_row_partitioned_solve_one_collective_per_iteration_world2_gloo():
+    """The common-shift column step: same plan / iterations as the oracle, and the collective count drops from 3 per
+    iteration (max + sum of the M-vector, tau flag) to 1 for every iteration but the first of a stage."""
+    a, b, la, lb = ot_dense.synthetic_embeddings(53, 41, 5, seed=78)
+    G = np.exp(np.random.default_rng(3).normal(0, 0.5, 53))
+    Cn, med = ot_dense.median_normalised_cost(a, b)
+    info_ref = {}
+    cfg_tau = dict(CFG)
+    want = ot_dense.duality_gap_solve(Cn, G, info=info_ref, **cfg_tau)
+    want2 = ot_dense.transport_stablev2(C=Cn, G=G, **dict(CFG, scaling_iter=120, extra_iter=30))
+    mgr = mp.Manager()
+    out, out_old = mgr.dict(), mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), a, b, G, la, lb, out, _CommonShiftOps), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), a, b, G, la, lb, out_old, NumpyOps), nprocs=2, join=True)
+    plan, plan2 = np.zeros_like(want), np.zeros_like(want)
+    total = sum(info_ref["iters_per_stage"])
+    for r in (0, 1):
+        o = out[r]
+        assert o["iters"] == info_ref["iters_per_stage"]
+        plan[o["rows"][0]:o["rows"][1]] = o["plan"]
+        plan2[o["rows"][0]:o["rows"][1]] = o["plan2"]
+        assert o["merged_steps"] >= total - 6 + 150 - 4           # all but the first iteration of each stage / schedule step
+        assert o["collectives"] < out_old[r]["collectives"] - 2 * (total - 6)
+    np.testing.assert_allclose(plan, want, rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(plan2, want2, rtol=1e-9, atol=1e-300)
 
 
 class _FaultyPredictingOps(NumpyOps):

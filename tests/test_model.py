@@ -74,3 +74,52 @@ def test_all_latent_samples_matches_oracle(golden_dir):
         gm, _ = ref.GATEncoder(y, torch.from_numpy(z["edge_index"]))
         want = torch.cat((pm, gm), dim=1).numpy()
     np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-10)
+
+
+# ------------------------------------------------------------------ multi-step training parity (north_star: loss curves 1e-3)
+def _train_setup(golden_dir, device, cls):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(golden_dir, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    z = np.load(os.path.join(golden_dir, "train_trace_small.npz"))
+    tps = mg.train_problem(int(z["seed"]))
+    cfg = dict(input_dim=40, dtype=torch.float64, device=device, timepoints=list(tps), **{k: mg.TRAIN_CFG[k] for k in
+               ("z_dim", "svgp_encoder_layers", "gat_encoder_hidden", "gat_attention_heads", "decoder_layers", "kernel_type", "kernel_scale")})
+    dl = dict(inducing_points={tp: d["inducing"] for tp, d in tps.items()}, N_train={tp: d["n"] for tp, d in tps.items()})
+    model = cls(cfg, dl).to(device)
+    sd = {k[len("param::"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param::")}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and not [m for m in missing if "svgp" not in m], (missing, unexpected)
+    return mg, z, tps, model
+
+
+def _check_trace(z, model, trace, rtol):
+    want = z["trace"]
+    assert trace.shape == want.shape and want.shape[0] >= 28
+    rel = np.abs(trace - want) / np.maximum(np.abs(want), 1e-12)
+    assert rel.max() < rtol, (rel.max(), np.unravel_index(rel.argmax(), rel.shape))
+    for k, v in model.state_dict().items():
+        if "final::" + k in z.files and v.dtype.is_floating_point:
+            w = z["final::" + k]
+            assert float(np.abs(v.cpu().numpy() - w).max()) <= rtol * 10 * max(1.0, float(np.abs(w).max())), k
+
+
+def test_model_oracle_reproduces_reference_training_trace(golden_dir):
+    """oracle/model_ref.py over 30 optimiser steps (3 epochs x 2 timepoints x 5 induced 2-hop batches; AdamW, clip 0.3,
+    beta1 cycle, BatchNorm running statistics, the ce > inside_elbo sign rule of SpaDOT.py:77) against the trace the
+    reference's own model class produced in the reference's loop (tests/golden/make_golden.py::train_case)."""
+    mg, z, tps, model = _train_setup(golden_dir, "cpu", model_ref.SpaDOTRef)
+    trace = mg.train_run(model, tps, int(z["epochs"]), noise_seed=int(z["seed"]) + 1)
+    _check_trace(z, model, trace, rtol=1e-8)
+
+
+@pytest.mark.gpu
+def test_cuda_model_reproduces_reference_training_trace(golden_dir):
+    """The CUDA-backed drop-in model through the same 30 steps.  north_star: "training loss curves within 1e-3 relative
+    with the same seed"; the gate here is 1e-6 (measured ~1e-12: fp64 kernels, only summation orders differ)."""
+    from spadot_b200 import model as product
+    dev = torch.device("cuda:0")
+    mg, z, tps, model = _train_setup(golden_dir, dev, product.SpaDOT)
+    trace = mg.train_run(model, tps, int(z["epochs"]), noise_seed=int(z["seed"]) + 1, device=dev)
+    _check_trace(z, model, trace, rtol=1e-6)
