@@ -198,6 +198,30 @@ int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int first_tick, i
 int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_sweeps, int first_tick, int lr_known_first,
                                    unsigned int* barrier2, void* stream);
 
+/* The whole duality-gap solve of a small problem (SIMT form) in ONE cooperative launch: six epsilon stages, stage 0-4
+ * criterion, final-stage duality gap, tau bookkeeping - everything optimal_transport_duality_gap does around its native
+ * loop (ref: ot_solvers.py:240-449, ot_func.cpp:831-930).  Two grid barriers per iteration: the CTA that finishes the last
+ * column split of a 64-row slab combines the slab's partials and updates its potentials.  On return (after the stream
+ * synchronises) f, g, u, v, Lr (row LSE at the final g), Lc hold the final state and *result the iteration counts.
+ * Caller-owned workspaces: flag2 (2 ints), barrier2 (2 uints), counters (ceil(n/64) + ceil(m/64) uints), scratch
+ * (SDB_SOLVE_MAX_CTAS * 10 doubles), result (device).  Iterations are stamped first_tick, first_tick + 1, ... */
+#define SDB_SOLVE_MAX_CTAS 1024
+typedef struct sdb_solve_params {
+    double lambda1, lambda2, epsilon, epsilon0, tolerance, tau, max_iter;
+    int32_t batch_size, reserved;
+} sdb_solve_params;
+typedef struct sdb_solve_result {
+    int32_t iters[6];            /* iterations per epsilon stage */
+    int32_t total_iters;
+    int32_t status;              /* 0 ok, 1 NaN gap (ref: ot_solvers.py:446-447) */
+    int32_t max_iter_reached;    /* a stage gave up at max_iter (ref: ot_func.cpp:821-824) */
+    int32_t last_tick;
+    double gap, eps_final;
+} sdb_solve_result;
+int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_solve_params* p, int first_tick, int* flag2,
+                                  unsigned int* barrier2, unsigned int* counters, double* scratch,
+                                  sdb_solve_result* result, void* stream);
+
 /* ------------------------------------------------------------------ K4: stopping rules */
 /* Stage 0-4 rule (ref: ot_func.cpp:897-922).  out[0..3] =
  *   sum (a~ - old_a e^{u/eps})^2, sum a~^2, sum (b~ - old_b e^{v/eps})^2, sum b~^2

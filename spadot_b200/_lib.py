@@ -28,6 +28,7 @@ SIGNATURES = {
     "sdb_lse_pass_simt": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_d, c_p, c_i, c_p, c_p],
     "sdb_sinkhorn_sweeps": [c_p, c_i, c_i, c_i, c_p],
     "sdb_sinkhorn_sweeps_persistent": [c_p, c_i, c_i, c_i, c_p, c_p],
+    "sdb_sinkhorn_solve_persistent": [c_p, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p],
     "sdb_lse_finalize": [c_p, c_i, c_l, c_p, c_d, c_p, c_p],
     "sdb_lse_finalize_pred": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_p, c_p],
     "sdb_finalize_update_pred": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p, c_p, c_p],
@@ -85,6 +86,20 @@ class SweepDesc(ctypes.Structure):
                 ("pow2_scale", c_d),
                 ("m_x", c_p), ("m_y", c_p), ("bad_flag", c_p), ("pred_from_row", ctypes.c_int32), ("pred_from_col", ctypes.c_int32)]
 
+
+class SolveParams(ctypes.Structure):
+    """struct sdb_solve_params"""
+    _fields_ = [("lambda1", c_d), ("lambda2", c_d), ("epsilon", c_d), ("epsilon0", c_d), ("tolerance", c_d), ("tau", c_d),
+                ("max_iter", c_d), ("batch_size", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+class SolveResult(ctypes.Structure):
+    """struct sdb_solve_result"""
+    _fields_ = [("iters", ctypes.c_int32 * 6), ("total_iters", ctypes.c_int32), ("status", ctypes.c_int32),
+                ("max_iter_reached", ctypes.c_int32), ("last_tick", ctypes.c_int32), ("gap", c_d), ("eps_final", c_d)]
+
+
+SOLVE_MAX_CTAS = 1024
 
 _lib = None
 

@@ -354,6 +354,295 @@ __global__ void __launch_bounds__(NT) sinkhorn_persistent_kernel(PersistArgs a) 
     }
 }
 
+
+// -------------------------------------------------------------------------------------------- whole solve, one launch
+// optimal_transport_duality_gap (ref: SpaDOT/utils/OT_loss/ot_solvers.py:240-449 driving update_process<double>,
+// ot_func.cpp:831-930) for a small problem in ONE cooperative launch: the six epsilon stages, their stopping rules
+// (stage 0-4 criterion :897-922, final-stage duality gap :493-544) and every iteration run on the device; the host
+// reads one small result record at the end.  An iteration costs TWO grid barriers: the (max, sum) partials of a
+// 64-row slab are combined, and the potential updated, by whichever CTA finishes the slab's last column split
+// (a per-slab arrival counter), so there is no separate update phase between a pass and the next one.
+// tau bookkeeping without a phase of its own: updaters of tick t stamp flag[t & 1]; an updater of tick t+1 that finds
+// flag[t & 1] == t first absorbs its own row (frame <- potential), which is all `absorb` is in total potentials.
+struct SolveArgs {
+    PairArgs row, col;
+    int ns_row, ns_col;
+    float2* partial_row; float2* partial_col;
+    float* bias_x; float* bias_y;
+    double *f, *g, *u, *v, *la_old, *lb_old, *Lr, *Lc;
+    const double* logp; const double* logq;
+    int* flag;                          // caller's absorb flag (left consistent: last tick that exceeded tau)
+    int* flag2;                         // [2] ping-pong flags of this kernel
+    double inv_med, lambda1, lambda2, epsilon, epsilon0, tolerance, log_tau, log_m, log_N, dx, dy;
+    int batch_size; long long max_iter; int first_tick;
+    unsigned int* barrier;              // [2]
+    unsigned int* counters;             // [row_tiles + col_tiles], zero on entry, left zero
+    double* scratch;                    // [gridDim.x * 10]
+    sdb_solve_result* result;
+};
+
+template <int K>
+__device__ void solve_grid_sums(double (&acc)[K], double* scratch, unsigned int* bar, unsigned int& gen, double (&out)[K]) {
+    __shared__ double sm[8][K];
+    __shared__ double tot[K];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double v = sdb_warp_sum(acc[k]);
+        if (lane == 0) sm[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += sm[w][threadIdx.x];
+        scratch[(size_t)blockIdx.x * K + threadIdx.x] = v;
+    }
+    grid_barrier(bar, gen);
+    // every CTA adds the per-CTA partials in the same order: identical sums, identical decisions everywhere
+    for (int k = warp; k < K; k += 8) {
+        double v = 0.0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) v += __ldcg(scratch + (size_t)b * K + k);
+        v = sdb_warp_sum(v);
+        if (lane == 0) tot[k] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[k] = tot[k];
+    __syncthreads();
+}
+
+__device__ __forceinline__ double solve_safe_ratio(double num2, double den2) {       // sinkhorn._safe_ratio
+    const double a = sqrt(num2), b = sqrt(den2);
+    if (isinf(a) && isinf(b)) return NAN;
+    return a / (1.0 + b);
+}
+
+// One pass over (slab, split) items; the CTA that completes a slab combines its partials and, with UPDATE, updates the
+// potential of those 64 rows (pot, frame, la_old, bias_out, flags) - else it only stores the LSE.
+template <bool UPDATE>
+__device__ void solve_pass(const PairArgs& pa, float scale_hi, float scale_lo, float2* partial, int ns, unsigned int* counters,
+                           double* L, const double* logmarg, double eps, double alpha, double log_n_other, double* pot,
+                           double* frame, double* la_old, float* bias_out, int* flag2, int tick, double log_tau, float* smem) {
+    __shared__ int s_last;
+    const int64_t n = pa.n_p;
+    const int tiles = (int)((n + BM - 1) / BM);
+    LseEpi::Params ep{scale_hi, scale_lo, partial};
+    const bool pending = UPDATE && (*reinterpret_cast<volatile int*>(flag2 + ((tick - 1) & 1)) == tick - 1);
+    for (int item = blockIdx.x; item < tiles * ns; item += gridDim.x) {
+        const int tile = item % tiles;
+        pair_tile_item<true, LseEpi>(pa, ep, tile, item / tiles, smem);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned prev = atomicAdd(counters + tile, 1u);
+            s_last = (prev == (unsigned)ns - 1u);
+            if (s_last) counters[tile] = 0u;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            // 4 threads per row, splits strided over them
+            const int64_t i = (int64_t)tile * BM + (threadIdx.x >> 2);
+            const int sub = threadIdx.x & 3;
+            float mx = -INFINITY;
+            if (i < n)
+                for (int sp = sub; sp < ns; sp += 4) {
+                    const float2 ps = __ldcg(partial + (int64_t)sp * n + i);
+                    if (ps.x > -1e29f && ps.y > 0.f) mx = fmaxf(mx, ps.x);
+                }
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            double S = 0.0;
+            if (i < n && mx > -INFINITY)
+                for (int sp = sub; sp < ns; sp += 4) {
+                    const float2 ps = __ldcg(partial + (int64_t)sp * n + i);
+                    if (ps.x > -1e29f && ps.y > 0.f) S += (double)ps.y * exp2((double)ps.x - (double)mx);
+                }
+            S += __shfl_xor_sync(0xffffffffu, S, 1);
+            S += __shfl_xor_sync(0xffffffffu, S, 2);
+            if (sub == 0 && i < n) {
+                const double Li = (mx > -INFINITY) ? SDB_LN2 * ((double)mx + log2(S)) : -INFINITY;
+                L[i] = Li;
+                if (UPDATE) {
+                    const double old = pot[i];
+                    double fr = frame[i];
+                    if (pending) { fr = old; frame[i] = old; }           // absorb of the previous tick, row by row
+                    la_old[i] = (old - fr) / eps;
+                    const double nv = eps * alpha * (logmarg[i] - (Li - log_n_other));
+                    pot[i] = nv;
+                    const double b = SDB_LOG2E * (nv / eps);
+                    bias_out[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
+                    if ((nv - fr) / eps > log_tau) atomicMax(flag2 + (tick & 1), tick);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    unsigned int gen = *reinterpret_cast<volatile unsigned int*>(a.barrier + 1);
+    const int64_t n = a.row.n_p, m = a.col.n_p;
+    const int row_tiles = (int)((n + BM - 1) / BM);
+    const int64_t gtid = (int64_t)blockIdx.x * NT + threadIdx.x, gsize = (int64_t)gridDim.x * NT;
+    unsigned int* cnt_row = a.counters;
+    unsigned int* cnt_col = a.counters + row_tiles;
+    const double scale_factor = exp(-log(a.epsilon) / 5.0);              // ot_solvers.py:218
+    double eps = a.epsilon0 * scale_factor;
+    int tick = a.first_tick - 1;
+    double gap = INFINITY, sumK = 0.0;
+    int status = 0, total = 0;
+    bool lr_known = false;
+    PairArgs row0 = a.row;                                               // row pass with g = 0 (sum of exp(-C/eps))
+    row0.bias = nullptr;
+    for (int e = 0; e <= 5 && status == 0; ++e) {
+        eps = eps / scale_factor;                                        // ot_solvers.py:254
+        const double c1 = a.inv_med / eps;
+        const double alpha1 = a.lambda1 / (a.lambda1 + eps), alpha2 = a.lambda2 / (a.lambda2 + eps);
+        const double sc = -c1 * SDB_LOG2E;
+        const float sc_hi = (float)sc, sc_lo = (float)(sc - (double)sc_hi);
+        const bool final_stage = (e == 5);
+        const double threshold = final_stage ? a.tolerance : 1e-6;       // ot_solvers.py:262
+        const int n_inner = final_stage ? a.batch_size : 5;              // ot_func.cpp:867
+        // stage start: absorb (u <- f, v <- g), old_a = old_b = 1, bias of the first row pass at the new epsilon
+        for (int64_t i = gtid; i < n; i += gsize) { a.u[i] = a.f[i]; a.la_old[i] = 0.0; }
+        for (int64_t j = gtid; j < m; j += gsize) {
+            const double gj = a.g[j];
+            a.v[j] = gj;
+            a.lb_old[j] = 0.0;
+            const double b = SDB_LOG2E * (gj / eps);
+            a.bias_y[j] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
+        }
+        if (gtid == 0) { a.flag2[0] = -1; a.flag2[1] = -1; }              // frames are fresh: nothing pending (ticks are >= 0)
+        grid_barrier(a.barrier, gen);
+        long long n_it = 0;
+        gap = INFINITY;
+        lr_known = false;
+        bool have_sumK = false;
+        while (true) {
+            for (int sw = 0; sw < n_inner; ++sw) {
+                ++tick;
+                if (sw == 0 && lr_known) {
+                    // Lr holds the row LSE at the current g (the gap check's pass): plain update of f
+                    const bool pending = (*reinterpret_cast<volatile int*>(a.flag2 + ((tick - 1) & 1)) == tick - 1);
+                    for (int64_t i = gtid; i < n; i += gsize) {
+                        const double old = a.f[i];
+                        double fr = a.u[i];
+                        if (pending) { fr = old; a.u[i] = old; }
+                        a.la_old[i] = (old - fr) / eps;
+                        const double nv = eps * alpha1 * (a.logp[i] - (a.Lr[i] - a.log_m));
+                        a.f[i] = nv;
+                        const double b = SDB_LOG2E * (nv / eps);
+                        a.bias_x[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
+                        if ((nv - fr) / eps > a.log_tau) atomicMax(a.flag2 + (tick & 1), tick);
+                    }
+                } else {
+                    solve_pass<true>(a.row, sc_hi, sc_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, a.logp, eps, alpha1, a.log_m, a.f, a.u,
+                                     a.la_old, a.bias_x, a.flag2, tick, a.log_tau, smem);
+                }
+                grid_barrier(a.barrier, gen);
+                solve_pass<true>(a.col, sc_hi, sc_lo, a.partial_col, a.ns_col, cnt_col, a.Lc, a.logq, eps, alpha2, a.log_N, a.g, a.v,
+                                 a.lb_old, a.bias_y, a.flag2, tick, a.log_tau, smem);
+                grid_barrier(a.barrier, gen);
+            }
+            n_it += n_inner;
+            lr_known = false;
+            // the last tick's absorption is still pending: apply it here, row by row, before the frames are read
+            const bool pending = (*reinterpret_cast<volatile int*>(a.flag2 + (tick & 1)) == tick);
+            if (final_stage) {
+                if (!have_sumK) {
+                    solve_pass<false>(row0, sc_hi, sc_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, nullptr, eps, 0.0, 0.0, nullptr, nullptr,
+                                      nullptr, nullptr, a.flag2, tick, a.log_tau, smem);
+                    grid_barrier(a.barrier, gen);
+                    double acc1[1] = {0.0}, out1[1];
+                    for (int64_t i = gtid; i < n; i += gsize) acc1[0] += exp(a.Lr[i]);
+                    solve_grid_sums<1>(acc1, a.scratch, a.barrier, gen, out1);
+                    sumK = out1[0];
+                    have_sumK = true;
+                }
+                // row LSE at the new g: the gap's row marginal, and the next iteration's row pass
+                solve_pass<false>(a.row, sc_hi, sc_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, nullptr, eps, 0.0, 0.0, nullptr, nullptr,
+                                  nullptr, nullptr, a.flag2, tick, a.log_tau, smem);
+                grid_barrier(a.barrier, gen);
+                lr_known = true;
+                double acc[8], t[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+                for (int64_t i = gtid; i < n; i += gsize) {               // gap_terms_kernel (sdb_vectors.cu), ot_func.cpp:358-544
+                    if (pending) a.u[i] = a.f[i];
+                    const double fi = a.f[i], lp = a.logp[i];
+                    const double R = exp(fi / eps + a.Lr[i]), p = exp(lp), r = R * a.dy;
+                    acc[0] += R;
+                    acc[1] += fi * R;
+                    acc[2] += a.dx * (r * (log(r) - lp) - r + p);
+                    acc[3] += p * a.dx * (exp(-fi / a.lambda1) - 1.0);
+                }
+                for (int64_t j = gtid; j < m; j += gsize) {
+                    if (pending) a.v[j] = a.g[j];
+                    const double gj = a.g[j], lq = a.logq[j];
+                    const double R = exp(gj / eps + a.Lc[j]), q = exp(lq), c = R * a.dx;
+                    acc[4] += R;
+                    acc[5] += gj * R;
+                    acc[6] += a.dy * (c * (log(c) - lq) - c + q);
+                    acc[7] += q * a.dy * (exp(-gj / a.lambda2) - 1.0);
+                }
+                solve_grid_sums<8>(acc, a.scratch, a.barrier, gen, t);
+                const double IJ = (double)(1.0 / a.dx) * (double)m;
+                const double pri = a.lambda1 * t[2] + a.lambda2 * t[6] + (t[1] + t[5] - eps * t[0] + eps * sumK) / IJ;
+                const double dua = -a.lambda1 * t[3] - a.lambda2 * t[7] - eps * (t[0] - sumK) / IJ;
+                gap = (pri - dua) / fabs(pri);                            // ot_func.cpp:543
+            } else {
+                double acc[4] = {0.0, 0.0, 0.0, 0.0}, c[4];
+                for (int64_t i = gtid; i < n; i += gsize) {               // stage_criterion_kernel, ot_func.cpp:878-922
+                    if (pending) a.u[i] = a.f[i];
+                    const double ui = a.u[i];
+                    const double eu = exp(ui / eps);
+                    const double at = exp((a.f[i] - ui) / eps) * eu;
+                    const double df = at - exp(a.la_old[i]) * eu;
+                    acc[0] += df * df;
+                    acc[1] += at * at;
+                }
+                for (int64_t j = gtid; j < m; j += gsize) {
+                    if (pending) a.v[j] = a.g[j];
+                    const double vj = a.v[j];
+                    const double ev = exp(vj / eps);
+                    const double bt = exp((a.g[j] - vj) / eps) * ev;
+                    const double df = bt - exp(a.lb_old[j]) * ev;
+                    acc[2] += df * df;
+                    acc[3] += bt * bt;
+                }
+                solve_grid_sums<4>(acc, a.scratch, a.barrier, gen, c);
+                const double va = solve_safe_ratio(c[0], c[1]), vb = solve_safe_ratio(c[2], c[3]);
+                gap = (vb > va) ? vb : va;                                // std::max(v1, v2) with its NaN behaviour
+            }
+            if (gap != gap) break;                                        // `while (nan > threshold)` is false
+            if (!(gap > threshold)) break;
+            if (n_it >= a.max_iter) { status = 2; break; }                // ot_func.cpp:821-824
+        }
+        total += (int)n_it;
+        if (gtid == 0) a.result->iters[e] = (int)n_it;
+        if (status == 2) { status = 0; if (gtid == 0) a.result->max_iter_reached = 1; }        // gives up on the stage, keeps going
+        if (gap != gap && final_stage) status = 1;       // a NaN ends its stage (ot_func.cpp:866); only the last one is fatal (:446)
+    }
+    if (!lr_known && status != 1) {
+        // row LSE at the final g (plan row sums, the growth loop's next G)
+        const double c1 = a.inv_med / eps;
+        const double sc = -c1 * SDB_LOG2E;
+        const float sc_hi = (float)sc;
+        solve_pass<false>(a.row, sc_hi, (float)(sc - (double)sc_hi), a.partial_row, a.ns_row, cnt_row, a.Lr, nullptr, eps, 0.0, 0.0,
+                          nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau, smem);
+    }
+    if (gtid == 0) {
+        a.result->total_iters = total;
+        a.result->status = status;
+        a.result->gap = gap;
+        a.result->eps_final = eps;
+        a.result->last_tick = tick;
+        if (a.flag2[tick & 1] == tick) *a.flag = tick;
+    }
+}
+
 }  // namespace
 
 extern "C" int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_sweeps, int first_tick, int lr_known_first,
@@ -414,6 +703,58 @@ extern "C" int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_swe
     if (e != cudaSuccess) return (int)e;
     void* params[] = {&a};
     e = cudaLaunchCooperativeKernel((const void*)sinkhorn_persistent_kernel, dim3((unsigned)grid), dim3(NT), params, smem, st);
+    return (int)e;
+}
+
+extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_solve_params* p, int first_tick, int* flag2,
+                                             unsigned int* barrier2, unsigned int* counters, double* scratch,
+                                             sdb_solve_result* result, void* stream) {
+    SDB_CHECK_ARG(d && p && flag2 && barrier2 && counters && scratch && result && d->n > 0 && d->m > 0);
+    if (d->use_tc) return SDB_E_UNSUPPORTED;
+    if (d->dpad <= 0 || d->dpad > MAX_DPAD || (d->dpad & 3)) return SDB_E_UNSUPPORTED;
+    SDB_CHECK_ARG(d->xt && d->yt && d->bounds_row && d->bounds_col && d->partial_row && d->partial_col && d->bias_x && d->bias_y);
+    SDB_CHECK_ARG(d->f && d->g && d->u && d->v && d->la_old && d->lb_old && d->Lr && d->Lc && d->logp && d->logq && d->flag);
+    SDB_CHECK_ARG(d->ns_row > 0 && d->ns_col > 0 && !(d->ldx & 3) && !(d->ldy & 3));
+    SDB_CHECK_ARG(p->epsilon > 0.0 && p->epsilon0 > 0.0 && p->batch_size > 0 && p->tau > 0.0 && p->max_iter > 0);
+    SolveArgs a;
+    a.row = PairArgs{d->xt, d->ldx, d->n, d->yt, d->ldy, d->m, d->dpad, d->bias_y, d->bounds_row};
+    a.col = PairArgs{d->yt, d->ldy, d->m, d->xt, d->ldx, d->n, d->dpad, d->bias_x, d->bounds_col};
+    a.ns_row = d->ns_row; a.ns_col = d->ns_col;
+    a.partial_row = reinterpret_cast<float2*>(d->partial_row); a.partial_col = reinterpret_cast<float2*>(d->partial_col);
+    a.bias_x = d->bias_x; a.bias_y = d->bias_y;
+    a.f = d->f; a.g = d->g; a.u = d->u; a.v = d->v; a.la_old = d->la_old; a.lb_old = d->lb_old; a.Lr = d->Lr; a.Lc = d->Lc;
+    a.logp = d->logp; a.logq = d->logq; a.flag = d->flag; a.flag2 = flag2;
+    a.inv_med = d->inv_med; a.lambda1 = p->lambda1; a.lambda2 = p->lambda2; a.epsilon = p->epsilon; a.epsilon0 = p->epsilon0;
+    a.tolerance = p->tolerance; a.log_tau = log(p->tau);
+    a.log_m = log((double)d->m); a.log_N = log((double)d->n_total); a.dx = 1.0 / (double)d->n_total; a.dy = 1.0 / (double)d->m;
+    a.batch_size = p->batch_size; a.max_iter = (long long)p->max_iter; a.first_tick = first_tick;
+    a.barrier = barrier2; a.counters = counters; a.scratch = scratch; a.result = result;
+    cudaStream_t st = sdb_stream(stream);
+    const size_t smem = sizeof(float) * ((size_t)d->dpad * BM + 2 * (size_t)d->dpad * BN + 2 * BN);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(sinkhorn_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        smem_set = smem;
+    }
+    int dev = 0, n_sm = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_solve_kernel, NT, smem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) return SDB_E_UNSUPPORTED;
+    const int64_t row_items = ((d->n + BM - 1) / BM) * d->ns_row, col_items = ((d->m + BM - 1) / BM) * d->ns_col;
+    int64_t want = d->n_ctas > 0 ? d->n_ctas : (row_items > col_items ? row_items : col_items);
+    const int64_t cap = (int64_t)n_sm * per_sm;
+    int grid = (int)(want < cap ? want : cap);
+    if (grid < 1) grid = 1;
+    if (grid > SDB_SOLVE_MAX_CTAS) grid = SDB_SOLVE_MAX_CTAS;
+    e = cudaMemsetAsync(barrier2, 0, 2 * sizeof(unsigned int), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(result, 0, sizeof(sdb_solve_result), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(counters, 0, sizeof(unsigned int) * (size_t)((d->n + BM - 1) / BM + (d->m + BM - 1) / BM), st);
+    if (e != cudaSuccess) return (int)e;
+    void* params[] = {&a};
+    e = cudaLaunchCooperativeKernel((const void*)sinkhorn_solve_kernel, dim3((unsigned)grid), dim3(NT), params, smem, st);
     return (int)e;
 }
 

@@ -246,7 +246,7 @@ struct TcArgs {
 };
 
 template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, int MODE = MODE_LSE, bool PIPE = false, bool XTILE = false,
-          bool FIXED_M = false>
+          bool FIXED_M = false, bool RUNSUM = false>
 __global__ void __launch_bounds__(32 * (2 + EPI_WARPS), 1)
 lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmQ, TcArgs a) {
     using S = TcSmem<DP>;
@@ -598,6 +598,10 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 // Software-pipelined form: the FP32 stage of chunk c+1 (t = scale*d + bias, chunk maximum) and the SFU
                 // stage of chunk c (ex2, sum) sit in one basic block with no dependence between them, so the scheduler
                 // interleaves FMA-pipe and MUFU work of the same warp instead of running them as alternating phases.
+                // RUNSUM (predicted stabiliser only: no rescale ever happens): the exponentials go into four packed running
+                // sums that live across chunks and tiles and are folded once per item - no reduction tree, no scalar adds and no
+                // end-of-chunk dependency on the last MUFU results (each FADD2 depends only on a pair issued four pairs earlier).
+                uint64_t racc[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};
                 for (int t = t0; t < t1; ++t, ++tile_ctr) {
                     const int acc = tile_ctr & 1;
                     const int bs = tile_ctr % BIAS_STAGES;
@@ -646,6 +650,14 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                             if (c + 2 < NCH) tmem_ld<CH>(tbase + (c + 2) * CH, d[c & 1]);   // d[c&1] was consumed by stage_a(c)
                             stage_a(c + 1);
                         }
+                        if constexpr (FIXED_M && RUNSUM) {
+#pragma unroll
+                            for (int k = 0; k < CH / 2; ++k) {                 // SFU stage of chunk c, running sums
+                                float a0, a1;
+                                unpack2(fadd2(tv2[c & 1][k], nm2), a0, a1);
+                                racc[k & 3] = fadd2(racc[k & 3], pack2(sdb_ex2(a0), sdb_ex2(a1)));
+                            }
+                        } else {
                         uint64_t acc2[CH / 2];
 #pragma unroll
                         for (int k = 0; k < CH / 2; ++k) {                     // SFU stage of chunk c
@@ -660,10 +672,16 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                         float e0, e1;
                         unpack2(acc2[0], e0, e1);
                         ssum += e0 + e1;
+                        }
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { mbar_arrive(t_empty + acc); mbar_arrive(b_empty + bs); }
+                }
+                if constexpr (FIXED_M && RUNSUM) {
+                    float e0, e1;
+                    unpack2(fadd2(fadd2(racc[0], racc[1]), fadd2(racc[2], racc[3])), e0, e1);
+                    ssum = e0 + e1;
                 }
             } else {
             for (int t = t0; t < t1; ++t, ++tile_ctr) {
@@ -835,9 +853,10 @@ int make_tmap(CUtensorMap* tm, const void* base, int64_t rows_pad, int dp, int b
     return r == CUDA_SUCCESS ? 0 : SDB_E_DRIVER;
 }
 
-template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, bool PIPE = false, bool XTILE = false, bool FIXED_M = false>
+template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, bool PIPE = false, bool XTILE = false, bool FIXED_M = false,
+          bool RUNSUM = false>
 int launch_tc_v(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
-    auto kern = lse_pass_tc_kernel<DP, EPI_WARPS, PACKED, POLY_EVERY, MODE_LSE, PIPE, XTILE, FIXED_M>;
+    auto kern = lse_pass_tc_kernel<DP, EPI_WARPS, PACKED, POLY_EVERY, MODE_LSE, PIPE, XTILE, FIXED_M, RUNSUM>;
     constexpr int smem = TcSmem<DP>::TOTAL;
     static bool attr_set = false;
     if (!attr_set) {
@@ -878,7 +897,12 @@ int tc_variant() {
 
 template <int DP>
 int launch_tc(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
-    if (a.row_m != nullptr) return launch_tc_v<DP, 8, true, 0, true, false, true>(tmP, tmQ, a, n_ctas, st);   // predicted stabiliser
+    if (a.row_m != nullptr) {                                                                                // predicted stabiliser
+        static int runsum = -1;          // development knob SDB_TC_RUNSUM=0: per-chunk reduction tree instead of running sums
+        if (runsum < 0) { const char* e = getenv("SDB_TC_RUNSUM"); runsum = (e && *e == '0') ? 0 : 1; }
+        return runsum ? launch_tc_v<DP, 8, true, 0, true, false, true, true>(tmP, tmQ, a, n_ctas, st)
+                      : launch_tc_v<DP, 8, true, 0, true, false, true, false>(tmP, tmQ, a, n_ctas, st);
+    }
     switch (tc_variant()) {
         case 0: return launch_tc_v<DP, 8, false>(tmP, tmQ, a, n_ctas, st);
         case 2: return launch_tc_v<DP, 8, true, 2>(tmP, tmQ, a, n_ctas, st);

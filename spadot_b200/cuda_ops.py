@@ -437,6 +437,62 @@ class CudaOps(VectorOps):
             self._pred.unmerged = False
             self._pred.bad.zero_()
 
+    def _persistent_eligible(self):
+        return (not self.use_tc) and self.persistent and 0 < self.n * self.m <= self.PERSISTENT_MAX_PAIRS
+
+    def fused_solve(self, st, lambda1, lambda2, epsilon, batch_size, tolerance, tau, epsilon0, max_iter):
+        """The whole duality-gap solve in ONE cooperative launch (sdb_sinkhorn_solve_persistent) for problems the persistent
+        SIMT kernel serves; None when this problem is not one of them (the caller then runs the host-driven stage loop)."""
+        if not self._persistent_eligible() or os.environ.get("SDB_FUSED_SOLVE", "1") == "0":
+            return None
+        d = self._sweep_desc(st, float(epsilon), 0.0, 0.0, 0.0, NEG_INF)
+        self._persistent_plan(d)
+        p = _lib.SolveParams(float(lambda1), float(lambda2), float(epsilon), float(epsilon0), float(tolerance), float(tau),
+                             float(max_iter), int(batch_size), 0)
+        if getattr(self, "_solve_ws", None) is None:
+            tiles = (self.n + 63) // 64 + (self.m + 63) // 64
+            self._solve_ws = dict(flag2=torch.zeros(2, dtype=torch.int32, device=self.device),
+                                  counters=torch.zeros(tiles, dtype=torch.int32, device=self.device),
+                                  scratch=torch.zeros(_lib.SOLVE_MAX_CTAS * 10, dtype=torch.float64, device=self.device),
+                                  result=torch.zeros(ctypes.sizeof(_lib.SolveResult), dtype=torch.uint8, device=self.device))
+        ws = self._solve_ws
+        _lib.call("sdb_sinkhorn_solve_persistent", ctypes.byref(d), ctypes.byref(p), self._tick + 1, _ptr(ws["flag2"]),
+                  _ptr(self._barrier), _ptr(ws["counters"]), _ptr(ws["scratch"]), _ptr(ws["result"]), self._stream())
+        self.launches += 1
+        raw = ws["result"].cpu().numpy().tobytes()                # the one synchronising read-back of the solve
+        res = _lib.SolveResult.from_buffer_copy(raw)
+        self._tick = max(self._tick, int(res.last_tick))
+        self._bias_key = {"x": None, "y": None}
+        return res
+
+    def _persistent_plan(self, d):
+        """Grid and column splits of the cooperative small-problem kernels: about one work item per CTA and pass."""
+        if self._barrier is None:
+            self._barrier = torch.zeros(2, dtype=torch.int32, device=self.device)
+            self._n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+        d.n_ctas = self._n_sm * self.PERSISTENT_CTAS_PER_SM
+        b_row, d.ns_row = self._persist_plan(self.n, self.m, d.n_ctas)
+        b_col, d.ns_col = self._persist_plan(self.m, self.n, d.n_ctas)
+        d.bounds_row, d.bounds_col = _ptr(b_row), _ptr(b_col)
+        d.partial_row = _ptr(self._partial(d.ns_row, self.n, "prow"))
+        d.partial_col = _ptr(self._partial(d.ns_col, self.m, "pcol"))
+
+    def _sweep_desc(self, st, eps, alpha1, alpha2, log_tau, log_floor):
+        """sdb_sweep_desc of this problem's SIMT form (the tensor-core fields are filled by fused_sweeps)."""
+        d = _lib.SweepDesc()
+        d.n, d.m, d.n_total = self.n, self.m, st.N
+        d.use_tc = 0
+        d.dpad, d.n_ctas = self.X.dpad, 0
+        d.xt, d.ldx, d.yt, d.ldy = _ptr(self.X.xt), self.X.ld, _ptr(self.Y.xt), self.Y.ld
+        d.norms_x, d.norms_y = _ptr(self.X.norms), _ptr(self.Y.norms)
+        d.bias_x, d.bias_y, d.m_bias = _ptr(self.bias_x), _ptr(self.bias_y), self.bias_y.numel()
+        d.f, d.g, d.u, d.v = _ptr(st.f), _ptr(st.g), _ptr(st.u), _ptr(st.v)
+        d.la_old, d.lb_old, d.Lr, d.Lc = _ptr(st.la_old), _ptr(st.lb_old), _ptr(st.Lr), _ptr(st.Lc)
+        d.logp, d.logq, d.flag = _ptr(st.logp), _ptr(st.logq), _ptr(self.flag)
+        d.eps, d.inv_med, d.alpha1, d.alpha2 = eps, self.inv_med, alpha1, alpha2
+        d.log_tau, d.log_floor, d.pow2_scale = log_tau, log_floor, 1.0
+        return d
+
     def fused_sweeps(self, st, eps, alpha1, alpha2, log_tau, log_floor, n_sweeps, lr_known_first):
         """n_sweeps full iterations issued by the native loop sdb_sinkhorn_sweeps (single rank)."""
         self._prep(eps)
@@ -483,18 +539,10 @@ class CudaOps(VectorOps):
             if key not in self._partials:
                 self._partials[key] = torch.empty((d.ns_col, self.m, 2), dtype=torch.float32, device=self.device)
             d.partial_col = _ptr(self._partials[key])
-        if not self.use_tc and self.persistent and self.n * self.m <= self.PERSISTENT_MAX_PAIRS:
+        if self._persistent_eligible():
             # small problem: all n_sweeps iterations in one cooperative launch (grid barriers instead of launches);
             # column splits sized so that one pass is about one work item per CTA
-            if self._barrier is None:
-                self._barrier = torch.zeros(2, dtype=torch.int32, device=self.device)
-                self._n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
-            d.n_ctas = self._n_sm * self.PERSISTENT_CTAS_PER_SM
-            b_row, d.ns_row = self._persist_plan(self.n, self.m, d.n_ctas)
-            b_col, d.ns_col = self._persist_plan(self.m, self.n, d.n_ctas)
-            d.bounds_row, d.bounds_col = _ptr(b_row), _ptr(b_col)
-            d.partial_row = _ptr(self._partial(d.ns_row, self.n, "prow"))
-            d.partial_col = _ptr(self._partial(d.ns_col, self.m, "pcol"))
+            self._persistent_plan(d)
             _lib.call("sdb_sinkhorn_sweeps_persistent", ctypes.byref(d), int(n_sweeps), first, int(bool(lr_known_first)),
                       _ptr(self._barrier), self._stream())
             self.launches += 1 + (0 if lr_known_first else 1)

@@ -242,6 +242,20 @@ def solve_duality_gap(ops, G_local, lambda1, lambda2, epsilon, batch_size=5, tol
     Raises RuntimeError on a NaN gap like the reference (ot_solvers.py:446-447)."""
     dist = dist or Dist(enabled=False)
     st = _State(ops, G_local, dist)
+    native = getattr(ops, "fused_solve", None)
+    if native is not None and dist.world == 1 and not profiling:
+        # small problems: the stage loop below runs on the device in one cooperative launch (sdb_sinkhorn_solve_persistent)
+        res = native(st, lambda1, lambda2, epsilon, batch_size, tolerance, tau, epsilon0, max_iter)
+        if res is not None:
+            if res.max_iter_reached:
+                import warnings
+                warnings.warn("Reached max_iter with duality gap still above threshold. Returning", RuntimeWarning, stacklevel=2)
+            if res.status == 1 or math.isnan(res.gap):
+                raise RuntimeError("Overflow encountered in duality gap computation, please report this incident")
+            if info is not None:
+                info.update(iters_per_stage=[int(v) for v in res.iters], total_iters=int(res.total_iters), gap=float(res.gap),
+                            epsilon_final=float(res.eps_final), max_iter_reached=bool(res.max_iter_reached))
+            return st, float(res.eps_final)
     scale_factor = math.exp(-math.log(epsilon) / EPSILON_SCALINGS)
     eps_i = epsilon0 * scale_factor
     log_tau = math.log(tau)

@@ -383,3 +383,42 @@ def test_persistent_sweeps_match_launch_loop(ot, n, m, d):
     assert float((cp1.f - cp2.f).abs().max()) < 1e-7
     assert float((cp1.g - cp2.g).abs().max()) < 1e-7
     assert abs(cp1.info["gap"]) <= 1e-8
+
+
+@pytest.mark.parametrize("n,m,d,tau", [(747, 1966, 20, 1000.0), (300, 411, 20, 1000.0), (130, 97, 6, 3.0), (1, 1, 3, 1000.0),
+                                       (65, 64, 33, 1.5), (1966, 1916, 20, 1000.0)])
+def test_whole_solve_in_one_launch_matches_host_stage_loop(ot, n, m, d, tau):
+    """sdb_sinkhorn_solve_persistent (six epsilon stages, stopping rules and tau bookkeeping on the device, two grid barriers
+    per iteration) against the host-driven stage loop over the same tile code: same iterations per stage, same potentials,
+    same frames; small tau forces absorptions (ot_func.cpp:778-819) so the row-by-row deferred absorb is exercised."""
+    ot_solvers, sinkhorn, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, d, seed=n + m)
+    G = np.exp(np.random.default_rng(n).normal(0, 0.4, n))
+    cfg = dict(CFG, tau=tau)
+    out = []
+    for fused in (True, False):
+        ops = CudaOps(a, b, tc="off")
+        if not fused:
+            ops.fused_solve = None
+        l0 = ops.launches
+        cp = ot_solvers.solve_coupling(a, b, cfg, G=G, ops=ops, dist=sinkhorn.Dist(enabled=False), median=1.7 * d)
+        out.append((cp, ops.launches - l0))
+    (c1, l1), (c2, l2) = out
+    assert l1 <= 2 and l2 > 20                                  # one launch vs the batch-by-batch loop
+    assert c1.info["iters_per_stage"] == c2.info["iters_per_stage"], (c1.info, c2.info)
+    assert c1.info["gap"] == pytest.approx(c2.info["gap"], rel=1e-6, abs=1e-13)
+    for name in ("f", "g", "u", "v", "Lr", "Lc"):
+        x, y = getattr(c1.state, name), getattr(c2.state, name)
+        assert float((x - y).abs().max()) < 1e-10, name
+
+
+def test_whole_solve_in_one_launch_nan_and_max_iter(ot):
+    ot_solvers, sinkhorn, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(40, 50, 4, seed=3)
+    G = np.ones(40)
+    G[7] = 0.0                                                  # r log(r/p) with p = 0 -> NaN gap (ot_func.cpp:309-322)
+    with pytest.raises(RuntimeError, match="Overflow encountered in duality gap computation"):
+        ot_solvers.solve_coupling(a, b, dict(CFG), G=G, ops=CudaOps(a, b, tc="off"), dist=sinkhorn.Dist(enabled=False))
+    with pytest.warns(RuntimeWarning, match="Reached max_iter"):
+        cp = ot_solvers.solve_coupling(a, b, dict(CFG, max_iter=5), ops=CudaOps(a, b, tc="off"), dist=sinkhorn.Dist(enabled=False))
+    assert cp.info["iters_per_stage"] == [5] * 6 and cp.info["max_iter_reached"]
