@@ -57,9 +57,16 @@ int sdb_prep_points_f64(const double* x, int64_t n, int d, const double* center,
                         float* xt, int64_t ld, int dpad, double* norms, void* stream);
 
 /* ------------------------------------------------------------------ K3: streamed LSE pass (SIMT fp32) */
-/* DIRECT-DIFFERENCE form: partial[(s*n_p + i)*2 + {0,1}] = (max, sum) of 2^(bias_j + scale*|x_i - y_j|^2 - max), with
- * scale = -c1*log2(e) and bias_j = log2(e)*g_j/eps — i.e. pass an all-zero `norms` vector to sdb_make_bias,
- * sdb_lse_finalize* and sdb_potential_update on this path (the squared norms live inside |x_i - y_j|^2).  Over the
+/* partial[(s*n_p + i)*2 + {0,1}] = (max, sum) of 2^(bias_j + scale*A_ij - max) over the columns of split s, where the sign
+ * of `scale` selects the tile arithmetic:
+ *   scale > 0: A_ij = x_i.y_j  (dot-product form, scale = 2*c1*log2(e), bias_j = log2(e)*(g_j/eps - |y_j|^2*c1); the row
+ *              norm is subtracted by the finalize kernels).  Half the inner-loop work, but its fp32 rounding is relative to
+ *              |x||y|: fine while scale*|x||y| stays below ~40 (eps = 0.05 on median-normalised costs).
+ *   scale < 0: A_ij = |x_i - y_j|^2 by direct differences like scipy's cdist (ref: ot_solvers.py:102), scale = -c1*log2(e),
+ *              bias_j = log2(e)*g_j/eps: pass an all-zero `norms` vector to sdb_make_bias, sdb_lse_finalize* and
+ *              sdb_potential_update.  Rounding relative to the COST of a pair: what small eps needs (at eps = 0.01 the dot
+ *              form put 1.3e-5 on the plan's marginals, this form 1e-6).
+ * Split s covers the
  * columns j in [split_bounds[s], split_bounds[s+1]) (device array of n_splits+1 entries; keep
  * each split <= 65536 columns so the fp32 running sums stay below 1e-6 relative error).
  * dpad <= 128, dpad % 4 == 0.  Grid = ceil(n_p/64) x n_splits CTAs of 256 threads.  `scale` is a double: the kernel applies
@@ -184,6 +191,9 @@ typedef struct sdb_sweep_desc {
      * n_sweeps if it is set. */
     float* m_x; float* m_y; int* bad_flag;
     int32_t pred_from_row, pred_from_col;
+    /* SIMT form only: 0 = dot-product tiles (norms_x / norms_y hold |x|^2, |y|^2), 1 = direct-difference tiles (they hold
+     * zeros); see sdb_lse_pass_simt. */
+    int32_t simt_direct, reserved0;
 } sdb_sweep_desc;
 /* Issues n_sweeps x [row pass, finalize+update f, column pass, finalize+update g, absorb] on `stream`.
  * lr_known_first != 0: Lr already holds the row LSE at the current g, the first row pass is skipped
@@ -208,6 +218,9 @@ int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_sweeps, int fi
 #define SDB_SOLVE_MAX_CTAS 1024
 typedef struct sdb_solve_params {
     double lambda1, lambda2, epsilon, epsilon0, tolerance, tau, max_iter;
+    double eps_stage[6];         /* the six regularisations, computed by the caller exactly as ot_solvers.py:218,240,254 does */
+    double xy_max;               /* max_i |x_i| * max_j |y_j| of the prepared points */
+    double dot_limit;            /* a stage uses dot-product tiles while 2*c1*log2(e)*xy_max <= dot_limit, else direct ones */
     int32_t batch_size, reserved;
 } sdb_solve_params;
 typedef struct sdb_solve_result {

@@ -84,13 +84,15 @@ class SweepDesc(ctypes.Structure):
                 ("logp", c_p), ("logq", c_p), ("flag", c_p),
                 ("eps", c_d), ("inv_med", c_d), ("alpha1", c_d), ("alpha2", c_d), ("log_tau", c_d), ("log_floor", c_d),
                 ("pow2_scale", c_d),
-                ("m_x", c_p), ("m_y", c_p), ("bad_flag", c_p), ("pred_from_row", ctypes.c_int32), ("pred_from_col", ctypes.c_int32)]
+                ("m_x", c_p), ("m_y", c_p), ("bad_flag", c_p), ("pred_from_row", ctypes.c_int32), ("pred_from_col", ctypes.c_int32),
+                ("simt_direct", ctypes.c_int32), ("reserved0", ctypes.c_int32)]
 
 
 class SolveParams(ctypes.Structure):
     """struct sdb_solve_params"""
     _fields_ = [("lambda1", c_d), ("lambda2", c_d), ("epsilon", c_d), ("epsilon0", c_d), ("tolerance", c_d), ("tau", c_d),
-                ("max_iter", c_d), ("batch_size", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("max_iter", c_d), ("eps_stage", c_d * 6), ("xy_max", c_d), ("dot_limit", c_d),
+                ("batch_size", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class SolveResult(ctypes.Structure):

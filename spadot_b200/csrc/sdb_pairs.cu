@@ -265,6 +265,7 @@ struct PersistArgs {
     PairArgs row, col;                 // row pass: P = x, Q = y, bias = bias_y;  column pass: P = y, Q = x, bias = bias_x
     int ns_row, ns_col;
     float scale, scale_lo;
+    int direct;
     float2* partial_row; float2* partial_col;
     const double* norms_x; const double* norms_y;
     float* bias_x; float* bias_y;
@@ -313,7 +314,8 @@ __global__ void __launch_bounds__(NT) sinkhorn_persistent_kernel(PersistArgs a) 
         if (!skip_row_pass) {
             LseEpi::Params ep{a.scale, a.scale_lo, a.partial_row};
             for (int item = blockIdx.x; item < row_tiles * a.ns_row; item += gridDim.x) {
-                pair_tile_item<true, LseEpi>(a.row, ep, item % row_tiles, item / row_tiles, smem);
+                if (a.direct) pair_tile_item<true, LseEpi>(a.row, ep, item % row_tiles, item / row_tiles, smem);
+                else pair_tile_item<false, LseEpi>(a.row, ep, item % row_tiles, item / row_tiles, smem);
                 __syncthreads();
             }
             grid_barrier(a.barrier, gen);
@@ -332,7 +334,8 @@ __global__ void __launch_bounds__(NT) sinkhorn_persistent_kernel(PersistArgs a) 
         {
             LseEpi::Params ep{a.scale, a.scale_lo, a.partial_col};
             for (int item = blockIdx.x; item < col_tiles * a.ns_col; item += gridDim.x) {
-                pair_tile_item<true, LseEpi>(a.col, ep, item % col_tiles, item / col_tiles, smem);
+                if (a.direct) pair_tile_item<true, LseEpi>(a.col, ep, item % col_tiles, item / col_tiles, smem);
+                else pair_tile_item<false, LseEpi>(a.col, ep, item % col_tiles, item / col_tiles, smem);
                 __syncthreads();
             }
         }
@@ -371,6 +374,8 @@ struct SolveArgs {
     float* bias_x; float* bias_y;
     double *f, *g, *u, *v, *la_old, *lb_old, *Lr, *Lc;
     const double* logp; const double* logq;
+    const double* norms_x; const double* norms_y;   // |x_i|^2, |y_j|^2 of the fp32 points (dot-product stages)
+    double eps_stage[6], xy_max, dot_limit;
     int* flag;                          // caller's absorb flag (left consistent: last tick that exceeded tau)
     int* flag2;                         // [2] ping-pong flags of this kernel
     double inv_med, lambda1, lambda2, epsilon, epsilon0, tolerance, log_tau, log_m, log_N, dx, dy;
@@ -419,10 +424,13 @@ __device__ __forceinline__ double solve_safe_ratio(double num2, double den2) {  
 
 // One pass over (slab, split) items; the CTA that completes a slab combines its partials and, with UPDATE, updates the
 // potential of those 64 rows (pot, frame, la_old, bias_out, flags) - else it only stores the LSE.
+// `direct`: tile arithmetic of this stage (see sdb_lse_pass_simt); c1n = c1 for dot-product tiles (row norm subtracted from the
+// LSE, norm inside the bias), 0 for direct ones.
 template <bool UPDATE>
-__device__ void solve_pass(const PairArgs& pa, float scale_hi, float scale_lo, float2* partial, int ns, unsigned int* counters,
-                           double* L, const double* logmarg, double eps, double alpha, double log_n_other, double* pot,
-                           double* frame, double* la_old, float* bias_out, int* flag2, int tick, double log_tau, float* smem) {
+__device__ void solve_pass(const PairArgs& pa, bool direct, float scale_hi, float scale_lo, float2* partial, int ns,
+                           unsigned int* counters, double* L, const double* norms, double c1n, const double* logmarg, double eps,
+                           double alpha, double log_n_other, double* pot, double* frame, double* la_old, float* bias_out,
+                           int* flag2, int tick, double log_tau, float* smem) {
     __shared__ int s_last;
     const int64_t n = pa.n_p;
     const int tiles = (int)((n + BM - 1) / BM);
@@ -430,7 +438,8 @@ __device__ void solve_pass(const PairArgs& pa, float scale_hi, float scale_lo, f
     const bool pending = UPDATE && (*reinterpret_cast<volatile int*>(flag2 + ((tick - 1) & 1)) == tick - 1);
     for (int item = blockIdx.x; item < tiles * ns; item += gridDim.x) {
         const int tile = item % tiles;
-        pair_tile_item<true, LseEpi>(pa, ep, tile, item / tiles, smem);
+        if (direct) pair_tile_item<true, LseEpi>(pa, ep, tile, item / tiles, smem);
+        else pair_tile_item<false, LseEpi>(pa, ep, tile, item / tiles, smem);
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -461,7 +470,8 @@ __device__ void solve_pass(const PairArgs& pa, float scale_hi, float scale_lo, f
             S += __shfl_xor_sync(0xffffffffu, S, 1);
             S += __shfl_xor_sync(0xffffffffu, S, 2);
             if (sub == 0 && i < n) {
-                const double Li = (mx > -INFINITY) ? SDB_LN2 * ((double)mx + log2(S)) : -INFINITY;
+                const double nc = norms[i] * c1n;
+                const double Li = (mx > -INFINITY) ? SDB_LN2 * ((double)mx + log2(S)) - nc : -INFINITY;
                 L[i] = Li;
                 if (UPDATE) {
                     const double old = pot[i];
@@ -470,7 +480,7 @@ __device__ void solve_pass(const PairArgs& pa, float scale_hi, float scale_lo, f
                     la_old[i] = (old - fr) / eps;
                     const double nv = eps * alpha * (logmarg[i] - (Li - log_n_other));
                     pot[i] = nv;
-                    const double b = SDB_LOG2E * (nv / eps);
+                    const double b = SDB_LOG2E * (nv / eps - nc);
                     bias_out[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
                     if ((nv - fr) / eps > log_tau) atomicMax(flag2 + (tick & 1), tick);
                 }
@@ -488,8 +498,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
     const int64_t gtid = (int64_t)blockIdx.x * NT + threadIdx.x, gsize = (int64_t)gridDim.x * NT;
     unsigned int* cnt_row = a.counters;
     unsigned int* cnt_col = a.counters + row_tiles;
-    const double scale_factor = exp(-log(a.epsilon) / 5.0);              // ot_solvers.py:218
-    double eps = a.epsilon0 * scale_factor;
+    double eps = a.eps_stage[0];
     int tick = a.first_tick - 1;
     double gap = INFINITY, sumK = 0.0;
     int status = 0, total = 0;
@@ -497,11 +506,15 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
     PairArgs row0 = a.row;                                               // row pass with g = 0 (sum of exp(-C/eps))
     row0.bias = nullptr;
     for (int e = 0; e <= 5 && status == 0; ++e) {
-        eps = eps / scale_factor;                                        // ot_solvers.py:254
+        eps = a.eps_stage[e];                                            // ot_solvers.py:218,240,254 (host arithmetic)
         const double c1 = a.inv_med / eps;
         const double alpha1 = a.lambda1 / (a.lambda1 + eps), alpha2 = a.lambda2 / (a.lambda2 + eps);
-        const double sc = -c1 * SDB_LOG2E;
+        const bool direct = 2.0 * c1 * SDB_LOG2E * a.xy_max > a.dot_limit;
+        const double c1n = direct ? 0.0 : c1;
+        const double sc = direct ? -c1 * SDB_LOG2E : 2.0 * c1 * SDB_LOG2E;
         const float sc_hi = (float)sc, sc_lo = (float)(sc - (double)sc_hi);
+        const double scd = -c1 * SDB_LOG2E;                               // the sum of exp(-C/eps) always runs on direct tiles
+        const float scd_hi = (float)scd, scd_lo = (float)(scd - (double)scd_hi);
         const bool final_stage = (e == 5);
         const double threshold = final_stage ? a.tolerance : 1e-6;       // ot_solvers.py:262
         const int n_inner = final_stage ? a.batch_size : 5;              // ot_func.cpp:867
@@ -511,7 +524,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
             const double gj = a.g[j];
             a.v[j] = gj;
             a.lb_old[j] = 0.0;
-            const double b = SDB_LOG2E * (gj / eps);
+            const double b = SDB_LOG2E * (gj / eps - a.norms_y[j] * c1n);
             a.bias_y[j] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
         }
         if (gtid == 0) { a.flag2[0] = -1; a.flag2[1] = -1; }              // frames are fresh: nothing pending (ticks are >= 0)
@@ -533,17 +546,17 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
                         a.la_old[i] = (old - fr) / eps;
                         const double nv = eps * alpha1 * (a.logp[i] - (a.Lr[i] - a.log_m));
                         a.f[i] = nv;
-                        const double b = SDB_LOG2E * (nv / eps);
+                        const double b = SDB_LOG2E * (nv / eps - a.norms_x[i] * c1n);
                         a.bias_x[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
                         if ((nv - fr) / eps > a.log_tau) atomicMax(a.flag2 + (tick & 1), tick);
                     }
                 } else {
-                    solve_pass<true>(a.row, sc_hi, sc_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, a.logp, eps, alpha1, a.log_m, a.f, a.u,
-                                     a.la_old, a.bias_x, a.flag2, tick, a.log_tau, smem);
+                    solve_pass<true>(a.row, direct, sc_hi, sc_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, a.norms_x, c1n, a.logp, eps, alpha1,
+                                     a.log_m, a.f, a.u, a.la_old, a.bias_x, a.flag2, tick, a.log_tau, smem);
                 }
                 grid_barrier(a.barrier, gen);
-                solve_pass<true>(a.col, sc_hi, sc_lo, a.partial_col, a.ns_col, cnt_col, a.Lc, a.logq, eps, alpha2, a.log_N, a.g, a.v,
-                                 a.lb_old, a.bias_y, a.flag2, tick, a.log_tau, smem);
+                solve_pass<true>(a.col, direct, sc_hi, sc_lo, a.partial_col, a.ns_col, cnt_col, a.Lc, a.norms_y, c1n, a.logq, eps, alpha2,
+                                 a.log_N, a.g, a.v, a.lb_old, a.bias_y, a.flag2, tick, a.log_tau, smem);
                 grid_barrier(a.barrier, gen);
             }
             n_it += n_inner;
@@ -552,8 +565,8 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
             const bool pending = (*reinterpret_cast<volatile int*>(a.flag2 + (tick & 1)) == tick);
             if (final_stage) {
                 if (!have_sumK) {
-                    solve_pass<false>(row0, sc_hi, sc_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, nullptr, eps, 0.0, 0.0, nullptr, nullptr,
-                                      nullptr, nullptr, a.flag2, tick, a.log_tau, smem);
+                    solve_pass<false>(row0, true, scd_hi, scd_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, a.norms_x, 0.0, nullptr, eps, 0.0, 0.0,
+                                      nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau, smem);
                     grid_barrier(a.barrier, gen);
                     double acc1[1] = {0.0}, out1[1];
                     for (int64_t i = gtid; i < n; i += gsize) acc1[0] += exp(a.Lr[i]);
@@ -562,8 +575,8 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
                     have_sumK = true;
                 }
                 // row LSE at the new g: the gap's row marginal, and the next iteration's row pass
-                solve_pass<false>(a.row, sc_hi, sc_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, nullptr, eps, 0.0, 0.0, nullptr, nullptr,
-                                  nullptr, nullptr, a.flag2, tick, a.log_tau, smem);
+                solve_pass<false>(a.row, direct, sc_hi, sc_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, a.norms_x, c1n, nullptr, eps, 0.0, 0.0,
+                                  nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau, smem);
                 grid_barrier(a.barrier, gen);
                 lr_known = true;
                 double acc[8], t[8];
@@ -627,11 +640,13 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
     }
     if (!lr_known && status != 1) {
         // row LSE at the final g (plan row sums, the growth loop's next G)
+        // (bias_y still holds the last stage's form: reuse that stage's choice)
         const double c1 = a.inv_med / eps;
-        const double sc = -c1 * SDB_LOG2E;
+        const bool direct = 2.0 * c1 * SDB_LOG2E * a.xy_max > a.dot_limit;
+        const double sc = direct ? -c1 * SDB_LOG2E : 2.0 * c1 * SDB_LOG2E;
         const float sc_hi = (float)sc;
-        solve_pass<false>(a.row, sc_hi, (float)(sc - (double)sc_hi), a.partial_row, a.ns_row, cnt_row, a.Lr, nullptr, eps, 0.0, 0.0,
-                          nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau, smem);
+        solve_pass<false>(a.row, direct, sc_hi, (float)(sc - (double)sc_hi), a.partial_row, a.ns_row, cnt_row, a.Lr, a.norms_x,
+                          direct ? 0.0 : c1, nullptr, eps, 0.0, 0.0, nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau, smem);
     }
     if (gtid == 0) {
         a.result->total_iters = total;
@@ -659,8 +674,10 @@ extern "C" int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_swe
     a.row = PairArgs{d->xt, d->ldx, d->n, d->yt, d->ldy, d->m, d->dpad, d->bias_y, d->bounds_row};
     a.col = PairArgs{d->yt, d->ldy, d->m, d->xt, d->ldx, d->n, d->dpad, d->bias_x, d->bounds_col};
     a.ns_row = d->ns_row; a.ns_col = d->ns_col;
-    a.scale = (float)(-c1 * SDB_LOG2E);                      // direct-difference form: t = bias_j - c1*log2(e)*|x_i - y_j|^2
-    a.scale_lo = (float)(-c1 * SDB_LOG2E - (double)a.scale);
+    a.direct = d->simt_direct ? 1 : 0;
+    const double sc = a.direct ? -c1 * SDB_LOG2E : 2.0 * c1 * SDB_LOG2E;   // direct: t = bias_j - c1*log2(e)*|x_i - y_j|^2
+    a.scale = (float)sc;
+    a.scale_lo = (float)(sc - (double)a.scale);
     a.partial_row = reinterpret_cast<float2*>(d->partial_row); a.partial_col = reinterpret_cast<float2*>(d->partial_col);
     a.norms_x = d->norms_x; a.norms_y = d->norms_y; a.bias_x = d->bias_x; a.bias_y = d->bias_y;
     a.f = d->f; a.g = d->g; a.u = d->u; a.v = d->v; a.la_old = d->la_old; a.lb_old = d->lb_old; a.Lr = d->Lr; a.Lc = d->Lc;
@@ -724,6 +741,10 @@ extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_
     a.bias_x = d->bias_x; a.bias_y = d->bias_y;
     a.f = d->f; a.g = d->g; a.u = d->u; a.v = d->v; a.la_old = d->la_old; a.lb_old = d->lb_old; a.Lr = d->Lr; a.Lc = d->Lc;
     a.logp = d->logp; a.logq = d->logq; a.flag = d->flag; a.flag2 = flag2;
+    SDB_CHECK_ARG(d->norms_x && d->norms_y);
+    a.norms_x = d->norms_x; a.norms_y = d->norms_y;
+    for (int k = 0; k < 6; ++k) { SDB_CHECK_ARG(p->eps_stage[k] > 0.0); a.eps_stage[k] = p->eps_stage[k]; }
+    a.xy_max = p->xy_max; a.dot_limit = p->dot_limit;
     a.inv_med = d->inv_med; a.lambda1 = p->lambda1; a.lambda2 = p->lambda2; a.epsilon = p->epsilon; a.epsilon0 = p->epsilon0;
     a.tolerance = p->tolerance; a.log_tau = log(p->tau);
     a.log_m = log((double)d->m); a.log_N = log((double)d->n_total); a.dx = 1.0 / (double)d->n_total; a.dy = 1.0 / (double)d->m;
@@ -765,7 +786,8 @@ extern "C" int sdb_lse_pass_simt(const float* pt, int64_t ldp, int64_t n_p, cons
     PairArgs a{pt, ldp, n_p, qt, ldq, n_q, dpad, bias, split_bounds};
     const float s_hi = (float)scale;
     LseEpi::Params ep{s_hi, (float)(scale - (double)s_hi), reinterpret_cast<float2*>(partial)};
-    return launch_pairs<true, LseEpi>(a, ep, n_splits, sdb_stream(stream));
+    return scale < 0.0 ? launch_pairs<true, LseEpi>(a, ep, n_splits, sdb_stream(stream))
+                       : launch_pairs<false, LseEpi>(a, ep, n_splits, sdb_stream(stream));
 }
 
 extern "C" int sdb_cost_histogram(const float* pt, int64_t ldp, int64_t n_p, const float* qt, int64_t ldq, int64_t n_q,

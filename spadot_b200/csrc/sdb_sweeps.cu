@@ -28,7 +28,8 @@ extern "C" int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int fi
     SDB_CHECK_ARG(d && n_sweeps >= 0 && d->n > 0 && d->m > 0 && d->eps > 0.0);
     const double c1 = d->inv_med / d->eps;
     const double scale = 2.0 * c1 * SDB_LOG2E;      // tensor-core form: exponent = bias_j + scale * x_i.y_j (norms inside the bias)
-    const double scale_direct = -c1 * SDB_LOG2E;    // SIMT form: exponent = bias_j + scale_direct * |x_i - y_j|^2 (norm vectors are zero)
+    // SIMT form: dot-product tiles with the same scale, or direct-difference tiles (negative scale, zero norm vectors)
+    const double scale_direct = d->simt_direct ? -c1 * SDB_LOG2E : scale;
     const double log_m = log((double)d->m), log_N = log((double)d->n_total);
     int rc = 0;
     PdlScope pdl(pdl_enabled() && d->use_tc);      // the SIMT pass kernel is not part of the PDL chain

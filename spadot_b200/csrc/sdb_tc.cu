@@ -898,8 +898,9 @@ int tc_variant() {
 template <int DP>
 int launch_tc(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
     if (a.row_m != nullptr) {                                                                                // predicted stabiliser
-        static int runsum = -1;          // development knob SDB_TC_RUNSUM=0: per-chunk reduction tree instead of running sums
-        if (runsum < 0) { const char* e = getenv("SDB_TC_RUNSUM"); runsum = (e && *e == '0') ? 0 : 1; }
+        static int runsum = -1;          // development knob SDB_TC_RUNSUM=1: running sums instead of the per-chunk reduction tree
+                                         // (measured r2: 0.793 vs 0.809 of the SFU peak at 131072^2 - not adopted)
+        if (runsum < 0) { const char* e = getenv("SDB_TC_RUNSUM"); runsum = (e && *e == '1') ? 1 : 0; }
         return runsum ? launch_tc_v<DP, 8, true, 0, true, false, true, true>(tmP, tmQ, a, n_ctas, st)
                       : launch_tc_v<DP, 8, true, 0, true, false, true, false>(tmP, tmQ, a, n_ctas, st);
     }

@@ -226,6 +226,7 @@ class CudaOps(VectorOps):
             self._build_splits(None)
         self._splits = {}
         self._partials = {}
+        self._direct = True
         self.inv_med = 1.0
         self.persistent = os.environ.get("SDB_PERSISTENT", "1") != "0"      # development knob (A/B against the launch loop)
         self._barrier = None
@@ -274,10 +275,29 @@ class CudaOps(VectorOps):
         self._nx32 = None
         self._bias_key = {"x": None, "y": None}
 
+    # SIMT tile arithmetic (see sdb_lse_pass_simt): dot-product tiles while the largest exponent 2*c1*log2(e)*|x||y| stays at or
+    # below this, direct-difference tiles (twice the inner-loop work, rounding relative to the cost of a pair) beyond it.
+    # 40 keeps the default eps = 0.05 on the fast form (measured LSE error 3e-6 there) and moves eps <= ~0.03 to the exact one.
+    SIMT_DOT_MAX = float(os.environ.get("SDB_SIMT_DOT_MAX", "40"))
+
+    def _xy_max(self):
+        if getattr(self, "_xy_max_v", None) is None:
+            nx = float(self.X.norms_sq.max().item()) if self.n else 0.0
+            ny = float(self.Y.norms_sq.max().item()) if self.m else 0.0
+            self._xy_max_v = math.sqrt(nx * ny)
+        return self._xy_max_v
+
     def _prep(self, eps):
-        """Called by every operation that takes eps, before anything derived from the split points (norms, bias) is used."""
-        if self.use_tc and self._split_key != (eps, self.inv_med):
-            self._build_splits(eps)
+        """Called by every operation that takes eps, before anything derived from the point representation (norms, bias) is
+        used: rebuilds the fp16 splits for the exponent scale of `eps` (tensor-core form), or picks the SIMT tile form."""
+        if self.use_tc:
+            if self._split_key != (eps, self.inv_med):
+                self._build_splits(eps)
+        else:
+            direct = 2.0 * (self.inv_med / eps) * math.log2(math.e) * self._xy_max() > self.SIMT_DOT_MAX
+            if direct != self._direct:
+                self._direct = direct
+                self._bias_key = {"x": None, "y": None}
 
     def _split_plan(self, n_p, n_q):
         key = (n_p, n_q)
@@ -365,7 +385,9 @@ class CudaOps(VectorOps):
 
     # ------------------------------------------------------------------ K3 passes
     def _norms(self, P: PointSet):
-        return P.norms16 if self.use_tc else P.norms
+        if self.use_tc:
+            return P.norms16
+        return P.norms if self._direct else P.norms_sq          # direct-difference tiles take zero norms
 
     def _tc_split_plan(self, n_p, n_q):
         """(tiles per split, number of splits) of one tensor-core pass, see plans.tc_split_plan."""
@@ -389,9 +411,10 @@ class CudaOps(VectorOps):
             if bounds is None:
                 bounds, ns = self._split_plan(P.n, Q.n)
             partial = self._partial(ns, P.n)
-            self._call("sdb_lse_pass_simt", _ptr(P.xt), P.ld, P.n, _ptr(Q.xt), Q.ld, Q.n, P.dpad, _ptr(bias), -0.5 * scale,
-                       _ptr(bounds), ns, _ptr(partial))
-            norms = P.norms
+            direct = simt or self._direct                       # (simt=True: the transition table's pass, always direct)
+            self._call("sdb_lse_pass_simt", _ptr(P.xt), P.ld, P.n, _ptr(Q.xt), Q.ld, Q.n, P.dpad, _ptr(bias),
+                       -0.5 * scale if direct else scale, _ptr(bounds), ns, _ptr(partial))
+            norms = P.norms if direct else P.norms_sq
         if not finalize:
             return partial
         if out is None:
@@ -446,9 +469,17 @@ class CudaOps(VectorOps):
         if not self._persistent_eligible() or os.environ.get("SDB_FUSED_SOLVE", "1") == "0":
             return None
         d = self._sweep_desc(st, float(epsilon), 0.0, 0.0, 0.0, NEG_INF)
+        d.norms_x, d.norms_y = _ptr(self.X.norms_sq), _ptr(self.Y.norms_sq)
         self._persistent_plan(d)
+        # the six regularisations in the host's own arithmetic (ot_solvers.py:218,240,254), so that the device walks the very
+        # same epsilons as the host-driven loop and the reference
+        scale_factor = math.exp(-math.log(epsilon) / 5)
+        eps_i, stages = epsilon0 * scale_factor, []
+        for _ in range(6):
+            eps_i = eps_i / scale_factor
+            stages.append(eps_i)
         p = _lib.SolveParams(float(lambda1), float(lambda2), float(epsilon), float(epsilon0), float(tolerance), float(tau),
-                             float(max_iter), int(batch_size), 0)
+                             float(max_iter), (ctypes.c_double * 6)(*stages), self._xy_max(), self.SIMT_DOT_MAX, int(batch_size), 0)
         if getattr(self, "_solve_ws", None) is None:
             tiles = (self.n + 63) // 64 + (self.m + 63) // 64
             self._solve_ws = dict(flag2=torch.zeros(2, dtype=torch.int32, device=self.device),
@@ -513,6 +544,7 @@ class CudaOps(VectorOps):
             b_col, d.ns_col = self._split_plan(self.m, self.n)
             d.bounds_row, d.bounds_col = _ptr(b_row), _ptr(b_col)
             d.pow2_scale = 1.0
+            d.simt_direct = int(self._direct)
         d.norms_x, d.norms_y = _ptr(self._norms(self.X)), _ptr(self._norms(self.Y))
         d.partial_row, d.partial_col = _ptr(self._partial(d.ns_row, self.n)), _ptr(self._partial(d.ns_col, self.m))
         d.bias_x, d.bias_y, d.m_bias = _ptr(self.bias_x), _ptr(self.bias_y), self.bias_y.numel()

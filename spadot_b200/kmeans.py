@@ -141,3 +141,36 @@ class KMeans:
 
     def fit_predict(self, X, y=None):
         return self.fit(X).labels_
+
+
+def select_n_clusters(wss, min_clusters=4, wss_threshold=0.1):
+    """The elbow rule of `Adaptive_clustering` (utils/_analyze_utils.py:73-88) on the within-cluster sums of squares of
+    k = min_clusters, min_clusters + 1, ...: among the k whose drop wss[k-1] - wss[k] exceeds `wss_threshold` of the WSS
+    range, the one with the largest ratio between its drop and the next drop.  Returns (k, table) where table holds the
+    reference's columns (clusters, wss, wss_diff, wss_diff_ratio; NaN where the reference has None)."""
+    wss = np.asarray(wss, dtype=np.float64)
+    K = wss.size
+    if K < 3:
+        raise ValueError("the elbow rule needs at least three cluster counts")
+    diff = np.full(K, np.nan)
+    diff[1:] = -(wss[1:] - wss[:-1])
+    ratio = np.full(K, np.nan)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio[1:K - 1] = diff[1:K - 1] / diff[2:K]
+    keep = diff > wss_threshold * (wss.max() - wss.min())            # NaN compares false, like pandas' filter
+    cand = np.where(keep & ~np.isnan(ratio))[0]
+    if cand.size == 0:
+        raise ValueError("no cluster count passes the WSS threshold")      # pandas' idxmax raises on an all-NA column
+    best = cand[np.argmax(ratio[cand])]                                       # first maximum, like idxmax
+    table = dict(clusters=np.arange(min_clusters, min_clusters + K), wss=wss, wss_diff=diff, wss_diff_ratio=ratio)
+    return int(min_clusters + best), table
+
+
+def adaptive_clustering(X, min_clusters=4, max_clusters=20, wss_threshold=0.1, random_state=1993, n_init=10, device=None):
+    """`Adaptive_clustering` for one timepoint's latent matrix (utils/_analyze_utils.py:42-105): k-means for every
+    k in [min_clusters, max_clusters] on the device, the elbow rule above, then the labels of the selected k.
+    Returns (labels, k, table).  (The reference re-fits the selected k with the same random_state, i.e. the same result.)"""
+    fits = [KMeans(n_clusters=k, random_state=random_state, n_init=n_init, device=device).fit(X)
+            for k in range(min_clusters, max_clusters + 1)]
+    k, table = select_n_clusters([f.inertia_ for f in fits], min_clusters, wss_threshold)
+    return fits[k - min_clusters].labels_, k, table
