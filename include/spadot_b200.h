@@ -101,6 +101,14 @@ int sdb_lse_pass_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q
                     int dp, const float* bias_padded, float scale, int tiles_per_split, int n_ctas,
                     float* partial, void* stream);
 
+/* The same pass with VARIABLE-length splits: split s covers the 256-column tiles [split_tiles[s], split_tiles[s+1]) (device
+ * array of n_splits + 1 ints, every split non-empty, split_tiles[n_splits] = n_q_pad / 256).  Used by the transition table
+ * (K6): columns permuted by domain label, every label group padded to a tile multiple (padding bias = SDB_NEG_SENTINEL), one
+ * (max, sum) per (label, row).  replaces the dense P0^T.T.P1 of ref: utils/_analyze_utils.py:135-137. */
+int sdb_lse_pass_tc_groups(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q_pad, int dp,
+                           const float* bias_padded, float scale, const int* split_tiles, int n_splits, int n_ctas, float* partial,
+                           void* stream);
+
 /* L[i] = ln2 * log2( sum_s sum_s,i * 2^(max_s,i - M_i) ) + ln2*M_i - norms[i]*c1   (fp64)
  *      = LSE_j[(g_j - C_ij)/eps]; -inf when every partial is empty. */
 int sdb_lse_finalize(const float* partial, int n_splits, int64_t n, const double* norms,
@@ -362,6 +370,14 @@ int sdb_gat_backward(const void* feat, const void* a_src, const void* a_dst, con
  * k <= 32 and k <= n-1.  out_idx (n,k) int32, out_dist (n,k) fp64 Euclidean distances (may be NULL).
  * replaces sklearn NearestNeighbors in _Cal_Spatial_Net (ref: utils/_utils.py:65-69). */
 int sdb_knn_f64(const double* pts, int64_t n, int dim, int k, int32_t* out_idx, double* out_dist, void* stream);
+/* The same result for 2-D points in O(n k): pts_sorted (n,2) = the points sorted by the cell of a uniform gx x gy grid of
+ * pitch h with origin (x0, y0), cell = min(gy-1, floor((y-y0)/h))*gx + min(gx-1, floor((x-x0)/h)); order[s] = original index of
+ * sorted slot s, cell_of_sorted[s] its cell, cell_start (gx*gy+1) the CSR offsets of the cells.  out_idx / out_dist are
+ * indexed by ORIGINAL point index.  A query scans rings of cells until its k-th distance is below the distance to the
+ * visited block's border, so neighbours and their (distance, index) order are exactly those of sdb_knn_f64. */
+int sdb_knn_grid_f64(const double* pts_sorted, const int32_t* order, const int32_t* cell_of_sorted, const int32_t* cell_start,
+                     int64_t n, int gx, int gy, double x0, double y0, double h, int k, int32_t* out_idx, double* out_dist,
+                     void* stream);
 
 /* ------------------------------------------------------------------ K7: k-means Lloyd iterations */
 /* One Lloyd E-step (+ accumulation for the M-step): labels[i] <- argmin_j |c_j|^2 - 2 x_i.c_j (first minimum on ties),

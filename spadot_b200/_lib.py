@@ -34,6 +34,7 @@ SIGNATURES = {
     "sdb_finalize_update_pred": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p, c_p, c_p],
     "sdb_partial_sums_f64": [c_p, c_i, c_l, c_p, c_p, c_p, c_i, c_p, c_p],
     "sdb_update_from_sums_f64": [c_p, c_p, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p, c_p],
+    "sdb_lse_pass_tc_groups": [c_p, c_l, c_l, c_p, c_l, c_i, c_p, c_f, c_p, c_i, c_i, c_p, c_p],
     "sdb_lse_pass_tc_pred": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_i, c_i, c_p, c_p, c_p],
     "sdb_potential_update": [c_l, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
     "sdb_finalize_update": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
@@ -67,6 +68,7 @@ SIGNATURES = {
     "sdb_kmeans_inertia": [c_p, c_p, c_p, c_l, c_i, c_p, c_p, c_p],
     "sdb_kmeans_lloyd_runs": [c_p, c_l, c_i, c_i, c_p, c_i, c_i, c_d, c_p, c_p, c_p, c_p, c_p, c_p],
     "sdb_knn_f64": [c_p, c_l, c_i, c_i, c_p, c_p, c_p],
+    "sdb_knn_grid_f64": [c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_p],
     "sdb_pipe_peak": [c_i, c_i, c_i, c_p, c_p, c_p],
     "sdb_gat_backward": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
 }

@@ -310,7 +310,80 @@ __global__ void __launch_bounds__(128) knn_kernel(const double* __restrict__ pts
         }
 }
 
+// Grid-binned form for 2-D coordinates: O(n k) instead of O(n^2).  Points are sorted by the cell of a uniform grid (about
+// four points per cell); a query walks the rings of cells around its own cell and stops as soon as its k-th best distance is
+// strictly smaller than the distance to the border of the block of cells it has already visited - every unvisited point lies
+// outside that block - so the result is exactly the brute-force one, including the (distance, index) order.
+__global__ void __launch_bounds__(128) knn_grid_kernel(const double* __restrict__ pts, const int32_t* __restrict__ order,
+                                                       const int32_t* __restrict__ cell_of, const int32_t* __restrict__ cell_start,
+                                                       int64_t n, int gx, int gy, double x0, double y0, double h, int k,
+                                                       int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // sorted slot: neighbouring threads, neighbouring cells
+    if (s >= n) return;
+    const double qx = pts[s * 2], qy = pts[s * 2 + 1];
+    const int32_t qi = order[s];
+    const int cell = cell_of[s], cx = cell % gx, cy = cell / gx;
+    double bd[KNN_MAX_K];
+    int32_t bi[KNN_MAX_K];
+    for (int t = 0; t < KNN_MAX_K; ++t) { bd[t] = INFINITY; bi[t] = 0x7fffffff; }
+    const int rmax = max(max(cx, gx - 1 - cx), max(cy, gy - 1 - cy));
+    for (int r = 0; r <= rmax; ++r) {
+        const int y_lo = max(cy - r, 0), y_hi = min(cy + r, gy - 1);
+        for (int yy = y_lo; yy <= y_hi; ++yy) {
+            const bool edge_row = (yy == cy - r) || (yy == cy + r);
+            // an edge row of the ring is scanned in full, an interior row only at its two end cells
+            const int step = edge_row ? 1 : max(2 * r, 1);
+            for (int xx = cx - r; xx <= cx + r; xx += step) {
+                if (xx < 0 || xx >= gx) continue;
+                const int c = yy * gx + xx;
+                for (int p = cell_start[c]; p < cell_start[c + 1]; ++p) {
+                    const int32_t j = order[p];
+                    if (j == qi) continue;
+                    double d2 = 0.0;
+                    { const double df = qx - pts[(int64_t)p * 2]; d2 += df * df; }
+                    { const double df = qy - pts[(int64_t)p * 2 + 1]; d2 += df * df; }
+                    if (d2 < bd[k - 1] || (d2 == bd[k - 1] && j < bi[k - 1])) {
+                        int pos = k - 1;
+                        while (pos > 0 && (bd[pos - 1] > d2 || (bd[pos - 1] == d2 && bi[pos - 1] > j))) {
+                            bd[pos] = bd[pos - 1];
+                            bi[pos] = bi[pos - 1];
+                            --pos;
+                        }
+                        bd[pos] = d2;
+                        bi[pos] = j;
+                    }
+                }
+            }
+        }
+        // distance from the query to the border of the visited block [cx-r, cx+r] x [cy-r, cy+r] (sides at the grid's edge do not
+        // count: nothing lies beyond them); a relative margin covers the rounding of the cell assignment
+        double dmin = INFINITY;
+        if (cx - r > 0) dmin = fmin(dmin, qx - (x0 + (double)(cx - r) * h));
+        if (cx + r < gx - 1) dmin = fmin(dmin, (x0 + (double)(cx + r + 1) * h) - qx);
+        if (cy - r > 0) dmin = fmin(dmin, qy - (y0 + (double)(cy - r) * h));
+        if (cy + r < gy - 1) dmin = fmin(dmin, (y0 + (double)(cy + r + 1) * h) - qy);
+        dmin -= 1e-9 * h;
+        if (dmin > 0.0 && bd[k - 1] < dmin * dmin) break;
+    }
+    for (int t = 0; t < k; ++t) {
+        out_idx[(int64_t)qi * k + t] = bi[t];
+        if (out_dist) out_dist[(int64_t)qi * k + t] = sqrt(bd[t]);
+    }
+}
+
 }  // namespace
+
+extern "C" int sdb_knn_grid_f64(const double* pts_sorted, const int32_t* order, const int32_t* cell_of_sorted, const int32_t* cell_start,
+                                int64_t n, int gx, int gy, double x0, double y0, double h, int k, int32_t* out_idx, double* out_dist,
+                                void* stream) {
+    SDB_CHECK_ARG(pts_sorted && order && cell_of_sorted && cell_start && out_idx && n >= 0 && gx > 0 && gy > 0 && h > 0.0 && k >= 1 &&
+                  k <= KNN_MAX_K);
+    if (n == 0) return 0;
+    if (k > n - 1 || n > 2147483647LL) return SDB_E_INVALID;
+    knn_grid_kernel<<<(unsigned)((n + 127) / 128), 128, 0, sdb_stream(stream)>>>(pts_sorted, order, cell_of_sorted, cell_start, n, gx, gy,
+                                                                                   x0, y0, h, k, out_idx, out_dist);
+    SDB_LAUNCH_STATUS();
+}
 
 extern "C" int sdb_knn_f64(const double* pts, int64_t n, int dim, int k, int32_t* out_idx, double* out_dist, void* stream) {
     SDB_CHECK_ARG(pts && out_idx && n >= 0 && dim >= 1 && dim <= 3 && k >= 1 && k <= KNN_MAX_K);

@@ -224,7 +224,11 @@ __device__ __noinline__ void sweep_collect_rare(uint32_t mask, const double* xi,
     }
 }
 
+struct TcArgs;
+__device__ __forceinline__ void split_range(const TcArgs& a, int sp, int& t0, int& t1);
+
 struct TcArgs {
+    const int* split_tiles;  // optional: n_splits + 1 tile boundaries of variable-length splits (label groups, K6); else uniform
     const float* bias;       // padded to a multiple of TILE_N with SDB_NEG_SENTINEL
     const float* row_m;      // predicted stabiliser per row (FIXED_M kernels), else unused
     float scale;
@@ -244,6 +248,16 @@ struct TcArgs {
     double* cand;
     unsigned long long cap;
 };
+
+__device__ __forceinline__ void split_range(const TcArgs& a, int sp, int& t0, int& t1) {
+    if (a.split_tiles) {
+        t0 = __ldg(a.split_tiles + sp);
+        t1 = __ldg(a.split_tiles + sp + 1);
+    } else {
+        t0 = sp * a.tiles_per_split;
+        t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
+    }
+}
 
 template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, int MODE = MODE_LSE, bool PIPE = false, bool XTILE = false,
           bool FIXED_M = false, bool RUNSUM = false>
@@ -301,8 +315,8 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             uint32_t tile_ctr = 0, item_ctr = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
                 const int rt = item % a.n_row_tiles, sp = item / a.n_row_tiles;
-                const int t0 = sp * a.tiles_per_split;
-                const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
+                int t0, t1;
+                split_range(a, sp, t0, t1);
                 const int as = item_ctr % S::A_STAGES;
                 uint8_t* sAs = sA + (size_t)as * 2 * S::A_BYTES;
                 mbar_wait(a_empty + as, ((item_ctr / S::A_STAGES) & 1) ^ 1);
@@ -331,8 +345,8 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         uint32_t tile_ctr = 0, item_ctr = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_ctr) {
             const int sp = item / a.n_row_tiles;
-            const int t0 = sp * a.tiles_per_split;
-            const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
+            int t0, t1;
+            split_range(a, sp, t0, t1);
             const int as = item_ctr % S::A_STAGES;
             const uint64_t dAh = make_desc<DP>(smem_u32(sA + (size_t)as * 2 * S::A_BYTES));
             const uint64_t dAl = make_desc<DP>(smem_u32(sA + (size_t)as * 2 * S::A_BYTES + S::A_BYTES));
@@ -398,8 +412,8 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
             uint32_t tile_ctr = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int rt = item % a.n_row_tiles, sp = item / a.n_row_tiles;
-                const int t0 = sp * a.tiles_per_split;
-                const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
+                int t0, t1;
+                split_range(a, sp, t0, t1);
                 const int64_t row = (int64_t)rt * TILE_M + row_in_tile;
                 // u = |x_i|^2 + |y_j|^2 - 2 x_i.y_j - lo; rows beyond n_p (and padded columns, |y_j|^2 >= 3e38) come out huge
                 // and positive: neither below nor inside
@@ -475,8 +489,8 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         uint32_t tile_ctr = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int rt = item % a.n_row_tiles, sp = item / a.n_row_tiles;
-            const int t0 = sp * a.tiles_per_split;
-            const int t1 = min(a.n_col_tiles, t0 + a.tiles_per_split);
+            int t0, t1;
+            split_range(a, sp, t0, t1);
             float m_used = SDB_NEG_SENTINEL, ssum = 0.f;
             if constexpr (FIXED_M) {
                 // predicted stabiliser: an upper bound of this row's largest exponent, supplied by the caller
@@ -969,6 +983,36 @@ int sdb_lse_pass_tc_pred(const void* p16, int64_t n_p, int64_t n_p_pad, const vo
     a.n_col_tiles = (int)((n_q + TILE_N - 1) / TILE_N);
     a.tiles_per_split = tiles_per_split;
     a.n_splits = (a.n_col_tiles + tiles_per_split - 1) / tiles_per_split;   // never empty, by construction
+    a.partial = reinterpret_cast<float2*>(partial);
+    cudaStream_t st = sdb_stream(stream);
+    switch (dp) {
+        case 16: return launch_tc<16>(tmP, tmQ, a, n_ctas, st);
+        case 32: return launch_tc<32>(tmP, tmQ, a, n_ctas, st);
+        default: return launch_tc<64>(tmP, tmQ, a, n_ctas, st);
+    }
+}
+
+int sdb_lse_pass_tc_groups(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q_pad, int dp,
+                           const float* bias_padded, float scale, const int* split_tiles, int n_splits, int n_ctas, float* partial,
+                           void* stream) {
+    SDB_CHECK_ARG(p16 && q16 && bias_padded && partial && split_tiles && n_p > 0 && n_q_pad > 0 && n_splits > 0 && n_ctas > 0);
+    SDB_CHECK_ARG((n_p_pad % TILE_N) == 0 && (n_q_pad % TILE_N) == 0 && n_p_pad >= n_p);
+    SDB_CHECK_ARG(((uintptr_t)p16 % 128) == 0 && ((uintptr_t)q16 % 128) == 0 && ((uintptr_t)bias_padded % 16) == 0);
+    if (!(dp == 16 || dp == 32 || dp == 64)) return SDB_E_UNSUPPORTED;
+    CUtensorMap tmP, tmQ;
+    int rc = make_tmap(&tmP, p16, n_p_pad, dp, TILE_M);
+    if (rc) return rc;
+    rc = make_tmap(&tmQ, q16, n_q_pad, dp, TILE_N);
+    if (rc) return rc;
+    TcArgs a{};
+    a.split_tiles = split_tiles;
+    a.bias = bias_padded;
+    a.scale = scale;
+    a.n_p = n_p;
+    a.n_row_tiles = (int)((n_p + TILE_M - 1) / TILE_M);
+    a.n_col_tiles = (int)(n_q_pad / TILE_N);
+    a.tiles_per_split = 0;
+    a.n_splits = n_splits;
     a.partial = reinterpret_cast<float2*>(partial);
     cudaStream_t st = sdb_stream(stream);
     switch (dp) {

@@ -277,8 +277,10 @@ class CudaOps(VectorOps):
 
     # SIMT tile arithmetic (see sdb_lse_pass_simt): dot-product tiles while the largest exponent 2*c1*log2(e)*|x||y| stays at or
     # below this, direct-difference tiles (twice the inner-loop work, rounding relative to the cost of a pair) beyond it.
-    # 40 keeps the default eps = 0.05 on the fast form (measured LSE error 3e-6 there) and moves eps <= ~0.03 to the exact one.
-    SIMT_DOT_MAX = float(os.environ.get("SDB_SIMT_DOT_MAX", "40"))
+    # BASELINE's mixture has 2*c1*log2(e)*|x||y| = 43 at eps = 0.05, 108 at 0.02, 215 at 0.01; measured with dot-product tiles
+    # (profiles/r2_tc_precision.jsonl, r2_sweep_parity_a.jsonl): max LSE error 3e-6 / 1e-5 / 4e-5, marginals 1e-6 / 2e-6 / 1.3e-5.
+    # 100 keeps eps >= ~0.025 on the fast form and moves smaller regularisations to the exact one.
+    SIMT_DOT_MAX = float(os.environ.get("SDB_SIMT_DOT_MAX", "100"))
 
     def _xy_max(self):
         if getattr(self, "_xy_max_v", None) is None:
@@ -748,10 +750,70 @@ class CudaOps(VectorOps):
         return hist
 
     # ------------------------------------------------------------------ K6 transition table
+    def _transition_table_tc(self, f, g, eps, lx, ly, k0, k1):
+        """K6 on the tensor-core pass: target spots permuted by domain label, every label group padded to whole 256-column
+        tiles, ONE pass with one variable-length split per label (sdb_lse_pass_tc_groups) -> (max, sum) per (label, row),
+        then the rows are folded by their own labels.  Same point representation (fp16 hi/lo split, norms) as the solve."""
+        self._prep(eps)
+        valid = torch.nonzero((ly >= 0) & (ly < k1)).flatten()         # labels outside [0, k1) take no part (as in the SIMT form)
+        lyv = ly[valid]
+        counts = torch.bincount(lyv, minlength=k1)[:k1]
+        counts_h = counts.cpu().numpy()
+        # one split per label, cut further so that no split exceeds MAX_SPLIT_COLS columns (fp32 running sums)
+        max_tiles = self.MAX_SPLIT_COLS // 256
+        split_label, split_tiles, group_start, t = [], [0], np.zeros(k1, dtype=np.int64), 0
+        for lab in range(k1):
+            nt = int(-(-int(counts_h[lab]) // 256))
+            group_start[lab] = t * 256
+            while nt > 0:
+                step = min(nt, max_tiles)
+                t += step
+                nt -= step
+                split_label.append(lab)
+                split_tiles.append(t)
+        table = torch.zeros((k0, k1), dtype=torch.float64, device=self.device)
+        if not split_label:
+            return table
+        m_pad = t * 256
+        order = torch.argsort(lyv, stable=True)
+        perm = valid[order]                                             # original column of each permuted column
+        lp = lyv[order]
+        first = torch.zeros(k1 + 1, dtype=torch.int64, device=self.device)
+        first[1:] = torch.cumsum(counts, 0)
+        gs = torch.from_numpy(group_start).to(self.device)
+        pos = gs[lp] + (torch.arange(perm.numel(), device=self.device) - first[lp])        # padded slot of permuted column
+        y_pad = torch.zeros((m_pad, self.d), dtype=torch.float64, device=self.device)
+        y_pad[pos] = self.Y.x64[perm]
+        g_pad = torch.full((m_pad,), NEG_INF, dtype=torch.float64, device=self.device)     # padding: bias = sentinel
+        g_pad[pos] = g[perm]
+        y16 = torch.empty((m_pad, 2 * self.Y.dp), dtype=torch.float16, device=self.device)
+        norms = torch.empty(m_pad, dtype=torch.float64, device=self.device)
+        self._call("sdb_prep_points_split_f16_scaled", _ptr(y_pad), m_pad, self.d, _ptr(self.center), float(self.prescale), _ptr(y16),
+                   m_pad, self.Y.dp, _ptr(norms))
+        bias = torch.empty(m_pad, dtype=torch.float32, device=self.device)
+        c1 = self.inv_med / eps
+        self._call("sdb_make_bias", m_pad, m_pad, _ptr(g_pad), _ptr(norms), eps, c1, _ptr(bias))
+        kk = len(split_label)
+        st_dev = torch.tensor(split_tiles, dtype=torch.int32, device=self.device)
+        sl_dev = torch.tensor(split_label, dtype=torch.int64, device=self.device)
+        chunk = max(1, 4096 // k0)                                      # sdb_transition_accumulate holds k0 x splits in shared memory
+        partial = torch.empty((kk, self.n, 2), dtype=torch.float32, device=self.device)
+        self._call("sdb_lse_pass_tc_groups", _ptr(self.X.x16), self.n, self.X.n_pad, _ptr(y16), m_pad, self.X.dp, _ptr(bias),
+                   self.tc_scale, _ptr(st_dev), kk, self.n_sm, _ptr(partial))
+        for s0 in range(0, kk, chunk):
+            s1 = min(kk, s0 + chunk)
+            sub = torch.zeros((k0, s1 - s0), dtype=torch.float64, device=self.device)
+            self._call("sdb_transition_accumulate", _ptr(partial[s0:s1]), s1 - s0, self.n, _ptr(self.X.norms16), c1, _ptr(f), eps,
+                       1.0 / self.m, _ptr(lx), k0, _ptr(sub))
+            table.index_add_(1, sl_dev[s0:s1], sub)
+        return table
+
     def transition_table(self, f, g, eps, labels_x, labels_y, k0, k1):
         """table[a,b] = sum_{i in a, j in b} exp((f_i+g_j-C_ij)/eps)/M for this rank's rows."""
         ly = torch.as_tensor(np.asarray(labels_y), dtype=torch.int64).to(self.device)
         lx = torch.as_tensor(np.asarray(labels_x), dtype=torch.int32).to(self.device)
+        if self.use_tc and self.n > 0 and k0 <= 4096:
+            return self._transition_table_tc(f, g, eps, lx, ly, k0, k1)
         perm = torch.argsort(ly, stable=True)
         counts = torch.bincount(ly, minlength=k1)[:k1]
         bounds = torch.zeros(k1 + 1, dtype=torch.int64, device=self.device)

@@ -12,6 +12,8 @@ adjacency and without torch_geometric.
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 import torch
 
@@ -22,14 +24,42 @@ def knn_cutoff(n, max_neighbors=30, knn_cutoff_base=6):
     return int(min(max_neighbors, knn_cutoff_base * round(n / 1000)))
 
 
-def knn(coords, k, device=None):
-    """(n,k) int64 indices of the k nearest other points, nearest first (CUDA brute force, fp64)."""
+GRID_MIN_POINTS = 4096        # below this the brute-force kernel is a single wave of CTAs anyway
+GRID_POINTS_PER_CELL = 4.0
+
+
+def knn(coords, k, device=None, method="auto"):
+    """(n,k) int64 indices of the k nearest other points, nearest first, ties by index (fp64 distances).
+    method: "brute" = O(n^2) scan (sdb_knn_f64), "grid" = uniform-grid ring search for 2-D points (sdb_knn_grid_f64, O(n k),
+    same result), "auto" = grid for 2-D sets of at least GRID_MIN_POINTS points."""
     _lib.require_device()
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     pts = torch.as_tensor(np.asarray(coords) if not isinstance(coords, torch.Tensor) else coords).to(dev, torch.float64).contiguous()
     n, dim = pts.shape
     idx = torch.empty((n, k), dtype=torch.int32, device=dev)
-    _lib.call("sdb_knn_f64", pts.data_ptr(), n, dim, int(k), idx.data_ptr(), 0, torch.cuda.current_stream(dev).cuda_stream)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    use_grid = method == "grid" or (method == "auto" and dim == 2 and n >= GRID_MIN_POINTS)
+    if use_grid and dim == 2 and n > k:
+        lo, hi = pts.min(0).values, pts.max(0).values
+        x0, y0 = float(lo[0]), float(lo[1])
+        w, hgt = float(hi[0]) - x0, float(hi[1]) - y0
+        if w > 0 and hgt > 0:
+            h = math.sqrt(w * hgt * GRID_POINTS_PER_CELL / n)
+            gx, gy = max(1, int(math.ceil(w / h))), max(1, int(math.ceil(hgt / h)))
+            if gx * gy <= (1 << 26):
+                cx = torch.clamp(((pts[:, 0] - x0) / h).floor().long(), 0, gx - 1)
+                cy = torch.clamp(((pts[:, 1] - y0) / h).floor().long(), 0, gy - 1)
+                cell = cy * gx + cx
+                order = torch.argsort(cell, stable=True)
+                cell_sorted = cell[order].to(torch.int32).contiguous()
+                start = torch.zeros(gx * gy + 1, dtype=torch.int32, device=dev)
+                start[1:] = torch.cumsum(torch.bincount(cell, minlength=gx * gy), 0).to(torch.int32)
+                pts_sorted = pts[order].contiguous()
+                order32 = order.to(torch.int32).contiguous()
+                _lib.call("sdb_knn_grid_f64", pts_sorted.data_ptr(), order32.data_ptr(), cell_sorted.data_ptr(), start.data_ptr(), n,
+                          gx, gy, x0, y0, h, int(k), idx.data_ptr(), 0, st)
+                return idx.long()
+    _lib.call("sdb_knn_f64", pts.data_ptr(), n, dim, int(k), idx.data_ptr(), 0, st)
     return idx.long()
 
 

@@ -407,9 +407,11 @@ def test_whole_solve_in_one_launch_matches_host_stage_loop(ot, n, m, d, tau):
     assert l1 <= 2 and l2 > 20                                  # one launch vs the batch-by-batch loop
     assert c1.info["iters_per_stage"] == c2.info["iters_per_stage"], (c1.info, c2.info)
     assert c1.info["gap"] == pytest.approx(c2.info["gap"], rel=1e-6, abs=1e-13)
-    for name in ("f", "g", "u", "v", "Lr", "Lc"):
+    # fp32-noise level: the host loop's gap-check row pass uses the launch path's column splits, the one-launch solve the
+    # cooperative grid's, so their fp32 partial sums differ in the last bit (6e-8 on an LSE, 2e-9 on a potential)
+    for name, tol in (("f", 2e-8), ("g", 2e-8), ("u", 2e-8), ("v", 2e-8), ("Lr", 5e-7), ("Lc", 5e-7)):
         x, y = getattr(c1.state, name), getattr(c2.state, name)
-        assert float((x - y).abs().max()) < 1e-10, name
+        assert float((x - y).abs().max()) < tol, name
 
 
 def test_whole_solve_in_one_launch_nan_and_max_iter(ot):

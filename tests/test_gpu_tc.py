@@ -279,3 +279,31 @@ def test_predicted_stabiliser_full_solve_same_iterations(ot):
     assert cp1.ops._pred is not None and cp1.ops._pred.ok
     assert cp0.info["iters_per_stage"] == cp1.info["iters_per_stage"]
     assert float((cp0.f - cp1.f).abs().max()) < 2e-6 and float((cp0.g - cp1.g).abs().max()) < 2e-6
+
+
+def test_transition_table_on_the_tensor_core_pass(ot):
+    """K6 on the tcgen05 pass (label-permuted, tile-padded target spots, one variable-length split per label,
+    sdb_lse_pass_tc_groups) against the dense oracle P0^T.T.P1 (ref: utils/_analyze_utils.py:135-137) and against the SIMT
+    form; labels with an empty class, a class larger than one split, and spots outside [0, k1)."""
+    ot_solvers, sinkhorn, CudaOps = ot
+    n, m, d = 2300, 3100, 32
+    a, b, la, lb = ot_dense.synthetic_embeddings(n, m, d, seed=41)
+    lb = lb.copy()
+    lb[lb == 3] = 4                       # class 3 is empty
+    lb[:5] = 12                           # outside [0, 10): takes no part
+    Cn, med = ot_dense.median_normalised_cost(a, b)
+    want = ot_dense.duality_gap_solve(Cn, np.ones(n), **CFG)
+    keep = lb < 10
+    tab_ref = ot_dense.transition_table(want[:, keep], la, lb[keep], 10, 10)
+    tabs = {}
+    for tc in ("on", "off"):
+        ops = CudaOps(a, b, tc=tc)
+        if tc == "on":
+            ops.MAX_SPLIT_COLS = 512      # forces classes to be cut into several splits
+        cp = ot_solvers.solve_coupling(a, b, CFG, ops=ops, dist=sinkhorn.Dist(enabled=False))
+        tabs[tc] = cp.transition_table(la, lb, 10, 10).cpu().numpy()
+    for tc in ("on", "off"):
+        assert np.abs(tabs[tc] - tab_ref).max() / tab_ref.max() < 1e-4, tc
+        assert np.array_equal(tabs[tc].argmax(1), tab_ref.argmax(1))
+        assert np.all(tabs[tc][:, 3] == 0.0)
+    assert np.abs(tabs["on"] - tabs["off"]).max() / tab_ref.max() < 2e-5
