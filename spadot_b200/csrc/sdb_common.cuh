@@ -38,6 +38,24 @@ static inline cudaError_t sdb_launch(void (*kern)(KArgs...), dim3 grid, dim3 blo
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// Opt-in to more than 48 KB of dynamic shared memory.  The attribute is per function AND per device, so the "already set"
+// memo is indexed by the current device (a process that drives several GPUs sets it on each); a racing second thread at
+// worst sets the same value again.
+#define SDB_MAX_DEVICES 64
+template <typename F>
+static inline cudaError_t sdb_ensure_smem(F kern, size_t smem, size_t (&memo)[SDB_MAX_DEVICES]) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= SDB_MAX_DEVICES) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > memo[dev]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        memo[dev] = smem;
+    }
+    return cudaSuccess;
+}
+
 __device__ __forceinline__ float sdb_ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

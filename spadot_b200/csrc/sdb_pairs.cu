@@ -243,12 +243,8 @@ int launch_pairs(const PairArgs& a, const typename Epi::Params& ep, int n_splits
     if (a.n_p <= 0) return 0;
     const size_t smem = sizeof(float) * ((size_t)a.dpad * BM + 2 * (size_t)a.dpad * BN + 2 * BN);
     auto kern = pair_tile_kernel<DIRECT, Epi>;
-    static size_t smem_set = 0;      // per instantiation: raise the opt-in limit only when it has to grow
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        smem_set = smem;
-    }
+    static size_t smem_set[SDB_MAX_DEVICES] = {0};      // per instantiation and device
+    { cudaError_t e = sdb_ensure_smem(kern, smem, smem_set); if (e != cudaSuccess) return (int)e; }
     dim3 grid((unsigned)((a.n_p + BM - 1) / BM), (unsigned)n_splits);
     kern<<<grid, NT, smem, st>>>(a, ep);
     SDB_LAUNCH_STATUS();
@@ -290,10 +286,13 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& ge
             asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
             asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
         } else {
+            // poll with relaxed loads (an acquire load per poll invalidates L1 every time: CCTL.IVALL was 4 % of the one-launch
+            // solve's samples), then one acquire fence once the new generation is seen
             unsigned int g;
             do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(bar + 1) : "memory");
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(bar + 1) : "memory");
             } while (g == gen);
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
     }
     gen += 1u;
@@ -440,33 +439,49 @@ __device__ void solve_pass(const PairArgs& pa, bool direct, float scale_hi, floa
         const int tile = item % tiles;
         if (direct) pair_tile_item<true, LseEpi>(pa, ep, tile, item / tiles, smem);
         else pair_tile_item<false, LseEpi>(pa, ep, tile, item / tiles, smem);
-        __threadfence();
+        // the partials of this item were stored by the CTA's threads before the bar.sync; thread 0's acq_rel atomic at gpu scope
+        // publishes them (release is cumulative over what happened-before it) and, for the last arriver, acquires the others'
         __syncthreads();
         if (threadIdx.x == 0) {
-            const unsigned prev = atomicAdd(counters + tile, 1u);
+            unsigned prev;
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(counters + tile) : "memory");
             s_last = (prev == (unsigned)ns - 1u);
             if (s_last) counters[tile] = 0u;
         }
         __syncthreads();
         if (s_last) {
-            __threadfence();
-            // 4 threads per row, splits strided over them
+            // 4 threads per row, splits strided over them; every partial is loaded once (all loads in flight together)
             const int64_t i = (int64_t)tile * BM + (threadIdx.x >> 2);
             const int sub = threadIdx.x & 3;
+            constexpr int MAXP = 4;                                  // ns <= 32 keeps them in registers; beyond that, reload
+            float2 pv[MAXP];
             float mx = -INFINITY;
+#pragma unroll
+            for (int q = 0; q < MAXP; ++q) {
+                const int sp = sub + 4 * q;
+                pv[q] = (i < n && sp < ns) ? __ldcg(partial + (int64_t)sp * n + i) : make_float2(SDB_NEG_SENTINEL, 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < MAXP; ++q)
+                if (pv[q].x > -1e29f && pv[q].y > 0.f) mx = fmaxf(mx, pv[q].x);
             if (i < n)
-                for (int sp = sub; sp < ns; sp += 4) {
+                for (int sp = sub + 4 * MAXP; sp < ns; sp += 4) {
                     const float2 ps = __ldcg(partial + (int64_t)sp * n + i);
                     if (ps.x > -1e29f && ps.y > 0.f) mx = fmaxf(mx, ps.x);
                 }
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             double S = 0.0;
-            if (i < n && mx > -INFINITY)
-                for (int sp = sub; sp < ns; sp += 4) {
-                    const float2 ps = __ldcg(partial + (int64_t)sp * n + i);
-                    if (ps.x > -1e29f && ps.y > 0.f) S += (double)ps.y * exp2((double)ps.x - (double)mx);
-                }
+            if (mx > -INFINITY) {
+#pragma unroll
+                for (int q = 0; q < MAXP; ++q)
+                    if (pv[q].x > -1e29f && pv[q].y > 0.f) S += (double)pv[q].y * exp2((double)pv[q].x - (double)mx);
+                if (i < n)
+                    for (int sp = sub + 4 * MAXP; sp < ns; sp += 4) {
+                        const float2 ps = __ldcg(partial + (int64_t)sp * n + i);
+                        if (ps.x > -1e29f && ps.y > 0.f) S += (double)ps.y * exp2((double)ps.x - (double)mx);
+                    }
+            }
             S += __shfl_xor_sync(0xffffffffu, S, 1);
             S += __shfl_xor_sync(0xffffffffu, S, 2);
             if (sub == 0 && i < n) {
@@ -692,20 +707,15 @@ extern "C" int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_swe
         if (rc) return rc;
     }
     const size_t smem = sizeof(float) * ((size_t)d->dpad * BM + 2 * (size_t)d->dpad * BN + 2 * BN);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(sinkhorn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        smem_set = smem;
-    }
-    static int n_sm = 0;
-    if (n_sm == 0) {
+    static size_t smem_set[SDB_MAX_DEVICES] = {0};
+    { cudaError_t e0 = sdb_ensure_smem(sinkhorn_persistent_kernel, smem, smem_set); if (e0 != cudaSuccess) return (int)e0; }
+    int n_sm = 0, per_sm = 0;
+    {
         int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return (int)e;
+        cudaError_t e1 = cudaGetDevice(&dev);
+        if (e1 == cudaSuccess) e1 = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (e1 != cudaSuccess) return (int)e1;
     }
-    int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_persistent_kernel, NT, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) return SDB_E_UNSUPPORTED;
@@ -752,12 +762,8 @@ extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_
     a.barrier = barrier2; a.counters = counters; a.scratch = scratch; a.result = result;
     cudaStream_t st = sdb_stream(stream);
     const size_t smem = sizeof(float) * ((size_t)d->dpad * BM + 2 * (size_t)d->dpad * BN + 2 * BN);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(sinkhorn_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        smem_set = smem;
-    }
+    static size_t smem_set[SDB_MAX_DEVICES] = {0};
+    { cudaError_t e0 = sdb_ensure_smem(sinkhorn_solve_kernel, smem, smem_set); if (e0 != cudaSuccess) return (int)e0; }
     int dev = 0, n_sm = 0, per_sm = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);

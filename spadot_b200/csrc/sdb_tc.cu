@@ -872,12 +872,8 @@ template <int DP, int EPI_WARPS, bool PACKED, int POLY_EVERY = 0, bool PIPE = fa
 int launch_tc_v(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
     auto kern = lse_pass_tc_kernel<DP, EPI_WARPS, PACKED, POLY_EVERY, MODE_LSE, PIPE, XTILE, FIXED_M, RUNSUM>;
     constexpr int smem = TcSmem<DP>::TOTAL;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    static size_t attr_set[SDB_MAX_DEVICES] = {0};
+    { cudaError_t e = sdb_ensure_smem(kern, (size_t)smem, attr_set); if (e != cudaSuccess) return (int)e; }
     return (int)sdb_launch(kern, dim3(n_ctas), dim3(32 * (2 + EPI_WARPS)), smem, st, tmP, tmQ, a);
 }
 
@@ -885,12 +881,8 @@ template <int DP, int MODE>
 int launch_tc_sweep(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, int n_ctas, cudaStream_t st) {
     auto kern = lse_pass_tc_kernel<DP, 8, false, 0, MODE>;
     constexpr int smem = TcSmem<DP>::TOTAL_SWEEP;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
+    static size_t attr_set[SDB_MAX_DEVICES] = {0};
+    { cudaError_t e = sdb_ensure_smem(kern, (size_t)smem, attr_set); if (e != cudaSuccess) return (int)e; }
     kern<<<n_ctas, 32 * (2 + 8), smem, st>>>(tmP, tmQ, a);
     SDB_LAUNCH_STATUS();
 }

@@ -405,7 +405,9 @@ def median_cost(ops, dist: Dist | None = None, n_samples=1 << 24, n_bins=4096, s
         cand, counts = ops.cost_collect(float(lo), float(hi), int(cap))
         below = int(dist.sum_(counts[:1].clone()).item())
         n_local = int(counts[1].item())
-        if n_local > cap:
+        # every rank must take the same branch (the gather below is collective): agree on "some rank overflowed its buffer"
+        over = torch.tensor([int(n_local > cap)], dtype=torch.int32, device=counts.device)
+        if int(dist.max_(over).item()):
             return None, below, n_local
         mark("collect_sweep")
         allc = dist.gather_cat(cand[:n_local].contiguous())

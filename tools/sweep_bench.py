@@ -73,13 +73,19 @@ def main():
         if world > 1:
             td.barrier()
         t0 = time.perf_counter()
+        c0 = dist.collectives
         cp = ot_solvers.solve_coupling(x, y, cfg, median=med, ops=ops, dist=dist)
+        ncoll = dist.collectives - c0
         mass = float(dist.sum_(cp.row_mass().sum().reshape(1)).item())
         dt = wall(t0)
         it = cp.info["total_iters"]
+        # checksums of the potentials: every world size solves the same problem, so these must agree across N
+        f_sum = float(dist.sum_(cp.f.sum().reshape(1).clone()).item())
         say(stage="solve", n=a.n, m=a.m, epsilon=eps, lambda1=l1, lambda2=l2, seconds=dt,
             iters_per_stage=cp.info["iters_per_stage"], total_iters=it, gap=cp.info["gap"],
-            iters_per_sec=it / dt, plan_mass=mass, tc=ops.use_tc, converged=bool(cp.info["gap"] <= cfg["tolerance"]))
+            iters_per_sec=it / dt, plan_mass=mass, tc=ops.use_tc, converged=bool(cp.info["gap"] <= cfg["tolerance"]),
+            collectives_per_iter=ncoll / max(it, 1), f_checksum=f_sum, g_checksum=float(cp.g.sum().item()),
+            predicted=bool(ops._pred is not None and ops._pred.ok))
     if world > 1:
         td.destroy_process_group()
 
