@@ -142,6 +142,30 @@ int sdb_update_from_sums_f64(const double* sums, float* shift, int64_t n, const 
                              const double* logmarg, double eps, double alpha, double log_n_other, double* pot, const double* frame,
                              double* la_old, float* bias, int* absorb_flag, int iter, double log_tau, double log_floor, int* bad_flag,
                              void* stream);
+/* FUSED pass + update (tensor-core form): the CTA that finishes the LAST column split of a 128-row tile (per-tile arrival
+ * counter) combines that tile's partials and performs exactly sdb_finalize_update_pred on its rows, so an iteration of the
+ * native loop is two launches (row pass, column pass) instead of five; tau bookkeeping is deferred (see
+ * sdb_update_row_deferred in csrc/sdb_common.cuh): flag2 = two ints (ping-pong by tick parity, initialise to -1), and
+ * sdb_absorb_pending flushes the last tick before anything reads the frames.  counters: ceil(n_p/128) zero-initialised uints
+ * (left zero). */
+typedef struct sdb_tc_update {
+    unsigned int* counters;
+    const double* norms; double c1;
+    double* L; const double* logmarg; double eps, alpha, log_n_other;
+    double* pot; double* frame; double* la_old; float* bias_out;
+    int* flag2; int32_t tick, reserved; double log_tau, log_floor;
+    float* m_next; int* bad_flag;
+} sdb_tc_update;
+int sdb_lse_pass_tc_fused(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad,
+                          int dp, const float* bias_padded, float scale, int tiles_per_split, int n_ctas,
+                          const float* row_m, float* partial, const sdb_tc_update* upd, void* stream);
+/* pot <- update from a known LSE (as sdb_potential_update) with the deferred tau bookkeeping. */
+int sdb_potential_update_deferred(int64_t n, const double* L, const double* logmarg, const double* norms, double eps, double alpha,
+                                  double log_n_other, double c1, double* pot, double* frame, double* la_old, float* bias,
+                                  int* flag2, int iter, double log_tau, double log_floor, void* stream);
+/* if flag2[last_tick & 1] == last_tick: u <- f, v <- g, *flag = last_tick (the legacy single flag, may be NULL). */
+int sdb_absorb_pending(int64_t n, int64_t m, const int* flag2, int last_tick, const double* f, const double* g, double* u,
+                       double* v, int* flag, void* stream);
 /* sdb_lse_pass_tc with the predicted stabiliser: row_m[i] for i < n_p (NULL = track the maximum, i.e. sdb_lse_pass_tc). */
 int sdb_lse_pass_tc_pred(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad,
                          int dp, const float* bias_padded, float scale, int tiles_per_split, int n_ctas,
@@ -202,6 +226,9 @@ typedef struct sdb_sweep_desc {
     /* SIMT form only: 0 = dot-product tiles (norms_x / norms_y hold |x|^2, |y|^2), 1 = direct-difference tiles (they hold
      * zeros); see sdb_lse_pass_simt. */
     int32_t simt_direct, reserved0;
+    /* tensor-core form: non-NULL flag2 (2 ints) + tile_counters (ceil(n/128) + ceil(m/128) uints) select the fused
+     * pass + update loop (two launches per iteration, see sdb_lse_pass_tc_fused). */
+    int* flag2; unsigned int* tile_counters;
 } sdb_sweep_desc;
 /* Issues n_sweeps x [row pass, finalize+update f, column pass, finalize+update g, absorb] on `stream`.
  * lr_known_first != 0: Lr already holds the row LSE at the current g, the first row pass is skipped

@@ -34,6 +34,9 @@ SIGNATURES = {
     "sdb_finalize_update_pred": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p, c_p, c_p],
     "sdb_partial_sums_f64": [c_p, c_i, c_l, c_p, c_p, c_p, c_i, c_p, c_p],
     "sdb_update_from_sums_f64": [c_p, c_p, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p, c_p],
+    "sdb_lse_pass_tc_fused": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_i, c_i, c_p, c_p, c_p, c_p],
+    "sdb_potential_update_deferred": [c_l, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
+    "sdb_absorb_pending": [c_l, c_l, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p],
     "sdb_lse_pass_tc_groups": [c_p, c_l, c_l, c_p, c_l, c_i, c_p, c_f, c_p, c_i, c_i, c_p, c_p],
     "sdb_lse_pass_tc_pred": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_i, c_i, c_p, c_p, c_p],
     "sdb_potential_update": [c_l, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
@@ -87,7 +90,7 @@ class SweepDesc(ctypes.Structure):
                 ("eps", c_d), ("inv_med", c_d), ("alpha1", c_d), ("alpha2", c_d), ("log_tau", c_d), ("log_floor", c_d),
                 ("pow2_scale", c_d),
                 ("m_x", c_p), ("m_y", c_p), ("bad_flag", c_p), ("pred_from_row", ctypes.c_int32), ("pred_from_col", ctypes.c_int32),
-                ("simt_direct", ctypes.c_int32), ("reserved0", ctypes.c_int32)]
+                ("simt_direct", ctypes.c_int32), ("reserved0", ctypes.c_int32), ("flag2", c_p), ("tile_counters", c_p)]
 
 
 class SolveParams(ctypes.Structure):

@@ -214,3 +214,30 @@ __device__ __forceinline__ void sdb_update_row(int64_t i, double Li, double logm
     }
     if (absorb_flag && (nv - fr) / eps > log_tau) atomicMax(absorb_flag, iter);
 }
+
+// The same update with the tau bookkeeping deferred instead of a separate absorb launch: updaters of tick t stamp
+// flag2[t & 1]; an updater of tick t+1 that finds flag2[t & 1] == t first absorbs its own row (frame <- potential), which is
+// all `absorb` is in total potentials (ref: ot_func.cpp:792-819).  Whoever reads the frames next (stopping rules) must flush
+// the last tick's pending absorption first (sdb_absorb_pending).
+__device__ __forceinline__ void sdb_update_row_deferred(int64_t i, double Li, double logmarg_i, double norm_i, double eps, double alpha,
+                                                        double log_n_other, double c1, double* pot, double* frame, double* la_old,
+                                                        float* bias, int* flag2, int iter, double log_tau, double log_floor) {
+    const bool pending = (*reinterpret_cast<volatile int*>(flag2 + ((iter - 1) & 1)) == iter - 1);
+    const double old = pot[i];
+    double fr = frame[i];
+    if (pending) { fr = old; frame[i] = old; }
+    la_old[i] = (old - fr) / eps;
+    double LA = Li - log_n_other;
+    if (log_floor > -INFINITY) {
+        const double t = log_floor - fr / eps;
+        const double hi = fmax(LA, t), lo = fmin(LA, t);
+        LA = (lo == -INFINITY) ? hi : hi + log1p(exp(lo - hi));
+    }
+    const double nv = eps * alpha * (logmarg_i - LA);
+    pot[i] = nv;
+    if (bias) {
+        const double b = SDB_LOG2E * (nv / eps - norm_i * c1);
+        bias[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
+    }
+    if ((nv - fr) / eps > log_tau) atomicMax(flag2 + (iter & 1), iter);
+}

@@ -48,6 +48,55 @@ extern "C" int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int fi
                                        d->ns_col, d->partial_col, stream);
     };
     const bool pred = d->use_tc && d->m_x && d->m_y && d->bad_flag;
+    if (d->use_tc && d->flag2 && d->tile_counters) {
+        // fused pass + update: two launches per iteration (the CTA that completes a row tile updates it), tau bookkeeping
+        // deferred to the next update of each row, flushed once at the end of the batch
+        const int64_t row_tiles = (d->n + 127) / 128;
+        auto fused = [&](bool row, bool predicted, int tick) -> int {
+            sdb_tc_update u{};
+            u.counters = row ? d->tile_counters : d->tile_counters + row_tiles;
+            u.norms = row ? d->norms_x : d->norms_y;
+            u.c1 = c1;
+            u.L = row ? d->Lr : d->Lc;
+            u.logmarg = row ? d->logp : d->logq;
+            u.eps = d->eps;
+            u.alpha = row ? d->alpha1 : d->alpha2;
+            u.log_n_other = row ? log_m : log_N;
+            u.pot = row ? d->f : d->g;
+            u.frame = row ? d->u : d->v;
+            u.la_old = row ? d->la_old : d->lb_old;
+            u.bias_out = row ? d->bias_x : d->bias_y;
+            u.flag2 = d->flag2;
+            u.tick = tick;
+            u.log_tau = d->log_tau;
+            u.log_floor = d->log_floor;
+            u.m_next = pred ? (row ? d->m_x : d->m_y) : nullptr;
+            u.bad_flag = pred ? d->bad_flag : nullptr;
+            return row ? sdb_lse_pass_tc_fused(d->x16, d->n, d->n_pad, d->y16, d->m, d->m_pad, d->dp, d->bias_y,
+                                               (float)(scale * d->pow2_scale), d->tps_row, d->n_ctas, predicted ? d->m_x : nullptr,
+                                               d->partial_row, &u, stream)
+                       : sdb_lse_pass_tc_fused(d->y16, d->m, d->m_pad, d->x16, d->n, d->n_pad, d->dp, d->bias_x,
+                                               (float)(scale * d->pow2_scale), d->tps_col, d->n_ctas, predicted ? d->m_y : nullptr,
+                                               d->partial_col, &u, stream);
+        };
+        if (!(lr_known_first && n_sweeps > 0)) {
+            rc = sdb_make_bias(d->m, d->m_bias, d->g, d->norms_y, d->eps, c1, d->bias_y, stream);
+            if (rc) return rc;
+        }
+        for (int i = 0; i < n_sweeps; ++i) {
+            const int tick = first_tick + i;
+            if (i == 0 && lr_known_first)
+                rc = sdb_potential_update_deferred(d->n, d->Lr, d->logp, d->norms_x, d->eps, d->alpha1, log_m, c1, d->f, d->u, d->la_old,
+                                                   d->bias_x, d->flag2, tick, d->log_tau, d->log_floor, stream);
+            else
+                rc = fused(true, pred && i >= d->pred_from_row, tick);
+            if (rc) return rc;
+            rc = fused(false, pred && i >= d->pred_from_col, tick);
+            if (rc) return rc;
+        }
+        if (n_sweeps > 0) rc = sdb_absorb_pending(d->n, d->m, d->flag2, first_tick + n_sweeps - 1, d->f, d->g, d->u, d->v, d->flag, stream);
+        return rc;
+    }
     if (!(lr_known_first && n_sweeps > 0)) {
         // bias of the first row pass from the current g (a previous call may have used another eps)
         rc = sdb_make_bias(d->m, d->m_bias, d->g, d->norms_y, d->eps, c1, d->bias_y, stream);

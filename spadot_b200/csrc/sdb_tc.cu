@@ -228,6 +228,7 @@ struct TcArgs;
 __device__ __forceinline__ void split_range(const TcArgs& a, int sp, int& t0, int& t1);
 
 struct TcArgs {
+    sdb_tc_update upd;       // upd.counters != NULL: the CTA completing a row tile also combines and updates it (fused pass + update)
     const int* split_tiles;  // optional: n_splits + 1 tile boundaries of variable-length splits (label groups, K6); else uniform
     const float* bias;       // padded to a multiple of TILE_N with SDB_NEG_SENTINEL
     const float* row_m;      // predicted stabiliser per row (FIXED_M kernels), else unused
@@ -791,6 +792,31 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                 if (row < a.n_p) a.partial[(int64_t)sp * a.n_p + row] = make_float2(m_used, ssum);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            if (a.upd.counters != nullptr) {
+                // fused update: the partials of this item were stored before the bar.sync above; one thread's acq_rel atomic on
+                // the row tile's arrival counter publishes them and tells whether every split of the tile is in
+                uint32_t* s_last = tmem_holder + 2;
+                if (threadIdx.x == 64) {
+                    unsigned prev;
+                    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(a.upd.counters + rt) : "memory");
+                    const bool last = (prev == (unsigned)a.n_splits - 1u);
+                    if (last) a.upd.counters[rt] = 0u;
+                    *s_last = last ? 1u : 0u;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+                if (*s_last != 0u && part == 0) {
+                    const int64_t row = (int64_t)rt * TILE_M + row_in_tile;
+                    if (row < a.n_p) {
+                        const sdb_tc_update& u = a.upd;
+                        const double norm = u.norms[row];
+                        const double Li = sdb_combine_partials(a.partial, a.n_splits, a.n_p, row, norm * u.c1, u.m_next, u.bad_flag);
+                        u.L[row] = Li;
+                        sdb_update_row_deferred(row, Li, u.logmarg[row], norm, u.eps, u.alpha, u.log_n_other, u.c1, u.pot, u.frame, u.la_old,
+                                                u.bias_out, u.flag2, u.tick, u.log_tau, u.log_floor);
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            }
         }
         }  // MODE_LSE
     }
@@ -957,7 +983,16 @@ int sdb_lse_pass_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q
 int sdb_lse_pass_tc_pred(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad, int dp,
                          const float* bias_padded, float scale, int tiles_per_split, int n_ctas, const float* row_m, float* partial,
                          void* stream) {
+    return sdb_lse_pass_tc_fused(p16, n_p, n_p_pad, q16, n_q, n_q_pad, dp, bias_padded, scale, tiles_per_split, n_ctas, row_m, partial,
+                                 nullptr, stream);
+}
+
+int sdb_lse_pass_tc_fused(const void* p16, int64_t n_p, int64_t n_p_pad, const void* q16, int64_t n_q, int64_t n_q_pad, int dp,
+                          const float* bias_padded, float scale, int tiles_per_split, int n_ctas, const float* row_m, float* partial,
+                          const sdb_tc_update* upd, void* stream) {
     SDB_CHECK_ARG(p16 && q16 && bias_padded && partial && n_p > 0 && n_q > 0 && tiles_per_split > 0 && n_ctas > 0);
+    if (upd) SDB_CHECK_ARG(upd->counters && upd->norms && upd->L && upd->logmarg && upd->pot && upd->frame && upd->la_old && upd->flag2 &&
+                           upd->eps > 0.0);
     SDB_CHECK_ARG((n_p_pad % TILE_N) == 0 && (n_q_pad % TILE_N) == 0 && n_p_pad >= n_p && n_q_pad >= n_q);
     SDB_CHECK_ARG(((uintptr_t)p16 % 128) == 0 && ((uintptr_t)q16 % 128) == 0 && ((uintptr_t)bias_padded % 16) == 0);
     if (!(dp == 16 || dp == 32 || dp == 64)) return SDB_E_UNSUPPORTED;
@@ -967,6 +1002,7 @@ int sdb_lse_pass_tc_pred(const void* p16, int64_t n_p, int64_t n_p_pad, const vo
     rc = make_tmap(&tmQ, q16, n_q_pad, dp, TILE_N);
     if (rc) return rc;
     TcArgs a{};
+    if (upd) a.upd = *upd;
     a.bias = bias_padded;
     a.row_m = row_m;
     a.scale = scale;

@@ -135,6 +135,30 @@ __global__ void update_from_sums_kernel(const double* __restrict__ sums, float* 
                    log_floor);
 }
 
+__global__ void potential_update_deferred_kernel(int64_t n, const double* __restrict__ L, const double* __restrict__ logmarg,
+                                                 const double* __restrict__ norms, double eps, double alpha, double log_n_other,
+                                                 double c1, double* __restrict__ pot, double* __restrict__ frame,
+                                                 double* __restrict__ la_old, float* __restrict__ bias, int* flag2, int iter,
+                                                 double log_tau, double log_floor) {
+    sdb_launch_dependents();
+    sdb_grid_dependency_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sdb_update_row_deferred(i, L[i], logmarg[i], norms[i], eps, alpha, log_n_other, c1, pot, frame, la_old, bias, flag2, iter, log_tau,
+                            log_floor);
+}
+
+__global__ void absorb_pending_kernel(int64_t n, int64_t m, const int* __restrict__ flag2, int last_tick, const double* __restrict__ f,
+                                      const double* __restrict__ g, double* __restrict__ u, double* __restrict__ v, int* flag) {
+    sdb_launch_dependents();
+    sdb_grid_dependency_wait();
+    if (flag2[last_tick & 1] != last_tick) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && flag) *flag = last_tick;
+    if (i < n) u[i] = f[i];
+    if (i < m) v[i] = g[i];
+}
+
 __global__ void make_bias_kernel(int64_t n, int64_t n_pad, const double* __restrict__ pot, const double* __restrict__ norms,
                                  double eps, double c1, float* __restrict__ bias) {
     sdb_launch_dependents();
@@ -387,6 +411,24 @@ int sdb_finalize_update(const float* partial, int n_splits, int64_t n, const dou
     if (n == 0) return 0;
     return sdb_finalize_update_pred(partial, n_splits, n, norms, c1, L, logmarg, eps, alpha, log_n_other, pot, frame, la_old, bias,
                                     absorb_flag, iter, log_tau, log_floor, nullptr, nullptr, stream);
+}
+
+int sdb_potential_update_deferred(int64_t n, const double* L, const double* logmarg, const double* norms, double eps, double alpha,
+                                  double log_n_other, double c1, double* pot, double* frame, double* la_old, float* bias,
+                                  int* flag2, int iter, double log_tau, double log_floor, void* stream) {
+    SDB_CHECK_ARG(L && logmarg && norms && pot && frame && la_old && flag2 && n >= 0 && eps > 0.0);
+    if (n == 0) return 0;
+    return (int)sdb_launch(potential_update_deferred_kernel, dim3(blocks_for(n)), dim3(256), 0, sdb_stream(stream), n, L, logmarg, norms,
+                           eps, alpha, log_n_other, c1, pot, frame, la_old, bias, flag2, iter, log_tau, log_floor);
+}
+
+int sdb_absorb_pending(int64_t n, int64_t m, const int* flag2, int last_tick, const double* f, const double* g, double* u,
+                       double* v, int* flag, void* stream) {
+    SDB_CHECK_ARG(flag2 && f && g && u && v && n >= 0 && m >= 0);
+    const int64_t mx = n > m ? n : m;
+    if (mx == 0) return 0;
+    return (int)sdb_launch(absorb_pending_kernel, dim3(blocks_for(mx)), dim3(256), 0, sdb_stream(stream), n, m, flag2, last_tick, f, g, u,
+                           v, flag);
 }
 
 int sdb_partial_sums_f64(const float* partial, int n_splits, int64_t n, const float* shift, double* sums, const int* absorb_flag,

@@ -189,6 +189,7 @@ class CudaOps(VectorOps):
     PREDICT_MIN_PAIRS = 1 << 28      # below this a batch of sweeps is too short for the verification read-back to pay
     PERSISTENT_MAX_PAIRS = 1 << 24   # SIMT problems up to this many pairs run their sweeps in one cooperative launch
     PERSISTENT_CTAS_PER_SM = int(os.environ.get("SDB_PERSISTENT_CTAS_PER_SM", "2"))
+    FUSED_UPDATE = os.environ.get("SDB_TC_FUSED_UPDATE", "1") != "0"   # tensor-core native loop: pass + update in one kernel
 
     def __init__(self, x_local, y, device=None, tc="auto"):
         self._init_vectors(device)
@@ -363,6 +364,9 @@ class CudaOps(VectorOps):
         self.flag.copy_(snap[1])
         self._tick = snap[2]
         self._bias_key = {"x": None, "y": None}
+        if getattr(self, "_flag2", None) is not None:
+            self._flag2.fill_(-1)            # snapshots are taken at batch boundaries, after the pending absorption was flushed
+            self._tile_counters.zero_()
 
     def settle(self, dist=None):
         """Verify the predicted passes issued since the last call (one small synchronising read-back).  False means a
@@ -454,6 +458,8 @@ class CudaOps(VectorOps):
         if dist is not None and dist.world > 1:
             ok = bool(int(dist.min_(torch.tensor([int(ok)], dtype=torch.int32, device=self.device)).item()))
         self._pred_allowed = ok
+        if getattr(self, "_flag2", None) is not None:
+            self._flag2.fill_(-1)
         if self._pred is not None:          # new potentials: old predictions mean nothing; a new solve may predict again
             self._pred.fresh = {"x": None, "y": None}
             self._pred.ok = True
@@ -539,6 +545,12 @@ class CudaOps(VectorOps):
             d.x16, d.n_pad, d.y16, d.m_pad = _ptr(self.X.x16), self.X.n_pad, _ptr(self.Y.x16), self.Y.n_pad
             d.tps_row, d.ns_row = self._tc_split_plan(self.n, self.m)
             d.tps_col, d.ns_col = self._tc_split_plan(self.m, self.n)
+            if self.FUSED_UPDATE:
+                # two launches per iteration: the CTA that completes a 128-row tile also combines and updates it
+                if getattr(self, "_flag2", None) is None:
+                    self._flag2 = torch.full((2,), -1, dtype=torch.int32, device=self.device)
+                    self._tile_counters = torch.zeros((self.n + 127) // 128 + (self.m + 127) // 128, dtype=torch.int32, device=self.device)
+                d.flag2, d.tile_counters = _ptr(self._flag2), _ptr(self._tile_counters)
             # the native loop multiplies 2*c1*log2(e) by this factor and rounds to fp32: exactly the power of two S
             d.pow2_scale = self.tc_scale / (2.0 * (self.inv_med / eps) * math.log2(math.e))
         else:
@@ -582,7 +594,8 @@ class CudaOps(VectorOps):
             self.launches += 1 + (0 if lr_known_first else 1)
         else:
             _lib.call("sdb_sinkhorn_sweeps", ctypes.byref(d), int(n_sweeps), first, int(bool(lr_known_first)), self._stream())
-            self.launches += n_sweeps * 5 + (0 if lr_known_first else 1)
+            per_iter = 2 if (self.use_tc and self.FUSED_UPDATE) else 5
+            self.launches += n_sweeps * per_iter + 1 + (0 if lr_known_first else 1)
         self._bias_key = {"x": None, "y": None}
 
     def fused_half_step(self, side, st, eps, alpha, it, log_tau, log_floor=NEG_INF, lse_known=False):

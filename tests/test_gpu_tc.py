@@ -307,3 +307,28 @@ def test_transition_table_on_the_tensor_core_pass(ot):
         assert np.array_equal(tabs[tc].argmax(1), tab_ref.argmax(1))
         assert np.all(tabs[tc][:, 3] == 0.0)
     assert np.abs(tabs["on"] - tabs["off"]).max() / tab_ref.max() < 2e-5
+
+
+@pytest.mark.parametrize("n,m,d,tau", [(2600, 2100, 20, 1000.0), (3000, 2600, 32, 2.0), (130, 300, 6, 1.5), (5000, 4100, 48, 1000.0)])
+@pytest.mark.parametrize("predict", [False, True])
+def test_fused_pass_and_update_matches_separate_kernels(ot, n, m, d, tau, predict):
+    """sdb_lse_pass_tc_fused (the CTA completing a 128-row tile combines and updates it; tau bookkeeping deferred, two launches
+    per iteration) against pass + sdb_finalize_update_pred + sdb_absorb (five launches): same partials, same combine code, so
+    the iterates must agree to rounding, the frames after the flush exactly in value; small tau forces absorptions."""
+    ot_solvers, sinkhorn, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(n, m, d, seed=n)
+    G = np.exp(np.random.default_rng(m).normal(0, 0.3, n))
+    out = []
+    for fused in (True, False):
+        ops = CudaOps(a, b, tc="on")
+        ops.FUSED_UPDATE = fused
+        ops.PREDICT, ops.PREDICT_MIN_PAIRS = predict, 0
+        l0 = ops.launches
+        cp = ot_solvers.solve_coupling(a, b, dict(CFG, tau=tau), G=G, ops=ops, dist=sinkhorn.Dist(enabled=False), median=1.9 * d)
+        out.append((cp, ops.launches - l0))
+    (c1, l1), (c2, l2) = out
+    assert l1 < 0.6 * l2, (l1, l2)
+    assert c1.info["iters_per_stage"] == c2.info["iters_per_stage"]
+    for name in ("f", "g", "u", "v", "Lr", "Lc"):
+        x, y = getattr(c1.state, name), getattr(c2.state, name)
+        assert float((x - y).abs().max()) < 1e-11, name
