@@ -38,7 +38,8 @@ extern "C" {
 #define SDB_E_INVALID   (-1)  /* bad argument (null pointer, size, alignment) */
 #define SDB_E_UNSUPPORTED (-2)/* shape outside what the kernel was built for */
 #define SDB_E_NOTFINITE (-3)  /* NaN / overflow detected (ref: ot_solvers.py:446-447) */
-#define SDB_E_DRIVER    (-4)  /* CUDA driver entry point unavailable */
+#define SDB_E_DRIVER    (-4)  /* CUDA driver entry point / libnccl unavailable */
+#define SDB_E_NCCL      (-5)  /* an NCCL call failed */
 
 #define SDB_NEG_SENTINEL (-1.0e30f) /* finite stand-in for -inf in fp32 bias vectors */
 
@@ -269,6 +270,22 @@ typedef struct sdb_solve_result {
 int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_solve_params* p, int first_tick, int* flag2,
                                   unsigned int* barrier2, unsigned int* counters, double* scratch,
                                   sdb_solve_result* result, void* stream);
+
+/* ------------------------------------------------------------------ row-partitioned solve: NCCL inside the ABI */
+/* The library binds NCCL at run time from the libnccl.so.2 already loaded in the process (PyTorch's); nothing here is needed
+ * for single-GPU use.  One communicator per process/GPU: rank 0 calls sdb_nccl_unique_id, ships the 128 bytes to the other
+ * ranks by any means (the Python driver broadcasts them with torch.distributed), every rank calls sdb_nccl_comm_create. */
+int sdb_nccl_available(void);
+int sdb_nccl_unique_id(void* id128_host);
+int sdb_nccl_comm_create(const void* id128_host, int world, int rank, void** comm_out);
+int sdb_nccl_comm_destroy(void* comm);
+int sdb_nccl_allreduce_sum_f64(void* comm, double* buf, int64_t count, void* stream);
+/* n_sweeps iterations of the row-partitioned solve, all launches and the ONE all-reduce per iteration issued from C on
+ * `stream`: row pass + update of the local f; column pass against the common shift d->m_y (see sdb_partial_sums_f64);
+ * ncclAllReduce(sum) of the M + 2 doubles in `sums`; sdb_update_from_sums_f64; sdb_absorb.  Preconditions: d->m_y holds the
+ * common shift for (eps, median), d->bias_y matches the current g, d->bad_flag / d->m_x as in sdb_sinkhorn_sweeps
+ * (the row pass uses predictions from sweep d->pred_from_row on).  A rank with n == 0 rows contributes zeros. */
+int sdb_sinkhorn_sweeps_dist(const sdb_sweep_desc* d, void* comm, double* sums, int n_sweeps, int first_tick, void* stream);
 
 /* ------------------------------------------------------------------ K4: stopping rules */
 /* Stage 0-4 rule (ref: ot_func.cpp:897-922).  out[0..3] =

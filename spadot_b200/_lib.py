@@ -34,6 +34,12 @@ SIGNATURES = {
     "sdb_finalize_update_pred": [c_p, c_i, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p, c_p, c_p],
     "sdb_partial_sums_f64": [c_p, c_i, c_l, c_p, c_p, c_p, c_i, c_p, c_p],
     "sdb_update_from_sums_f64": [c_p, c_p, c_l, c_p, c_d, c_p, c_p, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p, c_p],
+    "sdb_nccl_available": [],
+    "sdb_nccl_unique_id": [c_p],
+    "sdb_nccl_comm_create": [c_p, c_i, c_i, c_p],
+    "sdb_nccl_comm_destroy": [c_p],
+    "sdb_nccl_allreduce_sum_f64": [c_p, c_p, c_l, c_p],
+    "sdb_sinkhorn_sweeps_dist": [c_p, c_p, c_p, c_i, c_i, c_p],
     "sdb_lse_pass_tc_fused": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_f, c_i, c_i, c_p, c_p, c_p, c_p],
     "sdb_potential_update_deferred": [c_l, c_p, c_p, c_p, c_d, c_d, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_i, c_d, c_d, c_p],
     "sdb_absorb_pending": [c_l, c_l, c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p],

@@ -350,7 +350,8 @@ const char* sdb_error_string(int status) {
         case SDB_E_INVALID: return "spadot_b200: invalid argument";
         case SDB_E_UNSUPPORTED: return "spadot_b200: unsupported shape";
         case SDB_E_NOTFINITE: return "spadot_b200: non-finite value";
-        case SDB_E_DRIVER: return "spadot_b200: CUDA driver entry point unavailable";
+        case SDB_E_DRIVER: return "spadot_b200: CUDA driver entry point or libnccl unavailable";
+        case SDB_E_NCCL: return "spadot_b200: NCCL call failed";
         default: return status > 0 ? cudaGetErrorString((cudaError_t)status) : "spadot_b200: unknown status";
     }
 }

@@ -532,9 +532,8 @@ class CudaOps(VectorOps):
         d.log_tau, d.log_floor, d.pow2_scale = log_tau, log_floor, 1.0
         return d
 
-    def fused_sweeps(self, st, eps, alpha1, alpha2, log_tau, log_floor, n_sweeps, lr_known_first):
-        """n_sweeps full iterations issued by the native loop sdb_sinkhorn_sweeps (single rank)."""
-        self._prep(eps)
+    def _full_desc(self, st, eps, alpha1, alpha2, log_tau, log_floor, fused_update=True):
+        """sdb_sweep_desc of this problem in the form in use (tensor-core or SIMT), without the prediction fields."""
         d = _lib.SweepDesc()
         d.n, d.m, d.n_total = self.n, self.m, st.N
         d.use_tc = int(self.use_tc)
@@ -545,7 +544,7 @@ class CudaOps(VectorOps):
             d.x16, d.n_pad, d.y16, d.m_pad = _ptr(self.X.x16), self.X.n_pad, _ptr(self.Y.x16), self.Y.n_pad
             d.tps_row, d.ns_row = self._tc_split_plan(self.n, self.m)
             d.tps_col, d.ns_col = self._tc_split_plan(self.m, self.n)
-            if self.FUSED_UPDATE:
+            if self.FUSED_UPDATE and fused_update:
                 # two launches per iteration: the CTA that completes a 128-row tile also combines and updates it
                 if getattr(self, "_flag2", None) is None:
                     self._flag2 = torch.full((2,), -1, dtype=torch.int32, device=self.device)
@@ -561,12 +560,51 @@ class CudaOps(VectorOps):
             d.simt_direct = int(self._direct)
         d.norms_x, d.norms_y = _ptr(self._norms(self.X)), _ptr(self._norms(self.Y))
         d.partial_row, d.partial_col = _ptr(self._partial(d.ns_row, self.n)), _ptr(self._partial(d.ns_col, self.m))
+        if self.n == self.m and d.ns_row == d.ns_col:
+            # both passes would share one (ns, n, 2) workspace from the cache: give the column pass its own
+            key = ("col", d.ns_col, self.m)
+            if key not in self._partials:
+                self._partials[key] = torch.empty((d.ns_col, self.m, 2), dtype=torch.float32, device=self.device)
+            d.partial_col = _ptr(self._partials[key])
         d.bias_x, d.bias_y, d.m_bias = _ptr(self.bias_x), _ptr(self.bias_y), self.bias_y.numel()
         d.f, d.g, d.u, d.v = _ptr(st.f), _ptr(st.g), _ptr(st.u), _ptr(st.v)
         d.la_old, d.lb_old, d.Lr, d.Lc = _ptr(st.la_old), _ptr(st.lb_old), _ptr(st.Lr), _ptr(st.Lc)
         d.logp, d.logq, d.flag = _ptr(st.logp), _ptr(st.logq), _ptr(self.flag)
         d.eps, d.inv_med, d.alpha1, d.alpha2 = eps, self.inv_med, alpha1, alpha2
         d.log_tau, d.log_floor = log_tau, log_floor
+        return d
+
+    def fused_sweeps_dist(self, st, eps, alpha1, alpha2, log_tau, log_floor, n_sweeps, comm):
+        """n_sweeps iterations of the ROW-PARTITIONED solve issued by the native loop sdb_sinkhorn_sweeps_dist: kernels and the
+        one NCCL all-reduce per iteration back to back on the stream, no interpreter in between.  Requires the common column
+        shift (col_shift_ready) and a bias_y that matches the current g — the state every Python-driven iteration leaves."""
+        self._prep(eps)
+        ps = self._pred_state()
+        key = (eps, self.inv_med)
+        assert ps is not None and ps.common_y == key and self.use_tc
+        bkey = (_ptr(st.g), eps, self.inv_med)
+        if self._bias_key["y"] != bkey:
+            self._call("sdb_make_bias", self.m, self.bias_y.numel(), _ptr(st.g), _ptr(self._norms(self.Y)), eps, self.inv_med / eps,
+                       _ptr(self.bias_y))
+        d = self._full_desc(st, eps, alpha1, alpha2, log_tau, log_floor, fused_update=False)
+        d.m_x, d.m_y, d.bad_flag = _ptr(ps.m["x"]), _ptr(ps.m["y"]), _ptr(ps.bad)
+        d.pred_from_row = 0 if ps.fresh["x"] == key else 1
+        d.pred_from_col = 0
+        ps.fresh["x"] = key
+        ps.used = True
+        if getattr(self, "_sum_vec", None) is None:
+            self._sum_vec = torch.zeros(self.m + 2, dtype=torch.float64, device=self.device)
+        first = self._tick + 1
+        self._tick += n_sweeps
+        _lib.call("sdb_sinkhorn_sweeps_dist", ctypes.byref(d), comm, _ptr(self._sum_vec), int(n_sweeps), first, self._stream())
+        self.launches += n_sweeps * 6
+        self._bias_key = {"x": (_ptr(st.f), eps, self.inv_med), "y": (_ptr(st.g), eps, self.inv_med)}
+        ps.unmerged = False          # every iteration's all-reduce carried the verification flag
+
+    def fused_sweeps(self, st, eps, alpha1, alpha2, log_tau, log_floor, n_sweeps, lr_known_first):
+        """n_sweeps full iterations issued by the native loop sdb_sinkhorn_sweeps (single rank)."""
+        self._prep(eps)
+        d = self._full_desc(st, eps, alpha1, alpha2, log_tau, log_floor)
         ps = self._pred_state()
         if ps is not None:
             key = (eps, self.inv_med)
@@ -579,12 +617,6 @@ class CudaOps(VectorOps):
             ps.used = ps.used or d.pred_from_row < n_sweeps or d.pred_from_col < n_sweeps
         first = self._tick + 1
         self._tick += n_sweeps
-        if self.n == self.m and d.ns_row == d.ns_col:
-            # both passes would share one (ns, n, 2) workspace from the cache: give the column pass its own
-            key = ("col", d.ns_col, self.m)
-            if key not in self._partials:
-                self._partials[key] = torch.empty((d.ns_col, self.m, 2), dtype=torch.float32, device=self.device)
-            d.partial_col = _ptr(self._partials[key])
         if self._persistent_eligible():
             # small problem: all n_sweeps iterations in one cooperative launch (grid barriers instead of launches);
             # column splits sized so that one pass is about one work item per CTA

@@ -20,6 +20,7 @@ The drivers are written against the `ops` interface of cuda_ops.CudaOps.
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -65,6 +66,34 @@ class Dist:
             self.td.all_reduce(t, op=self.td.ReduceOp.MIN, group=self.group)
             self.collectives += 1
         return t
+
+    def native_comm(self, device):
+        """NCCL communicator owned by libspadot_b200.so for this group (sdb_nccl_comm_create), so that the native multi-rank
+        loop can issue its all-reduce from C.  Created on first use: rank 0 draws the unique id, torch.distributed ships the
+        128 bytes.  None when NCCL cannot be bound or the group is not a CUDA/NCCL one (e.g. the gloo test groups)."""
+        if self.world == 1 or getattr(device, "type", "cpu") != "cuda":
+            return None
+        if not hasattr(self, "_native"):
+            self._native = None
+            try:
+                import ctypes
+                from . import _lib
+                lib = _lib.load()
+                if os.environ.get("SDB_NATIVE_DIST", "1") != "0" and lib.sdb_nccl_available() and self.td.get_backend(self.group) == "nccl":
+                    buf = (ctypes.c_char * 128)()
+                    if self.rank == 0:
+                        _lib.check(lib.sdb_nccl_unique_id(buf), "sdb_nccl_unique_id")
+                    t = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8).to(device)
+                    self.td.broadcast(t, src=self.td.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+                    idb = (ctypes.c_char * 128).from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
+                    comm = ctypes.c_void_p()
+                    _lib.check(lib.sdb_nccl_comm_create(idb, self.world, self.rank, ctypes.byref(comm)), "sdb_nccl_comm_create")
+                    self._native = comm
+            except Exception as exc:           # the Python-driven loop is always available
+                import warnings
+                warnings.warn(f"spadot_b200: native NCCL loop unavailable ({exc!r}); using the Python-driven multi-rank loop")
+                self._native = None
+        return self._native
 
     def gather_cat(self, t):
         """Concatenate variable-length 1-D tensors from all ranks (used by the median only)."""
@@ -146,12 +175,25 @@ def _sweeps(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_known,
         return
     # per-iteration path (row-partitioned solve, or ops without a native loop): one snapshot / verification per batch
     snap = ops.snapshot(st) if _predicting(ops) and n_sweeps > 0 else None
-    for i in range(n_sweeps):
-        _sweep_body(ops, st, dist, eps, alpha1, alpha2, log_tau, lr_known and i == 0, log_floor)
+    _sweeps_multi(ops, st, dist, eps, alpha1, alpha2, log_tau, lr_known, n_sweeps, log_floor)
     if snap is not None and not ops.settle(dist):
         ops.restore(st, snap)
-        for i in range(n_sweeps):
-            _sweep_body(ops, st, dist, eps, alpha1, alpha2, log_tau, lr_known and i == 0, log_floor)
+        _sweeps_multi(ops, st, dist, eps, alpha1, alpha2, log_tau, lr_known, n_sweeps, log_floor)
+
+
+def _sweeps_multi(ops, st, dist, eps, alpha1, alpha2, log_tau, lr_known, n_sweeps, log_floor):
+    """Iterations of the row-partitioned solve: Python-driven while something special is due (a known row LSE to consume,
+    no common column shift yet: the first iteration of an epsilon stage), then the rest of the batch in ONE native call
+    (sdb_sinkhorn_sweeps_dist: kernels + the NCCL all-reduce of every iteration issued from C)."""
+    native = getattr(ops, "fused_sweeps_dist", None)
+    ready = getattr(ops, "col_shift_ready", None)
+    comm = dist.native_comm(ops.device) if (native is not None and ready is not None and dist.world > 1) else None
+    for i in range(n_sweeps):
+        if comm is not None and not (lr_known and i == 0) and ready(eps):
+            native(st, eps, alpha1, alpha2, log_tau, log_floor, n_sweeps - i, comm)
+            dist.collectives += n_sweeps - i
+            return
+        _sweep_body(ops, st, dist, eps, alpha1, alpha2, log_tau, lr_known and i == 0, log_floor)
 
 
 def _sweep(ops, st: _State, dist: Dist, eps, alpha1, alpha2, log_tau, lr_known, log_floor=NEG_INF):

@@ -324,11 +324,30 @@ class _LoopbackDist:
 
             def gather_cat(self, t):
                 return t
+
+            def native_comm(self, device):
+                return getattr(self, "comm", None)
         return Loop()
 
 
-@pytest.mark.parametrize("n,m,d,tc", [(1500, 1300, 20, "off"), (2600, 2100, 32, "on")])
-def test_multi_rank_code_path_matches_native_loop(ot, n, m, d, tc):
+def _world1_nccl_comm():
+    """An NCCL communicator of ONE rank owned by libspadot_b200.so: its all-reduce is the identity, like the loop-back
+    group's collectives, so the native multi-rank loop (sdb_sinkhorn_sweeps_dist) can run on a single GPU."""
+    import ctypes
+    from spadot_b200 import _lib
+    lib = _lib.load()
+    if not lib.sdb_nccl_available():
+        pytest.skip("libnccl.so.2 cannot be bound in this process")
+    buf = (ctypes.c_char * 128)()
+    _lib.check(lib.sdb_nccl_unique_id(buf))
+    comm = ctypes.c_void_p()
+    _lib.check(lib.sdb_nccl_comm_create(buf, 1, 0, ctypes.byref(comm)))
+    return comm
+
+
+@pytest.mark.parametrize("n,m,d,tc,native", [(1500, 1300, 20, "off", False), (2600, 2100, 32, "on", False),
+                                              (2600, 2100, 32, "on", True), (5000, 3300, 20, "on", True)])
+def test_multi_rank_code_path_matches_native_loop(ot, n, m, d, tc, native):
     """Regression: the per-iteration Python loop used for world > 1 (row pass fused, column pass + all-reduce +
     potential update) must walk the same iterates as the native single-rank loop — same iterations per epsilon
     stage, same potentials.  (A stale cached bias vector once froze g inside a stage on this path only.)"""
@@ -338,11 +357,18 @@ def test_multi_rank_code_path_matches_native_loop(ot, n, m, d, tc):
     cfg = dict(CFG)
     cp1 = ot_solvers.solve_coupling(a, b, cfg, G=G, ops=CudaOps(a, b, tc=tc), dist=sinkhorn.Dist(enabled=False))
     loop = _LoopbackDist(sinkhorn)
+    if native:
+        loop.comm = _world1_nccl_comm()                 # sdb_sinkhorn_sweeps_dist: kernels + ncclAllReduce issued from C
     ops2 = CudaOps(a, b, tc=tc)
     ops2.PREDICT_MIN_PAIRS = 0                          # the predicted stabiliser rides along on the tensor-core case
+    l0 = ops2.launches
     cp2 = ot_solvers.solve_coupling(a, b, cfg, G=G, ops=ops2, dist=loop)
     assert (ops2._pred is not None and ops2._pred.ok) == (tc == "on")
     assert loop.collectives > 0
+    if tc == "on":
+        # one collective per iteration except the first of a stage (3) + one per stopping-rule check
+        total = cp2.info["total_iters"]
+        assert loop.collectives <= 1.6 * total, (loop.collectives, total)
     assert cp1.median == cp2.median
     assert cp1.info["iters_per_stage"] == cp2.info["iters_per_stage"], (cp1.info, cp2.info)
     assert float((cp1.f - cp2.f).abs().max()) < 1e-6
