@@ -254,6 +254,23 @@ __global__ void k_row_update(const T* __restrict__ K, const T* __restrict__ wb, 
         const T* row = K + (size_t)i * n;
         T s0 = 0, s1 = 0, s2 = 0, s3 = 0;
         int j = lane;
+        if (sizeof(T) == 8 && (n & 1) == 0 && ((uintptr_t)K & 15) == 0 && ((uintptr_t)wb & 15) == 0) {
+            // 16-byte loads, four per lane in flight (2 KB per warp): the row is streamed once, this is the whole traffic
+            const double2* r2 = reinterpret_cast<const double2*>(row);
+            const double2* w2 = reinterpret_cast<const double2*>(wb);
+            const int n2 = n >> 1;
+            int q = lane;
+            for (; q + 96 < n2; q += 128) {
+                const double2 a0 = r2[q], a1 = r2[q + 32], a2 = r2[q + 64], a3 = r2[q + 96];
+                const double2 b0 = w2[q], b1 = w2[q + 32], b2 = w2[q + 64], b3 = w2[q + 96];
+                s0 += (T)(a0.x * b0.x + a0.y * b0.y);
+                s1 += (T)(a1.x * b1.x + a1.y * b1.y);
+                s2 += (T)(a2.x * b2.x + a2.y * b2.y);
+                s3 += (T)(a3.x * b3.x + a3.y * b3.y);
+            }
+            for (; q < n2; q += 32) { const double2 a0 = r2[q], b0 = w2[q]; s0 += (T)(a0.x * b0.x + a0.y * b0.y); }
+            j = n;
+        }
         for (; j + 96 < n; j += 128) {
             s0 += row[j] * wb[j];
             s1 += row[j + 32] * wb[j + 32];
@@ -283,6 +300,20 @@ __global__ void k_col_partial(const T* __restrict__ M, const T* __restrict__ w, 
     const int i1 = min(m, i0 + rows_per_chunk);
     T s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     int i = i0;
+    for (; i + 7 < i1; i += 8) {            // eight rows in flight per thread (2 KB per warp), streamed once
+        const T m0 = M[(size_t)i * n + j], m1 = M[(size_t)(i + 1) * n + j];
+        const T m2 = M[(size_t)(i + 2) * n + j], m3 = M[(size_t)(i + 3) * n + j];
+        const T m4 = M[(size_t)(i + 4) * n + j], m5 = M[(size_t)(i + 5) * n + j];
+        const T m6 = M[(size_t)(i + 6) * n + j], m7 = M[(size_t)(i + 7) * n + j];
+        s0 += m0 * w[i];
+        s1 += m1 * w[i + 1];
+        s2 += m2 * w[i + 2];
+        s3 += m3 * w[i + 3];
+        s0 += m4 * w[i + 4];
+        s1 += m5 * w[i + 5];
+        s2 += m6 * w[i + 6];
+        s3 += m7 * w[i + 7];
+    }
     for (; i + 3 < i1; i += 4) {
         s0 += M[(size_t)i * n + j] * w[i];
         s1 += M[(size_t)(i + 1) * n + j] * w[i + 1];
