@@ -257,7 +257,12 @@ typedef struct sdb_solve_params {
     double eps_stage[6];         /* the six regularisations, computed by the caller exactly as ot_solvers.py:218,240,254 does */
     double xy_max;               /* max_i |x_i| * max_j |y_j| of the prepared points */
     double dot_limit;            /* a stage uses dot-product tiles while 2*c1*log2(e)*xy_max <= dot_limit, else direct ones */
-    int32_t batch_size, reserved;
+    int32_t batch_size;
+    int32_t reserved;            /* 1 = RESIDENT form: every CTA keeps its 64x64 tiles of the scaled cost matrix
+                                  * c1*log2(e)*|x_i - y_j|^2 in shared memory for a whole epsilon stage (a ChickenHeart-sized
+                                  * problem fits on chip), so a half-iteration is bias - cost, ex2, add per pair.  The caller
+                                  * then sizes partial_row / partial_col for ns_row = ceil(m/64), ns_col = ceil(n/64) splits;
+                                  * SDB_E_UNSUPPORTED when the tiles do not fit (use 0 = streamed tiles). */
 } sdb_solve_params;
 typedef struct sdb_solve_result {
     int32_t iters[6];            /* iterations per epsilon stage */

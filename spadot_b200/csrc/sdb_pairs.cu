@@ -377,6 +377,7 @@ struct SolveArgs {
     double eps_stage[6], xy_max, dot_limit;
     int* flag;                          // caller's absorb flag (left consistent: last tick that exceeded tau)
     int* flag2;                         // [2] ping-pong flags of this kernel
+    int res_tiles;                      // resident form: tiles of shared memory per CTA (>= the tiles any CTA owns)
     double inv_med, lambda1, lambda2, epsilon, epsilon0, tolerance, log_tau, log_m, log_N, dx, dy;
     int batch_size; long long max_iter; int first_tick;
     unsigned int* barrier;              // [2]
@@ -423,6 +424,65 @@ __device__ __forceinline__ double solve_safe_ratio(double num2, double den2) {  
 
 // One pass over (slab, split) items; the CTA that completes a slab combines its partials and, with UPDATE, updates the
 // potential of those 64 rows (pot, frame, la_old, bias_out, flags) - else it only stores the LSE.
+// Combine the (max, sum) partials of the 64 rows of slab `tile` (ns splits each) and, with UPDATE, update their potentials:
+// the work of whichever CTA completed the slab.  4 threads per row, splits strided over them.
+template <bool UPDATE>
+__device__ __forceinline__ void solve_finish_slab(int tile, int64_t n, const float2* partial, int ns, double* L, const double* norms,
+                                                  double c1n, const double* logmarg, double eps, double alpha, double log_n_other,
+                                                  double* pot, double* frame, double* la_old, float* bias_out, int* flag2, int tick,
+                                                  double log_tau, bool pending) {
+        // 4 threads per row, splits strided over them; every partial is loaded once (all loads in flight together)
+        const int64_t i = (int64_t)tile * BM + (threadIdx.x >> 2);
+        const int sub = threadIdx.x & 3;
+        constexpr int MAXP = 4;                                  // ns <= 32 keeps them in registers; beyond that, reload
+        float2 pv[MAXP];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < MAXP; ++q) {
+            const int sp = sub + 4 * q;
+            pv[q] = (i < n && sp < ns) ? __ldcg(partial + (int64_t)sp * n + i) : make_float2(SDB_NEG_SENTINEL, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < MAXP; ++q)
+            if (pv[q].x > -1e29f && pv[q].y > 0.f) mx = fmaxf(mx, pv[q].x);
+        if (i < n)
+            for (int sp = sub + 4 * MAXP; sp < ns; sp += 4) {
+                const float2 ps = __ldcg(partial + (int64_t)sp * n + i);
+                if (ps.x > -1e29f && ps.y > 0.f) mx = fmaxf(mx, ps.x);
+            }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        double S = 0.0;
+        if (mx > -INFINITY) {
+#pragma unroll
+            for (int q = 0; q < MAXP; ++q)
+                if (pv[q].x > -1e29f && pv[q].y > 0.f) S += (double)pv[q].y * exp2((double)pv[q].x - (double)mx);
+            if (i < n)
+                for (int sp = sub + 4 * MAXP; sp < ns; sp += 4) {
+                    const float2 ps = __ldcg(partial + (int64_t)sp * n + i);
+                    if (ps.x > -1e29f && ps.y > 0.f) S += (double)ps.y * exp2((double)ps.x - (double)mx);
+                }
+        }
+        S += __shfl_xor_sync(0xffffffffu, S, 1);
+        S += __shfl_xor_sync(0xffffffffu, S, 2);
+        if (sub == 0 && i < n) {
+            const double nc = norms[i] * c1n;
+            const double Li = (mx > -INFINITY) ? SDB_LN2 * ((double)mx + log2(S)) - nc : -INFINITY;
+            L[i] = Li;
+            if (UPDATE) {
+                const double old = pot[i];
+                double fr = frame[i];
+                if (pending) { fr = old; frame[i] = old; }           // absorb of the previous tick, row by row
+                la_old[i] = (old - fr) / eps;
+                const double nv = eps * alpha * (logmarg[i] - (Li - log_n_other));
+                pot[i] = nv;
+                const double b = SDB_LOG2E * (nv / eps - nc);
+                bias_out[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
+                if ((nv - fr) / eps > log_tau) atomicMax(flag2 + (tick & 1), tick);
+            }
+        }
+    }
+
 // `direct`: tile arithmetic of this stage (see sdb_lse_pass_simt); c1n = c1 for dot-product tiles (row norm subtracted from the
 // LSE, norm inside the bias), 0 for direct ones.
 template <bool UPDATE>
@@ -449,62 +509,146 @@ __device__ void solve_pass(const PairArgs& pa, bool direct, float scale_hi, floa
             if (s_last) counters[tile] = 0u;
         }
         __syncthreads();
-        if (s_last) {
-            // 4 threads per row, splits strided over them; every partial is loaded once (all loads in flight together)
-            const int64_t i = (int64_t)tile * BM + (threadIdx.x >> 2);
-            const int sub = threadIdx.x & 3;
-            constexpr int MAXP = 4;                                  // ns <= 32 keeps them in registers; beyond that, reload
-            float2 pv[MAXP];
-            float mx = -INFINITY;
-#pragma unroll
-            for (int q = 0; q < MAXP; ++q) {
-                const int sp = sub + 4 * q;
-                pv[q] = (i < n && sp < ns) ? __ldcg(partial + (int64_t)sp * n + i) : make_float2(SDB_NEG_SENTINEL, 0.f);
-            }
-#pragma unroll
-            for (int q = 0; q < MAXP; ++q)
-                if (pv[q].x > -1e29f && pv[q].y > 0.f) mx = fmaxf(mx, pv[q].x);
-            if (i < n)
-                for (int sp = sub + 4 * MAXP; sp < ns; sp += 4) {
-                    const float2 ps = __ldcg(partial + (int64_t)sp * n + i);
-                    if (ps.x > -1e29f && ps.y > 0.f) mx = fmaxf(mx, ps.x);
-                }
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            double S = 0.0;
-            if (mx > -INFINITY) {
-#pragma unroll
-                for (int q = 0; q < MAXP; ++q)
-                    if (pv[q].x > -1e29f && pv[q].y > 0.f) S += (double)pv[q].y * exp2((double)pv[q].x - (double)mx);
-                if (i < n)
-                    for (int sp = sub + 4 * MAXP; sp < ns; sp += 4) {
-                        const float2 ps = __ldcg(partial + (int64_t)sp * n + i);
-                        if (ps.x > -1e29f && ps.y > 0.f) S += (double)ps.y * exp2((double)ps.x - (double)mx);
-                    }
-            }
-            S += __shfl_xor_sync(0xffffffffu, S, 1);
-            S += __shfl_xor_sync(0xffffffffu, S, 2);
-            if (sub == 0 && i < n) {
-                const double nc = norms[i] * c1n;
-                const double Li = (mx > -INFINITY) ? SDB_LN2 * ((double)mx + log2(S)) - nc : -INFINITY;
-                L[i] = Li;
-                if (UPDATE) {
-                    const double old = pot[i];
-                    double fr = frame[i];
-                    if (pending) { fr = old; frame[i] = old; }           // absorb of the previous tick, row by row
-                    la_old[i] = (old - fr) / eps;
-                    const double nv = eps * alpha * (logmarg[i] - (Li - log_n_other));
-                    pot[i] = nv;
-                    const double b = SDB_LOG2E * (nv / eps - nc);
-                    bias_out[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
-                    if ((nv - fr) / eps > log_tau) atomicMax(flag2 + (tick & 1), tick);
-                }
-            }
-        }
+        if (s_last)
+            solve_finish_slab<UPDATE>(tile, n, partial, ns, L, norms, c1n, logmarg, eps, alpha, log_n_other, pot, frame, la_old, bias_out,
+                                      flag2, tick, log_tau, pending);
         __syncthreads();
     }
 }
 
+// ---- resident cost tiles -----------------------------------------------------------------------------------------------------
+// A ChickenHeart-sized coupling has a few million pairs: its whole scaled cost matrix Cs_ij = c1*log2(e)*|x_i - y_j|^2 (fp32)
+// fits in the shared memory of the 148 SMs (4 x 16 KB tiles per CTA, two CTAs per SM hold 1 184 tiles = 4.8 M pairs).  Built
+// once per epsilon stage by direct differences and kept on chip, it turns a half-iteration into  t = bias - Cs,  ex2,  add  per
+// pair - no dot products, no coordinate traffic - and BOTH passes read the same tile (rows reduce along x, columns along y).
+// Tile k of a CTA is global tile blockIdx.x + k*gridDim.x (row-tile major); layout [rr][tid][4]: thread (ty, tx) owns rows
+// 4*ty + rr, columns 4*tx .. 4*tx + 3, so every access is a conflict-free LDS.128.
+constexpr int RES_MAX_TILES = 6;
+
+__device__ void res_build_tiles(const SolveArgs& a, float* tiles, int n_owned, int C, double c1) {
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t n = a.row.n_p, m = a.col.n_p;
+    const int dpad = a.row.dpad;
+    const double sc = c1 * SDB_LOG2E;
+    for (int k = 0; k < n_owned; ++k) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        const int64_t r0 = (int64_t)(tile / C) * BM + ty * 4, c0 = (int64_t)(tile % C) * BN + tx * 4;
+        float acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+        for (int q = 0; q < dpad; ++q) {                       // padded rows / columns of xt, yt are zero-filled and in bounds
+            const float4 xa = *reinterpret_cast<const float4*>(a.row.pt + (int64_t)q * a.row.ldp + r0);
+            const float4 yb = *reinterpret_cast<const float4*>(a.col.pt + (int64_t)q * a.col.ldp + c0);
+            const float xr[4] = {xa.x, xa.y, xa.z, xa.w}, yc[4] = {yb.x, yb.y, yb.z, yb.w};
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) { const float df = xr[r] - yc[c]; acc[r][c] = fmaf(df, df, acc[r][c]); }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float4 v;
+            float* e = reinterpret_cast<float*>(&v);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                e[c] = (r0 + r < n && c0 + c < m) ? (float)((double)acc[r][c] * sc) : 3.0e38f;      // masked pair: 2^(-3e38) = 0
+            *reinterpret_cast<float4*>(tiles + ((size_t)k * 4 + r) * (NT * 4) + tid * 4) = v;
+        }
+    }
+    __syncthreads();
+}
+
+// One half-iteration over the resident tiles.  ROWS: reduce along the columns of each tile with bias = bias of the columns
+// (NULL = 0: the sum of exp(-C/eps)), one (max, sum) per (column tile, row); else along the rows with the bias of the rows, one
+// per (row tile, column).  Then the same slab-completion protocol as solve_pass.
+template <bool UPDATE, bool ROWS>
+__device__ void res_pass(const SolveArgs& a, const float* tiles, int n_owned, int R, int C, const float* bias, float2* partial,
+                         unsigned int* counters, double* L, const double* norms, const double* logmarg, double eps, double alpha,
+                         double log_n_other, double* pot, double* frame, double* la_old, float* bias_out, int tick, float2* red) {
+    __shared__ int s_last;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
+    const int64_t n = a.row.n_p, m = a.col.n_p;
+    const int64_t n_out = ROWS ? n : m;
+    const int ns = ROWS ? C : R;
+    const bool pending = UPDATE && (*reinterpret_cast<volatile int*>(a.flag2 + ((tick - 1) & 1)) == tick - 1);
+    for (int k = 0; k < n_owned; ++k) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        const int rt = tile / C, ct = tile % C;
+        float4 cs[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) cs[r] = *reinterpret_cast<const float4*>(tiles + ((size_t)k * 4 + r) * (NT * 4) + tid * 4);
+        if (ROWS) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) b = __ldcg(reinterpret_cast<const float4*>(bias + (int64_t)ct * BN + tx * 4));    // bias_y is padded to 256
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float t0 = b.x - cs[r].x, t1 = b.y - cs[r].y, t2 = b.z - cs[r].z, t3 = b.w - cs[r].w;
+                float mx = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+                float sm = (sdb_ex2(t0 - mx) + sdb_ex2(t1 - mx)) + (sdb_ex2(t2 - mx) + sdb_ex2(t3 - mx));
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) {                 // the 16 threads of a row sit in one half-warp
+                    const float m2 = __shfl_xor_sync(0xffffffffu, mx, o), s2 = __shfl_xor_sync(0xffffffffu, sm, o);
+                    const float mn = fmaxf(mx, m2);
+                    sm = sm * sdb_ex2(mx - mn) + s2 * sdb_ex2(m2 - mn);
+                    mx = mn;
+                }
+                const int64_t row = (int64_t)rt * BM + ty * 4 + r;
+                if (tx == 0 && row < n) partial[(int64_t)ct * n + row] = make_float2(mx, sm);
+            }
+        } else {
+            float br[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) br[r] = __ldcg(bias + (int64_t)rt * BM + ty * 4 + r);             // bias_x is padded to 256
+            float mxc[4], smc[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float t0 = br[0] - reinterpret_cast<const float*>(&cs[0])[c], t1 = br[1] - reinterpret_cast<const float*>(&cs[1])[c];
+                const float t2 = br[2] - reinterpret_cast<const float*>(&cs[2])[c], t3 = br[3] - reinterpret_cast<const float*>(&cs[3])[c];
+                float mx = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+                float sm = (sdb_ex2(t0 - mx) + sdb_ex2(t1 - mx)) + (sdb_ex2(t2 - mx) + sdb_ex2(t3 - mx));
+                // the two ty of this warp (lanes tx and tx + 16)
+                const float m2 = __shfl_xor_sync(0xffffffffu, mx, 16), s2 = __shfl_xor_sync(0xffffffffu, sm, 16);
+                const float mn = fmaxf(mx, m2);
+                smc[c] = sm * sdb_ex2(mx - mn) + s2 * sdb_ex2(m2 - mn);
+                mxc[c] = mn;
+            }
+            if (lane < 16) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) red[warp * BN + tx * 4 + c] = make_float2(mxc[c], smc[c]);
+            }
+            __syncthreads();
+            if (tid < BN) {                                        // the 8 warps' contributions to column tid of the tile
+                float mx = red[tid].x, sm = red[tid].y;
+#pragma unroll
+                for (int w = 1; w < NT / 32; ++w) {
+                    const float2 o = red[w * BN + tid];
+                    const float mn = fmaxf(mx, o.x);
+                    sm = sm * sdb_ex2(mx - mn) + o.y * sdb_ex2(o.x - mn);
+                    mx = mn;
+                }
+                const int64_t col = (int64_t)ct * BN + tid;
+                if (col < m) partial[(int64_t)rt * m + col] = make_float2(mx, sm);
+            }
+        }
+        const int slab = ROWS ? rt : ct;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned prev;
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(counters + slab) : "memory");
+            s_last = (prev == (unsigned)ns - 1u);
+            if (s_last) counters[slab] = 0u;
+        }
+        __syncthreads();
+        if (s_last)
+            solve_finish_slab<UPDATE>(slab, n_out, partial, ns, L, norms, 0.0, logmarg, eps, alpha, log_n_other, pot, frame, la_old, bias_out,
+                                      a.flag2, tick, a.log_tau, pending);
+        __syncthreads();
+    }
+}
+
+template <bool RESIDENT>
 __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
     extern __shared__ __align__(16) float smem[];
     unsigned int gen = *reinterpret_cast<volatile unsigned int*>(a.barrier + 1);
@@ -520,11 +664,19 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
     bool lr_known = false;
     PairArgs row0 = a.row;                                               // row pass with g = 0 (sum of exp(-C/eps))
     row0.bias = nullptr;
+    // resident form: this CTA's tiles of the scaled cost matrix live in shared memory for a whole epsilon stage
+    const int col_tiles = (int)((m + BN - 1) / BN);
+    int n_owned = 0;
+    float2* red = nullptr;
+    if constexpr (RESIDENT) {
+        for (int k = 0; k < RES_MAX_TILES; ++k) n_owned += (blockIdx.x + k * (int)gridDim.x < row_tiles * col_tiles) ? 1 : 0;
+        red = reinterpret_cast<float2*>(smem + (size_t)a.res_tiles * 4 * NT * 4);
+    }
     for (int e = 0; e <= 5 && status == 0; ++e) {
         eps = a.eps_stage[e];                                            // ot_solvers.py:218,240,254 (host arithmetic)
         const double c1 = a.inv_med / eps;
         const double alpha1 = a.lambda1 / (a.lambda1 + eps), alpha2 = a.lambda2 / (a.lambda2 + eps);
-        const bool direct = 2.0 * c1 * SDB_LOG2E * a.xy_max > a.dot_limit;
+        const bool direct = RESIDENT || 2.0 * c1 * SDB_LOG2E * a.xy_max > a.dot_limit;
         const double c1n = direct ? 0.0 : c1;
         const double sc = direct ? -c1 * SDB_LOG2E : 2.0 * c1 * SDB_LOG2E;
         const float sc_hi = (float)sc, sc_lo = (float)(sc - (double)sc_hi);
@@ -543,6 +695,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
             a.bias_y[j] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
         }
         if (gtid == 0) { a.flag2[0] = -1; a.flag2[1] = -1; }              // frames are fresh: nothing pending (ticks are >= 0)
+        if constexpr (RESIDENT) res_build_tiles(a, smem, n_owned, col_tiles, c1);
         grid_barrier(a.barrier, gen);
         long long n_it = 0;
         gap = INFINITY;
@@ -566,10 +719,18 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
                         if ((nv - fr) / eps > a.log_tau) atomicMax(a.flag2 + (tick & 1), tick);
                     }
                 } else {
+                    if constexpr (RESIDENT)
+                        res_pass<true, true>(a, smem, n_owned, row_tiles, col_tiles, a.bias_y, a.partial_row, cnt_row, a.Lr, a.norms_x, a.logp,
+                                             eps, alpha1, a.log_m, a.f, a.u, a.la_old, a.bias_x, tick, red);
+                    else
                     solve_pass<true>(a.row, direct, sc_hi, sc_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, a.norms_x, c1n, a.logp, eps, alpha1,
                                      a.log_m, a.f, a.u, a.la_old, a.bias_x, a.flag2, tick, a.log_tau, smem);
                 }
                 grid_barrier(a.barrier, gen);
+                if constexpr (RESIDENT)
+                    res_pass<true, false>(a, smem, n_owned, row_tiles, col_tiles, a.bias_x, a.partial_col, cnt_col, a.Lc, a.norms_y, a.logq, eps,
+                                          alpha2, a.log_N, a.g, a.v, a.lb_old, a.bias_y, tick, red);
+                else
                 solve_pass<true>(a.col, direct, sc_hi, sc_lo, a.partial_col, a.ns_col, cnt_col, a.Lc, a.norms_y, c1n, a.logq, eps, alpha2,
                                  a.log_N, a.g, a.v, a.lb_old, a.bias_y, a.flag2, tick, a.log_tau, smem);
                 grid_barrier(a.barrier, gen);
@@ -580,6 +741,10 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
             const bool pending = (*reinterpret_cast<volatile int*>(a.flag2 + (tick & 1)) == tick);
             if (final_stage) {
                 if (!have_sumK) {
+                    if constexpr (RESIDENT)
+                        res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, nullptr, a.partial_row, cnt_row, a.Lr, a.norms_x, nullptr, eps,
+                                              0.0, 0.0, nullptr, nullptr, nullptr, nullptr, tick, red);
+                    else
                     solve_pass<false>(row0, true, scd_hi, scd_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, a.norms_x, 0.0, nullptr, eps, 0.0, 0.0,
                                       nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau, smem);
                     grid_barrier(a.barrier, gen);
@@ -590,6 +755,10 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
                     have_sumK = true;
                 }
                 // row LSE at the new g: the gap's row marginal, and the next iteration's row pass
+                if constexpr (RESIDENT)
+                    res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, a.bias_y, a.partial_row, cnt_row, a.Lr, a.norms_x, nullptr, eps,
+                                          0.0, 0.0, nullptr, nullptr, nullptr, nullptr, tick, red);
+                else
                 solve_pass<false>(a.row, direct, sc_hi, sc_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, a.norms_x, c1n, nullptr, eps, 0.0, 0.0,
                                   nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau, smem);
                 grid_barrier(a.barrier, gen);
@@ -657,9 +826,13 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
         // row LSE at the final g (plan row sums, the growth loop's next G)
         // (bias_y still holds the last stage's form: reuse that stage's choice)
         const double c1 = a.inv_med / eps;
-        const bool direct = 2.0 * c1 * SDB_LOG2E * a.xy_max > a.dot_limit;
+        const bool direct = RESIDENT || 2.0 * c1 * SDB_LOG2E * a.xy_max > a.dot_limit;
         const double sc = direct ? -c1 * SDB_LOG2E : 2.0 * c1 * SDB_LOG2E;
         const float sc_hi = (float)sc;
+        if constexpr (RESIDENT)
+            res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, a.bias_y, a.partial_row, cnt_row, a.Lr, a.norms_x, nullptr, eps, 0.0,
+                                  0.0, nullptr, nullptr, nullptr, nullptr, tick, red);
+        else
         solve_pass<false>(a.row, direct, sc_hi, (float)(sc - (double)sc_hi), a.partial_row, a.ns_row, cnt_row, a.Lr, a.norms_x,
                           direct ? 0.0 : c1, nullptr, eps, 0.0, 0.0, nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau, smem);
     }
@@ -761,27 +934,54 @@ extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_
     a.batch_size = p->batch_size; a.max_iter = (long long)p->max_iter; a.first_tick = first_tick;
     a.barrier = barrier2; a.counters = counters; a.scratch = scratch; a.result = result;
     cudaStream_t st = sdb_stream(stream);
-    const size_t smem = sizeof(float) * ((size_t)d->dpad * BM + 2 * (size_t)d->dpad * BN + 2 * BN);
-    static size_t smem_set[SDB_MAX_DEVICES] = {0};
-    { cudaError_t e0 = sdb_ensure_smem(sinkhorn_solve_kernel, smem, smem_set); if (e0 != cudaSuccess) return (int)e0; }
     int dev = 0, n_sm = 0, per_sm = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_solve_kernel, NT, smem);
     if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) return SDB_E_UNSUPPORTED;
-    const int64_t row_items = ((d->n + BM - 1) / BM) * d->ns_row, col_items = ((d->m + BM - 1) / BM) * d->ns_col;
-    int64_t want = d->n_ctas > 0 ? d->n_ctas : (row_items > col_items ? row_items : col_items);
-    const int64_t cap = (int64_t)n_sm * per_sm;
-    int grid = (int)(want < cap ? want : cap);
-    if (grid < 1) grid = 1;
+    const int64_t R = (d->n + BM - 1) / BM, C = (d->m + BN - 1) / BN;
+    const bool resident = p->reserved == 1;
+    size_t smem = 0;
+    int grid = 0;
+    a.res_tiles = 0;
+    if (resident) {
+        // resident cost tiles: the caller sized the partial buffers for one split per tile (ns_row = C, ns_col = R); find a
+        // co-resident grid whose CTAs can hold their share of the R*C tiles (16 KB each) in shared memory
+        SDB_CHECK_ARG(d->ns_row == C && d->ns_col == R);
+        static size_t smem_set_r[SDB_MAX_DEVICES] = {0};
+        for (int want_per_sm = 2; want_per_sm >= 1 && grid == 0; --want_per_sm) {
+            const int64_t g = (int64_t)n_sm * want_per_sm;
+            const int64_t T = (R * C + g - 1) / g;
+            if (T > RES_MAX_TILES) continue;
+            const size_t need = (size_t)T * 4 * NT * 4 * sizeof(float) + (size_t)(NT / 32) * BN * sizeof(float2);
+            if (need > 220 * 1024) continue;
+            cudaError_t e0 = sdb_ensure_smem(sinkhorn_solve_kernel<true>, need, smem_set_r);
+            if (e0 != cudaSuccess) return (int)e0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_solve_kernel<true>, NT, need);
+            if (e != cudaSuccess) return (int)e;
+            if (per_sm >= want_per_sm) { grid = (int)g; smem = need; a.res_tiles = (int)T; }
+        }
+        if (grid == 0) return SDB_E_UNSUPPORTED;      // too many tiles for the on-chip memory: the caller takes the streamed form
+    } else {
+        smem = sizeof(float) * ((size_t)d->dpad * BM + 2 * (size_t)d->dpad * BN + 2 * BN);
+        static size_t smem_set[SDB_MAX_DEVICES] = {0};
+        { cudaError_t e0 = sdb_ensure_smem(sinkhorn_solve_kernel<false>, smem, smem_set); if (e0 != cudaSuccess) return (int)e0; }
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_solve_kernel<false>, NT, smem);
+        if (e != cudaSuccess) return (int)e;
+        if (per_sm < 1) return SDB_E_UNSUPPORTED;
+        const int64_t row_items = R * d->ns_row, col_items = C * d->ns_col;
+        int64_t want = d->n_ctas > 0 ? d->n_ctas : (row_items > col_items ? row_items : col_items);
+        const int64_t cap = (int64_t)n_sm * per_sm;
+        grid = (int)(want < cap ? want : cap);
+        if (grid < 1) grid = 1;
+    }
     if (grid > SDB_SOLVE_MAX_CTAS) grid = SDB_SOLVE_MAX_CTAS;
     e = cudaMemsetAsync(barrier2, 0, 2 * sizeof(unsigned int), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(result, 0, sizeof(sdb_solve_result), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(counters, 0, sizeof(unsigned int) * (size_t)((d->n + BM - 1) / BM + (d->m + BM - 1) / BM), st);
     if (e != cudaSuccess) return (int)e;
     void* params[] = {&a};
-    e = cudaLaunchCooperativeKernel((const void*)sinkhorn_solve_kernel, dim3((unsigned)grid), dim3(NT), params, smem, st);
+    e = cudaLaunchCooperativeKernel(resident ? (const void*)sinkhorn_solve_kernel<true> : (const void*)sinkhorn_solve_kernel<false>,
+                                    dim3((unsigned)grid), dim3(NT), params, smem, st);
     return (int)e;
 }
 

@@ -190,6 +190,8 @@ class CudaOps(VectorOps):
     PERSISTENT_MAX_PAIRS = 1 << 24   # SIMT problems up to this many pairs run their sweeps in one cooperative launch
     PERSISTENT_CTAS_PER_SM = int(os.environ.get("SDB_PERSISTENT_CTAS_PER_SM", "2"))
     FUSED_UPDATE = os.environ.get("SDB_TC_FUSED_UPDATE", "1") != "0"   # tensor-core native loop: pass + update in one kernel
+    RESIDENT_TILES = os.environ.get("SDB_RESIDENT_TILES", "1") != "0"  # one-launch solve with the cost matrix resident on chip
+    RESIDENT_MAX_TILES_PER_CTA = 6
 
     def __init__(self, x_local, y, device=None, tc="auto"):
         self._init_vectors(device)
@@ -479,6 +481,13 @@ class CudaOps(VectorOps):
         d = self._sweep_desc(st, float(epsilon), 0.0, 0.0, 0.0, NEG_INF)
         d.norms_x, d.norms_y = _ptr(self.X.norms_sq), _ptr(self.Y.norms_sq)
         self._persistent_plan(d)
+        R, C = (self.n + 63) // 64, (self.m + 63) // 64
+        resident = self.RESIDENT_TILES and R * C <= 2 * self._n_sm * self.RESIDENT_MAX_TILES_PER_CTA
+        if resident:
+            # the whole scaled cost matrix stays in shared memory: one split per tile
+            d.ns_row, d.ns_col = C, R
+            d.partial_row = _ptr(self._partial(C, self.n, "rrow"))
+            d.partial_col = _ptr(self._partial(R, self.m, "rcol"))
         # the six regularisations in the host's own arithmetic (ot_solvers.py:218,240,254), so that the device walks the very
         # same epsilons as the host-driven loop and the reference
         scale_factor = math.exp(-math.log(epsilon) / 5)
@@ -487,7 +496,8 @@ class CudaOps(VectorOps):
             eps_i = eps_i / scale_factor
             stages.append(eps_i)
         p = _lib.SolveParams(float(lambda1), float(lambda2), float(epsilon), float(epsilon0), float(tolerance), float(tau),
-                             float(max_iter), (ctypes.c_double * 6)(*stages), self._xy_max(), self.SIMT_DOT_MAX, int(batch_size), 0)
+                             float(max_iter), (ctypes.c_double * 6)(*stages), self._xy_max(), self.SIMT_DOT_MAX, int(batch_size),
+                             int(resident))
         if getattr(self, "_solve_ws", None) is None:
             tiles = (self.n + 63) // 64 + (self.m + 63) // 64
             self._solve_ws = dict(flag2=torch.zeros(2, dtype=torch.int32, device=self.device),
@@ -495,8 +505,16 @@ class CudaOps(VectorOps):
                                   scratch=torch.zeros(_lib.SOLVE_MAX_CTAS * 10, dtype=torch.float64, device=self.device),
                                   result=torch.zeros(ctypes.sizeof(_lib.SolveResult), dtype=torch.uint8, device=self.device))
         ws = self._solve_ws
-        _lib.call("sdb_sinkhorn_solve_persistent", ctypes.byref(d), ctypes.byref(p), self._tick + 1, _ptr(ws["flag2"]),
-                  _ptr(self._barrier), _ptr(ws["counters"]), _ptr(ws["scratch"]), _ptr(ws["result"]), self._stream())
+        fn = _lib.load().sdb_sinkhorn_solve_persistent
+        args = (ctypes.byref(d), ctypes.byref(p), self._tick + 1, _ptr(ws["flag2"]), _ptr(self._barrier), _ptr(ws["counters"]),
+                _ptr(ws["scratch"]), _ptr(ws["result"]), self._stream())
+        status = fn(*args)
+        if status == -2 and resident:
+            # the tiles do not fit next to whatever else occupies the SMs: streamed tiles instead
+            self._persistent_plan(d)
+            p.reserved = 0
+            status = fn(*args)
+        _lib.check(status, "sdb_sinkhorn_solve_persistent")
         self.launches += 1
         raw = ws["result"].cpu().numpy().tobytes()                # the one synchronising read-back of the solve
         res = _lib.SolveResult.from_buffer_copy(raw)

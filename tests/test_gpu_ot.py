@@ -412,9 +412,10 @@ def test_persistent_sweeps_match_launch_loop(ot, n, m, d):
     assert abs(cp1.info["gap"]) <= 1e-8
 
 
+@pytest.mark.parametrize("resident", [True, False])
 @pytest.mark.parametrize("n,m,d,tau", [(747, 1966, 20, 1000.0), (300, 411, 20, 1000.0), (130, 97, 6, 3.0), (1, 1, 3, 1000.0),
-                                       (65, 64, 33, 1.5), (1966, 1916, 20, 1000.0)])
-def test_whole_solve_in_one_launch_matches_host_stage_loop(ot, n, m, d, tau):
+                                       (65, 64, 33, 1.5), (1966, 1916, 20, 1000.0), (2500, 3000, 32, 1000.0)])
+def test_whole_solve_in_one_launch_matches_host_stage_loop(ot, n, m, d, tau, resident):
     """sdb_sinkhorn_solve_persistent (six epsilon stages, stopping rules and tau bookkeeping on the device, two grid barriers
     per iteration) against the host-driven stage loop over the same tile code: same iterations per stage, same potentials,
     same frames; small tau forces absorptions (ot_func.cpp:778-819) so the row-by-row deferred absorb is exercised."""
@@ -425,6 +426,8 @@ def test_whole_solve_in_one_launch_matches_host_stage_loop(ot, n, m, d, tau):
     out = []
     for fused in (True, False):
         ops = CudaOps(a, b, tc="off")
+        ops.RESIDENT_TILES = resident                            # cost tiles resident in shared memory vs streamed tiles
+        ops.SIMT_DOT_MAX = 0.0 if resident else ops.SIMT_DOT_MAX  # the resident form is a direct-difference form: compare like with like
         if not fused:
             ops.fused_solve = None
         l0 = ops.launches
