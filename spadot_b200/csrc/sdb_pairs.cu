@@ -426,7 +426,7 @@ __device__ __forceinline__ double solve_safe_ratio(double num2, double den2) {  
 // potential of those 64 rows (pot, frame, la_old, bias_out, flags) - else it only stores the LSE.
 // Combine the (max, sum) partials of the 64 rows of slab `tile` (ns splits each) and, with UPDATE, update their potentials:
 // the work of whichever CTA completed the slab.  4 threads per row, splits strided over them.
-template <bool UPDATE>
+template <bool UPDATE, int MAXP = 4>
 __device__ __forceinline__ void solve_finish_slab(int tile, int64_t n, const float2* partial, int ns, double* L, const double* norms,
                                                   double c1n, const double* logmarg, double eps, double alpha, double log_n_other,
                                                   double* pot, double* frame, double* la_old, float* bias_out, int* flag2, int tick,
@@ -434,7 +434,7 @@ __device__ __forceinline__ void solve_finish_slab(int tile, int64_t n, const flo
         // 4 threads per row, splits strided over them; every partial is loaded once (all loads in flight together)
         const int64_t i = (int64_t)tile * BM + (threadIdx.x >> 2);
         const int sub = threadIdx.x & 3;
-        constexpr int MAXP = 4;                                  // ns <= 32 keeps them in registers; beyond that, reload
+        // MAXP partials per thread stay in registers (4 * MAXP splits); beyond that they are reloaded for the sum
         float2 pv[MAXP];
         float mx = -INFINITY;
 #pragma unroll
@@ -567,21 +567,33 @@ template <bool UPDATE, bool ROWS>
 __device__ void res_pass(const SolveArgs& a, const float* tiles, int n_owned, int R, int C, const float* bias, float2* partial,
                          unsigned int* counters, double* L, const double* norms, const double* logmarg, double eps, double alpha,
                          double log_n_other, double* pot, double* frame, double* la_old, float* bias_out, int tick, float2* red) {
-    __shared__ int s_last;
+    __shared__ int s_last[RES_MAX_TILES];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31, warp = tid >> 5;
     const int64_t n = a.row.n_p, m = a.col.n_p;
     const int64_t n_out = ROWS ? n : m;
     const int ns = ROWS ? C : R;
     const bool pending = UPDATE && (*reinterpret_cast<volatile int*>(a.flag2 + ((tick - 1) & 1)) == tick - 1);
-    for (int k = 0; k < n_owned; ++k) {
+    // all the bias loads of this CTA's tiles first: one L2 round trip for the whole pass instead of one per tile
+    float4 bq[RES_MAX_TILES];
+#pragma unroll
+    for (int k = 0; k < RES_MAX_TILES; ++k) {
+        bq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < n_owned && bias) {
+            const int tile = blockIdx.x + k * gridDim.x;
+            if (ROWS) bq[k] = __ldcg(reinterpret_cast<const float4*>(bias + (int64_t)(tile % C) * BN + tx * 4));       // padded to 256
+            else bq[k] = __ldcg(reinterpret_cast<const float4*>(bias + (int64_t)(tile / C) * BM + ty * 4));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RES_MAX_TILES; ++k) {
+        if (k >= n_owned) break;
         const int tile = blockIdx.x + k * gridDim.x;
         const int rt = tile / C, ct = tile % C;
         float4 cs[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) cs[r] = *reinterpret_cast<const float4*>(tiles + ((size_t)k * 4 + r) * (NT * 4) + tid * 4);
         if (ROWS) {
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bias) b = __ldcg(reinterpret_cast<const float4*>(bias + (int64_t)ct * BN + tx * 4));    // bias_y is padded to 256
+            const float4 b = bq[k];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const float t0 = b.x - cs[r].x, t1 = b.y - cs[r].y, t2 = b.z - cs[r].z, t3 = b.w - cs[r].w;
@@ -598,9 +610,7 @@ __device__ void res_pass(const SolveArgs& a, const float* tiles, int n_owned, in
                 if (tx == 0 && row < n) partial[(int64_t)ct * n + row] = make_float2(mx, sm);
             }
         } else {
-            float br[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) br[r] = __ldcg(bias + (int64_t)rt * BM + ty * 4 + r);             // bias_x is padded to 256
+            const float br[4] = {bq[k].x, bq[k].y, bq[k].z, bq[k].w};
             float mxc[4], smc[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -616,36 +626,48 @@ __device__ void res_pass(const SolveArgs& a, const float* tiles, int n_owned, in
             }
             if (lane < 16) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) red[warp * BN + tx * 4 + c] = make_float2(mxc[c], smc[c]);
-            }
-            __syncthreads();
-            if (tid < BN) {                                        // the 8 warps' contributions to column tid of the tile
-                float mx = red[tid].x, sm = red[tid].y;
-#pragma unroll
-                for (int w = 1; w < NT / 32; ++w) {
-                    const float2 o = red[w * BN + tid];
-                    const float mn = fmaxf(mx, o.x);
-                    sm = sm * sdb_ex2(mx - mn) + o.y * sdb_ex2(o.x - mn);
-                    mx = mn;
-                }
-                const int64_t col = (int64_t)ct * BN + tid;
-                if (col < m) partial[(int64_t)rt * m + col] = make_float2(mx, sm);
+                for (int c = 0; c < 4; ++c) red[((size_t)k * (NT / 32) + warp) * BN + tx * 4 + c] = make_float2(mxc[c], smc[c]);
             }
         }
-        const int slab = ROWS ? rt : ct;
-        __syncthreads();
-        if (tid == 0) {
-            unsigned prev;
-            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(counters + slab) : "memory");
-            s_last = (prev == (unsigned)ns - 1u);
-            if (s_last) counters[slab] = 0u;
-        }
-        __syncthreads();
-        if (s_last)
-            solve_finish_slab<UPDATE>(slab, n_out, partial, ns, L, norms, 0.0, logmarg, eps, alpha, log_n_other, pot, frame, la_old, bias_out,
-                                      a.flag2, tick, a.log_tau, pending);
-        __syncthreads();
     }
+    if (!ROWS) {
+        __syncthreads();
+        // the 8 warps' contributions to every column of every owned tile
+        for (int idx = tid; idx < n_owned * BN; idx += NT) {
+            const int k = idx / BN, cl = idx % BN;
+            const int tile = blockIdx.x + k * gridDim.x;
+            const float2* rk = red + (size_t)k * (NT / 32) * BN;
+            float mx = rk[cl].x, sm = rk[cl].y;
+#pragma unroll
+            for (int w = 1; w < NT / 32; ++w) {
+                const float2 o = rk[w * BN + cl];
+                const float mn = fmaxf(mx, o.x);
+                sm = sm * sdb_ex2(mx - mn) + o.y * sdb_ex2(o.x - mn);
+                mx = mn;
+            }
+            const int64_t col = (int64_t)(tile % C) * BN + cl;
+            if (col < m) partial[(int64_t)(tile / C) * m + col] = make_float2(mx, sm);
+        }
+    }
+    // slab completion for all owned tiles at once: one bar.sync, the arrivals issued by different threads in parallel
+    __syncthreads();
+    if (tid < n_owned) {
+        const int tile = blockIdx.x + tid * gridDim.x;
+        const int slab = ROWS ? tile / C : tile % C;
+        unsigned prev;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(counters + slab) : "memory");
+        const bool last = (prev == (unsigned)ns - 1u);
+        if (last) counters[slab] = 0u;
+        s_last[tid] = last ? 1 : 0;
+    }
+    __syncthreads();
+    for (int k = 0; k < n_owned; ++k) {
+        if (!s_last[k]) continue;
+        const int tile = blockIdx.x + k * gridDim.x;
+        solve_finish_slab<UPDATE, 8>(ROWS ? tile / C : tile % C, n_out, partial, ns, L, norms, 0.0, logmarg, eps, alpha, log_n_other, pot, frame,
+                                  la_old, bias_out, a.flag2, tick, a.log_tau, pending);
+    }
+    __syncthreads();
 }
 
 template <bool RESIDENT>
@@ -952,7 +974,7 @@ extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_
             const int64_t g = (int64_t)n_sm * want_per_sm;
             const int64_t T = (R * C + g - 1) / g;
             if (T > RES_MAX_TILES) continue;
-            const size_t need = (size_t)T * 4 * NT * 4 * sizeof(float) + (size_t)(NT / 32) * BN * sizeof(float2);
+            const size_t need = (size_t)T * 4 * NT * 4 * sizeof(float) + (size_t)T * (NT / 32) * BN * sizeof(float2);
             if (need > 220 * 1024) continue;
             cudaError_t e0 = sdb_ensure_smem(sinkhorn_solve_kernel<true>, need, smem_set_r);
             if (e0 != cudaSuccess) return (int)e0;
