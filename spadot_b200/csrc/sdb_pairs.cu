@@ -517,19 +517,19 @@ __device__ void solve_pass(const PairArgs& pa, bool direct, float scale_hi, floa
 }
 
 // ---- resident cost tiles -----------------------------------------------------------------------------------------------------
-// A ChickenHeart-sized coupling has a few million pairs: its whole scaled cost matrix Cs_ij = c1*log2(e)*|x_i - y_j|^2 (fp32)
-// fits in the shared memory of the 148 SMs (4 x 16 KB tiles per CTA, two CTAs per SM hold 1 184 tiles = 4.8 M pairs).  Built
-// once per epsilon stage by direct differences and kept on chip, it turns a half-iteration into  t = bias - Cs,  ex2,  add  per
-// pair - no dot products, no coordinate traffic - and BOTH passes read the same tile (rows reduce along x, columns along y).
+// A ChickenHeart-sized coupling has a few million pairs: its whole squared-distance matrix D_ij = |x_i - y_j|^2 (fp32, direct
+// differences) fits in the shared memory of the 148 SMs (4 x 16 KB tiles per CTA, two CTAs per SM hold 1 184 tiles = 4.8 M
+// pairs).  Built ONCE per solve and kept on chip, it turns a half-iteration into  t = fma(s, D, bias),  ex2,  add  per pair
+// (s = -c1*log2(e) as an fp32 pair, one rounding at the magnitude of t) - no dot products, no coordinate traffic - and BOTH
+// passes read the same tile (rows reduce along x, columns along y).
 // Tile k of a CTA is global tile blockIdx.x + k*gridDim.x (row-tile major); layout [rr][tid][4]: thread (ty, tx) owns rows
 // 4*ty + rr, columns 4*tx .. 4*tx + 3, so every access is a conflict-free LDS.128.
 constexpr int RES_MAX_TILES = 6;
 
-__device__ void res_build_tiles(const SolveArgs& a, float* tiles, int n_owned, int C, double c1) {
+__device__ void res_build_tiles(const SolveArgs& a, float* tiles, int n_owned, int C) {
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int64_t n = a.row.n_p, m = a.col.n_p;
     const int dpad = a.row.dpad;
-    const double sc = c1 * SDB_LOG2E;
     for (int k = 0; k < n_owned; ++k) {
         const int tile = blockIdx.x + k * gridDim.x;
         const int64_t r0 = (int64_t)(tile / C) * BM + ty * 4, c0 = (int64_t)(tile % C) * BN + tx * 4;
@@ -553,7 +553,7 @@ __device__ void res_build_tiles(const SolveArgs& a, float* tiles, int n_owned, i
             float* e = reinterpret_cast<float*>(&v);
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-                e[c] = (r0 + r < n && c0 + c < m) ? (float)((double)acc[r][c] * sc) : 3.0e38f;      // masked pair: 2^(-3e38) = 0
+                e[c] = (r0 + r < n && c0 + c < m) ? acc[r][c] : 1.0e30f;      // masked pair: scale * 1e30 stays finite, 2^that = 0
             *reinterpret_cast<float4*>(tiles + ((size_t)k * 4 + r) * (NT * 4) + tid * 4) = v;
         }
     }
@@ -564,7 +564,8 @@ __device__ void res_build_tiles(const SolveArgs& a, float* tiles, int n_owned, i
 // (NULL = 0: the sum of exp(-C/eps)), one (max, sum) per (column tile, row); else along the rows with the bias of the rows, one
 // per (row tile, column).  Then the same slab-completion protocol as solve_pass.
 template <bool UPDATE, bool ROWS>
-__device__ void res_pass(const SolveArgs& a, const float* tiles, int n_owned, int R, int C, const float* bias, float2* partial,
+__device__ void res_pass(const SolveArgs& a, const float* tiles, int n_owned, int R, int C, float s_hi, float s_lo, const float* bias,
+                         float2* partial,
                          unsigned int* counters, double* L, const double* norms, const double* logmarg, double eps, double alpha,
                          double log_n_other, double* pot, double* frame, double* la_old, float* bias_out, int tick, float2* red) {
     __shared__ int s_last[RES_MAX_TILES];
@@ -596,7 +597,8 @@ __device__ void res_pass(const SolveArgs& a, const float* tiles, int n_owned, in
             const float4 b = bq[k];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                const float t0 = b.x - cs[r].x, t1 = b.y - cs[r].y, t2 = b.z - cs[r].z, t3 = b.w - cs[r].w;
+                const float t0 = fmaf(s_hi, cs[r].x, fmaf(s_lo, cs[r].x, b.x)), t1 = fmaf(s_hi, cs[r].y, fmaf(s_lo, cs[r].y, b.y));
+                const float t2 = fmaf(s_hi, cs[r].z, fmaf(s_lo, cs[r].z, b.z)), t3 = fmaf(s_hi, cs[r].w, fmaf(s_lo, cs[r].w, b.w));
                 float mx = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
                 float sm = (sdb_ex2(t0 - mx) + sdb_ex2(t1 - mx)) + (sdb_ex2(t2 - mx) + sdb_ex2(t3 - mx));
 #pragma unroll
@@ -614,8 +616,10 @@ __device__ void res_pass(const SolveArgs& a, const float* tiles, int n_owned, in
             float mxc[4], smc[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const float t0 = br[0] - reinterpret_cast<const float*>(&cs[0])[c], t1 = br[1] - reinterpret_cast<const float*>(&cs[1])[c];
-                const float t2 = br[2] - reinterpret_cast<const float*>(&cs[2])[c], t3 = br[3] - reinterpret_cast<const float*>(&cs[3])[c];
+                const float d0 = reinterpret_cast<const float*>(&cs[0])[c], d1 = reinterpret_cast<const float*>(&cs[1])[c];
+                const float d2 = reinterpret_cast<const float*>(&cs[2])[c], d3 = reinterpret_cast<const float*>(&cs[3])[c];
+                const float t0 = fmaf(s_hi, d0, fmaf(s_lo, d0, br[0])), t1 = fmaf(s_hi, d1, fmaf(s_lo, d1, br[1]));
+                const float t2 = fmaf(s_hi, d2, fmaf(s_lo, d2, br[2])), t3 = fmaf(s_hi, d3, fmaf(s_lo, d3, br[3]));
                 float mx = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
                 float sm = (sdb_ex2(t0 - mx) + sdb_ex2(t1 - mx)) + (sdb_ex2(t2 - mx) + sdb_ex2(t3 - mx));
                 // the two ty of this warp (lanes tx and tx + 16)
@@ -693,6 +697,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
     if constexpr (RESIDENT) {
         for (int k = 0; k < RES_MAX_TILES; ++k) n_owned += (blockIdx.x + k * (int)gridDim.x < row_tiles * col_tiles) ? 1 : 0;
         red = reinterpret_cast<float2*>(smem + (size_t)a.res_tiles * 4 * NT * 4);
+        res_build_tiles(a, smem, n_owned, col_tiles);                     // once: the squared distances do not depend on epsilon
     }
     for (int e = 0; e <= 5 && status == 0; ++e) {
         eps = a.eps_stage[e];                                            // ot_solvers.py:218,240,254 (host arithmetic)
@@ -717,7 +722,6 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
             a.bias_y[j] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
         }
         if (gtid == 0) { a.flag2[0] = -1; a.flag2[1] = -1; }              // frames are fresh: nothing pending (ticks are >= 0)
-        if constexpr (RESIDENT) res_build_tiles(a, smem, n_owned, col_tiles, c1);
         grid_barrier(a.barrier, gen);
         long long n_it = 0;
         gap = INFINITY;
@@ -742,7 +746,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
                     }
                 } else {
                     if constexpr (RESIDENT)
-                        res_pass<true, true>(a, smem, n_owned, row_tiles, col_tiles, a.bias_y, a.partial_row, cnt_row, a.Lr, a.norms_x, a.logp,
+                        res_pass<true, true>(a, smem, n_owned, row_tiles, col_tiles, sc_hi, sc_lo, a.bias_y, a.partial_row, cnt_row, a.Lr, a.norms_x, a.logp,
                                              eps, alpha1, a.log_m, a.f, a.u, a.la_old, a.bias_x, tick, red);
                     else
                     solve_pass<true>(a.row, direct, sc_hi, sc_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, a.norms_x, c1n, a.logp, eps, alpha1,
@@ -750,7 +754,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
                 }
                 grid_barrier(a.barrier, gen);
                 if constexpr (RESIDENT)
-                    res_pass<true, false>(a, smem, n_owned, row_tiles, col_tiles, a.bias_x, a.partial_col, cnt_col, a.Lc, a.norms_y, a.logq, eps,
+                    res_pass<true, false>(a, smem, n_owned, row_tiles, col_tiles, sc_hi, sc_lo, a.bias_x, a.partial_col, cnt_col, a.Lc, a.norms_y, a.logq, eps,
                                           alpha2, a.log_N, a.g, a.v, a.lb_old, a.bias_y, tick, red);
                 else
                 solve_pass<true>(a.col, direct, sc_hi, sc_lo, a.partial_col, a.ns_col, cnt_col, a.Lc, a.norms_y, c1n, a.logq, eps, alpha2,
@@ -764,7 +768,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
             if (final_stage) {
                 if (!have_sumK) {
                     if constexpr (RESIDENT)
-                        res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, nullptr, a.partial_row, cnt_row, a.Lr, a.norms_x, nullptr, eps,
+                        res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, scd_hi, scd_lo, nullptr, a.partial_row, cnt_row, a.Lr, a.norms_x, nullptr, eps,
                                               0.0, 0.0, nullptr, nullptr, nullptr, nullptr, tick, red);
                     else
                     solve_pass<false>(row0, true, scd_hi, scd_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, a.norms_x, 0.0, nullptr, eps, 0.0, 0.0,
@@ -778,7 +782,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
                 }
                 // row LSE at the new g: the gap's row marginal, and the next iteration's row pass
                 if constexpr (RESIDENT)
-                    res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, a.bias_y, a.partial_row, cnt_row, a.Lr, a.norms_x, nullptr, eps,
+                    res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, sc_hi, sc_lo, a.bias_y, a.partial_row, cnt_row, a.Lr, a.norms_x, nullptr, eps,
                                           0.0, 0.0, nullptr, nullptr, nullptr, nullptr, tick, red);
                 else
                 solve_pass<false>(a.row, direct, sc_hi, sc_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, a.norms_x, c1n, nullptr, eps, 0.0, 0.0,
@@ -852,8 +856,8 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
         const double sc = direct ? -c1 * SDB_LOG2E : 2.0 * c1 * SDB_LOG2E;
         const float sc_hi = (float)sc;
         if constexpr (RESIDENT)
-            res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, a.bias_y, a.partial_row, cnt_row, a.Lr, a.norms_x, nullptr, eps, 0.0,
-                                  0.0, nullptr, nullptr, nullptr, nullptr, tick, red);
+            res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, sc_hi, (float)(sc - (double)sc_hi), a.bias_y, a.partial_row, cnt_row,
+                                  a.Lr, a.norms_x, nullptr, eps, 0.0, 0.0, nullptr, nullptr, nullptr, nullptr, tick, red);
         else
         solve_pass<false>(a.row, direct, sc_hi, (float)(sc - (double)sc_hi), a.partial_row, a.ns_row, cnt_row, a.Lr, a.norms_x,
                           direct ? 0.0 : c1, nullptr, eps, 0.0, 0.0, nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau, smem);
