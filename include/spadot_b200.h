@@ -237,7 +237,7 @@ typedef struct sdb_sweep_desc {
 int sdb_sinkhorn_sweeps(const sdb_sweep_desc* d, int n_sweeps, int first_tick, int lr_known_first, void* stream);
 /* The same n_sweeps iterations in ONE cooperative launch (SIMT form only, use_tc == 0): CTAs walk the (slab, split)
  * items of each pass and meet at a grid barrier between pass and update, so a ChickenHeart-sized iteration costs four
- * barriers instead of five launches.  barrier2: two unsigned ints owned by the caller (zeroed by every call, reusable across
+ * barriers instead of five launches.  barrier2: SDB_BARRIER_WORDS unsigned ints owned by the caller (zeroed by every call, reusable across
  * calls).  Grid = d->n_ctas CTAs (capped by co-residency; 0 = one per work item); the caller sizes the column splits
  * for it.  Same tile and update code as sdb_sinkhorn_sweeps; the partials of a row are combined by a warp instead of a
  * thread, so iterates agree to fp64 rounding of that sum. */
@@ -249,9 +249,10 @@ int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_sweeps, int fi
  * loop (ref: ot_solvers.py:240-449, ot_func.cpp:831-930).  Two grid barriers per iteration: the CTA that finishes the last
  * column split of a 64-row slab combines the slab's partials and updates its potentials.  On return (after the stream
  * synchronises) f, g, u, v, Lr (row LSE at the final g), Lc hold the final state and *result the iteration counts.
- * Caller-owned workspaces: flag2 (2 ints), barrier2 (2 uints), counters (ceil(n/64) + ceil(m/64) uints), scratch
+ * Caller-owned workspaces: flag2 (2 ints), barrier2 (SDB_BARRIER_WORDS uints), counters (ceil(n/64) + ceil(m/64) uints), scratch
  * (SDB_SOLVE_MAX_CTAS * 10 doubles), result (device).  Iterations are stamped first_tick, first_tick + 1, ... */
 #define SDB_SOLVE_MAX_CTAS 1024
+#define SDB_BARRIER_WORDS 1024   /* grid barrier of the cooperative kernels: top counter, generation, 16 group counters 128 B apart */
 typedef struct sdb_solve_params {
     double lambda1, lambda2, epsilon, epsilon0, tolerance, tau, max_iter;
     double eps_stage[6];         /* the six regularisations, computed by the caller exactly as ot_solvers.py:218,240,254 does */

@@ -277,21 +277,37 @@ struct PersistArgs {
 // the last arriver resets it and releases the next generation, the others poll the generation with acquire loads.
 // Release/acquire at gpu scope (instead of two membar.sc) orders every thread's earlier writes before, and every
 // later read after, the barrier: the bar.sync pair extends that from thread 0 to the whole CTA.
+// TWO-LEVEL arrival: the CTAs are spread over SDB_BARRIER_GROUPS group counters (128 bytes apart, so they live in different
+// L2 sectors) and only the last arriver of each group touches the top counter - ~20 + 16 same-address atomics deep instead of
+// ~300 (same-address atomics serialise in L2; with one counter the barrier cost 6 us of a 17 us ChickenHeart phase).
+// bar[0] = top counter, bar[1] = generation, bar[32 + 32*g] = counter of group g  (SDB_BARRIER_WORDS unsigned ints, zeroed).
+constexpr unsigned SDB_BARRIER_GROUPS = 16;
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& gen) {
     __syncthreads();
     if (threadIdx.x == 0) {
+        const unsigned n_groups = min(SDB_BARRIER_GROUPS, gridDim.x);
+        const unsigned g = blockIdx.x % n_groups;
+        const unsigned in_group = (gridDim.x - g + n_groups - 1) / n_groups;
+        unsigned int* sub = bar + 32 + 32 * g;
         unsigned int arrived;
-        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(bar) : "memory");
-        if (arrived == gridDim.x - 1) {
-            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
-        } else {
+        bool released = false;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(sub) : "memory");
+        if (arrived == in_group - 1) {
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(sub), "r"(0u) : "memory");
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(bar) : "memory");
+            if (arrived == n_groups - 1) {
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
+                released = true;
+            }
+        }
+        if (!released) {
             // poll with relaxed loads (an acquire load per poll invalidates L1 every time: CCTL.IVALL was 4 % of the one-launch
             // solve's samples), then one acquire fence once the new generation is seen
-            unsigned int g;
+            unsigned int gg;
             do {
-                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(bar + 1) : "memory");
-            } while (g == gen);
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(gg) : "l"(bar + 1) : "memory");
+            } while (gg == gen);
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
     }
@@ -925,7 +941,7 @@ extern "C" int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_swe
     int grid = (int)(want < cap ? want : cap);
     if (grid < 1) grid = 1;
     // a launch that died inside a barrier must not poison the next one: start every launch from a clean counter pair
-    e = cudaMemsetAsync(barrier2, 0, 2 * sizeof(unsigned int), st);
+    e = cudaMemsetAsync(barrier2, 0, SDB_BARRIER_WORDS * sizeof(unsigned int), st);
     if (e != cudaSuccess) return (int)e;
     void* params[] = {&a};
     e = cudaLaunchCooperativeKernel((const void*)sinkhorn_persistent_kernel, dim3((unsigned)grid), dim3(NT), params, smem, st);
@@ -1001,7 +1017,7 @@ extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_
         if (grid < 1) grid = 1;
     }
     if (grid > SDB_SOLVE_MAX_CTAS) grid = SDB_SOLVE_MAX_CTAS;
-    e = cudaMemsetAsync(barrier2, 0, 2 * sizeof(unsigned int), st);
+    e = cudaMemsetAsync(barrier2, 0, SDB_BARRIER_WORDS * sizeof(unsigned int), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(result, 0, sizeof(sdb_solve_result), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(counters, 0, sizeof(unsigned int) * (size_t)((d->n + BM - 1) / BM + (d->m + BM - 1) / BM), st);
     if (e != cudaSuccess) return (int)e;

@@ -525,7 +525,7 @@ class CudaOps(VectorOps):
     def _persistent_plan(self, d):
         """Grid and column splits of the cooperative small-problem kernels: about one work item per CTA and pass."""
         if self._barrier is None:
-            self._barrier = torch.zeros(2, dtype=torch.int32, device=self.device)
+            self._barrier = torch.zeros(1024, dtype=torch.int32, device=self.device)      # SDB_BARRIER_WORDS
             self._n_sm = torch.cuda.get_device_properties(self.device).multi_processor_count
         d.n_ctas = self._n_sm * self.PERSISTENT_CTAS_PER_SM
         b_row, d.ns_row = self._persist_plan(self.n, self.m, d.n_ctas)
