@@ -272,6 +272,7 @@ typedef struct sdb_solve_result {
     int32_t max_iter_reached;    /* a stage gave up at max_iter (ref: ot_func.cpp:821-824) */
     int32_t last_tick;
     double gap, eps_final;
+    double stage_gap[6];         /* criterion value that ended each stage (stage 0-4: relative change, stage 5: duality gap) */
 } sdb_solve_result;
 int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_solve_params* p, int first_tick, int* flag2,
                                   unsigned int* barrier2, unsigned int* counters, double* scratch,

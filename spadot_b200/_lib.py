@@ -109,7 +109,8 @@ class SolveParams(ctypes.Structure):
 class SolveResult(ctypes.Structure):
     """struct sdb_solve_result"""
     _fields_ = [("iters", ctypes.c_int32 * 6), ("total_iters", ctypes.c_int32), ("status", ctypes.c_int32),
-                ("max_iter_reached", ctypes.c_int32), ("last_tick", ctypes.c_int32), ("gap", c_d), ("eps_final", c_d)]
+                ("max_iter_reached", ctypes.c_int32), ("last_tick", ctypes.c_int32), ("gap", c_d), ("eps_final", c_d),
+                ("stage_gap", c_d * 6)]
 
 
 SOLVE_MAX_CTAS = 1024

@@ -860,7 +860,7 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
             if (n_it >= a.max_iter) { status = 2; break; }                // ot_func.cpp:821-824
         }
         total += (int)n_it;
-        if (gtid == 0) a.result->iters[e] = (int)n_it;
+        if (gtid == 0) { a.result->iters[e] = (int)n_it; a.result->stage_gap[e] = gap; }
         if (status == 2) { status = 0; if (gtid == 0) a.result->max_iter_reached = 1; }        // gives up on the stage, keeps going
         if (gap != gap && final_stage) status = 1;       // a NaN ends its stage (ot_func.cpp:866); only the last one is fatal (:446)
     }

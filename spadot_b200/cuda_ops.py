@@ -191,7 +191,9 @@ class CudaOps(VectorOps):
     PERSISTENT_CTAS_PER_SM = int(os.environ.get("SDB_PERSISTENT_CTAS_PER_SM", "2"))
     FUSED_UPDATE = os.environ.get("SDB_TC_FUSED_UPDATE", "1") != "0"   # tensor-core native loop: pass + update in one kernel
     RESIDENT_TILES = os.environ.get("SDB_RESIDENT_TILES", "1") != "0"  # one-launch solve with the cost matrix resident on chip
-    RESIDENT_MAX_TILES_PER_CTA = 6
+    # measured r2 (profiles/r2_ch_time.txt): with 1-2 tiles per CTA the resident form wins (747 x 1966: 2.48 vs 2.83 ms per solve),
+    # with 4 the per-tile reductions cost more than the streamed form's dot products (1966 x 1916: 4.0 vs 3.45 ms)
+    RESIDENT_MAX_TILES_PER_CTA = 2
 
     def __init__(self, x_local, y, device=None, tc="auto"):
         self._init_vectors(device)

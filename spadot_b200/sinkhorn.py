@@ -296,12 +296,13 @@ def solve_duality_gap(ops, G_local, lambda1, lambda2, epsilon, batch_size=5, tol
                 raise RuntimeError("Overflow encountered in duality gap computation, please report this incident")
             if info is not None:
                 info.update(iters_per_stage=[int(v) for v in res.iters], total_iters=int(res.total_iters), gap=float(res.gap),
-                            epsilon_final=float(res.eps_final), max_iter_reached=bool(res.max_iter_reached))
+                            epsilon_final=float(res.eps_final), max_iter_reached=bool(res.max_iter_reached),
+                            stage_criteria=[float(v) for v in res.stage_gap])
             return st, float(res.eps_final)
     scale_factor = math.exp(-math.log(epsilon) / EPSILON_SCALINGS)
     eps_i = epsilon0 * scale_factor
     log_tau = math.log(tau)
-    iters, total, gap = [], 0, math.inf
+    iters, total, gap, crits = [], 0, math.inf, []
     hit_max_iter = False
     trace = _StageTrace(ops, profiling and dist.rank == 0)
     for e in range(EPSILON_SCALINGS + 1):
@@ -360,13 +361,15 @@ def solve_duality_gap(ops, G_local, lambda1, lambda2, epsilon, batch_size=5, tol
                 break
         iters.append(n_it)
         total += n_it
+        crits.append(float(gap))
         trace.end(e, n_it, gap)
     if math.isnan(gap):
         raise RuntimeError("Overflow encountered in duality gap computation, please report this incident")
     if not lr_known:
         ops.row_lse(st.g, eps_i, out=st.Lr)
     if info is not None:
-        info.update(iters_per_stage=iters, total_iters=total, gap=float(gap), epsilon_final=eps_i, max_iter_reached=hit_max_iter)
+        info.update(iters_per_stage=iters, total_iters=total, gap=float(gap), epsilon_final=eps_i, max_iter_reached=hit_max_iter,
+                    stage_criteria=crits)
     return st, eps_i
 
 
