@@ -215,6 +215,7 @@ def gpu_main(a):
     if world > 1:
         td.init_process_group("nccl", device_id=dev)
     dist = sinkhorn.Dist(enabled=world > 1)
+    dist.native_comm(dev)          # the library's own NCCL communicator (multi-rank native loop): create it outside any timed region
 
     # rows partitioned across ranks; identical RNG stream on every rank
     r0, r1 = (a.n * rank) // world, (a.n * (rank + 1)) // world

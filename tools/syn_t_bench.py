@@ -67,6 +67,34 @@ def main(argv=None):
     losses = [step(b) for b in batches[1:]]
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / n_batches
+    # where the step goes: device time by kernel family over one more step (torch.profiler, CUDA activities)
+    breakdown = None
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step(batches[1])
+            torch.cuda.synchronize()
+        fam = {}
+        for ev in prof.key_averages():
+            name, t = ev.key, getattr(ev, "device_time_total", None) or getattr(ev, "cuda_time_total", 0.0)
+            low = name.lower()
+            if "gat_" in low:
+                k = "gat edge-softmax / aggregation kernels (K2/K2b)"
+            elif any(w in low for w in ("gemm", "cutlass", "xmma", "cublas", "gemv")):
+                k = "dense GEMMs (cuBLAS fp64: GAT lin layers, MLPs, SVGP algebra)"
+            elif any(w in low for w in ("kernel_block", "quad_form", "kernel_diag")):
+                k = "SVGP kernel blocks (K1)"
+            elif any(w in low for w in ("cusolver", "potrf", "trsm", "getrf", "syrk", "laswp", "inverse")):
+                k = "factorisations (cuSOLVER / MAGMA)"
+            elif "memcpy" in low or "memset" in low:
+                k = "copies / memsets"
+            else:
+                k = "elementwise / reductions / indexing (torch)"
+            fam[k] = fam.get(k, 0.0) + float(t)
+        tot = sum(fam.values())
+        breakdown = {k: dict(ms=v / 1e3, share=v / tot) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}
+    except Exception as exc:
+        breakdown = dict(error=repr(exc)[:200])
     sub_nodes = int(np.mean([b[0].numel() for b in batches[1:]]))
     sub_edges = int(np.mean([b[1].shape[1] for b in batches[1:]]))
     # full-timepoint inference (all_latent_samples) without n x n temporaries
@@ -79,7 +107,8 @@ def main(argv=None):
     print(json.dumps(dict(workload=f"{a.name} one timepoint: {n} spots x {genes} genes, z={z}, {m_ind} inducing, k=30, fp64",
                           graph_build_s=t_graph, sample_batch_s=t_sample, subgraph_nodes=sub_nodes, subgraph_edges=sub_edges,
                           train_step_s=dt, seeds_per_s=512 / dt, losses=losses, all_latent_samples_s=t_inf,
-                          latent_shape=list(lat.shape), peak_mem_gb=torch.cuda.max_memory_allocated() / 1e9)))
+                          latent_shape=list(lat.shape), peak_mem_gb=torch.cuda.max_memory_allocated() / 1e9,
+                          step_breakdown_device_time=breakdown)))
 
 
 if __name__ == "__main__":
