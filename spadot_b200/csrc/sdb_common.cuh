@@ -147,6 +147,30 @@ __device__ __forceinline__ void sdb_prediction_out(double M, double S, int64_t i
 __device__ __forceinline__ double sdb_combine_partials(const float2* partial, int n_splits, int64_t n, int64_t i, double norm_c1,
                                                        float* m_next = nullptr, int* bad_flag = nullptr) {
     double M = -INFINITY;
+    if (n_splits <= 8) {
+        // all partials of the row in flight at once (one L2 round trip instead of 2*n_splits dependent ones: this combine sits on
+        // the serial tail of every fused pass + update launch)
+        float2 pv[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) pv[s] = (s < n_splits) ? __ldcg(partial + (int64_t)s * n + i) : make_float2(SDB_NEG_SENTINEL, 0.f);
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            any |= (s < n_splits) && (pv[s].x > -1e29f);
+            if (pv[s].x > -1e29f && pv[s].y > 0.f) M = fmax(M, (double)pv[s].x);
+        }
+        if (!(M > -INFINITY)) {
+            if (m_next) m_next[i] = 0.0f;
+            if (bad_flag && any) atomicOr(bad_flag, 1);
+            return -INFINITY;
+        }
+        double S = 0.0;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+            if (pv[s].x > -1e29f && pv[s].y > 0.f) S += (double)pv[s].y * exp2((double)pv[s].x - M);
+        sdb_prediction_out(M, S, i, m_next, bad_flag);
+        return SDB_LN2 * (M + log2(S)) - norm_c1;
+    }
     for (int s = 0; s < n_splits; ++s) {
         const float2 ps = __ldcg(partial + (int64_t)s * n + i);      // L2: written by other CTAs (possibly of this very kernel)
         if (ps.x > -1e29f && ps.y > 0.f) M = fmax(M, (double)ps.x);
