@@ -89,7 +89,7 @@ class SpaDOT(nn.Module):
         SVGP_KL = -torch.abs(diff) / self.SVGP_z_dim          # SpaDOT.py:77 without the .item() round trip
         SVGP_latent_sample = p_m + self.noise_fn(p_m) * torch.sqrt(p_v)
 
-        GAT_m, GAT_v = self.GATEncoder(y, edge_index)
+        GAT_m, GAT_v = self.GATEncoder(y, edge_index, pos=x)
         GAT_m, GAT_v = GAT_m[:batch_size, :], GAT_v[:batch_size, :]
         GAT_latent_sample = GAT_m + self.noise_fn(GAT_m) * torch.sqrt(GAT_v)
         GAT_KL = -0.5 * torch.sum(1 + torch.log(GAT_v) - GAT_m.pow(2) - GAT_v) / self.GAT_z_dim
@@ -107,7 +107,7 @@ class SpaDOT(nn.Module):
         edge_index = torch.as_tensor(edge_index, dtype=torch.long, device=self.device)
         q_mu, q_var = self.SVGPEncoder(Y)
         p_m, _, _, _ = self.svgp_dict[str(tp)].posterior_and_loss_all_dims(X, q_mu, q_var)
-        GAT_m, _ = self.GATEncoder(Y, edge_index)
+        GAT_m, _ = self.GATEncoder(Y, edge_index, pos=X)
         return torch.cat((p_m, GAT_m), dim=1).data.cpu().detach().numpy()
 
     def _gauss_cross_entropy(self, mu1, var1, mu2, var2):

@@ -118,3 +118,38 @@ def test_gat_large_graph_with_locality_order_matches_oracle():
     out_r.sum().backward()
     out_m.sum().backward()
     np.testing.assert_allclose(xm.grad.cpu().numpy(), xr.grad.numpy(), rtol=1e-9, atol=1e-12)
+
+
+def test_morton_order_is_a_permutation_with_locality():
+    """The coordinate hint's Z-curve order: a permutation, and consecutive nodes are spatial neighbours."""
+    from spadot_b200 import gat
+    torch.manual_seed(0)
+    pos = torch.rand(5000, 2, dtype=torch.float64)
+    order = gat.morton_order(pos).long()
+    assert sorted(order.tolist()) == list(range(5000))
+    hop = (pos[order][1:] - pos[order][:-1]).norm(dim=1).mean()
+    assert hop < 0.2 * (pos[1:] - pos[:-1]).norm(dim=1).mean()
+    assert gat.morton_order(torch.zeros(7, 2)).numel() == 7                   # degenerate extent
+
+
+@pytest.mark.gpu
+def test_gat_coordinate_hint_orders_ctas_on_device_and_keeps_results():
+    """With `pos` the CTA order is the device-side Z-curve (no host round trip); outputs and gradients equal the unhinted run."""
+    from spadot_b200 import gat
+    dev = torch.device("cuda:0")
+    n = 21000
+    ei = make_graph(n, seed=5).to(dev)
+    torch.manual_seed(3)
+    conv = gat.GATConv(16, 8, heads=2).double().to(dev)
+    pos = torch.rand(n, 2, dtype=torch.float64, device=dev)
+    x = torch.randn(n, 16, dtype=torch.float64, device=dev)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ei_a, ei_b = ei.clone(), ei.clone()
+    out_a, out_b = conv(xa, ei_a), conv(xb, ei_b, pos)
+    ga, gb = gat.graph_for(ei_a, n), gat.graph_for(ei_b, n)
+    assert ga.order is not None and gb.order is not None and not torch.equal(ga.order, gb.order)
+    assert torch.equal(gb.order, gat.morton_order(pos))
+    assert torch.equal(out_a, out_b)
+    out_a.square().sum().backward()
+    out_b.square().sum().backward()
+    np.testing.assert_allclose(xb.grad.cpu().numpy(), xa.grad.cpu().numpy(), rtol=1e-12, atol=1e-14)
