@@ -25,6 +25,7 @@ def main(argv=None):
     ap.add_argument("--inducing", type=int, default=150)
     ap.add_argument("--batches", type=int, default=4)
     ap.add_argument("--name", default="SYN-T")
+    ap.add_argument("--host-profile", action="store_true", help="cProfile one more step and print the top host-side entries to stderr")
     a = ap.parse_args(argv)
     dev = torch.device("cuda:0")
     n, genes, z, m_ind, n_batches = a.n, a.genes, a.z, a.inducing, a.batches
@@ -95,6 +96,17 @@ def main(argv=None):
         breakdown = {k: dict(ms=v / 1e3, share=v / tot) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}
     except Exception as exc:
         breakdown = dict(error=repr(exc)[:200])
+    if a.host_profile:
+        import cProfile
+        import pstats
+        from spadot_b200 import gat
+        gat._GRAPH_CACHE.clear()                       # like a fresh batch of the loader: the sub-graph is built inside the step
+        pr = cProfile.Profile()
+        pr.enable()
+        step(batches[2 % len(batches)])
+        torch.cuda.synchronize()
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(45)
     sub_nodes = int(np.mean([b[0].numel() for b in batches[1:]]))
     sub_edges = int(np.mean([b[1].shape[1] for b in batches[1:]]))
     # full-timepoint inference (all_latent_samples) without n x n temporaries
