@@ -448,7 +448,9 @@ def test_whole_solve_in_one_launch_matches_host_stage_loop(ot, n, m, d, tau, res
     assert c1.info["gap"] == pytest.approx(c2.info["gap"], rel=0.05, abs=1e-12)      # a 1e-10 difference of O(1) sums of fp32-tile results
     # fp32-noise level: the host loop's gap-check row pass uses the launch path's column splits, the one-launch solve the
     # cooperative grid's, so their fp32 partial sums differ in the last bit (6e-8 on an LSE, 2e-9 on a potential)
-    for name, tol in (("f", 4e-7), ("g", 4e-7), ("u", 4e-7), ("v", 4e-7), ("Lr", 1e-6), ("Lc", 1e-6)):
+    # (a single-term LSE is the fp32 rounding of t itself: half an ulp of |t| ~ 120 is 4e-6)
+    lse_tol = 1e-6 if n * m > 1024 else 1e-5
+    for name, tol in (("f", 4e-7), ("g", 4e-7), ("u", 4e-7), ("v", 4e-7), ("Lr", lse_tol), ("Lc", lse_tol)):
         x, y = getattr(c1.state, name), getattr(c2.state, name)
         assert float((x - y).abs().max()) < tol * max(1.0, float(y.abs().max())), name      # relative to the vector's magnitude
 

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--full-sweep", action="store_true")
     ap.add_argument("--grid", action="store_true", help="SURVEY 8d grid: eps {0.01,0.02,0.05,0.1} x 4 lambda pairs")
     ap.add_argument("--max-iter", type=float, default=3000)
+    ap.add_argument("--repeat", type=int, default=1, help="solve every setting this many times (first-use effects show as a slower first line)")
     ap.add_argument("--stages", action="store_true", help="print the per-stage times (the reference's profiling switch)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -73,7 +74,7 @@ def main():
         settings += [(0.05, 1.0, 50.0), (0.01, 0.1, 5.0), (0.1, 1.0, 1.0)]
     if a.grid:
         settings = [(e, l1, l2) for e in (0.01, 0.02, 0.05, 0.1) for l1, l2 in ((0.1, 5.0), (1.0, 1.0), (1.0, 50.0), (50.0, 50.0))]
-    for eps, l1, l2 in settings:
+    for eps, l1, l2 in [s_ for s_ in settings for _ in range(a.repeat)]:
         cfg = dict(ot_solvers.default_config, epsilon=eps, lambda1=l1, lambda2=l2, tau=1000.0, max_iter=a.max_iter, profiling=a.stages)
         torch.cuda.synchronize()
         if world > 1:
