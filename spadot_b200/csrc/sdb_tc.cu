@@ -140,8 +140,8 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
 __device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
     float x0, x1;
     unpack2(x2, x0, x1);
-    x0 = fmaxf(x0, -126.f);
-    x1 = fmaxf(x1, -126.f);
+    x0 = fminf(fmaxf(x0, -126.f), 127.f);                          // (an exponent above 127 must stay huge, not wrap: the
+    x1 = fminf(fmaxf(x1, -126.f), 127.f);                          //  predicted-stabiliser range check relies on it)
     x2 = pack2(x0, x1);
     const uint64_t magic = pack2(12582912.f, 12582912.f);        // 1.5 * 2^23: rounds to nearest integer
     const uint64_t r2 = fadd2(x2, magic);
@@ -676,9 +676,14 @@ lse_pass_tc_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
                         uint64_t acc2[CH / 2];
 #pragma unroll
                         for (int k = 0; k < CH / 2; ++k) {                     // SFU stage of chunk c
-                            float a0, a1;
-                            unpack2(fadd2(tv2[c & 1][k], nm2), a0, a1);
-                            acc2[k] = pack2(sdb_ex2(a0), sdb_ex2(a1));
+                            const uint64_t x2 = fadd2(tv2[c & 1][k], nm2);
+                            if (POLY_EVERY > 0 && (k % POLY_EVERY) == POLY_EVERY - 1) {
+                                acc2[k] = exp2_poly2(x2);                      // development knob: this pair on the FMA pipe
+                            } else {
+                                float a0, a1;
+                                unpack2(x2, a0, a1);
+                                acc2[k] = pack2(sdb_ex2(a0), sdb_ex2(a1));
+                            }
                         }
 #pragma unroll
                         for (int w = CH / 4; w > 0; w >>= 1)
@@ -933,6 +938,12 @@ int launch_tc(const CUtensorMap& tmP, const CUtensorMap& tmQ, const TcArgs& a, i
         static int runsum = -1;          // development knob SDB_TC_RUNSUM=1: running sums instead of the per-chunk reduction tree
                                          // (measured r2: 0.793 vs 0.809 of the SFU peak at 131072^2 - not adopted)
         if (runsum < 0) { const char* e = getenv("SDB_TC_RUNSUM"); runsum = (e && *e == '1') ? 1 : 0; }
+        static int poly = -1;            // development knob SDB_TC_POLY=4|8|16: every 4th/8th/16th pair of exponentials by the
+                                         // FMA-pipe polynomial inside the pipelined predicted pass
+        if (poly < 0) { const char* e = getenv("SDB_TC_POLY"); poly = e ? atoi(e) : 0; }
+        if (poly == 4) return launch_tc_v<DP, 8, true, 4, true, false, true, false>(tmP, tmQ, a, n_ctas, st);
+        if (poly == 8) return launch_tc_v<DP, 8, true, 8, true, false, true, false>(tmP, tmQ, a, n_ctas, st);
+        if (poly == 16) return launch_tc_v<DP, 8, true, 16, true, false, true, false>(tmP, tmQ, a, n_ctas, st);
         return runsum ? launch_tc_v<DP, 8, true, 0, true, false, true, true>(tmP, tmQ, a, n_ctas, st)
                       : launch_tc_v<DP, 8, true, 0, true, false, true, false>(tmP, tmQ, a, n_ctas, st);
     }

@@ -55,8 +55,10 @@ def main():
     r0, r1 = (a.n * rank) // world, (a.n * (rank + 1)) // world
     x = x[r0:r1]
     # untimed warm-up on a slice (first-use costs: allocator growth, kernel attributes, the library's NCCL communicator)
+    # ALL columns: the per-iteration all-reduce then has the message size of the timed solve; at 8 ranks the first collectives of
+    # a new size class cost 0.1-1.5 s once per process (profiles/r2_sweep250k_x3_8gpu.jsonl: 1.73 s, then 0.433 s, 0.433 s)
     nw = max(4096, min(a.n, 32768))
-    xw, yw = x[:max(1, nw // world)], y[:nw]
+    xw, yw = x[:max(1, nw // world)], y
     ot_solvers.solve_coupling(xw, yw, dict(ot_solvers.default_config, epsilon=0.05, lambda1=0.1, lambda2=5.0, tau=1000.0),
                               ops=CudaOps(xw, yw), dist=dist, median=160.0)
     if world > 1:
