@@ -416,6 +416,18 @@ int sdb_gat_backward(const void* feat, const void* a_src, const void* a_dst, con
                      int64_t n, int H, int C, double negative_slope, int is_double, const void* alpha,
                      const void* grad_out, void* dlogit, void* grad_feat, void* grad_a_src, void* grad_a_dst,
                      void* stream);
+/* The same backward for a layer whose destinations are the first n_dst nodes of a graph with n_src >= n_dst source nodes
+ * (hop-ordered mini-batches: seeds first, then the nodes each hop adds; ref: utils/_train_utils.py:80-85 NeighborLoader order,
+ * model/SpaDOT.py:83-84 only rows [:batch_size] of the encoder output are used).  rowptr / col are the by-destination CSR of the
+ * WHOLE batch graph: its first rowptr[n_dst] edges are exactly the layer's edges, so nothing is rebuilt; the by-source lists
+ * (also of the whole graph) are filtered on the fly with src_eid < rowptr[n_dst].  order_dst permutes [0,n_dst), order_src
+ * [0,n_src) (either may be NULL).  feat/a_src/grad_feat/grad_a_src have n_src rows, a_dst/grad_out/grad_a_dst n_dst rows.
+ * sdb_gat_forward serves this form unchanged with n = n_dst. */
+int sdb_gat_backward_prefix(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
+                            const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, const int32_t* order_dst,
+                            const int32_t* order_src, int64_t n_dst, int64_t n_src, int H, int C, double negative_slope,
+                            int is_double, const void* alpha, const void* grad_out, void* dlogit, void* grad_feat,
+                            void* grad_a_src, void* grad_a_dst, void* stream);
 
 /* k nearest OTHER points (self excluded) of every point, sorted by (distance, index); pts (n,dim) fp64, dim <= 3,
  * k <= 32 and k <= n-1.  out_idx (n,k) int32, out_dist (n,k) fp64 Euclidean distances (may be NULL).

@@ -80,6 +80,8 @@ SIGNATURES = {
     "sdb_knn_grid_f64": [c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_d, c_d, c_i, c_p, c_p, c_p],
     "sdb_pipe_peak": [c_i, c_i, c_i, c_p, c_p, c_p],
     "sdb_gat_backward": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
+    "sdb_gat_backward_prefix": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p,
+                                c_p, c_p],
 }
 
 class SweepDesc(ctypes.Structure):

@@ -172,11 +172,15 @@ __global__ void __launch_bounds__(128) gat_bwd_dst_kernel(const T* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restrict__ src_rowptr, const int32_t* __restrict__ src_dst,
                                                           const int32_t* __restrict__ src_eid, const int32_t* __restrict__ order,
-                                                          int64_t n, int H, int C, const T* __restrict__ alpha,
+                                                          const int64_t* __restrict__ e_limit_ptr, int H, int C,
+                                                          const T* __restrict__ alpha,
                                                           const T* __restrict__ dlogit, const T* __restrict__ grad_out,
                                                           T* __restrict__ grad_feat, T* __restrict__ grad_a_src) {
     const int64_t j = order ? order[blockIdx.x] : blockIdx.x;
     const int64_t p0 = src_rowptr[j], p1 = src_rowptr[j + 1];
+    // prefix form: only the edges into the first n_dst destinations exist for this layer; in the by-destination order they
+    // are the edge ids below rowptr[n_dst] (*e_limit_ptr), so the full by-source lists are filtered instead of rebuilt
+    const int64_t e_limit = *e_limit_ptr;
     const int HC = H * C;
     constexpr int W = Vec<T>::W;
     if (C % W == 0) {
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restr
 #pragma unroll
             for (int q = 0; q < W; ++q) acc[q] = T(0);
             for (int64_t p = p0; p < p1; ++p) {
+                if (src_eid[p] >= e_limit) continue;
                 const T a = alpha[(int64_t)src_eid[p] * H + h];
                 T v[W];
                 vec_load(grad_out + (int64_t)src_dst[p] * HC + c, v);
@@ -198,13 +203,15 @@ __global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restr
         for (int c = threadIdx.x; c < HC; c += 128) {
             const int h = c / C;
             T acc = T(0);
-            for (int64_t p = p0; p < p1; ++p) acc += alpha[(int64_t)src_eid[p] * H + h] * grad_out[(int64_t)src_dst[p] * HC + c];
+            for (int64_t p = p0; p < p1; ++p)
+                if (src_eid[p] < e_limit) acc += alpha[(int64_t)src_eid[p] * H + h] * grad_out[(int64_t)src_dst[p] * HC + c];
             grad_feat[j * HC + c] = acc;
         }
     }
     for (int h = threadIdx.x; h < H; h += 128) {
         T acc = T(0);
-        for (int64_t p = p0; p < p1; ++p) acc += dlogit[(int64_t)src_eid[p] * H + h];
+        for (int64_t p = p0; p < p1; ++p)
+            if (src_eid[p] < e_limit) acc += dlogit[(int64_t)src_eid[p] * H + h];
         grad_a_src[j * H + h] = acc;
     }
 }
@@ -219,15 +226,17 @@ int gat_forward_t(const void* feat, const void* a_src, const void* a_dst, const 
 
 template <typename T>
 int gat_backward_t(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
-                   const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, const int32_t* order, int64_t n, int H,
-                   int C, double slope, const void* alpha, const void* grad_out, void* dlogit, void* grad_feat, void* grad_a_src,
-                   void* grad_a_dst, cudaStream_t st) {
-    gat_bwd_dst_kernel<T><<<(unsigned)n, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order, n, H, C,
-                                                      (T)slope, (const T*)alpha, (const T*)grad_out, (T*)dlogit, (T*)grad_a_dst);
+                   const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, const int32_t* order_dst,
+                   const int32_t* order_src, int64_t n_dst, int64_t n_src, int H, int C, double slope, const void* alpha,
+                   const void* grad_out, void* dlogit, void* grad_feat, void* grad_a_src, void* grad_a_dst, cudaStream_t st) {
+    gat_bwd_dst_kernel<T><<<(unsigned)n_dst, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst,
+                                                          n_dst, H, C, (T)slope, (const T*)alpha, (const T*)grad_out, (T*)dlogit,
+                                                          (T*)grad_a_dst);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    gat_bwd_src_kernel<T><<<(unsigned)n, 128, 0, st>>>(src_rowptr, src_dst, src_eid, order, n, H, C, (const T*)alpha,
-                                                      (const T*)dlogit, (const T*)grad_out, (T*)grad_feat, (T*)grad_a_src);
+    gat_bwd_src_kernel<T><<<(unsigned)n_src, 128, 0, st>>>(src_rowptr, src_dst, src_eid, order_src, rowptr + n_dst, H, C,
+                                                          (const T*)alpha, (const T*)dlogit, (const T*)grad_out, (T*)grad_feat,
+                                                          (T*)grad_a_src);
     SDB_LAUNCH_STATUS();
 }
 
@@ -245,6 +254,24 @@ int sdb_gat_forward(const void* feat, const void* a_src, const void* a_dst, cons
                      : gat_forward_t<float>(feat, a_src, a_dst, rowptr, col, node_order, n, H, C, negative_slope, out, alpha, sdb_stream(stream));
 }
 
+int sdb_gat_backward_prefix(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
+                            const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, const int32_t* order_dst,
+                            const int32_t* order_src, int64_t n_dst, int64_t n_src, int H, int C, double negative_slope,
+                            int is_double, const void* alpha, const void* grad_out, void* dlogit, void* grad_feat,
+                            void* grad_a_src, void* grad_a_dst, void* stream) {
+    SDB_CHECK_ARG(feat && a_src && a_dst && rowptr && col && src_rowptr && src_dst && src_eid && alpha && grad_out && dlogit &&
+                  grad_feat && grad_a_src && grad_a_dst && n_dst >= 0 && n_src >= n_dst && H > 0 && C > 0);
+    if (n_src == 0) return 0;
+    if (n_src > 2147483647LL) return SDB_E_UNSUPPORTED;
+    if (n_dst == 0) return SDB_E_INVALID;                 // a layer without destinations has no backward
+    return is_double ? gat_backward_t<double>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, order_dst, order_src,
+                                              n_dst, n_src, H, C, negative_slope, alpha, grad_out, dlogit, grad_feat, grad_a_src,
+                                              grad_a_dst, sdb_stream(stream))
+                     : gat_backward_t<float>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, order_dst, order_src,
+                                             n_dst, n_src, H, C, negative_slope, alpha, grad_out, dlogit, grad_feat, grad_a_src,
+                                             grad_a_dst, sdb_stream(stream));
+}
+
 int sdb_gat_backward(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
                      const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, const int32_t* node_order, int64_t n,
                      int H, int C, double negative_slope, int is_double, const void* alpha, const void* grad_out, void* dlogit,
@@ -252,11 +279,8 @@ int sdb_gat_backward(const void* feat, const void* a_src, const void* a_dst, con
     SDB_CHECK_ARG(feat && a_src && a_dst && rowptr && col && src_rowptr && src_dst && src_eid && alpha && grad_out && dlogit &&
                   grad_feat && grad_a_src && grad_a_dst && n >= 0 && H > 0 && C > 0);
     if (n == 0) return 0;
-    if (n > 2147483647LL) return SDB_E_UNSUPPORTED;
-    return is_double ? gat_backward_t<double>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, node_order, n, H, C,
-                                              negative_slope, alpha, grad_out, dlogit, grad_feat, grad_a_src, grad_a_dst, sdb_stream(stream))
-                     : gat_backward_t<float>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, node_order, n, H, C,
-                                             negative_slope, alpha, grad_out, dlogit, grad_feat, grad_a_src, grad_a_dst, sdb_stream(stream));
+    return sdb_gat_backward_prefix(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, node_order, node_order, n, n, H, C,
+                                   negative_slope, is_double, alpha, grad_out, dlogit, grad_feat, grad_a_src, grad_a_dst, stream);
 }
 
 }  // extern "C"

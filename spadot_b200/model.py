@@ -89,7 +89,8 @@ class SpaDOT(nn.Module):
         SVGP_KL = -torch.abs(diff) / self.SVGP_z_dim          # SpaDOT.py:77 without the .item() round trip
         SVGP_latent_sample = p_m + self.noise_fn(p_m) * torch.sqrt(p_v)
 
-        GAT_m, GAT_v = self.GATEncoder(y, edge_index, pos=x)
+        # only the seeds' rows are used (SpaDOT.py:83-84): the encoder computes each layer on the rows the next one reads
+        GAT_m, GAT_v = self.GATEncoder(y, edge_index, pos=x, n_out=batch_size)
         GAT_m, GAT_v = GAT_m[:batch_size, :], GAT_v[:batch_size, :]
         GAT_latent_sample = GAT_m + self.noise_fn(GAT_m) * torch.sqrt(GAT_v)
         GAT_KL = -0.5 * torch.sum(1 + torch.log(GAT_v) - GAT_m.pow(2) - GAT_v) / self.GAT_z_dim

@@ -153,3 +153,45 @@ def test_gat_coordinate_hint_orders_ctas_on_device_and_keeps_results():
     out_a.square().sum().backward()
     out_b.square().sum().backward()
     np.testing.assert_allclose(xb.grad.cpu().numpy(), xa.grad.cpu().numpy(), rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("hop_ordered", [True, False])
+def test_gat_encoder_seed_rows_only_equals_full_run(hop_ordered):
+    """GATEncoder(n_out=seeds) runs every layer on the rows the next one reads (prefix form of the kernels): the seeds' outputs
+    and every parameter gradient equal the full run's; with hop-ordered nodes the prefixes are the hop sets, with arbitrary
+    numbering they degrade to (correct) supersets."""
+    from spadot_b200 import gat, graph
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(11)
+    n_all, bs = 6000, 64
+    coords = rng.uniform(0, 100, size=(n_all, 2))
+    ei_all = graph.spatial_edge_index(coords, 8, device=dev)
+    nodes, lei, ns = next(iter(graph.two_hop_batches(ei_all, n_all, batch_size=bs)))
+    n = nodes.numel()
+    if not hop_ordered:                                  # scramble the non-seed numbering
+        perm = torch.cat([torch.arange(ns), ns + torch.from_numpy(rng.permutation(n - ns))]).to(dev)
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(n, device=dev)
+        lei = inv[lei]
+    torch.manual_seed(5)
+    enc = gat.GATEncoder(40, 6, hidden_dim=16, num_heads=4).double().to(dev)
+    x = torch.randn(n, 40, dtype=torch.float64, device=dev)
+    g = gat.graph_for(lei, n, True)
+    plan = g.prefix_plan(ns, 3)
+    assert plan[-1][0] == ns and all(d <= s for d, s in plan) and plan[0][1] <= n
+    if hop_ordered:
+        assert plan[2][1] < n // 2 and plan[1][1] == n          # 1-hop prefix for the last layer, everything below it
+    res = []
+    for n_out in (None, ns):
+        enc.zero_grad()
+        mu, var = enc(x, lei, n_out=n_out)
+        ((mu[:ns] ** 2).sum() + var[:ns].sum()).backward()
+        res.append((mu[:ns].detach().clone(), var[:ns].detach().clone(), [p.grad.clone() for p in enc.parameters()]))
+    (mu_a, var_a, ga), (mu_b, var_b, gb) = res
+    assert mu_b.shape == (ns, 6)
+    np.testing.assert_allclose(mu_b.cpu().numpy(), mu_a.cpu().numpy(), rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(var_b.cpu().numpy(), var_a.cpu().numpy(), rtol=1e-11, atol=1e-13)
+    for a, b in zip(ga, gb):
+        scale = float(a.abs().max()) + 1e-30
+        assert float((a - b).abs().max()) <= 1e-11 * scale
