@@ -362,6 +362,12 @@ int sdb_cost_collect_tc(const void* p16, int64_t n_p, int64_t n_p_pad, const voi
  * (key = IEEE bits of a non-negative double); one radix-select digit. hist256 must be zeroed. */
 int sdb_radix_digit_hist(const double* cand, unsigned long long n, int shift, unsigned long long prefix,
                          unsigned long long* hist256, void* stream);
+/* out[s] (device) = the ranks[s]-th smallest (0-based; ranks is a HOST array of n_ranks = 1 or 2 values) of the n non-negative
+ * doubles cand[] - the two middle order statistics np.median averages (ref: ot_solvers.py:103).  Eight radix-256 digit passes
+ * issued back to back on `stream`, no host round trip in between.  workspace: SDB_SELECT_WORKSPACE_BYTES of device memory. */
+#define SDB_SELECT_WORKSPACE_BYTES 4128
+int sdb_select_ranks_f64(const double* cand, unsigned long long n, const unsigned long long* ranks, int n_ranks, double* out,
+                         void* workspace, void* stream);
 
 /* ------------------------------------------------------------------ K6: domain transition table */
 /* table[a*k1+b] += sum_{i: label_row[i]=a} exp(f_i/eps + ln2*(M + log2 S) - norms_i*c1) * inv_m

@@ -64,6 +64,7 @@ SIGNATURES = {
     "sdb_cost_histogram_tc": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_p, c_f, c_i, c_i, c_f, c_f, c_i, c_p, c_p, c_p],
     "sdb_cost_collect_tc": [c_p, c_l, c_l, c_p, c_l, c_l, c_i, c_p, c_p, c_f, c_i, c_i, c_f, c_f, c_p, c_p, c_i, c_p, c_u, c_p, c_p],
     "sdb_radix_digit_hist": [c_p, c_u, c_i, c_u, c_p, c_p],
+    "sdb_select_ranks_f64": [c_p, c_u, c_p, c_i, c_p, c_p, c_p],
     "sdb_transition_accumulate": [c_p, c_i, c_l, c_p, c_d, c_p, c_d, c_d, c_p, c_i, c_p, c_p],
     "sdb_dense_row_lse_f64": [c_p, c_l, c_l, c_l, c_p, c_d, c_p, c_p],
     "sdb_dense_col_lse_f64": [c_p, c_l, c_l, c_l, c_p, c_d, c_p, c_p, c_i, c_p],

@@ -312,6 +312,75 @@ __global__ void radix_digit_hist_kernel(const double* __restrict__ cand, unsigne
     if (sh[threadIdx.x]) atomicAdd(hist256 + threadIdx.x, (unsigned long long)sh[threadIdx.x]);
 }
 
+// Radix select of up to two order statistics without host round trips: eight (histogram, digit) kernel pairs on one stream.
+// state: prefix[2], remaining[2], hist[2][256] (device).  Same digit rule as the host loop it replaces
+// (sinkhorn._select_rank: digit = #{b : cumsum(hist)[b] <= remaining}).
+struct SelectState {
+    unsigned long long prefix[2];
+    unsigned long long remaining[2];
+    unsigned long long hist[2][256];
+};
+
+__global__ void select_init_kernel(SelectState* st, unsigned long long k0, unsigned long long k1) {
+    const int t = threadIdx.x;
+    st->hist[0][t] = 0ull;
+    st->hist[1][t] = 0ull;
+    if (t == 0) { st->prefix[0] = st->prefix[1] = 0ull; st->remaining[0] = k0; st->remaining[1] = k1; }
+}
+
+__global__ void select_hist_kernel(const double* __restrict__ cand, unsigned long long n, int shift, int n_ranks,
+                                   SelectState* __restrict__ st) {
+    __shared__ unsigned int sh[2][256];
+    sh[0][threadIdx.x] = 0;
+    sh[1][threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned long long p0 = st->prefix[0], p1 = st->prefix[1];
+    const bool same = n_ranks < 2 || p0 == p1;          // the two ranks usually share every digit but the last ones
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(cand[i]);
+        const unsigned long long hi = (shift >= 56) ? 0ull : (key >> (shift + 8));
+        const unsigned int b = (unsigned int)((key >> shift) & 255ull);
+        if (hi == p0) atomicAdd(&sh[0][b], 1u);
+        if (!same && hi == p1) atomicAdd(&sh[1][b], 1u);
+    }
+    __syncthreads();
+    if (sh[0][threadIdx.x]) {
+        atomicAdd(&st->hist[0][threadIdx.x], (unsigned long long)sh[0][threadIdx.x]);
+        if (same && n_ranks > 1) atomicAdd(&st->hist[1][threadIdx.x], (unsigned long long)sh[0][threadIdx.x]);
+    }
+    if (!same && sh[1][threadIdx.x]) atomicAdd(&st->hist[1][threadIdx.x], (unsigned long long)sh[1][threadIdx.x]);
+}
+
+__global__ void select_digit_kernel(SelectState* st, int shift, int n_ranks, double* __restrict__ out) {
+    __shared__ unsigned long long cs[256];
+    __shared__ unsigned int digit_s;
+    const int t = threadIdx.x;
+    for (int s = 0; s < n_ranks; ++s) {
+        cs[t] = st->hist[s][t];
+        if (t == 0) digit_s = 0u;
+        __syncthreads();
+        for (int o = 1; o < 256; o <<= 1) {                       // inclusive scan
+            const unsigned long long v = t >= o ? cs[t - o] : 0ull;
+            __syncthreads();
+            cs[t] += v;
+            __syncthreads();
+        }
+        const unsigned long long rem = st->remaining[s];
+        if (cs[t] <= rem) atomicAdd(&digit_s, 1u);
+        __syncthreads();
+        const unsigned int digit = digit_s < 255u ? digit_s : 255u;
+        if (t == 0) {
+            st->remaining[s] = rem - (digit > 0 ? cs[digit - 1] : 0ull);
+            const unsigned long long p = (st->prefix[s] << 8) | (unsigned long long)digit;
+            st->prefix[s] = p;
+            if (shift == 0) out[s] = __longlong_as_double((long long)p);
+        }
+        st->hist[s][t] = 0ull;
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------ transition table
 __global__ void transition_accumulate_kernel(const float2* __restrict__ partial, int k1, int64_t n,
                                              const double* __restrict__ norms, double c1, const double* __restrict__ f,
@@ -531,6 +600,22 @@ int sdb_radix_digit_hist(const double* cand, unsigned long long n, int shift, un
     unsigned grid = (unsigned)((n + 256 * 16 - 1) / (256 * 16));
     if (grid > 1184) grid = 1184;
     radix_digit_hist_kernel<<<grid, 256, 0, sdb_stream(stream)>>>(cand, n, shift, prefix, hist256);
+    SDB_LAUNCH_STATUS();
+}
+
+int sdb_select_ranks_f64(const double* cand, unsigned long long n, const unsigned long long* ranks, int n_ranks, double* out,
+                         void* workspace, void* stream) {
+    SDB_CHECK_ARG(cand && ranks && out && workspace && n > 0 && (n_ranks == 1 || n_ranks == 2));
+    for (int s = 0; s < n_ranks; ++s) SDB_CHECK_ARG(ranks[s] < n);
+    cudaStream_t st = sdb_stream(stream);
+    SelectState* state = reinterpret_cast<SelectState*>(workspace);
+    select_init_kernel<<<1, 256, 0, st>>>(state, ranks[0], n_ranks > 1 ? ranks[1] : ranks[0]);
+    unsigned grid = (unsigned)((n + 256 * 16 - 1) / (256 * 16));
+    if (grid > 1184) grid = 1184;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        select_hist_kernel<<<grid, 256, 0, st>>>(cand, n, shift, n_ranks, state);
+        select_digit_kernel<<<1, 256, 0, st>>>(state, shift, n_ranks, out);
+    }
     SDB_LAUNCH_STATUS();
 }
 

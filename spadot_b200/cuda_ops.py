@@ -809,6 +809,16 @@ class CudaOps(VectorOps):
                    _ptr(counts))
         return cand, counts
 
+    def select_ranks(self, cand, n, ranks):
+        """The ranks[s]-th smallest (0-based, one or two ranks) of cand[:n]: all eight digit passes on the device, one read-back."""
+        import ctypes
+        ranks = [int(r) for r in ranks]
+        arr = (ctypes.c_uint64 * len(ranks))(*ranks)
+        out = torch.empty(2, dtype=torch.float64, device=self.device)
+        work = torch.empty(4128 // 8, dtype=torch.int64, device=self.device)       # SDB_SELECT_WORKSPACE_BYTES
+        self._call("sdb_select_ranks_f64", _ptr(cand), int(n), ctypes.addressof(arr), len(ranks), _ptr(out), _ptr(work))
+        return [float(v) for v in out[:len(ranks)].tolist()]
+
     def radix_digit_hist(self, cand, n, shift, prefix):
         hist = torch.zeros(256, dtype=torch.int64, device=self.device)
         self._call("sdb_radix_digit_hist", _ptr(cand), n, shift, prefix, _ptr(hist))

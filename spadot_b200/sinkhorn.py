@@ -510,8 +510,13 @@ def median_cost(ops, dist: Dist | None = None, n_samples=1 << 24, n_bins=4096, s
             raise RuntimeError("median_cost: candidate buffer too small for an exhaustive collect")
         lo, hi = 0.0, math.inf
         cap = int(min(total, 1 << 28))
-    v_lo = _select_rank(ops, cand, n_cand, k_lo - below)
-    v_hi = v_lo if k_hi == k_lo else _select_rank(ops, cand, n_cand, k_hi - below)
+    native = getattr(ops, "select_ranks", None)
+    if native is not None:                       # eight digit passes on the device, one read-back (sdb_select_ranks_f64)
+        vals = native(cand, n_cand, [k_lo - below] if k_hi == k_lo else [k_lo - below, k_hi - below])
+        v_lo, v_hi = vals[0], vals[-1]
+    else:
+        v_lo = _select_rank(ops, cand, n_cand, k_lo - below)
+        v_hi = v_lo if k_hi == k_lo else _select_rank(ops, cand, n_cand, k_hi - below)
     mark("select")
     if info is not None:
         info.update(sweeps=sweeps, candidates=n_cand, below=below, phases_s=phases)

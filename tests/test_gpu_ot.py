@@ -97,6 +97,26 @@ def test_median_scipy_bit_exact(ot):
     assert got == want
 
 
+@pytest.mark.parametrize("n", [1, 2, 7, 4096, 100001])
+def test_device_radix_select_matches_sort(ot, n):
+    """sdb_select_ranks_f64 (eight digit passes on the device, no host round trip) = sorted()[k], ties and zeros included,
+    and equal to the host-driven digit loop it replaces (sinkhorn._select_rank)."""
+    _, sinkhorn, CudaOps = ot
+    a, b, _, _ = ot_dense.synthetic_embeddings(8, 9, 3, seed=1)
+    ops = CudaOps(a, b)
+    rng = np.random.default_rng(n)
+    v = rng.gamma(2.0, 30.0, size=n)
+    v[rng.integers(0, n, size=max(1, n // 5))] = v[0]            # ties
+    if n > 2:
+        v[1] = 0.0
+    srt = np.sort(v)
+    cand = ops.tensor(v)
+    for ranks in ([0], [n - 1], [(n - 1) // 2, n // 2], [n // 3]):
+        got = ops.select_ranks(cand, n, ranks)
+        assert got == [float(srt[k]) for k in ranks]
+        assert got[0] == sinkhorn._select_rank(ops, cand, n, ranks[0])
+
+
 # ------------------------------------------------------------------ full solves
 @pytest.mark.parametrize("n,m,d,seed", [(747, 1966, 20, 1), (1966, 1916, 20, 2), (400, 300, 32, 3)])
 def test_duality_gap_solve_matches_oracle(ot, n, m, d, seed):

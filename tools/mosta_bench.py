@@ -33,7 +33,16 @@ def main():
     ap.add_argument("--d", type=int, default=20)
     ap.add_argument("--k", type=int, default=10)
     a = ap.parse_args()
-    torch.cuda.set_device(0)
+    # under torchrun: the rows of every source timepoint are partitioned over the ranks (k-means is replicated, it is 1 % of the time)
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    dist = None
+    if world > 1:
+        import torch.distributed as td
+        from spadot_b200 import sinkhorn
+        td.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0))))
+        dist = sinkhorn.Dist()
+    say = print if rank == 0 else (lambda *args, **kw: None)
     sizes = [max(64, int(s * a.scale)) for s in SPOTS]
     lat = []
     for t, n in enumerate(sizes):
@@ -50,28 +59,40 @@ def main():
         t_km.append(time.perf_counter() - t0)
         labels.append(np.asarray(km.labels_))
     rows = []
+    if dist is not None:                                     # first-use costs of the communicators stay out of the pair times
+        analyze.transport_between(lat[0][rank::world][:256], lat[1], dist=dist)
     for t in range(len(lat) - 1):
+        r0, r1 = (sizes[t] * rank) // world, (sizes[t] * (rank + 1)) // world
         torch.cuda.synchronize()
+        if dist is not None:
+            td.barrier()
         t0 = time.perf_counter()
-        cp, growth = analyze.transport_between(lat[t], lat[t + 1])
+        cp, growth = analyze.transport_between(lat[t][r0:r1], lat[t + 1], dist=dist)
         torch.cuda.synchronize()
+        if dist is not None:
+            td.barrier()
         t_solve = time.perf_counter() - t0
         t0 = time.perf_counter()
-        table = cp.transition_table(labels[t], labels[t + 1], a.k, a.k).cpu().numpy()
+        table = cp.transition_table(labels[t][r0:r1], labels[t + 1], a.k, a.k).cpu().numpy()
         torch.cuda.synchronize()
         t_table = time.perf_counter() - t0
         prob = analyze.transition_probabilities(table)
-        row = dict(pair=f"{STAGES[t]}->{STAGES[t + 1]}", n=sizes[t], m=sizes[t + 1], seconds=t_solve, table_s=t_table,
+        mass = float(growth[-1].sum())
+        if dist is not None:
+            mass = float(dist.sum_(torch.tensor([mass], dtype=torch.float64, device="cuda")).item())
+        row = dict(pair=f"{STAGES[t]}->{STAGES[t + 1]}", n=sizes[t], m=sizes[t + 1], n_gpus=world, seconds=t_solve, table_s=t_table,
                    iters_last_growth=cp.info["total_iters"], gap=cp.info["gap"], tc=bool(cp.ops.use_tc),
-                   plan_mass=float(growth[-1].sum()), table_mass=float(table.sum()),
+                   plan_mass=mass, table_mass=float(table.sum()),
                    argmax=[int(v) for v in prob.argmax(axis=1)],
                    dense_fp64_gb_reference=4 * 8.0 * sizes[t] * sizes[t + 1] / 1e9)
         rows.append(row)
-        print(json.dumps(row), flush=True)
+        say(json.dumps(row), flush=True)
     total = time.perf_counter() - t_all
-    print(json.dumps(dict(workload="MouseOrganogenesis-shaped analyze (8 stages, MOSTA bin-50 spot counts x %.3g, d=%d, k=%d)"
+    say(json.dumps(dict(n_gpus=world, workload="MouseOrganogenesis-shaped analyze (8 stages, MOSTA bin-50 spot counts x %.3g, d=%d, k=%d)"
                                    % (a.scale, a.d, a.k), kmeans_s=t_km, ot_pairs_s=[r["seconds"] for r in rows],
                           total_s=total, peak_mem_gb=torch.cuda.max_memory_allocated() / 1e9)))
+    if dist is not None:
+        td.destroy_process_group()
 
 
 if __name__ == "__main__":
