@@ -20,11 +20,12 @@ def main():
     comm = dist.native_comm(dev)
     lib = _lib.load()
     stream = torch.cuda.current_stream().cuda_stream
-    for count in (4, 32770, 250002, 1000002):
+    for count in (4, 18410, 30126, 51367, 77371, 121769, 250002, 1000002):
         buf = torch.ones(count, dtype=torch.float64, device=dev)
         res = {"n_gpus": world, "doubles": count}
         for name, call in (("native", lambda: _lib.check(lib.sdb_nccl_allreduce_sum_f64(comm, buf.data_ptr(), count, stream), "ar")),
-                           ("torch", lambda: td.all_reduce(buf))):
+                           ("torch", lambda: td.all_reduce(buf)),
+                           ("torch_max", lambda: td.all_reduce(buf, op=td.ReduceOp.MAX))):
             if name == "native" and comm is None:
                 continue
             first = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
