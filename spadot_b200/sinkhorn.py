@@ -67,10 +67,28 @@ class Dist:
             self.collectives += 1
         return t
 
+    def _shared_comm(self, device):
+        """The ncclComm_t torch.distributed already holds for this group (ProcessGroupNCCL._comm_ptr), or None.  The library
+        binds the libnccl.so.2 this process has loaded (RTLD_NOLOAD), i.e. torch's, so the handle is valid there; sharing it
+        saves the second communicator's creation (0.3-1.5 s on 2-8 ranks, once per process) and its buffers.  NCCL orders
+        operations issued on one communicator from different streams in host issue order, and every rank issues torch's and
+        the library's collectives in the same program order."""
+        import ctypes
+        if os.environ.get("SDB_NATIVE_COMM", "shared") != "shared":
+            return None
+        try:
+            pg = self.group if self.group is not None else self.td.distributed_c10d._get_default_group()
+            self.td.all_reduce(torch.zeros(1, device=device), group=self.group)        # makes sure the communicator exists
+            ptr = int(pg._get_backend(torch.device(device))._comm_ptr())
+            return ctypes.c_void_p(ptr) if ptr else None
+        except Exception:
+            return None
+
     def native_comm(self, device):
-        """NCCL communicator owned by libspadot_b200.so for this group (sdb_nccl_comm_create), so that the native multi-rank
-        loop can issue its all-reduce from C.  Created on first use: rank 0 draws the unique id, torch.distributed ships the
-        128 bytes.  None when NCCL cannot be bound or the group is not a CUDA/NCCL one (e.g. the gloo test groups)."""
+        """NCCL communicator for the native multi-rank loop (sdb_sinkhorn_sweeps_dist issues its all-reduce from C): torch's
+        own communicator of this group when it can be reached (_shared_comm), else one created by the library
+        (sdb_nccl_comm_create: rank 0 draws the unique id, torch.distributed ships the 128 bytes).  None when NCCL cannot be
+        bound or the group is not a CUDA/NCCL one (e.g. the gloo test groups)."""
         if self.world == 1 or getattr(device, "type", "cpu") != "cuda":
             return None
         if not hasattr(self, "_native"):
@@ -79,7 +97,11 @@ class Dist:
                 import ctypes
                 from . import _lib
                 lib = _lib.load()
-                if os.environ.get("SDB_NATIVE_DIST", "1") != "0" and lib.sdb_nccl_available() and self.td.get_backend(self.group) == "nccl":
+                usable = os.environ.get("SDB_NATIVE_DIST", "1") != "0" and lib.sdb_nccl_available() and self.td.get_backend(self.group) == "nccl"
+                if usable:
+                    self._native = self._shared_comm(device)
+                    self.native_comm_kind = "torch's (shared)" if self._native is not None else "library's own"
+                if usable and self._native is None:
                     buf = (ctypes.c_char * 128)()
                     if self.rank == 0:
                         _lib.check(lib.sdb_nccl_unique_id(buf), "sdb_nccl_unique_id")

@@ -43,7 +43,7 @@ def main():
         if rank == 0:
             print(f"dist check {n}x{m} d={d} tc={tc}: world={world} |df|={df:.2e} |dg|={dg:.2e} table rel={dt:.2e} "
                   f"iters={cp.info['iters_per_stage']} collectives={dist.collectives} "
-                  f"predicted={ops._pred is not None and ops._pred.ok}", flush=True)
+                  f"predicted={ops._pred is not None and ops._pred.ok} comm={getattr(dist, 'native_comm_kind', None)}", flush=True)
     td.destroy_process_group()
 
 

@@ -94,7 +94,7 @@ def main():
             iters_per_stage=cp.info["iters_per_stage"], total_iters=it, gap=cp.info["gap"],
             iters_per_sec=it / dt, plan_mass=mass, tc=ops.use_tc, converged=bool(cp.info["gap"] <= cfg["tolerance"]),
             collectives_per_iter=ncoll / max(it, 1), f_checksum=f_sum, g_checksum=float(cp.g.sum().item()),
-            predicted=bool(ops._pred is not None and ops._pred.ok))
+            predicted=bool(ops._pred is not None and ops._pred.ok), native_comm=getattr(dist, "native_comm_kind", None))
     if world > 1:
         td.destroy_process_group()
 
