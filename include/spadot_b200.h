@@ -263,7 +263,13 @@ typedef struct sdb_solve_params {
                                   * c1*log2(e)*|x_i - y_j|^2 in shared memory for a whole epsilon stage (a ChickenHeart-sized
                                   * problem fits on chip), so a half-iteration is bias - cost, ex2, add per pair.  The caller
                                   * then sizes partial_row / partial_col for ns_row = ceil(m/64), ns_col = ceil(n/64) splits;
-                                  * SDB_E_UNSUPPORTED when the tiles do not fit (use 0 = streamed tiles). */
+                                  * SDB_E_UNSUPPORTED when the tiles do not fit (use 0 = streamed tiles).
+                                  * 2 = STRIP form (owner computes): one CTA per SM holds ceil(n/grid) whole rows and
+                                  * ceil(m/grid) whole columns of |x_i - y_j|^2 plus one bias vector in shared memory
+                                  * (<= 225 KB: the ChickenHeart sizes, up to about 2000 x 2000); a half-iteration has no
+                                  * partial results and no arrival counters - the owner reduces, updates, and the only
+                                  * exchange is the updated vector.  partial_* / ns_* are not used.  SDB_E_UNSUPPORTED when
+                                  * the strips do not fit. */
 } sdb_solve_params;
 typedef struct sdb_solve_result {
     int32_t iters[6];            /* iterations per epsilon stage */

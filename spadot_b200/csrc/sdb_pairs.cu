@@ -394,6 +394,7 @@ struct SolveArgs {
     int* flag;                          // caller's absorb flag (left consistent: last tick that exceeded tau)
     int* flag2;                         // [2] ping-pong flags of this kernel
     int res_tiles;                      // resident form: tiles of shared memory per CTA (>= the tiles any CTA owns)
+    int strip_rows, strip_cols;         // strip form: rows / columns owned by every CTA (the last owners get fewer)
     double inv_med, lambda1, lambda2, epsilon, epsilon0, tolerance, log_tau, log_m, log_N, dx, dy;
     int batch_size; long long max_iter; int first_tick;
     unsigned int* barrier;              // [2]
@@ -690,8 +691,85 @@ __device__ void res_pass(const SolveArgs& a, const float* tiles, int n_owned, in
     __syncthreads();
 }
 
-template <bool RESIDENT>
+// ---- strips: the owner-computes form ------------------------------------------------------------------------------------------
+// For the reference's own example sizes (ChickenHeart: <= 1967 spots per side) a CTA can hold, in shared memory, BOTH the rows of
+// D_ij = |x_i - y_j|^2 it owns (n/grid full rows) and the columns it owns (m/grid full columns).  A half-iteration then needs no
+// partial results at all: the owner reduces its whole rows (a warp per row), updates their potential on the spot and the only
+// traffic between CTAs is the updated vector itself - one read of the other side's bias after the grid barrier.  Against the
+// tile forms this removes, per half-iteration, the partial stores, the per-slab arrival atomics and the last arriver's combine
+// from the dependent chain between two barriers (profiles/r2_ncu_solve_kernel_hot_lines.txt: 48 % of the one-launch solve was
+// waiting in barriers for exactly that tail).  Same tile arithmetic as the resident form: t = fma(s_hi, D, fma(s_lo, D, bias)).
+__device__ void strip_build(const float* __restrict__ pt, int64_t ldp, const float* __restrict__ qt, int64_t ldq, int64_t n_q,
+                            int dpad, int first, int n_owned, int ld, float* strip) {
+    for (int idx = threadIdx.x; idx < n_owned * ld; idx += NT) {
+        const int r = idx / ld, j = idx - r * ld;
+        float acc = 1.0e30f;                                     // padding: scale * 1e30 stays finite, 2^that = 0
+        if (j < n_q) {
+            acc = 0.f;
+            for (int q = 0; q < dpad; ++q) {                     // the accumulation order of res_build_tiles / the direct tiles
+                const float df = pt[(int64_t)q * ldp + first + r] - qt[(int64_t)q * ldq + j];
+                acc = fmaf(df, df, acc);
+            }
+        }
+        strip[idx] = acc;
+    }
+}
+
+// One half-iteration over this CTA's strip: (max, sum) of 2^t over each owned row, then its LSE and, with UPDATE, the potential
+// update of solve_finish_slab - by the warp that reduced the row.  bias: the other side's vector (global; NULL = 0).
+template <bool UPDATE>
+__device__ void strip_pass(const float* strip, int first, int n_owned, int len, int ld, float s_hi, float s_lo, const float* bias,
+                           float* sbias, double* L, const double* logmarg, double eps, double alpha, double log_n_other, double* pot,
+                           double* frame, double* la_old, float* bias_out, int* flag2, int tick, double log_tau) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool pending = UPDATE && (*reinterpret_cast<volatile int*>(flag2 + ((tick - 1) & 1)) == tick - 1);
+    for (int j = threadIdx.x; j < ld; j += NT) sbias[j] = (bias && j < len) ? __ldcg(bias + j) : 0.f;
+    __syncthreads();
+    for (int r = warp; r < n_owned; r += NT / 32) {
+        const float* row = strip + (size_t)r * ld;
+        float mx = SDB_NEG_SENTINEL, sm = 0.f;
+        for (int j0 = lane * 4; j0 < ld; j0 += 128) {            // ld is a multiple of 4: conflict-free LDS.128
+            const float4 dv = *reinterpret_cast<const float4*>(row + j0);
+            const float4 bv = *reinterpret_cast<const float4*>(sbias + j0);
+            const float t0 = fmaf(s_hi, dv.x, fmaf(s_lo, dv.x, bv.x)), t1 = fmaf(s_hi, dv.y, fmaf(s_lo, dv.y, bv.y));
+            const float t2 = fmaf(s_hi, dv.z, fmaf(s_lo, dv.z, bv.z)), t3 = fmaf(s_hi, dv.w, fmaf(s_lo, dv.w, bv.w));
+            const float cm = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+            if (cm > mx) { sm *= sdb_ex2(mx - cm); mx = cm; }
+            sm += (sdb_ex2(t0 - mx) + sdb_ex2(t1 - mx)) + (sdb_ex2(t2 - mx) + sdb_ex2(t3 - mx));
+        }
+        double S = (double)sm;                                   // the 32 lane sums are combined in fp64
+        float mall = mx;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) mall = fmaxf(mall, __shfl_xor_sync(0xffffffffu, mall, o));
+        S *= (double)sdb_ex2(mx - mall);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+        if (lane == 0) {
+            const int64_t i = (int64_t)first + r;
+            const bool valid = mall > -1e29f && S > 0.0;
+            const double Li = valid ? SDB_LN2 * ((double)mall + log2(S)) : -INFINITY;
+            L[i] = Li;
+            if (UPDATE) {
+                const double old = pot[i];
+                double fr = frame[i];
+                if (pending) { fr = old; frame[i] = old; }       // absorb of the previous tick, row by row
+                la_old[i] = (old - fr) / eps;
+                const double nv = eps * alpha * (logmarg[i] - (Li - log_n_other));
+                pot[i] = nv;
+                const double b = SDB_LOG2E * (nv / eps);
+                bias_out[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
+                if ((nv - fr) / eps > log_tau) atomicMax(flag2 + (tick & 1), tick);
+            }
+        }
+    }
+    __syncthreads();                                             // sbias is rewritten by the next pass
+}
+
+// FORM: 0 streamed tiles (coordinates re-read every pass), 1 resident 64x64 cost tiles, 2 strips (owner computes whole rows)
+template <int FORM>
 __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
+    constexpr bool RESIDENT = (FORM == 1);
+    constexpr bool STRIPS = (FORM == 2);
     extern __shared__ __align__(16) float smem[];
     unsigned int gen = *reinterpret_cast<volatile unsigned int*>(a.barrier + 1);
     const int64_t n = a.row.n_p, m = a.col.n_p;
@@ -715,11 +793,27 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
         red = reinterpret_cast<float2*>(smem + (size_t)a.res_tiles * 4 * NT * 4);
         res_build_tiles(a, smem, n_owned, col_tiles);                     // once: the squared distances do not depend on epsilon
     }
+    // strip form: the rows and the columns of D this CTA owns, and a staging buffer for the other side's bias
+    const int ldm = (int)((m + 3) & ~(int64_t)3), ldn = (int)((n + 3) & ~(int64_t)3);
+    float *srow = nullptr, *scol = nullptr, *sbias = nullptr;
+    int first_row = 0, n_rows = 0, first_col = 0, n_cols = 0;
+    if constexpr (STRIPS) {
+        srow = smem;
+        scol = srow + (size_t)a.strip_rows * ldm;
+        sbias = scol + (size_t)a.strip_cols * ldn;
+        first_row = (int)blockIdx.x * a.strip_rows;
+        first_col = (int)blockIdx.x * a.strip_cols;
+        n_rows = (int)n - first_row; n_rows = n_rows < 0 ? 0 : (n_rows > a.strip_rows ? a.strip_rows : n_rows);
+        n_cols = (int)m - first_col; n_cols = n_cols < 0 ? 0 : (n_cols > a.strip_cols ? a.strip_cols : n_cols);
+        strip_build(a.row.pt, a.row.ldp, a.col.pt, a.col.ldp, m, a.row.dpad, first_row, n_rows, ldm, srow);
+        strip_build(a.col.pt, a.col.ldp, a.row.pt, a.row.ldp, n, a.row.dpad, first_col, n_cols, ldn, scol);
+        __syncthreads();
+    }
     for (int e = 0; e <= 5 && status == 0; ++e) {
         eps = a.eps_stage[e];                                            // ot_solvers.py:218,240,254 (host arithmetic)
         const double c1 = a.inv_med / eps;
         const double alpha1 = a.lambda1 / (a.lambda1 + eps), alpha2 = a.lambda2 / (a.lambda2 + eps);
-        const bool direct = RESIDENT || 2.0 * c1 * SDB_LOG2E * a.xy_max > a.dot_limit;
+        const bool direct = RESIDENT || STRIPS || 2.0 * c1 * SDB_LOG2E * a.xy_max > a.dot_limit;
         const double c1n = direct ? 0.0 : c1;
         const double sc = direct ? -c1 * SDB_LOG2E : 2.0 * c1 * SDB_LOG2E;
         const float sc_hi = (float)sc, sc_lo = (float)(sc - (double)sc_hi);
@@ -761,7 +855,10 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
                         if ((nv - fr) / eps > a.log_tau) atomicMax(a.flag2 + (tick & 1), tick);
                     }
                 } else {
-                    if constexpr (RESIDENT)
+                    if constexpr (STRIPS)
+                        strip_pass<true>(srow, first_row, n_rows, (int)m, ldm, sc_hi, sc_lo, a.bias_y, sbias, a.Lr, a.logp, eps, alpha1, a.log_m,
+                                         a.f, a.u, a.la_old, a.bias_x, a.flag2, tick, a.log_tau);
+                    else if constexpr (RESIDENT)
                         res_pass<true, true>(a, smem, n_owned, row_tiles, col_tiles, sc_hi, sc_lo, a.bias_y, a.partial_row, cnt_row, a.Lr, a.norms_x, a.logp,
                                              eps, alpha1, a.log_m, a.f, a.u, a.la_old, a.bias_x, tick, red);
                     else
@@ -769,7 +866,10 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
                                      a.log_m, a.f, a.u, a.la_old, a.bias_x, a.flag2, tick, a.log_tau, smem);
                 }
                 grid_barrier(a.barrier, gen);
-                if constexpr (RESIDENT)
+                if constexpr (STRIPS)
+                    strip_pass<true>(scol, first_col, n_cols, (int)n, ldn, sc_hi, sc_lo, a.bias_x, sbias, a.Lc, a.logq, eps, alpha2, a.log_N,
+                                     a.g, a.v, a.lb_old, a.bias_y, a.flag2, tick, a.log_tau);
+                else if constexpr (RESIDENT)
                     res_pass<true, false>(a, smem, n_owned, row_tiles, col_tiles, sc_hi, sc_lo, a.bias_x, a.partial_col, cnt_col, a.Lc, a.norms_y, a.logq, eps,
                                           alpha2, a.log_N, a.g, a.v, a.lb_old, a.bias_y, tick, red);
                 else
@@ -783,7 +883,10 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
             const bool pending = (*reinterpret_cast<volatile int*>(a.flag2 + (tick & 1)) == tick);
             if (final_stage) {
                 if (!have_sumK) {
-                    if constexpr (RESIDENT)
+                    if constexpr (STRIPS)
+                        strip_pass<false>(srow, first_row, n_rows, (int)m, ldm, scd_hi, scd_lo, nullptr, sbias, a.Lr, nullptr, eps, 0.0, 0.0,
+                                          nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau);
+                    else if constexpr (RESIDENT)
                         res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, scd_hi, scd_lo, nullptr, a.partial_row, cnt_row, a.Lr, a.norms_x, nullptr, eps,
                                               0.0, 0.0, nullptr, nullptr, nullptr, nullptr, tick, red);
                     else
@@ -797,7 +900,10 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
                     have_sumK = true;
                 }
                 // row LSE at the new g: the gap's row marginal, and the next iteration's row pass
-                if constexpr (RESIDENT)
+                if constexpr (STRIPS)
+                    strip_pass<false>(srow, first_row, n_rows, (int)m, ldm, sc_hi, sc_lo, a.bias_y, sbias, a.Lr, nullptr, eps, 0.0, 0.0,
+                                      nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau);
+                else if constexpr (RESIDENT)
                     res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, sc_hi, sc_lo, a.bias_y, a.partial_row, cnt_row, a.Lr, a.norms_x, nullptr, eps,
                                           0.0, 0.0, nullptr, nullptr, nullptr, nullptr, tick, red);
                 else
@@ -868,10 +974,13 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
         // row LSE at the final g (plan row sums, the growth loop's next G)
         // (bias_y still holds the last stage's form: reuse that stage's choice)
         const double c1 = a.inv_med / eps;
-        const bool direct = RESIDENT || 2.0 * c1 * SDB_LOG2E * a.xy_max > a.dot_limit;
+        const bool direct = RESIDENT || STRIPS || 2.0 * c1 * SDB_LOG2E * a.xy_max > a.dot_limit;
         const double sc = direct ? -c1 * SDB_LOG2E : 2.0 * c1 * SDB_LOG2E;
         const float sc_hi = (float)sc;
-        if constexpr (RESIDENT)
+        if constexpr (STRIPS)
+            strip_pass<false>(srow, first_row, n_rows, (int)m, ldm, sc_hi, (float)(sc - (double)sc_hi), a.bias_y, sbias, a.Lr, nullptr, eps,
+                              0.0, 0.0, nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau);
+        else if constexpr (RESIDENT)
             res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, sc_hi, (float)(sc - (double)sc_hi), a.bias_y, a.partial_row, cnt_row,
                                   a.Lr, a.norms_x, nullptr, eps, 0.0, 0.0, nullptr, nullptr, nullptr, nullptr, tick, red);
         else
@@ -981,11 +1090,26 @@ extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return (int)e;
     const int64_t R = (d->n + BM - 1) / BM, C = (d->m + BN - 1) / BN;
-    const bool resident = p->reserved == 1;
+    const bool resident = p->reserved == 1, strips = p->reserved == 2;
     size_t smem = 0;
     int grid = 0;
     a.res_tiles = 0;
-    if (resident) {
+    a.strip_rows = a.strip_cols = 0;
+    if (strips) {
+        // one CTA per SM; every CTA keeps ceil(n/grid) full rows and ceil(m/grid) full columns of D plus one bias vector
+        static size_t smem_set_s[SDB_MAX_DEVICES] = {0};
+        const int64_t g = n_sm;
+        const int64_t rp = (d->n + g - 1) / g, cp = (d->m + g - 1) / g;
+        const int64_t ldm = (d->m + 3) & ~(int64_t)3, ldn = (d->n + 3) & ~(int64_t)3;
+        const size_t need = sizeof(float) * (size_t)(rp * ldm + cp * ldn + (ldm > ldn ? ldm : ldn));
+        if (need > 225 * 1024) return SDB_E_UNSUPPORTED;
+        cudaError_t e0 = sdb_ensure_smem(sinkhorn_solve_kernel<2>, need, smem_set_s);
+        if (e0 != cudaSuccess) return (int)e0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_solve_kernel<2>, NT, need);
+        if (e != cudaSuccess) return (int)e;
+        if (per_sm < 1) return SDB_E_UNSUPPORTED;
+        grid = (int)g; smem = need; a.strip_rows = (int)rp; a.strip_cols = (int)cp;
+    } else if (resident) {
         // resident cost tiles: the caller sized the partial buffers for one split per tile (ns_row = C, ns_col = R); find a
         // co-resident grid whose CTAs can hold their share of the R*C tiles (16 KB each) in shared memory
         SDB_CHECK_ARG(d->ns_row == C && d->ns_col == R);
@@ -996,9 +1120,9 @@ extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_
             if (T > RES_MAX_TILES) continue;
             const size_t need = (size_t)T * 4 * NT * 4 * sizeof(float) + (size_t)T * (NT / 32) * BN * sizeof(float2);
             if (need > 220 * 1024) continue;
-            cudaError_t e0 = sdb_ensure_smem(sinkhorn_solve_kernel<true>, need, smem_set_r);
+            cudaError_t e0 = sdb_ensure_smem(sinkhorn_solve_kernel<1>, need, smem_set_r);
             if (e0 != cudaSuccess) return (int)e0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_solve_kernel<true>, NT, need);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_solve_kernel<1>, NT, need);
             if (e != cudaSuccess) return (int)e;
             if (per_sm >= want_per_sm) { grid = (int)g; smem = need; a.res_tiles = (int)T; }
         }
@@ -1006,8 +1130,8 @@ extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_
     } else {
         smem = sizeof(float) * ((size_t)d->dpad * BM + 2 * (size_t)d->dpad * BN + 2 * BN);
         static size_t smem_set[SDB_MAX_DEVICES] = {0};
-        { cudaError_t e0 = sdb_ensure_smem(sinkhorn_solve_kernel<false>, smem, smem_set); if (e0 != cudaSuccess) return (int)e0; }
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_solve_kernel<false>, NT, smem);
+        { cudaError_t e0 = sdb_ensure_smem(sinkhorn_solve_kernel<0>, smem, smem_set); if (e0 != cudaSuccess) return (int)e0; }
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_solve_kernel<0>, NT, smem);
         if (e != cudaSuccess) return (int)e;
         if (per_sm < 1) return SDB_E_UNSUPPORTED;
         const int64_t row_items = R * d->ns_row, col_items = C * d->ns_col;
@@ -1022,7 +1146,8 @@ extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_
     if (e == cudaSuccess) e = cudaMemsetAsync(counters, 0, sizeof(unsigned int) * (size_t)((d->n + BM - 1) / BM + (d->m + BM - 1) / BM), st);
     if (e != cudaSuccess) return (int)e;
     void* params[] = {&a};
-    e = cudaLaunchCooperativeKernel(resident ? (const void*)sinkhorn_solve_kernel<true> : (const void*)sinkhorn_solve_kernel<false>,
+    e = cudaLaunchCooperativeKernel(strips ? (const void*)sinkhorn_solve_kernel<2>
+                                           : resident ? (const void*)sinkhorn_solve_kernel<1> : (const void*)sinkhorn_solve_kernel<0>,
                                     dim3((unsigned)grid), dim3(NT), params, smem, st);
     return (int)e;
 }

@@ -194,6 +194,7 @@ class CudaOps(VectorOps):
     # measured r2 (profiles/r2_ch_time.txt): with 1-2 tiles per CTA the resident form wins (747 x 1966: 2.48 vs 2.83 ms per solve),
     # with 4 the per-tile reductions cost more than the streamed form's dot products (1966 x 1916: 4.0 vs 3.45 ms)
     RESIDENT_MAX_TILES_PER_CTA = 2
+    STRIP_FORM = os.environ.get("SDB_STRIP_FORM", "1") != "0"   # owner-computes strips in the one-launch solve when a CTA can hold its rows and columns
 
     def __init__(self, x_local, y, device=None, tc="auto"):
         self._init_vectors(device)
@@ -484,12 +485,26 @@ class CudaOps(VectorOps):
         d.norms_x, d.norms_y = _ptr(self.X.norms_sq), _ptr(self.Y.norms_sq)
         self._persistent_plan(d)
         R, C = (self.n + 63) // 64, (self.m + 63) // 64
-        resident = self.RESIDENT_TILES and R * C <= 2 * self._n_sm * self.RESIDENT_MAX_TILES_PER_CTA
-        if resident:
-            # the whole scaled cost matrix stays in shared memory: one split per tile
-            d.ns_row, d.ns_col = C, R
-            d.partial_row = _ptr(self._partial(C, self.n, "rrow"))
-            d.partial_col = _ptr(self._partial(R, self.m, "rcol"))
+        # forms of the kernel, best first: 2 = strips (every CTA owns whole rows and whole columns of the cost matrix in shared
+        # memory - the ChickenHeart sizes), 1 = resident 64x64 tiles, 0 = streamed tiles
+        g = self._n_sm
+        ldm, ldn = (self.m + 3) & ~3, (self.n + 3) & ~3
+        strip_bytes = 4 * (-(-self.n // g) * ldm + -(-self.m // g) * ldn + max(ldm, ldn))
+        forms = []
+        if self.STRIP_FORM and strip_bytes <= 225 * 1024:
+            forms.append(2)
+        if self.RESIDENT_TILES and R * C <= 2 * self._n_sm * self.RESIDENT_MAX_TILES_PER_CTA:
+            forms.append(1)
+        forms.append(0)
+
+        def plan(form):
+            if form == 1:       # the whole scaled cost matrix stays in shared memory: one split per tile
+                d.ns_row, d.ns_col = C, R
+                d.partial_row = _ptr(self._partial(C, self.n, "rrow"))
+                d.partial_col = _ptr(self._partial(R, self.m, "rcol"))
+            else:
+                self._persistent_plan(d)
+        plan(forms[0])
         # the six regularisations in the host's own arithmetic (ot_solvers.py:218,240,254), so that the device walks the very
         # same epsilons as the host-driven loop and the reference
         scale_factor = math.exp(-math.log(epsilon) / 5)
@@ -499,7 +514,7 @@ class CudaOps(VectorOps):
             stages.append(eps_i)
         p = _lib.SolveParams(float(lambda1), float(lambda2), float(epsilon), float(epsilon0), float(tolerance), float(tau),
                              float(max_iter), (ctypes.c_double * 6)(*stages), self._xy_max(), self.SIMT_DOT_MAX, int(batch_size),
-                             int(resident))
+                             int(forms[0]))
         if getattr(self, "_solve_ws", None) is None:
             tiles = (self.n + 63) // 64 + (self.m + 63) // 64
             self._solve_ws = dict(flag2=torch.zeros(2, dtype=torch.int32, device=self.device),
@@ -511,11 +526,14 @@ class CudaOps(VectorOps):
         args = (ctypes.byref(d), ctypes.byref(p), self._tick + 1, _ptr(ws["flag2"]), _ptr(self._barrier), _ptr(ws["counters"]),
                 _ptr(ws["scratch"]), _ptr(ws["result"]), self._stream())
         status = fn(*args)
-        if status == -2 and resident:
-            # the tiles do not fit next to whatever else occupies the SMs: streamed tiles instead
-            self._persistent_plan(d)
-            p.reserved = 0
+        for form in forms[1:]:
+            if status != -2:
+                break
+            # the strips / tiles do not fit next to whatever else occupies the SMs: the next form
+            plan(form)
+            p.reserved = form
             status = fn(*args)
+        self.solve_form = int(p.reserved)
         _lib.check(status, "sdb_sinkhorn_solve_persistent")
         self.launches += 1
         raw = ws["result"].cpu().numpy().tobytes()                # the one synchronising read-back of the solve

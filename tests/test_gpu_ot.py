@@ -433,10 +433,10 @@ def test_persistent_sweeps_match_launch_loop(ot, n, m, d):
     assert abs(cp1.info["gap"]) <= 1e-8
 
 
-@pytest.mark.parametrize("resident", [True, False])
+@pytest.mark.parametrize("form", ["strips", "resident", "streamed"])
 @pytest.mark.parametrize("n,m,d,tau", [(747, 1966, 20, 1000.0), (300, 411, 20, 1000.0), (130, 97, 6, 3.0), (1, 1, 3, 1000.0),
                                        (65, 64, 33, 1.5), (1966, 1916, 20, 1000.0), (2500, 3000, 32, 1000.0)])
-def test_whole_solve_in_one_launch_matches_host_stage_loop(ot, n, m, d, tau, resident):
+def test_whole_solve_in_one_launch_matches_host_stage_loop(ot, n, m, d, tau, form):
     """sdb_sinkhorn_solve_persistent (six epsilon stages, stopping rules and tau bookkeeping on the device, two grid barriers
     per iteration) against the host-driven stage loop over the same tile code: same iterations per stage, same potentials,
     same frames; small tau forces absorptions (ot_func.cpp:778-819) so the row-by-row deferred absorb is exercised."""
@@ -447,7 +447,9 @@ def test_whole_solve_in_one_launch_matches_host_stage_loop(ot, n, m, d, tau, res
     out = []
     for fused in (True, False):
         ops = CudaOps(a, b, tc="off")
-        ops.RESIDENT_TILES = resident                            # cost tiles resident in shared memory vs streamed tiles
+        resident = form != "streamed"
+        ops.STRIP_FORM = form == "strips"                        # whole rows / columns of the cost matrix per CTA (owner computes),
+        ops.RESIDENT_TILES = form == "resident"                  # 64x64 cost tiles resident in shared memory, or streamed tiles
         ops.RESIDENT_MAX_TILES_PER_CTA = 6                       # (the default gate keeps larger problems on streamed tiles)
         ops.SIMT_DOT_MAX = 0.0 if resident else ops.SIMT_DOT_MAX  # the resident form is a direct-difference form: compare like with like
         if not fused:
@@ -457,6 +459,11 @@ def test_whole_solve_in_one_launch_matches_host_stage_loop(ot, n, m, d, tau, res
         out.append((cp, ops.launches - l0))
     (c1, l1), (c2, l2) = out
     assert l1 <= 2 and l2 > 20                                  # one launch vs the batch-by-batch loop
+    fits = 4 * (-(-n // 148) * ((m + 3) & ~3) + -(-m // 148) * ((n + 3) & ~3) + max(n, m) + 3) <= 225 * 1024
+    if form == "strips" and fits and torch.cuda.get_device_properties(0).multi_processor_count == 148:
+        assert c1.ops.solve_form == 2                           # the strip form really ran
+    elif form == "resident" and n * m <= 64 * 64 * 2 * 148 * 6:
+        assert c1.ops.solve_form == 1
     if n * m > 1024:
         assert c1.info["iters_per_stage"] == c2.info["iters_per_stage"], (c1.info, c2.info)
     else:
