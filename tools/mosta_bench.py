@@ -50,14 +50,24 @@ def main():
         rng = np.random.default_rng(t)
         lat.append(x[rng.permutation(n)] + 0.05 * t)
     t_all = time.perf_counter()
-    labels, t_km = [], []
-    for x in lat:
+    labels, t_km = [None] * len(lat), [0.0] * len(lat)
+    for t, x in enumerate(lat):
+        if t % world != rank:                                # the timepoints' k-means runs are independent: dealt over the ranks
+            continue
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         km = kmeans.KMeans(n_clusters=a.k, n_init=10, random_state=1993).fit(x)
         torch.cuda.synchronize()
-        t_km.append(time.perf_counter() - t0)
-        labels.append(np.asarray(km.labels_))
+        t_km[t] = time.perf_counter() - t0
+        labels[t] = np.asarray(km.labels_)
+    if dist is not None:
+        for t in range(len(lat)):
+            buf = torch.from_numpy(labels[t].astype(np.int64)).cuda() if labels[t] is not None else torch.empty(sizes[t], dtype=torch.int64, device="cuda")
+            td.broadcast(buf, src=t % world)
+            labels[t] = buf.cpu().numpy()
+            tk = torch.tensor([t_km[t]], dtype=torch.float64, device="cuda")
+            td.broadcast(tk, src=t % world)
+            t_km[t] = float(tk.item())
     rows = []
     if dist is not None:                                     # first-use costs of the communicators stay out of the pair times
         analyze.transport_between(lat[0][rank::world][:256], lat[1], dist=dist)
