@@ -281,24 +281,36 @@ struct PersistArgs {
 // L2 sectors) and only the last arriver of each group touches the top counter - ~20 + 16 same-address atomics deep instead of
 // ~300 (same-address atomics serialise in L2; with one counter the barrier cost 6 us of a 17 us ChickenHeart phase).
 // bar[0] = top counter, bar[1] = generation, bar[32 + 32*g] = counter of group g  (SDB_BARRIER_WORDS unsigned ints, zeroed).
-constexpr unsigned SDB_BARRIER_GROUPS = 16;
+// Measured (ChickenHeart 1966 x 1916, 95 iterations): 3.70 ms with 16 groups against 3.45 ms with ONE counter - the second
+// dependent atomic of the group's last arriver costs more than the same-address serialisation it saves - so the group count is 1
+// (one counter, one atomic per CTA); the two-level code stays for grids far beyond 300 CTAs.
+constexpr unsigned SDB_BARRIER_GROUPS = 1;
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int& gen) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned n_groups = min(SDB_BARRIER_GROUPS, gridDim.x);
-        const unsigned g = blockIdx.x % n_groups;
-        const unsigned in_group = (gridDim.x - g + n_groups - 1) / n_groups;
-        unsigned int* sub = bar + 32 + 32 * g;
         unsigned int arrived;
         bool released = false;
-        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(sub) : "memory");
-        if (arrived == in_group - 1) {
-            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(sub), "r"(0u) : "memory");
+        if constexpr (SDB_BARRIER_GROUPS == 1) {
             asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(bar) : "memory");
-            if (arrived == n_groups - 1) {
+            if (arrived == gridDim.x - 1) {
                 asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
                 asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
                 released = true;
+            }
+        } else {
+            const unsigned n_groups = min(SDB_BARRIER_GROUPS, gridDim.x);
+            const unsigned g = blockIdx.x % n_groups;
+            const unsigned in_group = (gridDim.x - g + n_groups - 1) / n_groups;
+            unsigned int* sub = bar + 32 + 32 * g;
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(sub) : "memory");
+            if (arrived == in_group - 1) {
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(sub), "r"(0u) : "memory");
+                asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(bar) : "memory");
+                if (arrived == n_groups - 1) {
+                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
+                    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + 1) : "memory");
+                    released = true;
+                }
             }
         }
         if (!released) {
@@ -699,6 +711,8 @@ __device__ void res_pass(const SolveArgs& a, const float* tiles, int n_owned, in
 // tile forms this removes, per half-iteration, the partial stores, the per-slab arrival atomics and the last arriver's combine
 // from the dependent chain between two barriers (profiles/r2_ncu_solve_kernel_hot_lines.txt: 48 % of the one-launch solve was
 // waiting in barriers for exactly that tail).  Same tile arithmetic as the resident form: t = fma(s_hi, D, fma(s_lo, D, bias)).
+constexpr int STRIP_REG_LEN = 2048;      // rows up to this length are reduced from registers
+
 __device__ void strip_build(const float* __restrict__ pt, int64_t ldp, const float* __restrict__ qt, int64_t ldq, int64_t n_q,
                             int dpad, int first, int n_owned, int ld, float* strip) {
     for (int idx = threadIdx.x; idx < n_owned * ld; idx += NT) {
@@ -727,34 +741,69 @@ __device__ void strip_pass(const float* strip, int first, int n_owned, int len, 
     __syncthreads();
     for (int r = warp; r < n_owned; r += NT / 32) {
         const float* row = strip + (size_t)r * ld;
-        float mx = SDB_NEG_SENTINEL, sm = 0.f;
-        for (int j0 = lane * 4; j0 < ld; j0 += 128) {            // ld is a multiple of 4: conflict-free LDS.128
-            const float4 dv = *reinterpret_cast<const float4*>(row + j0);
-            const float4 bv = *reinterpret_cast<const float4*>(sbias + j0);
-            const float t0 = fmaf(s_hi, dv.x, fmaf(s_lo, dv.x, bv.x)), t1 = fmaf(s_hi, dv.y, fmaf(s_lo, dv.y, bv.y));
-            const float t2 = fmaf(s_hi, dv.z, fmaf(s_lo, dv.z, bv.z)), t3 = fmaf(s_hi, dv.w, fmaf(s_lo, dv.w, bv.w));
-            const float cm = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
-            if (cm > mx) { sm *= sdb_ex2(mx - cm); mx = cm; }
-            sm += (sdb_ex2(t0 - mx) + sdb_ex2(t1 - mx)) + (sdb_ex2(t2 - mx) + sdb_ex2(t3 - mx));
+        float mall;
+        double S;
+        // what the update of this row reads from global memory is requested now, so that its L2 round trip overlaps the reduction
+        double u_old = 0.0, u_fr = 0.0, u_lm = 0.0;
+        if (UPDATE && lane == 0) { u_old = pot[first + r]; u_fr = frame[first + r]; u_lm = logmarg[first + r]; }
+        if (ld <= STRIP_REG_LEN) {
+            // the whole row in registers (64 values per lane): every exponent first, one maximum for the warp, then 64 independent
+            // ex2 per lane - no running maximum, no dependency from one chunk to the next (a CTA runs alone on its SM: 255
+            // registers per thread are there to be used)
+            float t[STRIP_REG_LEN / 128][4];
+            float mx = SDB_NEG_SENTINEL;
+#pragma unroll
+            for (int q = 0; q < STRIP_REG_LEN / 128; ++q) {
+                const int j0 = lane * 4 + q * 128;               // ld is a multiple of 4: conflict-free LDS.128
+                if (j0 < ld) {
+                    const float4 dv = *reinterpret_cast<const float4*>(row + j0);
+                    const float4 bv = *reinterpret_cast<const float4*>(sbias + j0);
+                    t[q][0] = fmaf(s_hi, dv.x, fmaf(s_lo, dv.x, bv.x)); t[q][1] = fmaf(s_hi, dv.y, fmaf(s_lo, dv.y, bv.y));
+                    t[q][2] = fmaf(s_hi, dv.z, fmaf(s_lo, dv.z, bv.z)); t[q][3] = fmaf(s_hi, dv.w, fmaf(s_lo, dv.w, bv.w));
+                } else {
+                    t[q][0] = t[q][1] = t[q][2] = t[q][3] = SDB_NEG_SENTINEL;
+                }
+                mx = fmaxf(mx, fmaxf(fmaxf(t[q][0], t[q][1]), fmaxf(t[q][2], t[q][3])));
+            }
+            mall = mx;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) mall = fmaxf(mall, __shfl_xor_sync(0xffffffffu, mall, o));
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int q = 0; q < STRIP_REG_LEN / 128; ++q) {
+                s0 += sdb_ex2(t[q][0] - mall); s1 += sdb_ex2(t[q][1] - mall);
+                s2 += sdb_ex2(t[q][2] - mall); s3 += sdb_ex2(t[q][3] - mall);
+            }
+            S = (double)((s0 + s1) + (s2 + s3));
+        } else {
+            float mx = SDB_NEG_SENTINEL, sm = 0.f;
+            for (int j0 = lane * 4; j0 < ld; j0 += 128) {
+                const float4 dv = *reinterpret_cast<const float4*>(row + j0);
+                const float4 bv = *reinterpret_cast<const float4*>(sbias + j0);
+                const float t0 = fmaf(s_hi, dv.x, fmaf(s_lo, dv.x, bv.x)), t1 = fmaf(s_hi, dv.y, fmaf(s_lo, dv.y, bv.y));
+                const float t2 = fmaf(s_hi, dv.z, fmaf(s_lo, dv.z, bv.z)), t3 = fmaf(s_hi, dv.w, fmaf(s_lo, dv.w, bv.w));
+                const float cm = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+                if (cm > mx) { sm *= sdb_ex2(mx - cm); mx = cm; }
+                sm += (sdb_ex2(t0 - mx) + sdb_ex2(t1 - mx)) + (sdb_ex2(t2 - mx) + sdb_ex2(t3 - mx));
+            }
+            mall = mx;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) mall = fmaxf(mall, __shfl_xor_sync(0xffffffffu, mall, o));
+            S = (double)sm * (double)sdb_ex2(mx - mall);
         }
-        double S = (double)sm;                                   // the 32 lane sums are combined in fp64
-        float mall = mx;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) mall = fmaxf(mall, __shfl_xor_sync(0xffffffffu, mall, o));
-        S *= (double)sdb_ex2(mx - mall);
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+        for (int o = 1; o < 32; o <<= 1) S += __shfl_xor_sync(0xffffffffu, S, o);      // the 32 lane sums are combined in fp64
         if (lane == 0) {
             const int64_t i = (int64_t)first + r;
             const bool valid = mall > -1e29f && S > 0.0;
             const double Li = valid ? SDB_LN2 * ((double)mall + log2(S)) : -INFINITY;
             L[i] = Li;
             if (UPDATE) {
-                const double old = pot[i];
-                double fr = frame[i];
+                const double old = u_old;
+                double fr = u_fr;
                 if (pending) { fr = old; frame[i] = old; }       // absorb of the previous tick, row by row
                 la_old[i] = (old - fr) / eps;
-                const double nv = eps * alpha * (logmarg[i] - (Li - log_n_other));
+                const double nv = eps * alpha * (u_lm - (Li - log_n_other));
                 pot[i] = nv;
                 const double b = SDB_LOG2E * (nv / eps);
                 bias_out[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
