@@ -250,7 +250,8 @@ int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_sweeps, int fi
  * column split of a 64-row slab combines the slab's partials and updates its potentials.  On return (after the stream
  * synchronises) f, g, u, v, Lr (row LSE at the final g), Lc hold the final state and *result the iteration counts.
  * Caller-owned workspaces: flag2 (2 ints), barrier2 (SDB_BARRIER_WORDS uints), counters (ceil(n/64) + ceil(m/64) uints), scratch
- * (SDB_SOLVE_MAX_CTAS * 10 doubles), result (device).  Iterations are stamped first_tick, first_tick + 1, ... */
+ * (SDB_SOLVE_MAX_CTAS * 10 + n + m doubles: per-CTA sums, then the strip form's tagged bias vectors), result (device).
+ * Iterations are stamped first_tick, first_tick + 1, ... */
 #define SDB_SOLVE_MAX_CTAS 1024
 #define SDB_BARRIER_WORDS 1024   /* grid barrier of the cooperative kernels: top counter, generation, 16 group counters 128 B apart */
 typedef struct sdb_solve_params {
@@ -268,8 +269,10 @@ typedef struct sdb_solve_params {
                                   * ceil(m/grid) whole columns of |x_i - y_j|^2 plus one bias vector in shared memory
                                   * (<= 225 KB: the ChickenHeart sizes, up to about 2000 x 2000); a half-iteration has no
                                   * partial results and no arrival counters - the owner reduces, updates, and the only
-                                  * exchange is the updated vector.  partial_* / ns_* are not used.  SDB_E_UNSUPPORTED when
-                                  * the strips do not fit. */
+                                  * exchange is the updated vector, which travels as 64-bit (bias, production number, tau bit)
+                                  * words that the consumers poll: inside a batch of iterations there is NO grid barrier, a
+                                  * pass starts when the entries it reads carry the number it expects.  partial_* / ns_* are
+                                  * not used.  SDB_E_UNSUPPORTED when the strips do not fit. */
 } sdb_solve_params;
 typedef struct sdb_solve_result {
     int32_t iters[6];            /* iterations per epsilon stage */

@@ -730,15 +730,60 @@ __device__ void strip_build(const float* __restrict__ pt, int64_t ldp, const flo
 }
 
 // One half-iteration over this CTA's strip: (max, sum) of 2^t over each owned row, then its LSE and, with UPDATE, the potential
-// update of solve_finish_slab - by the warp that reduced the row.  bias: the other side's vector (global; NULL = 0).
+// update of solve_finish_slab - by the warp that reduced the row.
+//
+// DATAFLOW instead of a grid barrier between the passes of a batch.  The other side's bias vector travels as 64-bit words
+// (fp32 bias | 31-bit production number | 1 tau bit): `tin` is polled (relaxed gpu-scope loads, eight in flight per thread) until
+// every entry carries production number `expect`, and the owner publishes its own updated entries to `tout` with number
+// `out_seq`.  A pass can only start when every CTA has finished the previous one (every CTA owns at least one row and one
+// column, so its entries are part of what is waited for), which is also what makes overwriting the arrays safe.  The value and
+// its number arrive in one single-copy-atomic load, so no fence is needed for them; everything else an update writes (pot,
+// frame, la_old, L) is read by other CTAs only after the full barrier that ends the batch.  The tau bookkeeping rides in the
+// tags: bit 63 says "this update exceeded tau", the OR over a staged vector is returned in `bits`.
+// tin == NULL: zero bias, nothing to wait for.
 template <bool UPDATE>
-__device__ void strip_pass(const float* strip, int first, int n_owned, int len, int ld, float s_hi, float s_lo, const float* bias,
-                           float* sbias, double* L, const double* logmarg, double eps, double alpha, double log_n_other, double* pot,
-                           double* frame, double* la_old, float* bias_out, int* flag2, int tick, double log_tau) {
+__device__ void strip_pass(const float* strip, int first, int n_owned, int len, int ld, float s_hi, float s_lo,
+                           const unsigned long long* tin, unsigned expect, float* sbias, double* L, const double* logmarg, double eps,
+                           double alpha, double log_n_other, double* pot, double* frame, double* la_old, unsigned long long* tout,
+                           unsigned out_seq, int* flag2, int tick, double log_tau, bool pend_base, bool add_bits, bool& pending_out,
+                           bool& bits_out) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool pending = UPDATE && (*reinterpret_cast<volatile int*>(flag2 + ((tick - 1) & 1)) == tick - 1);
-    for (int j = threadIdx.x; j < ld; j += NT) sbias[j] = (bias && j < len) ? __ldcg(bias + j) : 0.f;
-    __syncthreads();
+    int my_bits = 0;
+    for (int base = 0; base < ld; base += 8 * NT) {
+        unsigned long long v[8];
+        if (tin) {
+            unsigned spins = 0;
+            bool ok;
+            do {
+                ok = true;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int j = base + k * NT + (int)threadIdx.x;
+                    v[k] = 0ull;
+                    if (j < len) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v[k]) : "l"(tin + j) : "memory");
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int j = base + k * NT + (int)threadIdx.x;
+                    if (j < len && (((unsigned)(v[k] >> 32)) & 0x7fffffffu) != expect) ok = false;
+                }
+                if (!ok && ++spins > (1u << 22)) __trap();       // a protocol error must end the launch, not hang the device
+            } while (!ok);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int j = base + k * NT + (int)threadIdx.x;
+            if (j < ld) {
+                float b = 0.f;
+                if (tin && j < len) { b = __uint_as_float((unsigned)v[k]); my_bits |= (int)(v[k] >> 63); }
+                sbias[j] = b;
+            }
+        }
+    }
+    const bool bits = __syncthreads_or(my_bits) != 0;            // (also the barrier between staging and use)
+    bits_out = bits;
+    const bool pending = UPDATE && (pend_base || (add_bits && bits));
+    pending_out = pending;
     for (int r = warp; r < n_owned; r += NT / 32) {
         const float* row = strip + (size_t)r * ld;
         float mall;
@@ -806,12 +851,21 @@ __device__ void strip_pass(const float* strip, int first, int n_owned, int len, 
                 const double nv = eps * alpha * (u_lm - (Li - log_n_other));
                 pot[i] = nv;
                 const double b = SDB_LOG2E * (nv / eps);
-                bias_out[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
-                if ((nv - fr) / eps > log_tau) atomicMax(flag2 + (tick & 1), tick);
+                const float bf = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
+                const bool over = (nv - fr) / eps > log_tau;
+                if (over) atomicMax(flag2 + (tick & 1), tick);   // the batch-end checks read this one (after a full barrier)
+                const unsigned long long word = ((unsigned long long)(out_seq | (over ? 0x80000000u : 0u)) << 32) |
+                                                (unsigned long long)__float_as_uint(bf);
+                asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(tout + i), "l"(word) : "memory");
             }
         }
     }
     __syncthreads();                                             // sbias is rewritten by the next pass
+}
+
+__device__ __forceinline__ unsigned long long strip_word(double b, unsigned seq, bool over) {
+    const float bf = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
+    return ((unsigned long long)(seq | (over ? 0x80000000u : 0u)) << 32) | (unsigned long long)__float_as_uint(bf);
 }
 
 // FORM: 0 streamed tiles (coordinates re-read every pass), 1 resident 64x64 cost tiles, 2 strips (owner computes whole rows)
@@ -846,14 +900,21 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
     const int ldm = (int)((m + 3) & ~(int64_t)3), ldn = (int)((n + 3) & ~(int64_t)3);
     float *srow = nullptr, *scol = nullptr, *sbias = nullptr;
     int first_row = 0, n_rows = 0, first_col = 0, n_cols = 0;
+    // tagged bias vectors of the strip form (see strip_pass), behind the per-CTA partial sums in `scratch`
+    unsigned long long* tagx = reinterpret_cast<unsigned long long*>(a.scratch + (size_t)SDB_SOLVE_MAX_CTAS * 10);
+    unsigned long long* tagy = tagx + n;
+    unsigned seq_x = 0, seq_y = 0;                   // productions of bias_x / bias_y so far (the arrays start zeroed)
+    bool fl_row_prev = false, pend = false, bits = false;
     if constexpr (STRIPS) {
         srow = smem;
         scol = srow + (size_t)a.strip_rows * ldm;
         sbias = scol + (size_t)a.strip_cols * ldn;
-        first_row = (int)blockIdx.x * a.strip_rows;
-        first_col = (int)blockIdx.x * a.strip_cols;
-        n_rows = (int)n - first_row; n_rows = n_rows < 0 ? 0 : (n_rows > a.strip_rows ? a.strip_rows : n_rows);
-        n_cols = (int)m - first_col; n_cols = n_cols < 0 ? 0 : (n_cols > a.strip_cols ? a.strip_cols : n_cols);
+        // balanced partition: with gridDim.x <= min(n, m) every CTA owns at least one row and one column (the dataflow
+        // protocol of strip_pass relies on it), and never more than strip_rows / strip_cols
+        first_row = (int)(((int64_t)blockIdx.x * n) / gridDim.x);
+        first_col = (int)(((int64_t)blockIdx.x * m) / gridDim.x);
+        n_rows = (int)(((int64_t)(blockIdx.x + 1) * n) / gridDim.x) - first_row;
+        n_cols = (int)(((int64_t)(blockIdx.x + 1) * m) / gridDim.x) - first_col;
         strip_build(a.row.pt, a.row.ldp, a.col.pt, a.col.ldp, m, a.row.dpad, first_row, n_rows, ldm, srow);
         strip_build(a.col.pt, a.col.ldp, a.row.pt, a.row.ldp, n, a.row.dpad, first_col, n_cols, ldn, scol);
         __syncthreads();
@@ -879,7 +940,9 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
             a.lb_old[j] = 0.0;
             const double b = SDB_LOG2E * (gj / eps - a.norms_y[j] * c1n);
             a.bias_y[j] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
+            if constexpr (STRIPS) tagy[j] = strip_word(b, seq_y + 1, false);
         }
+        if constexpr (STRIPS) { ++seq_y; fl_row_prev = false; pend = false; }
         if (gtid == 0) { a.flag2[0] = -1; a.flag2[1] = -1; }              // frames are fresh: nothing pending (ticks are >= 0)
         grid_barrier(a.barrier, gen);
         long long n_it = 0;
@@ -901,12 +964,18 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
                         a.f[i] = nv;
                         const double b = SDB_LOG2E * (nv / eps - a.norms_x[i] * c1n);
                         a.bias_x[i] = (b > (double)SDB_NEG_SENTINEL) ? (float)b : SDB_NEG_SENTINEL;
-                        if ((nv - fr) / eps > a.log_tau) atomicMax(a.flag2 + (tick & 1), tick);
+                        const bool over = (nv - fr) / eps > a.log_tau;
+                        if (over) atomicMax(a.flag2 + (tick & 1), tick);
+                        if constexpr (STRIPS) tagx[i] = strip_word(b, seq_x + 1, over);
                     }
+                    if constexpr (STRIPS) { ++seq_x; pend = pending; }
                 } else {
                     if constexpr (STRIPS)
-                        strip_pass<true>(srow, first_row, n_rows, (int)m, ldm, sc_hi, sc_lo, a.bias_y, sbias, a.Lr, a.logp, eps, alpha1, a.log_m,
-                                         a.f, a.u, a.la_old, a.bias_x, a.flag2, tick, a.log_tau);
+                        {
+                            ++seq_x;
+                            strip_pass<true>(srow, first_row, n_rows, (int)m, ldm, sc_hi, sc_lo, tagy, seq_y, sbias, a.Lr, a.logp, eps, alpha1,
+                                             a.log_m, a.f, a.u, a.la_old, tagx, seq_x, a.flag2, tick, a.log_tau, fl_row_prev, true, pend, bits);
+                        }
                     else if constexpr (RESIDENT)
                         res_pass<true, true>(a, smem, n_owned, row_tiles, col_tiles, sc_hi, sc_lo, a.bias_y, a.partial_row, cnt_row, a.Lr, a.norms_x, a.logp,
                                              eps, alpha1, a.log_m, a.f, a.u, a.la_old, a.bias_x, tick, red);
@@ -914,17 +983,22 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
                     solve_pass<true>(a.row, direct, sc_hi, sc_lo, a.partial_row, a.ns_row, cnt_row, a.Lr, a.norms_x, c1n, a.logp, eps, alpha1,
                                      a.log_m, a.f, a.u, a.la_old, a.bias_x, a.flag2, tick, a.log_tau, smem);
                 }
-                grid_barrier(a.barrier, gen);
-                if constexpr (STRIPS)
-                    strip_pass<true>(scol, first_col, n_cols, (int)n, ldn, sc_hi, sc_lo, a.bias_x, sbias, a.Lc, a.logq, eps, alpha2, a.log_N,
-                                     a.g, a.v, a.lb_old, a.bias_y, a.flag2, tick, a.log_tau);
-                else if constexpr (RESIDENT)
+                // strips: the column pass waits for the rows' tagged entries themselves; only the vector-loop update above (it
+                // wrote rows it does not own) needs the full barrier
+                if (!STRIPS || (sw == 0 && lr_known)) grid_barrier(a.barrier, gen);
+                if constexpr (STRIPS) {
+                    ++seq_y;
+                    bool pend_unused;
+                    strip_pass<true>(scol, first_col, n_cols, (int)n, ldn, sc_hi, sc_lo, tagx, seq_x, sbias, a.Lc, a.logq, eps, alpha2, a.log_N,
+                                     a.g, a.v, a.lb_old, tagy, seq_y, a.flag2, tick, a.log_tau, pend, false, pend_unused, bits);
+                    fl_row_prev = bits;                                   // the tau bits of this tick's row updates
+                } else if constexpr (RESIDENT)
                     res_pass<true, false>(a, smem, n_owned, row_tiles, col_tiles, sc_hi, sc_lo, a.bias_x, a.partial_col, cnt_col, a.Lc, a.norms_y, a.logq, eps,
                                           alpha2, a.log_N, a.g, a.v, a.lb_old, a.bias_y, tick, red);
                 else
                 solve_pass<true>(a.col, direct, sc_hi, sc_lo, a.partial_col, a.ns_col, cnt_col, a.Lc, a.norms_y, c1n, a.logq, eps, alpha2,
                                  a.log_N, a.g, a.v, a.lb_old, a.bias_y, a.flag2, tick, a.log_tau, smem);
-                grid_barrier(a.barrier, gen);
+                if (!STRIPS || sw == n_inner - 1) grid_barrier(a.barrier, gen);     // strips: the batch's checks read every row
             }
             n_it += n_inner;
             lr_known = false;
@@ -933,8 +1007,12 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
             if (final_stage) {
                 if (!have_sumK) {
                     if constexpr (STRIPS)
-                        strip_pass<false>(srow, first_row, n_rows, (int)m, ldm, scd_hi, scd_lo, nullptr, sbias, a.Lr, nullptr, eps, 0.0, 0.0,
-                                          nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau);
+                        {
+                            bool p_unused, b_unused;
+                            strip_pass<false>(srow, first_row, n_rows, (int)m, ldm, scd_hi, scd_lo, nullptr, 0u, sbias, a.Lr, nullptr, eps, 0.0,
+                                              0.0, nullptr, nullptr, nullptr, nullptr, 0u, a.flag2, tick, a.log_tau, false, false, p_unused,
+                                              b_unused);
+                        }
                     else if constexpr (RESIDENT)
                         res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, scd_hi, scd_lo, nullptr, a.partial_row, cnt_row, a.Lr, a.norms_x, nullptr, eps,
                                               0.0, 0.0, nullptr, nullptr, nullptr, nullptr, tick, red);
@@ -950,8 +1028,11 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
                 }
                 // row LSE at the new g: the gap's row marginal, and the next iteration's row pass
                 if constexpr (STRIPS)
-                    strip_pass<false>(srow, first_row, n_rows, (int)m, ldm, sc_hi, sc_lo, a.bias_y, sbias, a.Lr, nullptr, eps, 0.0, 0.0,
-                                      nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau);
+                {
+                    bool p_unused, b_unused;
+                    strip_pass<false>(srow, first_row, n_rows, (int)m, ldm, sc_hi, sc_lo, tagy, seq_y, sbias, a.Lr, nullptr, eps, 0.0, 0.0,
+                                      nullptr, nullptr, nullptr, nullptr, 0u, a.flag2, tick, a.log_tau, false, false, p_unused, b_unused);
+                }
                 else if constexpr (RESIDENT)
                     res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, sc_hi, sc_lo, a.bias_y, a.partial_row, cnt_row, a.Lr, a.norms_x, nullptr, eps,
                                           0.0, 0.0, nullptr, nullptr, nullptr, nullptr, tick, red);
@@ -1027,8 +1108,11 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
         const double sc = direct ? -c1 * SDB_LOG2E : 2.0 * c1 * SDB_LOG2E;
         const float sc_hi = (float)sc;
         if constexpr (STRIPS)
-            strip_pass<false>(srow, first_row, n_rows, (int)m, ldm, sc_hi, (float)(sc - (double)sc_hi), a.bias_y, sbias, a.Lr, nullptr, eps,
-                              0.0, 0.0, nullptr, nullptr, nullptr, nullptr, a.flag2, tick, a.log_tau);
+        {
+            bool p_unused, b_unused;
+            strip_pass<false>(srow, first_row, n_rows, (int)m, ldm, sc_hi, (float)(sc - (double)sc_hi), tagy, seq_y, sbias, a.Lr, nullptr, eps,
+                              0.0, 0.0, nullptr, nullptr, nullptr, nullptr, 0u, a.flag2, tick, a.log_tau, false, false, p_unused, b_unused);
+        }
         else if constexpr (RESIDENT)
             res_pass<false, true>(a, smem, n_owned, row_tiles, col_tiles, sc_hi, (float)(sc - (double)sc_hi), a.bias_y, a.partial_row, cnt_row,
                                   a.Lr, a.norms_x, nullptr, eps, 0.0, 0.0, nullptr, nullptr, nullptr, nullptr, tick, red);
@@ -1147,7 +1231,9 @@ extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_
     if (strips) {
         // one CTA per SM; every CTA keeps ceil(n/grid) full rows and ceil(m/grid) full columns of D plus one bias vector
         static size_t smem_set_s[SDB_MAX_DEVICES] = {0};
-        const int64_t g = n_sm;
+        int64_t g = n_sm;                               // every CTA must own at least one row and one column (dataflow protocol)
+        if (g > d->n) g = d->n;
+        if (g > d->m) g = d->m;
         const int64_t rp = (d->n + g - 1) / g, cp = (d->m + g - 1) / g;
         const int64_t ldm = (d->m + 3) & ~(int64_t)3, ldn = (d->n + 3) & ~(int64_t)3;
         const size_t need = sizeof(float) * (size_t)(rp * ldm + cp * ldn + (ldm > ldn ? ldm : ldn));
@@ -1192,6 +1278,9 @@ extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_
     if (grid > SDB_SOLVE_MAX_CTAS) grid = SDB_SOLVE_MAX_CTAS;
     e = cudaMemsetAsync(barrier2, 0, SDB_BARRIER_WORDS * sizeof(unsigned int), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(result, 0, sizeof(sdb_solve_result), st);
+    // strip form: the tagged bias vectors live behind the per-CTA sums in `scratch`; production number 0 = "nothing yet"
+    if (e == cudaSuccess && strips)
+        e = cudaMemsetAsync(scratch + (size_t)SDB_SOLVE_MAX_CTAS * 10, 0, sizeof(double) * (size_t)(d->n + d->m), st);
     if (e == cudaSuccess) e = cudaMemsetAsync(counters, 0, sizeof(unsigned int) * (size_t)((d->n + BM - 1) / BM + (d->m + BM - 1) / BM), st);
     if (e != cudaSuccess) return (int)e;
     void* params[] = {&a};

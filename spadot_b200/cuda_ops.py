@@ -519,7 +519,8 @@ class CudaOps(VectorOps):
             tiles = (self.n + 63) // 64 + (self.m + 63) // 64
             self._solve_ws = dict(flag2=torch.zeros(2, dtype=torch.int32, device=self.device),
                                   counters=torch.zeros(tiles, dtype=torch.int32, device=self.device),
-                                  scratch=torch.zeros(_lib.SOLVE_MAX_CTAS * 10, dtype=torch.float64, device=self.device),
+                                  # per-CTA partial sums + the strip form's tagged bias vectors (n + m 64-bit words)
+                                  scratch=torch.zeros(_lib.SOLVE_MAX_CTAS * 10 + self.n + self.m, dtype=torch.float64, device=self.device),
                                   result=torch.zeros(ctypes.sizeof(_lib.SolveResult), dtype=torch.uint8, device=self.device))
         ws = self._solve_ws
         fn = _lib.load().sdb_sinkhorn_solve_persistent
