@@ -784,13 +784,19 @@ __device__ void strip_pass(const float* strip, int first, int n_owned, int len, 
     bits_out = bits;
     const bool pending = UPDATE && (pend_base || (add_bits && bits));
     pending_out = pending;
-    for (int r = warp; r < n_owned; r += NT / 32) {
+    // Lane k of a warp finishes (LSE, update, publication) the k-th row the warp reduced: the rows' fp64 tails run side by side
+    // instead of one after the other.  What the update reads from global memory is requested before the reductions, so that
+    // its L2 round trip overlaps them.
+    const int my_r = warp + lane * (NT / 32);                     // the row this lane finishes
+    double u_old = 0.0, u_fr = 0.0, u_lm = 0.0;
+    if (UPDATE && my_r < n_owned) { u_old = pot[first + my_r]; u_fr = frame[first + my_r]; u_lm = logmarg[first + my_r]; }
+    float my_mall = SDB_NEG_SENTINEL;
+    double my_S = 0.0;
+    for (int r0 = warp; r0 < n_owned; r0 += 32 * (NT / 32)) {     // (more than 32 rows per warp: finish them group by group)
+    for (int r = r0, k = 0; r < n_owned && k < 32; r += NT / 32, ++k) {
         const float* row = strip + (size_t)r * ld;
         float mall;
         double S;
-        // what the update of this row reads from global memory is requested now, so that its L2 round trip overlaps the reduction
-        double u_old = 0.0, u_fr = 0.0, u_lm = 0.0;
-        if (UPDATE && lane == 0) { u_old = pot[first + r]; u_fr = frame[first + r]; u_lm = logmarg[first + r]; }
         if (ld <= STRIP_REG_LEN) {
             // the whole row in registers (64 values per lane): every exponent first, one maximum for the warp, then 64 independent
             // ex2 per lane - no running maximum, no dependency from one chunk to the next (a CTA runs alone on its SM: 255
@@ -838,8 +844,14 @@ __device__ void strip_pass(const float* strip, int first, int n_owned, int len, 
         }
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) S += __shfl_xor_sync(0xffffffffu, S, o);      // the 32 lane sums are combined in fp64
-        if (lane == 0) {
-            const int64_t i = (int64_t)first + r;
+        if (lane == k) { my_mall = mall; my_S = S; }
+    }
+        const int fin_r = r0 + lane * (NT / 32);
+        if (fin_r < n_owned) {
+            const int64_t i = (int64_t)first + fin_r;
+            const float mall = my_mall;
+            const double S = my_S;
+            if (UPDATE && r0 != warp) { u_old = pot[i]; u_fr = frame[i]; u_lm = logmarg[i]; }      // later groups: no prefetch
             const bool valid = mall > -1e29f && S > 0.0;
             const double Li = valid ? SDB_LN2 * ((double)mall + log2(S)) : -INFINITY;
             L[i] = Li;
