@@ -253,6 +253,8 @@ int sdb_sinkhorn_sweeps_persistent(const sdb_sweep_desc* d, int n_sweeps, int fi
  * (SDB_SOLVE_MAX_CTAS * 10 + n + m doubles: per-CTA sums, then the strip form's tagged bias vectors), result (device).
  * Iterations are stamped first_tick, first_tick + 1, ... */
 #define SDB_SOLVE_MAX_CTAS 1024
+#define SDB_STRIP_SMEM_MAX (223 * 1024)  /* strip form: 4*(ceil(n/g)*pad4(m) + ceil(m/g)*pad4(n) + max(pad4(n), pad4(m), ceil(max(n,m)/g)*dpad))
+                                          * bytes with g = min(#SM, n, m) must not exceed this */
 #define SDB_BARRIER_WORDS 1024   /* grid barrier of the cooperative kernels: top counter, generation, 16 group counters 128 B apart */
 typedef struct sdb_solve_params {
     double lambda1, lambda2, epsilon, epsilon0, tolerance, tau, max_iter;
@@ -267,7 +269,7 @@ typedef struct sdb_solve_params {
                                   * SDB_E_UNSUPPORTED when the tiles do not fit (use 0 = streamed tiles).
                                   * 2 = STRIP form (owner computes): one CTA per SM holds ceil(n/grid) whole rows and
                                   * ceil(m/grid) whole columns of |x_i - y_j|^2 plus one bias vector in shared memory
-                                  * (<= 225 KB: the ChickenHeart sizes, up to about 2000 x 2000); a half-iteration has no
+                                  * (<= SDB_STRIP_SMEM_MAX: the ChickenHeart sizes, up to about 2000 x 2000); a half-iteration has no
                                   * partial results and no arrival counters - the owner reduces, updates, and the only
                                   * exchange is the updated vector, which travels as 64-bit (bias, production number, tau bit)
                                   * words that the consumers poll: inside a batch of iterations there is NO grid barrier, a

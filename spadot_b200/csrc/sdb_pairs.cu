@@ -417,9 +417,9 @@ struct SolveArgs {
 
 template <int K>
 __device__ void solve_grid_sums(double (&acc)[K], double* scratch, unsigned int* bar, unsigned int& gen, double (&out)[K]) {
-    __shared__ double sm[8][K];
+    __shared__ double sm[32][K];
     __shared__ double tot[K];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (int)(blockDim.x >> 5);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const double v = sdb_warp_sum(acc[k]);
@@ -428,12 +428,12 @@ __device__ void solve_grid_sums(double (&acc)[K], double* scratch, unsigned int*
     __syncthreads();
     if (threadIdx.x < K) {
         double v = 0.0;
-        for (int w = 0; w < 8; ++w) v += sm[w][threadIdx.x];
+        for (int w = 0; w < n_warps; ++w) v += sm[w][threadIdx.x];
         scratch[(size_t)blockIdx.x * K + threadIdx.x] = v;
     }
     grid_barrier(bar, gen);
     // every CTA adds the per-CTA partials in the same order: identical sums, identical decisions everywhere
-    for (int k = warp; k < K; k += 8) {
+    for (int k = warp; k < K; k += n_warps) {
         double v = 0.0;
         for (unsigned b = lane; b < gridDim.x; b += 32) v += __ldcg(scratch + (size_t)b * K + k);
         v = sdb_warp_sum(v);
@@ -712,21 +712,41 @@ __device__ void res_pass(const SolveArgs& a, const float* tiles, int n_owned, in
 // from the dependent chain between two barriers (profiles/r2_ncu_solve_kernel_hot_lines.txt: 48 % of the one-launch solve was
 // waiting in barriers for exactly that tail).  Same tile arithmetic as the resident form: t = fma(s_hi, D, fma(s_lo, D, bias)).
 constexpr int STRIP_REG_LEN = 2048;      // rows up to this length are reduced from registers
+constexpr int STRIP_NT = 512;            // threads per CTA of the strip form: 16 warps = one owned row per warp at ChickenHeart sizes
+
+constexpr int STRIP_DREG = 32;           // points of up to this (padded) dimension are held in registers while a strip is built
 
 __device__ void strip_build(const float* __restrict__ pt, int64_t ldp, const float* __restrict__ qt, int64_t ldq, int64_t n_q,
-                            int dpad, int first, int n_owned, int ld, float* strip) {
-    for (int idx = threadIdx.x; idx < n_owned * ld; idx += NT) {
-        const int r = idx / ld, j = idx - r * ld;
-        float acc = 1.0e30f;                                     // padding: scale * 1e30 stays finite, 2^that = 0
-        if (j < n_q) {
-            acc = 0.f;
-            for (int q = 0; q < dpad; ++q) {                     // the accumulation order of res_build_tiles / the direct tiles
-                const float df = pt[(int64_t)q * ldp + first + r] - qt[(int64_t)q * ldq + j];
-                acc = fmaf(df, df, acc);
+                            int dpad, int first, int n_owned, int ld, float* strip, float* stage) {
+    // stage: the owned points' coordinates, [n_owned][dpad] (borrowed space, see the caller)
+    for (int idx = threadIdx.x; idx < n_owned * dpad; idx += blockDim.x) {
+        const int r = idx / dpad, q = idx - r * dpad;
+        stage[idx] = pt[(int64_t)q * ldp + first + r];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < ld; j += blockDim.x) {
+        if (j >= n_q) {
+            for (int r = 0; r < n_owned; ++r) strip[(size_t)r * ld + j] = 1.0e30f;    // padding: scale * 1e30 stays finite, 2^that = 0
+        } else if (dpad <= STRIP_DREG) {
+            float yq[STRIP_DREG];                                // this column's coordinates: read once (coalesced over j)
+#pragma unroll
+            for (int q = 0; q < STRIP_DREG; ++q) yq[q] = q < dpad ? qt[(int64_t)q * ldq + j] : 0.f;
+            for (int r = 0; r < n_owned; ++r) {
+                float acc = 0.f;
+#pragma unroll
+                for (int q = 0; q < STRIP_DREG; ++q)             // the accumulation order of res_build_tiles / the direct tiles
+                    if (q < dpad) { const float df = stage[r * dpad + q] - yq[q]; acc = fmaf(df, df, acc); }
+                strip[(size_t)r * ld + j] = acc;
+            }
+        } else {
+            for (int r = 0; r < n_owned; ++r) {
+                float acc = 0.f;
+                for (int q = 0; q < dpad; ++q) { const float df = stage[r * dpad + q] - qt[(int64_t)q * ldq + j]; acc = fmaf(df, df, acc); }
+                strip[(size_t)r * ld + j] = acc;
             }
         }
-        strip[idx] = acc;
     }
+    __syncthreads();
 }
 
 // One half-iteration over this CTA's strip: (max, sum) of 2^t over each owned row, then its LSE and, with UPDATE, the potential
@@ -747,9 +767,9 @@ __device__ void strip_pass(const float* strip, int first, int n_owned, int len, 
                            double alpha, double log_n_other, double* pot, double* frame, double* la_old, unsigned long long* tout,
                            unsigned out_seq, int* flag2, int tick, double log_tau, bool pend_base, bool add_bits, bool& pending_out,
                            bool& bits_out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (int)(blockDim.x >> 5);
     int my_bits = 0;
-    for (int base = 0; base < ld; base += 8 * NT) {
+    for (int base = 0; base < ld; base += 8 * (int)blockDim.x) {
         unsigned long long v[8];
         if (tin) {
             unsigned spins = 0;
@@ -758,13 +778,13 @@ __device__ void strip_pass(const float* strip, int first, int n_owned, int len, 
                 ok = true;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const int j = base + k * NT + (int)threadIdx.x;
+                    const int j = base + k * (int)blockDim.x + (int)threadIdx.x;
                     v[k] = 0ull;
                     if (j < len) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v[k]) : "l"(tin + j) : "memory");
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const int j = base + k * NT + (int)threadIdx.x;
+                    const int j = base + k * (int)blockDim.x + (int)threadIdx.x;
                     if (j < len && (((unsigned)(v[k] >> 32)) & 0x7fffffffu) != expect) ok = false;
                 }
                 if (!ok && ++spins > (1u << 22)) __trap();       // a protocol error must end the launch, not hang the device
@@ -772,7 +792,7 @@ __device__ void strip_pass(const float* strip, int first, int n_owned, int len, 
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int j = base + k * NT + (int)threadIdx.x;
+            const int j = base + k * (int)blockDim.x + (int)threadIdx.x;
             if (j < ld) {
                 float b = 0.f;
                 if (tin && j < len) { b = __uint_as_float((unsigned)v[k]); my_bits |= (int)(v[k] >> 63); }
@@ -787,13 +807,13 @@ __device__ void strip_pass(const float* strip, int first, int n_owned, int len, 
     // Lane k of a warp finishes (LSE, update, publication) the k-th row the warp reduced: the rows' fp64 tails run side by side
     // instead of one after the other.  What the update reads from global memory is requested before the reductions, so that
     // its L2 round trip overlaps them.
-    const int my_r = warp + lane * (NT / 32);                     // the row this lane finishes
+    const int my_r = warp + lane * n_warps;                     // the row this lane finishes
     double u_old = 0.0, u_fr = 0.0, u_lm = 0.0;
     if (UPDATE && my_r < n_owned) { u_old = pot[first + my_r]; u_fr = frame[first + my_r]; u_lm = logmarg[first + my_r]; }
     float my_mall = SDB_NEG_SENTINEL;
     double my_S = 0.0;
-    for (int r0 = warp; r0 < n_owned; r0 += 32 * (NT / 32)) {     // (more than 32 rows per warp: finish them group by group)
-    for (int r = r0, k = 0; r < n_owned && k < 32; r += NT / 32, ++k) {
+    for (int r0 = warp; r0 < n_owned; r0 += 32 * n_warps) {     // (more than 32 rows per warp: finish them group by group)
+    for (int r = r0, k = 0; r < n_owned && k < 32; r += n_warps, ++k) {
         const float* row = strip + (size_t)r * ld;
         float mall;
         double S;
@@ -846,7 +866,7 @@ __device__ void strip_pass(const float* strip, int first, int n_owned, int len, 
         for (int o = 1; o < 32; o <<= 1) S += __shfl_xor_sync(0xffffffffu, S, o);      // the 32 lane sums are combined in fp64
         if (lane == k) { my_mall = mall; my_S = S; }
     }
-        const int fin_r = r0 + lane * (NT / 32);
+        const int fin_r = r0 + lane * n_warps;
         if (fin_r < n_owned) {
             const int64_t i = (int64_t)first + fin_r;
             const float mall = my_mall;
@@ -882,14 +902,15 @@ __device__ __forceinline__ unsigned long long strip_word(double b, unsigned seq,
 
 // FORM: 0 streamed tiles (coordinates re-read every pass), 1 resident 64x64 cost tiles, 2 strips (owner computes whole rows)
 template <int FORM>
-__global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
+__global__ void __launch_bounds__(FORM == 2 ? STRIP_NT : NT) sinkhorn_solve_kernel(SolveArgs a) {
     constexpr bool RESIDENT = (FORM == 1);
     constexpr bool STRIPS = (FORM == 2);
+    constexpr int NTK = STRIPS ? STRIP_NT : NT;                  // threads per CTA of this form
     extern __shared__ __align__(16) float smem[];
     unsigned int gen = *reinterpret_cast<volatile unsigned int*>(a.barrier + 1);
     const int64_t n = a.row.n_p, m = a.col.n_p;
     const int row_tiles = (int)((n + BM - 1) / BM);
-    const int64_t gtid = (int64_t)blockIdx.x * NT + threadIdx.x, gsize = (int64_t)gridDim.x * NT;
+    const int64_t gtid = (int64_t)blockIdx.x * NTK + threadIdx.x, gsize = (int64_t)gridDim.x * NTK;
     unsigned int* cnt_row = a.counters;
     unsigned int* cnt_col = a.counters + row_tiles;
     double eps = a.eps_stage[0];
@@ -927,8 +948,9 @@ __global__ void __launch_bounds__(NT) sinkhorn_solve_kernel(SolveArgs a) {
         first_col = (int)(((int64_t)blockIdx.x * m) / gridDim.x);
         n_rows = (int)(((int64_t)(blockIdx.x + 1) * n) / gridDim.x) - first_row;
         n_cols = (int)(((int64_t)(blockIdx.x + 1) * m) / gridDim.x) - first_col;
-        strip_build(a.row.pt, a.row.ldp, a.col.pt, a.col.ldp, m, a.row.dpad, first_row, n_rows, ldm, srow);
-        strip_build(a.col.pt, a.col.ldp, a.row.pt, a.row.ldp, n, a.row.dpad, first_col, n_cols, ldn, scol);
+        // (the coordinate staging borrows the bias buffer: max(ldm, ldn) floats; the host checked strip_rows/cols * dpad fits)
+        strip_build(a.row.pt, a.row.ldp, a.col.pt, a.col.ldp, m, a.row.dpad, first_row, n_rows, ldm, srow, sbias);
+        strip_build(a.col.pt, a.col.ldp, a.row.pt, a.row.ldp, n, a.row.dpad, first_col, n_cols, ldn, scol, sbias);
         __syncthreads();
     }
     for (int e = 0; e <= 5 && status == 0; ++e) {
@@ -1248,11 +1270,14 @@ extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_
         if (g > d->m) g = d->m;
         const int64_t rp = (d->n + g - 1) / g, cp = (d->m + g - 1) / g;
         const int64_t ldm = (d->m + 3) & ~(int64_t)3, ldn = (d->n + 3) & ~(int64_t)3;
-        const size_t need = sizeof(float) * (size_t)(rp * ldm + cp * ldn + (ldm > ldn ? ldm : ldn));
-        if (need > 225 * 1024) return SDB_E_UNSUPPORTED;
+        // the last buffer stages the other side's bias in every pass and, once, the owned points' coordinates
+        int64_t stage = ldm > ldn ? ldm : ldn;
+        if ((rp > cp ? rp : cp) * d->dpad > stage) stage = (rp > cp ? rp : cp) * d->dpad;
+        const size_t need = sizeof(float) * (size_t)(rp * ldm + cp * ldn + stage);
+        if (need > SDB_STRIP_SMEM_MAX) return SDB_E_UNSUPPORTED;
         cudaError_t e0 = sdb_ensure_smem(sinkhorn_solve_kernel<2>, need, smem_set_s);
         if (e0 != cudaSuccess) return (int)e0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_solve_kernel<2>, NT, need);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sinkhorn_solve_kernel<2>, STRIP_NT, need);
         if (e != cudaSuccess) return (int)e;
         if (per_sm < 1) return SDB_E_UNSUPPORTED;
         grid = (int)g; smem = need; a.strip_rows = (int)rp; a.strip_cols = (int)cp;
@@ -1298,7 +1323,7 @@ extern "C" int sdb_sinkhorn_solve_persistent(const sdb_sweep_desc* d, const sdb_
     void* params[] = {&a};
     e = cudaLaunchCooperativeKernel(strips ? (const void*)sinkhorn_solve_kernel<2>
                                            : resident ? (const void*)sinkhorn_solve_kernel<1> : (const void*)sinkhorn_solve_kernel<0>,
-                                    dim3((unsigned)grid), dim3(NT), params, smem, st);
+                                    dim3((unsigned)grid), dim3(strips ? STRIP_NT : NT), params, smem, st);
     return (int)e;
 }
 

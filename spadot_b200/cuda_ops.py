@@ -476,6 +476,15 @@ class CudaOps(VectorOps):
     def _persistent_eligible(self):
         return (not self.use_tc) and self.persistent and 0 < self.n * self.m <= self.PERSISTENT_MAX_PAIRS
 
+    STRIP_SMEM_MAX = 223 * 1024        # SDB_STRIP_SMEM_MAX
+
+    def strip_bytes(self, n_sm):
+        """Shared memory per CTA of the strip form (include/spadot_b200.h, SDB_STRIP_SMEM_MAX)."""
+        g = max(1, min(n_sm, self.n, self.m))
+        ldm, ldn = (self.m + 3) & ~3, (self.n + 3) & ~3
+        rp, cp = -(-self.n // g), -(-self.m // g)
+        return 4 * (rp * ldm + cp * ldn + max(ldm, ldn, max(rp, cp) * self.X.dpad))
+
     def fused_solve(self, st, lambda1, lambda2, epsilon, batch_size, tolerance, tau, epsilon0, max_iter):
         """The whole duality-gap solve in ONE cooperative launch (sdb_sinkhorn_solve_persistent) for problems the persistent
         SIMT kernel serves; None when this problem is not one of them (the caller then runs the host-driven stage loop)."""
@@ -487,11 +496,8 @@ class CudaOps(VectorOps):
         R, C = (self.n + 63) // 64, (self.m + 63) // 64
         # forms of the kernel, best first: 2 = strips (every CTA owns whole rows and whole columns of the cost matrix in shared
         # memory - the ChickenHeart sizes), 1 = resident 64x64 tiles, 0 = streamed tiles
-        g = self._n_sm
-        ldm, ldn = (self.m + 3) & ~3, (self.n + 3) & ~3
-        strip_bytes = 4 * (-(-self.n // g) * ldm + -(-self.m // g) * ldn + max(ldm, ldn))
         forms = []
-        if self.STRIP_FORM and strip_bytes <= 225 * 1024:
+        if self.STRIP_FORM and self.strip_bytes(self._n_sm) <= self.STRIP_SMEM_MAX:
             forms.append(2)
         if self.RESIDENT_TILES and R * C <= 2 * self._n_sm * self.RESIDENT_MAX_TILES_PER_CTA:
             forms.append(1)

@@ -460,8 +460,8 @@ def test_whole_solve_in_one_launch_matches_host_stage_loop(ot, n, m, d, tau, for
         out.append((cp, ops.launches - l0))
     (c1, l1), (c2, l2) = out
     assert l1 <= 2 and l2 > 20                                  # one launch vs the batch-by-batch loop
-    fits = 4 * (-(-n // 148) * ((m + 3) & ~3) + -(-m // 148) * ((n + 3) & ~3) + max(n, m) + 3) <= 225 * 1024
-    if form == "strips" and fits and torch.cuda.get_device_properties(0).multi_processor_count == 148:
+    fits = c1.ops.strip_bytes(torch.cuda.get_device_properties(0).multi_processor_count) <= c1.ops.STRIP_SMEM_MAX
+    if form == "strips" and fits:
         assert c1.ops.solve_form == 2                           # the strip form really ran
     elif form == "resident" and n * m <= 64 * 64 * 2 * 148 * 6:
         assert c1.ops.solve_form == 1
