@@ -195,3 +195,28 @@ def test_gat_encoder_seed_rows_only_equals_full_run(hop_ordered):
     for a, b in zip(ga, gb):
         scale = float(a.abs().max()) + 1e-30
         assert float((a - b).abs().max()) <= 1e-11 * scale
+
+
+def test_prefix_plan_is_the_hop_closure():
+    """CsrGraph.prefix_plan: for every layer, the source prefix contains every in-neighbour of the destination prefix (brute
+    force over the edge list), the last layer's destinations are the seeds, and each layer's destinations are the next layer's
+    sources; on a hop-ordered batch the prefixes are exactly the hop sets."""
+    from spadot_b200 import gat, graph
+    rng = np.random.default_rng(3)
+    coords = rng.uniform(0, 50, size=(1500, 2))
+    from oracle import graph_ref
+    ei_all = torch.as_tensor(np.asarray(graph_ref.spatial_edge_index(coords, 6)), dtype=torch.long)     # (the product's kNN needs the GPU)
+    nodes, lei, ns = next(iter(graph.two_hop_batches(ei_all, 1500, batch_size=32)))
+    n = int(nodes.numel())
+    g = gat.CsrGraph(lei, n, add_self_loops=True)
+    plan = g.prefix_plan(ns, 3)
+    assert plan[-1][0] == ns
+    src, dst = lei[0].numpy(), lei[1].numpy()
+    for (d, s_), nxt in zip(plan, plan[1:] + [None]):
+        need = int(max(src[dst < d].max() + 1, d))
+        assert s_ == need                                           # the smallest prefix that holds every source
+        if nxt is not None:
+            assert nxt[1] == d                                      # this layer produces exactly what the next one reads
+    hop1 = int(np.unique(np.concatenate([src[dst < ns], np.arange(ns)])).size)
+    assert plan[2] == (ns, hop1) and plan[1] == (hop1, n) and plan[0] == (n, n)
+    assert g.prefix_plan(ns, 3) is plan                             # cached
