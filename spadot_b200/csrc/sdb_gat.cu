@@ -10,6 +10,7 @@
 // backward uses the by-source CSR so there are no atomics and results are deterministic.
 // HBM/L2 gather-bound:  bytes ~ E*H*C*s (row gathers) + n*H*C*s (write) + E*(4 + 2*H*s).
 #include "sdb_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -50,18 +51,17 @@ __device__ __forceinline__ void vec_store(T* p, const T (&v)[Vec<T>::W]) {
     *reinterpret_cast<typename Vec<T>::type*>(p) = t;
 }
 
-// ---------------------------------------------------------------------------------------- forward
+// ======================================================================================== per-node form
+// One node at a time, every thread of the CTA cooperating.  This is the general form (any H, any C, any degree); the tile
+// kernels below call it for the tiles that exceed their shared-memory budget.  Must be called by ALL threads of the CTA.
+
+// forward: segment softmax of node i (one warp per head), then the weighted sum of its gathered source rows
 template <typename T>
-__global__ void __launch_bounds__(128) gat_fwd_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
-                                                      const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
-                                                      const int32_t* __restrict__ col, const int32_t* __restrict__ order,
-                                                      int64_t n, int H, int C, T slope, T* __restrict__ out,
-                                                      T* __restrict__ alpha) {
-    const int64_t i = order ? order[blockIdx.x] : blockIdx.x;   // locality order of the CTAs (L2 reuse of gathered rows)
-    const int64_t e0 = rowptr[i], e1 = rowptr[i + 1];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // segment softmax: one warp per head (round-robin when H > 4)
-    for (int h = warp; h < H; h += 4) {
+__device__ void gat_fwd_node(const T* __restrict__ feat, const T* __restrict__ a_src, const T* __restrict__ a_dst,
+                             const int32_t* __restrict__ col, int64_t i, int64_t e0, int64_t e1, int H, int C, T slope,
+                             T* __restrict__ out, T* __restrict__ alpha) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5, nt = blockDim.x;
+    for (int h = warp; h < H; h += nw) {
         const T ad = a_dst[i * H + h];
         T mx = -INFINITY;
         for (int64_t e = e0 + lane; e < e1; e += 32) {
@@ -84,11 +84,11 @@ __global__ void __launch_bounds__(128) gat_fwd_kernel(const T* __restrict__ feat
         }
     }
     __syncthreads();
-    // aggregation: thread owns feature columns c, c+128, ...; each source row is read once, coalesced
+    // aggregation: thread owns feature columns c, c+nt, ...; each source row is read once, coalesced
     const int HC = H * C;
     constexpr int W = Vec<T>::W;
     if (C % W == 0) {
-        for (int c = threadIdx.x * W; c < HC; c += 128 * W) {
+        for (int c = threadIdx.x * W; c < HC; c += nt * W) {
             const int h = c / C;
             T acc[W];
 #pragma unroll
@@ -103,31 +103,27 @@ __global__ void __launch_bounds__(128) gat_fwd_kernel(const T* __restrict__ feat
             vec_store(out + i * HC + c, acc);
         }
     } else {
-        for (int c = threadIdx.x; c < HC; c += 128) {
+        for (int c = threadIdx.x; c < HC; c += nt) {
             const int h = c / C;
             T acc = T(0);
             for (int64_t e = e0; e < e1; ++e) acc += alpha[e * H + h] * feat[(int64_t)col[e] * HC + c];
             out[i * HC + c] = acc;
         }
     }
+    __syncthreads();
 }
 
-// ---------------------------------------------------------------------------------------- backward, by destination
-// dlogit[e,h] = d loss / d (a_src[j,h] + a_dst[i,h]);  grad_a_dst[i,h] = sum_e dlogit[e,h]
+// backward, by destination:  dlogit[e,h] = d loss / d (a_src[j,h] + a_dst[i,h]);  grad_a_dst[i,h] = sum_e dlogit[e,h]
 template <typename T>
-__global__ void __launch_bounds__(128) gat_bwd_dst_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
-                                                          const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
-                                                          const int32_t* __restrict__ col, const int32_t* __restrict__ order,
-                                                          int64_t n, int H, int C, T slope, const T* __restrict__ alpha,
-                                                          const T* __restrict__ grad_out, T* __restrict__ dlogit,
-                                                          T* __restrict__ grad_a_dst) {
-    const int64_t i = order ? order[blockIdx.x] : blockIdx.x;
-    const int64_t e0 = rowptr[i], e1 = rowptr[i + 1];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ void gat_bdst_node(const T* __restrict__ feat, const T* __restrict__ a_src, const T* __restrict__ a_dst,
+                              const int32_t* __restrict__ col, int64_t i, int64_t e0, int64_t e1, int H, int C, T slope,
+                              const T* __restrict__ alpha, const T* __restrict__ grad_out, T* __restrict__ dlogit,
+                              T* __restrict__ grad_a_dst) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int HC = H * C;
     const int64_t n_eh = (e1 - e0) * H;
     // d alpha[e,h] = <grad_out[i,h,:], feat[j,h,:]>  (one warp per (edge, head), coalesced over C)
-    for (int64_t p = warp; p < n_eh; p += 4) {
+    for (int64_t p = warp; p < n_eh; p += nw) {
         const int64_t e = e0 + p / H;
         const int h = (int)(p % H);
         const T* go = grad_out + i * HC + h * C;
@@ -149,7 +145,7 @@ __global__ void __launch_bounds__(128) gat_bwd_dst_kernel(const T* __restrict__ 
         if (lane == 0) dlogit[e * H + h] = acc;
     }
     __syncthreads();
-    for (int h = warp; h < H; h += 4) {
+    for (int h = warp; h < H; h += nw) {
         T s = T(0);
         for (int64_t e = e0 + lane; e < e1; e += 32) s += alpha[e * H + h] * dlogit[e * H + h];
         s = warp_sum_t(s);
@@ -165,26 +161,21 @@ __global__ void __launch_bounds__(128) gat_bwd_dst_kernel(const T* __restrict__ 
         gd = warp_sum_t(gd);
         if (lane == 0) grad_a_dst[i * H + h] = gd;
     }
+    __syncthreads();
 }
 
-// ---------------------------------------------------------------------------------------- backward, by source
-// grad_feat[j,h,:] = sum_{e: j->i} alpha[e,h] * grad_out[i,h,:];  grad_a_src[j,h] = sum_e dlogit[e,h]
+// backward, by source:  grad_feat[j,h,:] = sum_{e: j->i} alpha[e,h] * grad_out[i,h,:];  grad_a_src[j,h] = sum_e dlogit[e,h]
+// prefix form: only the edges into the first n_dst destinations exist for this layer; in the by-destination order they
+// are the edge ids below rowptr[n_dst] (e_limit), so the full by-source lists are filtered instead of rebuilt
 template <typename T>
-__global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restrict__ src_rowptr, const int32_t* __restrict__ src_dst,
-                                                          const int32_t* __restrict__ src_eid, const int32_t* __restrict__ order,
-                                                          const int64_t* __restrict__ e_limit_ptr, int H, int C,
-                                                          const T* __restrict__ alpha,
-                                                          const T* __restrict__ dlogit, const T* __restrict__ grad_out,
-                                                          T* __restrict__ grad_feat, T* __restrict__ grad_a_src) {
-    const int64_t j = order ? order[blockIdx.x] : blockIdx.x;
-    const int64_t p0 = src_rowptr[j], p1 = src_rowptr[j + 1];
-    // prefix form: only the edges into the first n_dst destinations exist for this layer; in the by-destination order they
-    // are the edge ids below rowptr[n_dst] (*e_limit_ptr), so the full by-source lists are filtered instead of rebuilt
-    const int64_t e_limit = *e_limit_ptr;
-    const int HC = H * C;
+__device__ void gat_bsrc_node(const int32_t* __restrict__ src_dst, const int32_t* __restrict__ src_eid, int64_t j, int64_t p0,
+                              int64_t p1, int64_t e_limit, int H, int C, const T* __restrict__ alpha,
+                              const T* __restrict__ dlogit, const T* __restrict__ grad_out, T* __restrict__ grad_feat,
+                              T* __restrict__ grad_a_src) {
+    const int HC = H * C, nt = blockDim.x;
     constexpr int W = Vec<T>::W;
     if (C % W == 0) {
-        for (int c = threadIdx.x * W; c < HC; c += 128 * W) {
+        for (int c = threadIdx.x * W; c < HC; c += nt * W) {
             const int h = c / C;
             T acc[W];
 #pragma unroll
@@ -200,7 +191,7 @@ __global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restr
             vec_store(grad_feat + j * HC + c, acc);
         }
     } else {
-        for (int c = threadIdx.x; c < HC; c += 128) {
+        for (int c = threadIdx.x; c < HC; c += nt) {
             const int h = c / C;
             T acc = T(0);
             for (int64_t p = p0; p < p1; ++p)
@@ -208,7 +199,7 @@ __global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restr
             grad_feat[j * HC + c] = acc;
         }
     }
-    for (int h = threadIdx.x; h < H; h += 128) {
+    for (int h = threadIdx.x; h < H; h += nt) {
         T acc = T(0);
         for (int64_t p = p0; p < p1; ++p)
             if (src_eid[p] < e_limit) acc += dlogit[(int64_t)src_eid[p] * H + h];
@@ -217,8 +208,427 @@ __global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restr
 }
 
 template <typename T>
+__global__ void __launch_bounds__(128) gat_fwd_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
+                                                      const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
+                                                      const int32_t* __restrict__ col, const int32_t* __restrict__ order,
+                                                      int64_t n, int H, int C, T slope, T* __restrict__ out,
+                                                      T* __restrict__ alpha) {
+    const int64_t i = order ? order[blockIdx.x] : blockIdx.x;   // locality order of the CTAs (L2 reuse of gathered rows)
+    gat_fwd_node<T>(feat, a_src, a_dst, col, i, rowptr[i], rowptr[i + 1], H, C, slope, out, alpha);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) gat_bwd_dst_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
+                                                          const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
+                                                          const int32_t* __restrict__ col, const int32_t* __restrict__ order,
+                                                          int64_t n, int H, int C, T slope, const T* __restrict__ alpha,
+                                                          const T* __restrict__ grad_out, T* __restrict__ dlogit,
+                                                          T* __restrict__ grad_a_dst) {
+    const int64_t i = order ? order[blockIdx.x] : blockIdx.x;
+    gat_bdst_node<T>(feat, a_src, a_dst, col, i, rowptr[i], rowptr[i + 1], H, C, slope, alpha, grad_out, dlogit, grad_a_dst);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restrict__ src_rowptr, const int32_t* __restrict__ src_dst,
+                                                          const int32_t* __restrict__ src_eid, const int32_t* __restrict__ order,
+                                                          const int64_t* __restrict__ e_limit_ptr, int H, int C,
+                                                          const T* __restrict__ alpha,
+                                                          const T* __restrict__ dlogit, const T* __restrict__ grad_out,
+                                                          T* __restrict__ grad_feat, T* __restrict__ grad_a_src) {
+    const int64_t j = order ? order[blockIdx.x] : blockIdx.x;
+    gat_bsrc_node<T>(src_dst, src_eid, j, src_rowptr[j], src_rowptr[j + 1], *e_limit_ptr, H, C, alpha, dlogit, grad_out, grad_feat,
+                     grad_a_src);
+}
+
+// ======================================================================================== tile form
+// GT_TD consecutive nodes of the locality order per CTA.  Neighbouring spots share most of their neighbours (k = 30 nearest
+// + self: eight Z-curve neighbours reference 50-90 DISTINCT sources through their ~250 edges), so the tile first
+// de-duplicates the rows it gathers (shared-memory hash set, then a rank sort so that the order - and with it every
+// floating-point sum - is reproducible), computes every edge logit ONCE, keeps the attention weights in shared memory as
+// a small dense (distinct row) x (tile member) matrix per head, and then streams every distinct row exactly once:
+//     forward / by-source backward:  acc[member][cols] += w[h][row][member] * row[cols]      (thread = column group)
+//     by-destination backward:       d alpha[row][member] = <grad_out[member], row> per head  (thread = column group,
+//                                    eight partial sums per lane reduced across the warp with a 9-shuffle butterfly)
+// That cuts the L2 gather traffic of the per-node form (E*H*C*s bytes) by the sharing factor (3-5x) and turns the
+// per-edge dependent loads into independent, unrollable ones.  The weights that are zero (a row some member does not
+// read) are multiplied like the others: a dense 8-wide update is cheaper than a branch per (row, member).
+// A tile whose edges or distinct rows do not fit (hubs) runs the per-node form above, member by member.
+constexpr int GT_TD = 8;          // tile members (destinations; sources in the by-source pass)
+constexpr int GT_EMAX = 512;      // edges of a tile held in shared memory
+constexpr int GT_UMAX = 256;      // distinct gathered rows of a tile (8 x 32 edges fit even when nothing is shared)
+constexpr int GT_UCHUNK = 128;    // by-destination backward: rows per pass through the per-warp partial sums
+constexpr int GT_HMAX = 4;        // heads (the reference's num_heads; more heads run the per-node kernels)
+constexpr int GT_HASH = 1024;     // hash-set slots (>= 2 * GT_EMAX: the probe loop always ends)
+constexpr int GT_THREADS = 256;
+
+template <typename T, int LEAD, int UROWS>
+struct GatTile {
+    T w[LEAD][UROWS][GT_TD];      // (heads, GT_UMAX): dense attention weights;  (warps, GT_UCHUNK): per-warp partial dot products
+    T ev[GT_EMAX][GT_HMAX];       // per edge and head: logit -> alpha (forward), alpha (by source), d alpha (by destination)
+    int32_t tab[GT_HASH];
+    int32_t e_nbr[GT_EMAX];       // the row an edge gathers (-1: filtered out by the prefix form)
+    int32_t e_gid[GT_EMAX];       // position of the edge in the by-destination order (index into alpha / dlogit)
+    int32_t u_tmp[GT_UMAX];
+    int32_t u_id[GT_UMAX];        // distinct rows, ascending
+    uint16_t e_loc[GT_EMAX];      // index of e_nbr in u_id
+    uint8_t e_own[GT_EMAX];       // tile member the edge belongs to
+    int64_t node[GT_TD];
+    int64_t p0[GT_TD];
+    int len[GT_TD];
+    int off[GT_TD + 1];
+    int n_u;
+};
+
+// Phase A of every tile kernel: members, their edges, the distinct rows.  Returns false (uniformly) when the tile does not fit.
+template <typename S>
+__device__ bool gat_tile_edges(S& sm, const int64_t* __restrict__ ptr, const int32_t* __restrict__ nbr,
+                               const int32_t* __restrict__ eid, int64_t e_limit, const int32_t* __restrict__ order, int64_t n) {
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * GT_TD;
+    if (tid < GT_TD) {
+        int64_t node = -1, a = 0, b = 0;
+        if (base + tid < n) {
+            node = order ? (int64_t)order[base + tid] : base + tid;
+            a = ptr[node];
+            b = ptr[node + 1];
+        }
+        sm.node[tid] = node;
+        sm.p0[tid] = a;
+        sm.len[tid] = (b - a > (int64_t)GT_EMAX) ? GT_EMAX + 1 : (int)(b - a);
+    }
+    for (int i = tid; i < GT_HASH; i += GT_THREADS) sm.tab[i] = -1;
+    if (tid == 0) sm.n_u = 0;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+#pragma unroll
+        for (int m = 0; m < GT_TD; ++m) { sm.off[m] = acc; acc += sm.len[m]; }
+        sm.off[GT_TD] = acc;
+    }
+    __syncthreads();
+    const int Et = sm.off[GT_TD];
+    if (Et > GT_EMAX) return false;
+    for (int s = tid; s < Et; s += GT_THREADS) {
+        int m = 0;
+#pragma unroll
+        for (int k = 1; k < GT_TD; ++k) m += (s >= sm.off[k]) ? 1 : 0;
+        const int64_t p = sm.p0[m] + (s - sm.off[m]);
+        const int32_t g = eid ? eid[p] : (int32_t)p;
+        int32_t v = nbr[p];
+        if ((int64_t)g >= e_limit) v = -1;
+        sm.e_nbr[s] = v;
+        sm.e_gid[s] = g;
+        sm.e_own[s] = (uint8_t)m;
+        if (v >= 0) {
+            unsigned slot = ((unsigned)v * 2654435761u) >> 22;          // 10 bits
+            while (true) {
+                const int32_t old = atomicCAS(&sm.tab[slot], -1, v);
+                if (old == -1) {
+                    const int idx = atomicAdd(&sm.n_u, 1);
+                    if (idx < GT_UMAX) sm.u_tmp[idx] = v;
+                    break;
+                }
+                if (old == v) break;
+                slot = (slot + 1) & (GT_HASH - 1);
+            }
+        }
+    }
+    __syncthreads();
+    const int U = sm.n_u;
+    if (U > GT_UMAX) return false;
+    for (int u = tid; u < U; u += GT_THREADS) {                         // rank sort: distinct keys, so ranks are a permutation
+        const int32_t my = sm.u_tmp[u];
+        int r = 0;
+        for (int k = 0; k < U; ++k) r += (sm.u_tmp[k] < my) ? 1 : 0;
+        sm.u_id[r] = my;
+    }
+    __syncthreads();
+    for (int s = tid; s < Et; s += GT_THREADS) {
+        const int32_t v = sm.e_nbr[s];
+        if (v < 0) continue;
+        int lo = 0, hi = U;                                             // lower bound of v in u_id[0, U): v is present
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (sm.u_id[mid] <= v) lo = mid; else hi = mid;
+        }
+        sm.e_loc[s] = (uint16_t)lo;
+    }
+    return true;                                                       // the caller synchronises before reading e_loc
+}
+
+// Phase B of the forward and of the by-source backward: out[member] = sum over distinct rows of w[h][row][member] * rows[row].
+template <typename T, int W, typename S>
+__device__ __forceinline__ void gat_tile_aggregate(const S& sm, const T* __restrict__ rows, T* __restrict__ out, int U, int H, int C) {
+    const int HC = H * C;
+    for (int c = threadIdx.x * W; c < HC; c += GT_THREADS * W) {
+        const int h = c / C;
+        T acc[GT_TD][W];
+#pragma unroll
+        for (int t = 0; t < GT_TD; ++t)
+#pragma unroll
+            for (int q = 0; q < W; ++q) acc[t][q] = T(0);
+#pragma unroll 8
+        for (int u = 0; u < U; ++u) {
+            T v[W];
+            if constexpr (W == 1) v[0] = rows[(int64_t)sm.u_id[u] * HC + c];
+            else vec_load(rows + (int64_t)sm.u_id[u] * HC + c, *reinterpret_cast<T(*)[Vec<T>::W]>(&v[0]));
+            T a[GT_TD];
+            constexpr int VW = Vec<T>::W;
+#pragma unroll
+            for (int t = 0; t < GT_TD; t += VW) vec_load(&sm.w[h][u][t], *reinterpret_cast<T(*)[VW]>(&a[t]));
+#pragma unroll
+            for (int t = 0; t < GT_TD; ++t)
+#pragma unroll
+                for (int q = 0; q < W; ++q) acc[t][q] += a[t] * v[q];
+        }
+#pragma unroll
+        for (int t = 0; t < GT_TD; ++t) {
+            const int64_t node = sm.node[t];
+            if (node < 0) continue;
+            if constexpr (W == 1) out[node * HC + c] = acc[t][0];
+            else vec_store(out + node * HC + c, *reinterpret_cast<T(*)[Vec<T>::W]>(&acc[t][0]));
+        }
+    }
+}
+
+extern __shared__ __align__(16) unsigned char gat_smem_raw[];
+
+// MODE 0: forward.  members = destinations, (ptr, nbr) = by-destination CSR, rows = feat, out = out; alpha is WRITTEN.
+// MODE 1: by-source backward.  members = sources, (ptr, nbr, eid) = by-source lists, rows = grad_out, out = grad_feat;
+//         alpha and dlogit are READ, grad_a (= grad_a_src) is written.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_agg_kernel(const T* __restrict__ rows, const T* __restrict__ a_src,
+                                                                     const T* __restrict__ a_dst, const int64_t* __restrict__ ptr,
+                                                                     const int32_t* __restrict__ nbr, const int32_t* __restrict__ eid,
+                                                                     const int64_t* __restrict__ e_limit_ptr,
+                                                                     const int32_t* __restrict__ order, int64_t n, int H, int C, T slope,
+                                                                     T* __restrict__ alpha, const T* __restrict__ dlogit,
+                                                                     T* __restrict__ out, T* __restrict__ grad_a) {
+    using S = GatTile<T, GT_HMAX, GT_UMAX>;
+    S& sm = *reinterpret_cast<S*>(gat_smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t e_limit = e_limit_ptr ? *e_limit_ptr : INT64_MAX;
+    if (!gat_tile_edges(sm, ptr, nbr, eid, e_limit, order, n)) {
+        for (int m = 0; m < GT_TD; ++m) {                               // a tile that does not fit: node by node (uniform branch)
+            const int64_t node = sm.node[m];
+            if (node < 0) continue;
+            const int64_t p0 = sm.p0[m], p1 = ptr[node + 1];
+            if constexpr (MODE == 0) gat_fwd_node<T>(rows, a_src, a_dst, nbr, node, p0, p1, H, C, slope, out, alpha);
+            else gat_bsrc_node<T>(nbr, eid, node, p0, p1, e_limit, H, C, alpha, dlogit, rows, out, grad_a);
+        }
+        return;
+    }
+    const int Et = sm.off[GT_TD], U = sm.n_u;
+    {   // clear the dense weights of the rows in use
+        T* wf = &sm.w[0][0][0];
+        const int per_h = U * GT_TD;
+        for (int i = tid; i < H * per_h; i += GT_THREADS) {
+            const int h = i / per_h;
+            wf[h * (GT_UMAX * GT_TD) + (i - h * per_h)] = T(0);
+        }
+        // (U == 0: nothing to clear and the division above is never reached)
+    }
+    if constexpr (MODE == 0) {
+        for (int i = tid; i < Et * H; i += GT_THREADS) {                // every logit once
+            const int s = i / H, h = i - s * H;
+            T r = a_src[(int64_t)sm.e_nbr[s] * H + h] + a_dst[sm.node[sm.e_own[s]] * H + h];
+            sm.ev[s][h] = r > T(0) ? r : r * slope;
+        }
+        __syncthreads();
+        for (int seg = warp; seg < GT_TD * H; seg += GT_THREADS / 32) { // segment softmax: one warp per (member, head)
+            const int m = seg / H, h = seg - m * H;
+            const int s0 = sm.off[m], s1 = sm.off[m + 1];
+            T mx = -INFINITY;
+            for (int s = s0 + lane; s < s1; s += 32) mx = max(mx, sm.ev[s][h]);
+            mx = warp_max(mx);
+            T sum = T(0);
+            for (int s = s0 + lane; s < s1; s += 32) sum += t_exp(sm.ev[s][h] - mx);
+            sum = warp_sum_t(sum) + T(1e-16);
+            for (int s = s0 + lane; s < s1; s += 32) {
+                const T a = t_exp(sm.ev[s][h] - mx) / sum;
+                sm.ev[s][h] = a;
+                alpha[(int64_t)sm.e_gid[s] * H + h] = a;
+            }
+        }
+    } else {
+        for (int i = tid; i < Et * H; i += GT_THREADS) {
+            const int s = i / H, h = i - s * H;
+            sm.ev[s][h] = sm.e_nbr[s] >= 0 ? alpha[(int64_t)sm.e_gid[s] * H + h] : T(0);
+        }
+        for (int seg = warp; seg < GT_TD * H; seg += GT_THREADS / 32) { // grad_a_src[member, head] = sum of its edges' dlogit
+            const int m = seg / H, h = seg - m * H;
+            const int64_t node = sm.node[m];
+            if (node < 0) continue;
+            T acc = T(0);
+            for (int s = sm.off[m] + lane; s < sm.off[m + 1]; s += 32)
+                if (sm.e_nbr[s] >= 0) acc += dlogit[(int64_t)sm.e_gid[s] * H + h];
+            acc = warp_sum_t(acc);
+            if (lane == 0) grad_a[node * H + h] = acc;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < Et * H; i += GT_THREADS) {                    // scatter into the dense form (+=: parallel edges add up)
+        const int s = i / H, h = i - s * H;
+        if (sm.e_nbr[s] >= 0) atomicAdd(&sm.w[h][sm.e_loc[s]][sm.e_own[s]], sm.ev[s][h]);
+    }
+    __syncthreads();
+    if (C % Vec<T>::W == 0) gat_tile_aggregate<T, Vec<T>::W>(sm, rows, out, U, H, C);
+    else gat_tile_aggregate<T, 1>(sm, rows, out, U, H, C);
+}
+
+// By-destination backward in tile form.  Needs C = 2 * W * tph with tph (threads per head) in {32, 64, 128, 256}: every thread
+// owns two W-wide column groups of ONE head, half a head apart, so a warp never straddles heads and the butterfly is uniform.
+template <typename T>
+__global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
+                                                                      const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
+                                                                      const int32_t* __restrict__ col, const int32_t* __restrict__ order,
+                                                                      int64_t n, int H, int C, T slope, const T* __restrict__ alpha,
+                                                                      const T* __restrict__ grad_out, T* __restrict__ dlogit,
+                                                                      T* __restrict__ grad_a_dst) {
+    using S = GatTile<T, GT_THREADS / 32, GT_UCHUNK>;
+    S& sm = *reinterpret_cast<S*>(gat_smem_raw);
+    constexpr int W = Vec<T>::W;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (!gat_tile_edges(sm, rowptr, col, nullptr, INT64_MAX, order, n)) {
+        for (int m = 0; m < GT_TD; ++m) {
+            const int64_t node = sm.node[m];
+            if (node < 0) continue;
+            gat_bdst_node<T>(feat, a_src, a_dst, col, node, sm.p0[m], rowptr[node + 1], H, C, slope, alpha, grad_out, dlogit, grad_a_dst);
+        }
+        return;
+    }
+    const int Et = sm.off[GT_TD], U = sm.n_u;
+    const int HC = H * C;
+    const int tph = C / (2 * W);          // threads per head
+    const int hps = GT_THREADS / tph;     // heads per sweep
+    const int wph = tph >> 5;             // warps per head
+    const int hl = tid / tph;             // head slot of this thread within a sweep
+    const int j = tid - hl * tph;
+    __syncthreads();                      // e_loc
+    for (int h0 = 0; h0 < H; h0 += hps) {
+        const int h = h0 + hl;
+        const bool live = h < H;          // uniform per warp (tph is a multiple of 32)
+        const int c0 = (live ? h : 0) * C + j * W, c1 = c0 + (C >> 1);
+        T go[GT_TD][2 * W];
+#pragma unroll
+        for (int t = 0; t < GT_TD; ++t) {
+            const int64_t node = sm.node[t];
+            if (live && node >= 0) {
+                vec_load(grad_out + node * HC + c0, *reinterpret_cast<T(*)[W]>(&go[t][0]));
+                vec_load(grad_out + node * HC + c1, *reinterpret_cast<T(*)[W]>(&go[t][W]));
+            } else {
+#pragma unroll
+                for (int q = 0; q < 2 * W; ++q) go[t][q] = T(0);
+            }
+        }
+        for (int ub = 0; ub < U; ub += GT_UCHUNK) {
+        const int ue = min(U, ub + GT_UCHUNK);
+#pragma unroll 2
+        for (int u = ub; u < ue; ++u) {
+            T v[2 * W];
+            const T* row = feat + (int64_t)sm.u_id[u] * HC;
+            vec_load(row + c0, *reinterpret_cast<T(*)[W]>(&v[0]));
+            vec_load(row + c1, *reinterpret_cast<T(*)[W]>(&v[W]));
+            T p[GT_TD];
+#pragma unroll
+            for (int t = 0; t < GT_TD; ++t) {
+                T acc = go[t][0] * v[0];
+#pragma unroll
+                for (int q = 1; q < 2 * W; ++q) acc += go[t][q] * v[q];
+                p[t] = acc;
+            }
+            // eight sums across 32 lanes in 9 shuffles: halve the number of values while doubling the lanes that own each
+            T q4[4], q2[2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool up = lane & 16;
+                const T send = up ? p[k] : p[k + 4], keep = up ? p[k + 4] : p[k];
+                q4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const bool up = lane & 8;
+                const T send = up ? q4[k] : q4[k + 2], keep = up ? q4[k + 2] : q4[k];
+                q2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            T r1;
+            {
+                const bool up = lane & 4;
+                const T send = up ? q2[0] : q2[1], keep = up ? q2[1] : q2[0];
+                r1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+            r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+            // lane bits 4,3,2 chose members +4, +2, +1
+            if ((lane & 3) == 0) sm.w[warp][u - ub][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = r1;
+        }
+        __syncthreads();
+        for (int i = tid; i < Et * hps; i += GT_THREADS) {              // d alpha of the edges that read these rows, heads of this sweep
+            const int s = i / hps, k = i - s * hps;
+            const int loc = sm.e_loc[s];
+            if (h0 + k >= H || loc < ub || loc >= ue) continue;
+            T acc = T(0);
+            for (int wi = 0; wi < wph; ++wi) acc += sm.w[k * wph + wi][loc - ub][sm.e_own[s]];
+            sm.ev[s][h0 + k] = acc;
+        }
+        __syncthreads();
+        }
+    }
+    // softmax backward per (member, head): dlogit = alpha (d alpha - sum alpha d alpha), through the LeakyReLU
+    for (int seg = warp; seg < GT_TD * H; seg += GT_THREADS / 32) {
+        const int m = seg / H, h = seg - m * H;
+        const int64_t node = sm.node[m];
+        if (node < 0) continue;
+        const int s0 = sm.off[m], s1 = sm.off[m + 1];
+        T sa = T(0);
+        for (int s = s0 + lane; s < s1; s += 32) sa += alpha[(int64_t)sm.e_gid[s] * H + h] * sm.ev[s][h];
+        sa = warp_sum_t(sa);
+        const T ad = a_dst[node * H + h];
+        T gd = T(0);
+        for (int s = s0 + lane; s < s1; s += 32) {
+            const T r = a_src[(int64_t)sm.e_nbr[s] * H + h] + ad;
+            T g = alpha[(int64_t)sm.e_gid[s] * H + h] * (sm.ev[s][h] - sa);
+            g = r > T(0) ? g : g * slope;
+            dlogit[(int64_t)sm.e_gid[s] * H + h] = g;
+            gd += g;
+        }
+        gd = warp_sum_t(gd);
+        if (lane == 0) grad_a_dst[node * H + h] = gd;
+    }
+}
+
+// Which form runs.  The tile form pays off when consecutive CTA members share neighbours, i.e. when the caller supplies a
+// locality order (spadot_b200/gat.py does for graphs of >= 20000 nodes: Z-curve of the spot coordinates, or reverse
+// Cuthill-McKee); without one - small graphs, where these kernels are launch-bound anyway - the per-node form runs.
+// SDB_GAT_TILES=0 / 1 forces the per-node / the tile form (A/B measurements, tests).
+static bool gat_use_tiles(int H, const int32_t* order) {
+    if (H > GT_HMAX) return false;
+    const char* e = getenv("SDB_GAT_TILES");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    return order != nullptr;
+}
+template <typename T>
+static bool gat_bdst_tile_shape(int C) {
+    constexpr int W = Vec<T>::W;
+    if (C % (2 * W)) return false;
+    const int tph = C / (2 * W);
+    return tph == 32 || tph == 64 || tph == 128 || tph == 256;
+}
+
+template <typename T>
 int gat_forward_t(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
                   const int32_t* order, int64_t n, int H, int C, double slope, void* out, void* alpha, cudaStream_t st) {
+    if (gat_use_tiles(H, order)) {
+        static size_t memo[SDB_MAX_DEVICES];
+        using S = GatTile<T, GT_HMAX, GT_UMAX>;
+        cudaError_t e = sdb_ensure_smem(gat_tile_agg_kernel<T, 0>, sizeof(S), memo);
+        if (e != cudaSuccess) return (int)e;
+        gat_tile_agg_kernel<T, 0><<<(unsigned)((n + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(
+            (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, nullptr, nullptr, order, n, H, C, (T)slope, (T*)alpha,
+            nullptr, (T*)out, nullptr);
+        SDB_LAUNCH_STATUS();
+    }
     gat_fwd_kernel<T><<<(unsigned)n, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order, n, H, C,
                                                   (T)slope, (T*)out, (T*)alpha);
     SDB_LAUNCH_STATUS();
@@ -229,11 +639,32 @@ int gat_backward_t(const void* feat, const void* a_src, const void* a_dst, const
                    const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, const int32_t* order_dst,
                    const int32_t* order_src, int64_t n_dst, int64_t n_src, int H, int C, double slope, const void* alpha,
                    const void* grad_out, void* dlogit, void* grad_feat, void* grad_a_src, void* grad_a_dst, cudaStream_t st) {
-    gat_bwd_dst_kernel<T><<<(unsigned)n_dst, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst,
-                                                          n_dst, H, C, (T)slope, (const T*)alpha, (const T*)grad_out, (T*)dlogit,
-                                                          (T*)grad_a_dst);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e;
+    if (gat_use_tiles(H, order_dst) && gat_bdst_tile_shape<T>(C)) {
+        static size_t memo[SDB_MAX_DEVICES];
+        using S = GatTile<T, GT_THREADS / 32, GT_UCHUNK>;
+        e = sdb_ensure_smem(gat_tile_bdst_kernel<T>, sizeof(S), memo);
+        if (e != cudaSuccess) return (int)e;
+        gat_tile_bdst_kernel<T><<<(unsigned)((n_dst + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(
+            (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst, n_dst, H, C, (T)slope, (const T*)alpha,
+            (const T*)grad_out, (T*)dlogit, (T*)grad_a_dst);
+    } else {
+        gat_bwd_dst_kernel<T><<<(unsigned)n_dst, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst,
+                                                              n_dst, H, C, (T)slope, (const T*)alpha, (const T*)grad_out, (T*)dlogit,
+                                                              (T*)grad_a_dst);
+    }
+    e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
+    if (gat_use_tiles(H, order_src)) {
+        static size_t memo[SDB_MAX_DEVICES];
+        using S = GatTile<T, GT_HMAX, GT_UMAX>;
+        e = sdb_ensure_smem(gat_tile_agg_kernel<T, 1>, sizeof(S), memo);
+        if (e != cudaSuccess) return (int)e;
+        gat_tile_agg_kernel<T, 1><<<(unsigned)((n_src + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(
+            (const T*)grad_out, nullptr, nullptr, src_rowptr, src_dst, src_eid, rowptr + n_dst, order_src, n_src, H, C, (T)slope,
+            const_cast<T*>((const T*)alpha), (const T*)dlogit, (T*)grad_feat, (T*)grad_a_src);
+        SDB_LAUNCH_STATUS();
+    }
     gat_bwd_src_kernel<T><<<(unsigned)n_src, 128, 0, st>>>(src_rowptr, src_dst, src_eid, order_src, rowptr + n_dst, H, C,
                                                           (const T*)alpha, (const T*)dlogit, (const T*)grad_out, (T*)grad_feat,
                                                           (T*)grad_a_src);

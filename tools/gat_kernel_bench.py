@@ -12,7 +12,7 @@ def main():
     H, C, k = 4, 512, 30
     coords = np.random.default_rng(0).uniform(0, 1000, size=(n, 2))
     ei = graph.spatial_edge_index(coords, k)
-    g = gat.graph_for(ei, n, True)
+    g = gat.graph_for(ei, n, True, torch.from_numpy(coords).to(dev))      # CTA order: Z-curve of the coordinates, as in training
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
@@ -20,7 +20,9 @@ def main():
         pass
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     out = {}
-    for dtype, s in ((torch.float32, 4), (torch.float64, 8)):
+    modes = (("per_node", "0"), ("tiles", "1"))          # SDB_GAT_TILES: the per-node kernels vs the tile kernels (default)
+    for (mode, flag), (dtype, s) in ((m, d) for m in modes for d in ((torch.float32, 4), (torch.float64, 8))):
+        os.environ["SDB_GAT_TILES"] = flag
         feat = torch.randn(n, H, C, dtype=dtype, device=dev, requires_grad=True)
         a_s = torch.randn(n, H, dtype=dtype, device=dev, requires_grad=True)
         a_d = torch.randn(n, H, dtype=dtype, device=dev, requires_grad=True)
@@ -44,9 +46,10 @@ def main():
         # (b) SURVEY.md §8d algorithmic HBM bytes: every feature row read once, outputs written once
         hbm_f = 2 * n * H * C * s + E * (4 + 2 * H * s)
         hbm_b = 3 * n * H * C * s + E * (8 + 4 * H * s)
-        out[str(dtype).split(".")[1]] = dict(fwd_ms=tf, bwd_ms=tb, fwd_gather_GBs=gather_f / tf / 1e6, bwd_gather_GBs=gather_b / tb / 1e6,
+        out[mode + "_" + str(dtype).split(".")[1]] = dict(fwd_ms=tf, bwd_ms=tb, fwd_gather_GBs=gather_f / tf / 1e6, bwd_gather_GBs=gather_b / tb / 1e6,
                                              fwd_hbm_algorithmic_GBs=hbm_f / tf / 1e6, bwd_hbm_algorithmic_GBs=hbm_b / tb / 1e6,
                                              fwd_frac_of_hbm=hbm_f / tf / 1e6 / hbm, bwd_frac_of_hbm=hbm_b / tb / 1e6 / hbm)
+    os.environ.pop("SDB_GAT_TILES", None)
     print(json.dumps(dict(n=n, edges=g.E, H=H, C=C, hbm_peak_gbs=hbm, **out)))
 
 if __name__ == "__main__":
