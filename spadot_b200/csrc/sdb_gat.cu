@@ -31,6 +31,21 @@ __device__ __forceinline__ T warp_sum_t(T v) {
     return v;
 }
 
+// reductions over aligned groups of eight lanes (all 32 lanes of the warp take part in the shuffles)
+template <typename T>
+__device__ __forceinline__ T oct_max(T v) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T oct_sum(T v) {
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // 16-byte vector access: 4 floats or 2 doubles per thread per load (used when C is a multiple of the width)
 template <typename T> struct Vec;
 template <> struct Vec<float> { static constexpr int W = 4; using type = float4; };
@@ -357,7 +372,7 @@ __device__ bool gat_tile_edges(S& sm, const int64_t* __restrict__ ptr, const int
 }
 
 // Phase B of the forward and of the by-source backward: out[member] = sum over distinct rows of w[h][row][member] * rows[row].
-template <typename T, int W, typename S>
+template <typename T, int W, int UNR, int PF, typename S>
 __device__ __forceinline__ void gat_tile_aggregate(const S& sm, const T* __restrict__ rows, T* __restrict__ out, int U, int H, int C) {
     const int HC = H * C;
     for (int c = threadIdx.x * W; c < HC; c += GT_THREADS * W) {
@@ -367,8 +382,14 @@ __device__ __forceinline__ void gat_tile_aggregate(const S& sm, const T* __restr
         for (int t = 0; t < GT_TD; ++t)
 #pragma unroll
             for (int q = 0; q < W; ++q) acc[t][q] = T(0);
-#pragma unroll 8
+        if constexpr (PF > 0) {
+            for (int u = 0; u < PF && u < U; ++u) prefetch_l1(rows + (int64_t)sm.u_id[u] * HC + c);
+        }
+#pragma unroll UNR
         for (int u = 0; u < U; ++u) {
+            if constexpr (PF > 0) {
+                if (u + PF < U) prefetch_l1(rows + (int64_t)sm.u_id[u + PF] * HC + c);
+            }
             T v[W];
             if constexpr (W == 1) v[0] = rows[(int64_t)sm.u_id[u] * HC + c];
             else vec_load(rows + (int64_t)sm.u_id[u] * HC + c, *reinterpret_cast<T(*)[Vec<T>::W]>(&v[0]));
@@ -396,8 +417,8 @@ extern __shared__ __align__(16) unsigned char gat_smem_raw[];
 // MODE 0: forward.  members = destinations, (ptr, nbr) = by-destination CSR, rows = feat, out = out; alpha is WRITTEN.
 // MODE 1: by-source backward.  members = sources, (ptr, nbr, eid) = by-source lists, rows = grad_out, out = grad_feat;
 //         alpha and dlogit are READ, grad_a (= grad_a_src) is written.
-template <typename T, int MODE>
-__global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_agg_kernel(const T* __restrict__ rows, const T* __restrict__ a_src,
+template <typename T, int MODE, int UNR, int PF, int MINB>
+__global__ void __launch_bounds__(GT_THREADS, MINB) gat_tile_agg_kernel(const T* __restrict__ rows, const T* __restrict__ a_src,
                                                                      const T* __restrict__ a_dst, const int64_t* __restrict__ ptr,
                                                                      const int32_t* __restrict__ nbr, const int32_t* __restrict__ eid,
                                                                      const int64_t* __restrict__ e_limit_ptr,
@@ -435,17 +456,23 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_agg_kernel(const T* __
             sm.ev[s][h] = r > T(0) ? r : r * slope;
         }
         __syncthreads();
-        for (int seg = warp; seg < GT_TD * H; seg += GT_THREADS / 32) { // segment softmax: one warp per (member, head)
-            const int m = seg / H, h = seg - m * H;
-            const int s0 = sm.off[m], s1 = sm.off[m + 1];
+        {   // segment softmax: eight lanes per (member, head) - the 8 x H <= 32 segments of a tile run side by side
+            const int seg = tid >> 3, gl = tid & 7;
+            const bool on = seg < GT_TD * H;
+            const int m = on ? seg / H : 0, h = on ? seg - m * H : 0;
+            const int s0 = on ? sm.off[m] : 0, s1 = on ? sm.off[m + 1] : 0;
             T mx = -INFINITY;
-            for (int s = s0 + lane; s < s1; s += 32) mx = max(mx, sm.ev[s][h]);
-            mx = warp_max(mx);
+            for (int s = s0 + gl; s < s1; s += 8) mx = max(mx, sm.ev[s][h]);
+            mx = oct_max(mx);
             T sum = T(0);
-            for (int s = s0 + lane; s < s1; s += 32) sum += t_exp(sm.ev[s][h] - mx);
-            sum = warp_sum_t(sum) + T(1e-16);
-            for (int s = s0 + lane; s < s1; s += 32) {
-                const T a = t_exp(sm.ev[s][h] - mx) / sum;
+            for (int s = s0 + gl; s < s1; s += 8) {
+                const T e = t_exp(sm.ev[s][h] - mx);
+                sm.ev[s][h] = e;
+                sum += e;
+            }
+            sum = oct_sum(sum) + T(1e-16);
+            for (int s = s0 + gl; s < s1; s += 8) {
+                const T a = sm.ev[s][h] / sum;
                 sm.ev[s][h] = a;
                 alpha[(int64_t)sm.e_gid[s] * H + h] = a;
             }
@@ -455,15 +482,17 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_agg_kernel(const T* __
             const int s = i / H, h = i - s * H;
             sm.ev[s][h] = sm.e_nbr[s] >= 0 ? alpha[(int64_t)sm.e_gid[s] * H + h] : T(0);
         }
-        for (int seg = warp; seg < GT_TD * H; seg += GT_THREADS / 32) { // grad_a_src[member, head] = sum of its edges' dlogit
-            const int m = seg / H, h = seg - m * H;
-            const int64_t node = sm.node[m];
-            if (node < 0) continue;
+        {   // grad_a_src[member, head] = sum of its edges' dlogit (eight lanes per segment)
+            const int seg = tid >> 3, gl = tid & 7;
+            const bool on = seg < GT_TD * H;
+            const int m = on ? seg / H : 0, h = on ? seg - m * H : 0;
+            const int64_t node = on ? sm.node[m] : -1;
             T acc = T(0);
-            for (int s = sm.off[m] + lane; s < sm.off[m + 1]; s += 32)
-                if (sm.e_nbr[s] >= 0) acc += dlogit[(int64_t)sm.e_gid[s] * H + h];
-            acc = warp_sum_t(acc);
-            if (lane == 0) grad_a[node * H + h] = acc;
+            if (node >= 0)
+                for (int s = sm.off[m] + gl; s < sm.off[m + 1]; s += 8)
+                    if (sm.e_nbr[s] >= 0) acc += dlogit[(int64_t)sm.e_gid[s] * H + h];
+            acc = oct_sum(acc);
+            if (node >= 0 && gl == 0) grad_a[node * H + h] = acc;
         }
     }
     __syncthreads();
@@ -472,13 +501,13 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_agg_kernel(const T* __
         if (sm.e_nbr[s] >= 0) atomicAdd(&sm.w[h][sm.e_loc[s]][sm.e_own[s]], sm.ev[s][h]);
     }
     __syncthreads();
-    if (C % Vec<T>::W == 0) gat_tile_aggregate<T, Vec<T>::W>(sm, rows, out, U, H, C);
-    else gat_tile_aggregate<T, 1>(sm, rows, out, U, H, C);
+    if (C % Vec<T>::W == 0) gat_tile_aggregate<T, Vec<T>::W, UNR, PF>(sm, rows, out, U, H, C);
+    else gat_tile_aggregate<T, 1, UNR, PF>(sm, rows, out, U, H, C);
 }
 
 // By-destination backward in tile form.  Needs C = 2 * W * tph with tph (threads per head) in {32, 64, 128, 256}: every thread
 // owns two W-wide column groups of ONE head, half a head apart, so a warp never straddles heads and the butterfly is uniform.
-template <typename T>
+template <typename T, int UNR, int PF>
 __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
                                                                       const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
                                                                       const int32_t* __restrict__ col, const int32_t* __restrict__ order,
@@ -523,8 +552,20 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* _
         }
         for (int ub = 0; ub < U; ub += GT_UCHUNK) {
         const int ue = min(U, ub + GT_UCHUNK);
-#pragma unroll 2
+        if constexpr (PF > 0) {
+            for (int u = ub; u < ub + PF && u < ue; ++u) {
+                prefetch_l1(feat + (int64_t)sm.u_id[u] * HC + c0);
+                prefetch_l1(feat + (int64_t)sm.u_id[u] * HC + c1);
+            }
+        }
+#pragma unroll UNR
         for (int u = ub; u < ue; ++u) {
+            if constexpr (PF > 0) {
+                if (u + PF < ue) {
+                    prefetch_l1(feat + (int64_t)sm.u_id[u + PF] * HC + c0);
+                    prefetch_l1(feat + (int64_t)sm.u_id[u + PF] * HC + c1);
+                }
+            }
             T v[2 * W];
             const T* row = feat + (int64_t)sm.u_id[u] * HC;
             vec_load(row + c0, *reinterpret_cast<T(*)[W]>(&v[0]));
@@ -575,25 +616,26 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* _
         }
     }
     // softmax backward per (member, head): dlogit = alpha (d alpha - sum alpha d alpha), through the LeakyReLU
-    for (int seg = warp; seg < GT_TD * H; seg += GT_THREADS / 32) {
-        const int m = seg / H, h = seg - m * H;
-        const int64_t node = sm.node[m];
-        if (node < 0) continue;
-        const int s0 = sm.off[m], s1 = sm.off[m + 1];
+    {   // eight lanes per (member, head): all segments of the tile side by side
+        const int seg = tid >> 3, gl = tid & 7;
+        const bool on = seg < GT_TD * H;
+        const int m = on ? seg / H : 0, h = on ? seg - m * H : 0;
+        const int64_t node = on ? sm.node[m] : -1;
+        const int s0 = node >= 0 ? sm.off[m] : 0, s1 = node >= 0 ? sm.off[m + 1] : 0;
         T sa = T(0);
-        for (int s = s0 + lane; s < s1; s += 32) sa += alpha[(int64_t)sm.e_gid[s] * H + h] * sm.ev[s][h];
-        sa = warp_sum_t(sa);
-        const T ad = a_dst[node * H + h];
+        for (int s = s0 + gl; s < s1; s += 8) sa += alpha[(int64_t)sm.e_gid[s] * H + h] * sm.ev[s][h];
+        sa = oct_sum(sa);
+        const T ad = node >= 0 ? a_dst[node * H + h] : T(0);
         T gd = T(0);
-        for (int s = s0 + lane; s < s1; s += 32) {
+        for (int s = s0 + gl; s < s1; s += 8) {
             const T r = a_src[(int64_t)sm.e_nbr[s] * H + h] + ad;
             T g = alpha[(int64_t)sm.e_gid[s] * H + h] * (sm.ev[s][h] - sa);
             g = r > T(0) ? g : g * slope;
             dlogit[(int64_t)sm.e_gid[s] * H + h] = g;
             gd += g;
         }
-        gd = warp_sum_t(gd);
-        if (lane == 0) grad_a_dst[node * H + h] = gd;
+        gd = oct_sum(gd);
+        if (node >= 0 && gl == 0) grad_a_dst[node * H + h] = gd;
     }
 }
 
@@ -616,19 +658,60 @@ static bool gat_bdst_tile_shape(int C) {
     return tph == 32 || tph == 64 || tph == 128 || tph == 256;
 }
 
+static int gat_env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+template <typename T, int MODE, int UNR, int PF, int MINB, typename... Args>
+static int gat_launch_agg(int64_t n, cudaStream_t st, Args... args) {
+    static size_t memo[SDB_MAX_DEVICES];
+    using S = GatTile<T, GT_HMAX, GT_UMAX>;
+    auto kern = gat_tile_agg_kernel<T, MODE, UNR, PF, MINB>;
+    cudaError_t e = sdb_ensure_smem(kern, sizeof(S), memo);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<(unsigned)((n + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(args...);
+    SDB_LAUNCH_STATUS();
+}
+template <typename T, int MODE, typename... Args>
+static int gat_launch_agg_variant(int64_t n, cudaStream_t st, Args... args) {
+    switch (gat_env_int("SDB_GAT_AGG_VARIANT", 0)) {
+        case 1: return gat_launch_agg<T, MODE, 8, 8, 2>(n, st, args...);
+        case 2: return gat_launch_agg<T, MODE, 4, 8, 2>(n, st, args...);
+        case 3: return gat_launch_agg<T, MODE, 4, 0, 3>(n, st, args...);
+        case 4: return gat_launch_agg<T, MODE, 4, 8, 3>(n, st, args...);
+        case 5: return gat_launch_agg<T, MODE, 8, 16, 2>(n, st, args...);
+        default: return gat_launch_agg<T, MODE, 8, 0, 2>(n, st, args...);
+    }
+}
+template <typename T, int UNR, int PF, typename... Args>
+static int gat_launch_bdst(int64_t n, cudaStream_t st, Args... args) {
+    static size_t memo[SDB_MAX_DEVICES];
+    using S = GatTile<T, GT_THREADS / 32, GT_UCHUNK>;
+    auto kern = gat_tile_bdst_kernel<T, UNR, PF>;
+    cudaError_t e = sdb_ensure_smem(kern, sizeof(S), memo);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<(unsigned)((n + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(args...);
+    SDB_LAUNCH_STATUS();
+}
+template <typename T, typename... Args>
+static int gat_launch_bdst_variant(int64_t n, cudaStream_t st, Args... args) {
+    switch (gat_env_int("SDB_GAT_BDST_VARIANT", 0)) {
+        case 1: return gat_launch_bdst<T, 2, 4>(n, st, args...);
+        case 2: return gat_launch_bdst<T, 2, 8>(n, st, args...);
+        case 3: return gat_launch_bdst<T, 4, 0>(n, st, args...);
+        case 4: return gat_launch_bdst<T, 1, 8>(n, st, args...);
+        default: return gat_launch_bdst<T, 2, 0>(n, st, args...);
+    }
+}
+
 template <typename T>
 int gat_forward_t(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
                   const int32_t* order, int64_t n, int H, int C, double slope, void* out, void* alpha, cudaStream_t st) {
-    if (gat_use_tiles(H, order)) {
-        static size_t memo[SDB_MAX_DEVICES];
-        using S = GatTile<T, GT_HMAX, GT_UMAX>;
-        cudaError_t e = sdb_ensure_smem(gat_tile_agg_kernel<T, 0>, sizeof(S), memo);
-        if (e != cudaSuccess) return (int)e;
-        gat_tile_agg_kernel<T, 0><<<(unsigned)((n + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(
-            (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, nullptr, nullptr, order, n, H, C, (T)slope, (T*)alpha,
-            nullptr, (T*)out, nullptr);
-        SDB_LAUNCH_STATUS();
-    }
+    if (gat_use_tiles(H, order))
+        return gat_launch_agg_variant<T, 0>(n, st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, (const int32_t*)nullptr,
+                                            (const int64_t*)nullptr, order, n, H, C, (T)slope, (T*)alpha, (const T*)nullptr, (T*)out,
+                                            (T*)nullptr);
     gat_fwd_kernel<T><<<(unsigned)n, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order, n, H, C,
                                                   (T)slope, (T*)out, (T*)alpha);
     SDB_LAUNCH_STATUS();
@@ -641,13 +724,9 @@ int gat_backward_t(const void* feat, const void* a_src, const void* a_dst, const
                    const void* grad_out, void* dlogit, void* grad_feat, void* grad_a_src, void* grad_a_dst, cudaStream_t st) {
     cudaError_t e;
     if (gat_use_tiles(H, order_dst) && gat_bdst_tile_shape<T>(C)) {
-        static size_t memo[SDB_MAX_DEVICES];
-        using S = GatTile<T, GT_THREADS / 32, GT_UCHUNK>;
-        e = sdb_ensure_smem(gat_tile_bdst_kernel<T>, sizeof(S), memo);
-        if (e != cudaSuccess) return (int)e;
-        gat_tile_bdst_kernel<T><<<(unsigned)((n_dst + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(
-            (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst, n_dst, H, C, (T)slope, (const T*)alpha,
-            (const T*)grad_out, (T*)dlogit, (T*)grad_a_dst);
+        const int rc = gat_launch_bdst_variant<T>(n_dst, st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst, n_dst,
+                                                  H, C, (T)slope, (const T*)alpha, (const T*)grad_out, (T*)dlogit, (T*)grad_a_dst);
+        if (rc) return rc;
     } else {
         gat_bwd_dst_kernel<T><<<(unsigned)n_dst, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst,
                                                               n_dst, H, C, (T)slope, (const T*)alpha, (const T*)grad_out, (T*)dlogit,
@@ -655,16 +734,10 @@ int gat_backward_t(const void* feat, const void* a_src, const void* a_dst, const
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    if (gat_use_tiles(H, order_src)) {
-        static size_t memo[SDB_MAX_DEVICES];
-        using S = GatTile<T, GT_HMAX, GT_UMAX>;
-        e = sdb_ensure_smem(gat_tile_agg_kernel<T, 1>, sizeof(S), memo);
-        if (e != cudaSuccess) return (int)e;
-        gat_tile_agg_kernel<T, 1><<<(unsigned)((n_src + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(
-            (const T*)grad_out, nullptr, nullptr, src_rowptr, src_dst, src_eid, rowptr + n_dst, order_src, n_src, H, C, (T)slope,
-            const_cast<T*>((const T*)alpha), (const T*)dlogit, (T*)grad_feat, (T*)grad_a_src);
-        SDB_LAUNCH_STATUS();
-    }
+    if (gat_use_tiles(H, order_src))
+        return gat_launch_agg_variant<T, 1>(n_src, st, (const T*)grad_out, (const T*)nullptr, (const T*)nullptr, src_rowptr, src_dst, src_eid,
+                                            rowptr + n_dst, order_src, n_src, H, C, (T)slope, const_cast<T*>((const T*)alpha),
+                                            (const T*)dlogit, (T*)grad_feat, (T*)grad_a_src);
     gat_bwd_src_kernel<T><<<(unsigned)n_src, 128, 0, st>>>(src_rowptr, src_dst, src_eid, order_src, rowptr + n_dst, H, C,
                                                           (const T*)alpha, (const T*)dlogit, (const T*)grad_out, (T*)grad_feat,
                                                           (T*)grad_a_src);

@@ -149,7 +149,9 @@ def test_gat_coordinate_hint_orders_ctas_on_device_and_keeps_results():
     ga, gb = gat.graph_for(ei_a, n), gat.graph_for(ei_b, n)
     assert ga.order is not None and gb.order is not None and not torch.equal(ga.order, gb.order)
     assert torch.equal(gb.order, gat.morton_order(pos))
-    assert torch.equal(out_a, out_b)
+    # the tile form groups eight consecutive nodes of the order, so the order changes which rows are summed together:
+    # equal to rounding, not bitwise
+    np.testing.assert_allclose(out_b.detach().cpu().numpy(), out_a.detach().cpu().numpy(), rtol=1e-12, atol=1e-14)
     out_a.square().sum().backward()
     out_b.square().sum().backward()
     np.testing.assert_allclose(xb.grad.cpu().numpy(), xa.grad.cpu().numpy(), rtol=1e-12, atol=1e-14)
