@@ -419,15 +419,20 @@ int sdb_quad_form_rows_f64(const double* W, const double* A, int64_t b, int m, d
  * (self loops included, PyG GATConv add_self_loops semantics are the caller's job).  feat (n,H,C),
  * a_src / a_dst (n,H) in float or double (is_double).  Writes out (n,H,C) = sum_j alpha_ij feat_j and
  * alpha (E,H) = softmax_j(leaky_relu(a_src[j]+a_dst[i])) with PyG's +1e-16 denominator.
- * node_order (n, int32, may be NULL): CTA b works on node node_order[b]; a locality-preserving order (e.g. reverse
- * Cuthill-McKee) makes concurrently running CTAs gather the same source rows, which then hit L2 instead of HBM.
+ * node_order (n, int32, may be NULL): the order in which nodes are dealt to CTAs.  With a locality-preserving order (Z-curve of
+ * the spot coordinates, reverse Cuthill-McKee) the kernels run in TILE form: eight consecutive nodes of the order per CTA, the
+ * rows they gather de-duplicated in shared memory (neighbouring spots share most neighbours), every distinct row streamed once
+ * per tile; results are reproducible and independent of the order up to rounding.  Without an order (small graphs) one CTA
+ * per node runs.  Tiles that exceed the shared-memory budget (512 edges / 256 distinct rows) and layers with more than four
+ * heads use the per-node form.  SDB_GAT_TILES=0/1 in the environment forces either form.
  * replaces torch_geometric GATConv message passing used at ref: model/encoder.py:41-45,56-58. */
 int sdb_gat_forward(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
                     const int32_t* node_order, int64_t n, int H, int C, double negative_slope, int is_double,
                     void* out, void* alpha, void* stream);
 /* Backward of the above.  src_rowptr / src_dst / src_eid: the same edges grouped by SOURCE node
  * (destination node and position in the by-destination order).  dlogit (E,H) is workspace.
- * Outputs grad_feat (n,H,C), grad_a_src (n,H), grad_a_dst (n,H).  Deterministic (no atomics). */
+ * Outputs grad_feat (n,H,C), grad_a_src (n,H), grad_a_dst (n,H).  Deterministic (no global atomics; in the tile form
+ * parallel edges - the same (source, target) pair listed twice - are merged by a shared-memory add, the only order-dependent sum). */
 int sdb_gat_backward(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
                      const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, const int32_t* node_order,
                      int64_t n, int H, int C, double negative_slope, int is_double, const void* alpha,

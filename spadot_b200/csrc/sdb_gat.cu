@@ -44,7 +44,6 @@ __device__ __forceinline__ T oct_sum(T v) {
     for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // 16-byte vector access: 4 floats or 2 doubles per thread per load (used when C is a multiple of the width)
 template <typename T> struct Vec;
@@ -372,7 +371,7 @@ __device__ bool gat_tile_edges(S& sm, const int64_t* __restrict__ ptr, const int
 }
 
 // Phase B of the forward and of the by-source backward: out[member] = sum over distinct rows of w[h][row][member] * rows[row].
-template <typename T, int W, int UNR, int PF, typename S>
+template <typename T, int W, typename S>
 __device__ __forceinline__ void gat_tile_aggregate(const S& sm, const T* __restrict__ rows, T* __restrict__ out, int U, int H, int C) {
     const int HC = H * C;
     for (int c = threadIdx.x * W; c < HC; c += GT_THREADS * W) {
@@ -382,14 +381,10 @@ __device__ __forceinline__ void gat_tile_aggregate(const S& sm, const T* __restr
         for (int t = 0; t < GT_TD; ++t)
 #pragma unroll
             for (int q = 0; q < W; ++q) acc[t][q] = T(0);
-        if constexpr (PF > 0) {
-            for (int u = 0; u < PF && u < U; ++u) prefetch_l1(rows + (int64_t)sm.u_id[u] * HC + c);
-        }
-#pragma unroll UNR
+        // eight independent row loads in flight per thread (the batch is hoisted above the FMAs); a software prefetch into L1
+        // (prefetch.global.L1, distance 8 / 16) and three CTAs per SM at unroll 4 were measured and change nothing (+-3 %)
+#pragma unroll 8
         for (int u = 0; u < U; ++u) {
-            if constexpr (PF > 0) {
-                if (u + PF < U) prefetch_l1(rows + (int64_t)sm.u_id[u + PF] * HC + c);
-            }
             T v[W];
             if constexpr (W == 1) v[0] = rows[(int64_t)sm.u_id[u] * HC + c];
             else vec_load(rows + (int64_t)sm.u_id[u] * HC + c, *reinterpret_cast<T(*)[Vec<T>::W]>(&v[0]));
@@ -417,8 +412,8 @@ extern __shared__ __align__(16) unsigned char gat_smem_raw[];
 // MODE 0: forward.  members = destinations, (ptr, nbr) = by-destination CSR, rows = feat, out = out; alpha is WRITTEN.
 // MODE 1: by-source backward.  members = sources, (ptr, nbr, eid) = by-source lists, rows = grad_out, out = grad_feat;
 //         alpha and dlogit are READ, grad_a (= grad_a_src) is written.
-template <typename T, int MODE, int UNR, int PF, int MINB>
-__global__ void __launch_bounds__(GT_THREADS, MINB) gat_tile_agg_kernel(const T* __restrict__ rows, const T* __restrict__ a_src,
+template <typename T, int MODE>
+__global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_agg_kernel(const T* __restrict__ rows, const T* __restrict__ a_src,
                                                                      const T* __restrict__ a_dst, const int64_t* __restrict__ ptr,
                                                                      const int32_t* __restrict__ nbr, const int32_t* __restrict__ eid,
                                                                      const int64_t* __restrict__ e_limit_ptr,
@@ -501,13 +496,13 @@ __global__ void __launch_bounds__(GT_THREADS, MINB) gat_tile_agg_kernel(const T*
         if (sm.e_nbr[s] >= 0) atomicAdd(&sm.w[h][sm.e_loc[s]][sm.e_own[s]], sm.ev[s][h]);
     }
     __syncthreads();
-    if (C % Vec<T>::W == 0) gat_tile_aggregate<T, Vec<T>::W, UNR, PF>(sm, rows, out, U, H, C);
-    else gat_tile_aggregate<T, 1, UNR, PF>(sm, rows, out, U, H, C);
+    if (C % Vec<T>::W == 0) gat_tile_aggregate<T, Vec<T>::W>(sm, rows, out, U, H, C);
+    else gat_tile_aggregate<T, 1>(sm, rows, out, U, H, C);
 }
 
 // By-destination backward in tile form.  Needs C = 2 * W * tph with tph (threads per head) in {32, 64, 128, 256}: every thread
 // owns two W-wide column groups of ONE head, half a head apart, so a warp never straddles heads and the butterfly is uniform.
-template <typename T, int UNR, int PF>
+template <typename T>
 __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
                                                                       const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
                                                                       const int32_t* __restrict__ col, const int32_t* __restrict__ order,
@@ -552,20 +547,8 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* _
         }
         for (int ub = 0; ub < U; ub += GT_UCHUNK) {
         const int ue = min(U, ub + GT_UCHUNK);
-        if constexpr (PF > 0) {
-            for (int u = ub; u < ub + PF && u < ue; ++u) {
-                prefetch_l1(feat + (int64_t)sm.u_id[u] * HC + c0);
-                prefetch_l1(feat + (int64_t)sm.u_id[u] * HC + c1);
-            }
-        }
-#pragma unroll UNR
+#pragma unroll 2
         for (int u = ub; u < ue; ++u) {
-            if constexpr (PF > 0) {
-                if (u + PF < ue) {
-                    prefetch_l1(feat + (int64_t)sm.u_id[u + PF] * HC + c0);
-                    prefetch_l1(feat + (int64_t)sm.u_id[u + PF] * HC + c1);
-                }
-            }
             T v[2 * W];
             const T* row = feat + (int64_t)sm.u_id[u] * HC;
             vec_load(row + c0, *reinterpret_cast<T(*)[W]>(&v[0]));
@@ -658,58 +641,32 @@ static bool gat_bdst_tile_shape(int C) {
     return tph == 32 || tph == 64 || tph == 128 || tph == 256;
 }
 
-static int gat_env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-
-template <typename T, int MODE, int UNR, int PF, int MINB, typename... Args>
+template <typename T, int MODE, typename... Args>
 static int gat_launch_agg(int64_t n, cudaStream_t st, Args... args) {
     static size_t memo[SDB_MAX_DEVICES];
     using S = GatTile<T, GT_HMAX, GT_UMAX>;
-    auto kern = gat_tile_agg_kernel<T, MODE, UNR, PF, MINB>;
-    cudaError_t e = sdb_ensure_smem(kern, sizeof(S), memo);
-    if (e != cudaSuccess) return (int)e;
-    kern<<<(unsigned)((n + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(args...);
-    SDB_LAUNCH_STATUS();
-}
-template <typename T, int MODE, typename... Args>
-static int gat_launch_agg_variant(int64_t n, cudaStream_t st, Args... args) {
-    switch (gat_env_int("SDB_GAT_AGG_VARIANT", 0)) {
-        case 1: return gat_launch_agg<T, MODE, 8, 8, 2>(n, st, args...);
-        case 2: return gat_launch_agg<T, MODE, 4, 8, 2>(n, st, args...);
-        case 3: return gat_launch_agg<T, MODE, 4, 0, 3>(n, st, args...);
-        case 4: return gat_launch_agg<T, MODE, 4, 8, 3>(n, st, args...);
-        case 5: return gat_launch_agg<T, MODE, 8, 16, 2>(n, st, args...);
-        default: return gat_launch_agg<T, MODE, 8, 0, 2>(n, st, args...);
-    }
-}
-template <typename T, int UNR, int PF, typename... Args>
-static int gat_launch_bdst(int64_t n, cudaStream_t st, Args... args) {
-    static size_t memo[SDB_MAX_DEVICES];
-    using S = GatTile<T, GT_THREADS / 32, GT_UCHUNK>;
-    auto kern = gat_tile_bdst_kernel<T, UNR, PF>;
+    auto kern = gat_tile_agg_kernel<T, MODE>;
     cudaError_t e = sdb_ensure_smem(kern, sizeof(S), memo);
     if (e != cudaSuccess) return (int)e;
     kern<<<(unsigned)((n + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(args...);
     SDB_LAUNCH_STATUS();
 }
 template <typename T, typename... Args>
-static int gat_launch_bdst_variant(int64_t n, cudaStream_t st, Args... args) {
-    switch (gat_env_int("SDB_GAT_BDST_VARIANT", 0)) {
-        case 1: return gat_launch_bdst<T, 2, 4>(n, st, args...);
-        case 2: return gat_launch_bdst<T, 2, 8>(n, st, args...);
-        case 3: return gat_launch_bdst<T, 4, 0>(n, st, args...);
-        case 4: return gat_launch_bdst<T, 1, 8>(n, st, args...);
-        default: return gat_launch_bdst<T, 2, 0>(n, st, args...);
-    }
+static int gat_launch_bdst(int64_t n, cudaStream_t st, Args... args) {
+    static size_t memo[SDB_MAX_DEVICES];
+    using S = GatTile<T, GT_THREADS / 32, GT_UCHUNK>;
+    auto kern = gat_tile_bdst_kernel<T>;
+    cudaError_t e = sdb_ensure_smem(kern, sizeof(S), memo);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<(unsigned)((n + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(args...);
+    SDB_LAUNCH_STATUS();
 }
 
 template <typename T>
 int gat_forward_t(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
                   const int32_t* order, int64_t n, int H, int C, double slope, void* out, void* alpha, cudaStream_t st) {
     if (gat_use_tiles(H, order))
-        return gat_launch_agg_variant<T, 0>(n, st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, (const int32_t*)nullptr,
+        return gat_launch_agg<T, 0>(n, st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, (const int32_t*)nullptr,
                                             (const int64_t*)nullptr, order, n, H, C, (T)slope, (T*)alpha, (const T*)nullptr, (T*)out,
                                             (T*)nullptr);
     gat_fwd_kernel<T><<<(unsigned)n, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order, n, H, C,
@@ -724,7 +681,7 @@ int gat_backward_t(const void* feat, const void* a_src, const void* a_dst, const
                    const void* grad_out, void* dlogit, void* grad_feat, void* grad_a_src, void* grad_a_dst, cudaStream_t st) {
     cudaError_t e;
     if (gat_use_tiles(H, order_dst) && gat_bdst_tile_shape<T>(C)) {
-        const int rc = gat_launch_bdst_variant<T>(n_dst, st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst, n_dst,
+        const int rc = gat_launch_bdst<T>(n_dst, st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst, n_dst,
                                                   H, C, (T)slope, (const T*)alpha, (const T*)grad_out, (T*)dlogit, (T*)grad_a_dst);
         if (rc) return rc;
     } else {
@@ -735,7 +692,7 @@ int gat_backward_t(const void* feat, const void* a_src, const void* a_dst, const
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (gat_use_tiles(H, order_src))
-        return gat_launch_agg_variant<T, 1>(n_src, st, (const T*)grad_out, (const T*)nullptr, (const T*)nullptr, src_rowptr, src_dst, src_eid,
+        return gat_launch_agg<T, 1>(n_src, st, (const T*)grad_out, (const T*)nullptr, (const T*)nullptr, src_rowptr, src_dst, src_eid,
                                             rowptr + n_dst, order_src, n_src, H, C, (T)slope, const_cast<T*>((const T*)alpha),
                                             (const T*)dlogit, (T*)grad_feat, (T*)grad_a_src);
     gat_bwd_src_kernel<T><<<(unsigned)n_src, 128, 0, st>>>(src_rowptr, src_dst, src_eid, order_src, rowptr + n_dst, H, C,

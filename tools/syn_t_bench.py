@@ -65,7 +65,11 @@ def main(argv=None):
     step(batches[0])                                   # warm-up (cuBLAS/cuSOLVER handles, graph caches)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    losses = [step(b) for b in batches[1:]]
+    losses, step_times = [], []
+    for b in batches[1:]:
+        t1 = time.perf_counter()
+        losses.append(step(b))                       # float(loss) synchronises
+        step_times.append(time.perf_counter() - t1)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / n_batches
     # where the step goes: device time by kernel family over one more step (torch.profiler, CUDA activities)
@@ -118,7 +122,7 @@ def main(argv=None):
     t_inf = time.perf_counter() - t0
     print(json.dumps(dict(workload=f"{a.name} one timepoint: {n} spots x {genes} genes, z={z}, {m_ind} inducing, k=30, fp64",
                           graph_build_s=t_graph, sample_batch_s=t_sample, subgraph_nodes=sub_nodes, subgraph_edges=sub_edges,
-                          train_step_s=dt, seeds_per_s=512 / dt, losses=losses, all_latent_samples_s=t_inf,
+                          train_step_s=dt, step_times_s=[round(t, 4) for t in step_times], seeds_per_s=512 / dt, losses=losses, all_latent_samples_s=t_inf,
                           latent_shape=list(lat.shape), peak_mem_gb=torch.cuda.max_memory_allocated() / 1e9,
                           step_breakdown_device_time=breakdown)))
 
