@@ -11,7 +11,6 @@
 // HBM/L2 gather-bound:  bytes ~ E*H*C*s (row gathers) + n*H*C*s (write) + E*(4 + 2*H*s).
 #include "sdb_common.cuh"
 #include <stdlib.h>
-#include <stddef.h>
 
 namespace {
 
@@ -45,15 +44,6 @@ __device__ __forceinline__ T oct_sum(T v) {
     for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-
-// cp.async: 16 bytes global -> shared without a register in between; groups complete in commit order
-__device__ __forceinline__ void gat_cp16(void* smem, const void* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void gat_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void gat_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // 16-byte vector access: 4 floats or 2 doubles per thread per load (used when C is a multiple of the width)
 template <typename T> struct Vec;
@@ -280,43 +270,28 @@ __global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restr
 constexpr int GT_TD = 8;          // tile members (destinations; sources in the by-source pass)
 constexpr int GT_EMAX = 512;      // edges of a tile held in shared memory
 constexpr int GT_UMAX = 256;      // distinct gathered rows of a tile (8 x 32 edges fit even when nothing is shared)
-constexpr int GT_UCHUNK = 64;     // by-destination backward: rows per pass through the per-warp partial sums
-constexpr int GT_RING = 8;        // aggregation: rows in flight per thread (cp.async ring of 16-byte slots)
-constexpr int GT_RING_B = 4;      // by-destination backward: rows in flight per thread (two 16-byte slots each)
-constexpr int GT_RING_BYTES = 32768;   // = GT_RING * GT_THREADS * 16 = GT_RING_B * GT_THREADS * 32
+constexpr int GT_UCHUNK = 128;    // by-destination backward: rows per pass through the per-warp partial sums
 constexpr int GT_HMAX = 4;        // heads (the reference's num_heads; more heads run the per-node kernels)
 constexpr int GT_HASH = 1024;     // hash-set slots (>= 2 * GT_EMAX: the probe loop always ends)
 constexpr int GT_THREADS = 256;
 
-// Bytes of the per-edge state (ev .. e_own below).  The aggregation kernels are done with it once the dense weights are
-// built, so their row ring lives on top of it (PAD tops it up to GT_RING_BYTES); the by-destination kernel needs both.
-template <typename T>
-constexpr int gat_edge_state_bytes() {
-    return (int)sizeof(T) * GT_EMAX * GT_HMAX + 4 * GT_HASH + 4 * GT_EMAX * 2 + 4 * GT_UMAX + 2 * GT_EMAX + GT_EMAX;
-}
-
-template <typename T, int LEAD, int UROWS, int PAD>
+template <typename T, int LEAD, int UROWS>
 struct GatTile {
     T w[LEAD][UROWS][GT_TD];      // (heads, GT_UMAX): dense attention weights;  (warps, GT_UCHUNK): per-warp partial dot products
-    int32_t u_id[GT_UMAX];        // distinct rows, ascending
     T ev[GT_EMAX][GT_HMAX];       // per edge and head: logit -> alpha (forward), alpha (by source), d alpha (by destination)
     int32_t tab[GT_HASH];
     int32_t e_nbr[GT_EMAX];       // the row an edge gathers (-1: filtered out by the prefix form)
     int32_t e_gid[GT_EMAX];       // position of the edge in the by-destination order (index into alpha / dlogit)
     int32_t u_tmp[GT_UMAX];
+    int32_t u_id[GT_UMAX];        // distinct rows, ascending
     uint16_t e_loc[GT_EMAX];      // index of e_nbr in u_id
     uint8_t e_own[GT_EMAX];       // tile member the edge belongs to
-    alignas(16) unsigned char pad[PAD];
     int64_t node[GT_TD];
     int64_t p0[GT_TD];
     int len[GT_TD];
     int off[GT_TD + 1];
     int n_u;
 };
-#define GAT_TILE_LAYOUT_CHECK(S)                                                                                         \
-    static_assert(offsetof(S, ev) % 16 == 0 && offsetof(S, pad) % 16 == 0 && offsetof(S, node) - offsetof(S, ev) >= GT_RING_BYTES && \
-                      sizeof(((S*)nullptr)->pad) + 0 >= 0,                                                                \
-                  "row ring does not fit over the per-edge state")
 
 // Phase A of every tile kernel: members, their edges, the distinct rows.  Returns false (uniformly) when the tile does not fit.
 template <typename S>
@@ -396,15 +371,9 @@ __device__ bool gat_tile_edges(S& sm, const int64_t* __restrict__ ptr, const int
 }
 
 // Phase B of the forward and of the by-source backward: out[member] = sum over distinct rows of w[h][row][member] * rows[row].
-// Every thread owns W columns and streams its 16 bytes of every distinct row through a private ring of GT_RING cp.async
-// slots in shared memory (on top of the per-edge state, dead by now): eight rows are in flight per thread all the time and
-// cost no registers - with plain loads the kernel alternated between a burst of loads and a burst of FMAs (ncu: 38 % FMA
-// pipe, the FMAs waiting on the long scoreboard).  A thread reads back only what it copied itself, so there is no barrier.
 template <typename T, int W, typename S>
-__device__ __forceinline__ void gat_tile_aggregate(S& sm, const T* __restrict__ rows, T* __restrict__ out, int U, int H, int C) {
+__device__ __forceinline__ void gat_tile_aggregate(const S& sm, const T* __restrict__ rows, T* __restrict__ out, int U, int H, int C) {
     const int HC = H * C;
-    constexpr int VW = Vec<T>::W;
-    T* const ring = reinterpret_cast<T*>(&sm.ev[0][0]) + threadIdx.x * VW;           // slot d at ring + d * GT_THREADS * VW
     for (int c = threadIdx.x * W; c < HC; c += GT_THREADS * W) {
         const int h = c / C;
         T acc[GT_TD][W];
@@ -412,26 +381,15 @@ __device__ __forceinline__ void gat_tile_aggregate(S& sm, const T* __restrict__ 
         for (int t = 0; t < GT_TD; ++t)
 #pragma unroll
             for (int q = 0; q < W; ++q) acc[t][q] = T(0);
-        if constexpr (W == VW) {
-#pragma unroll
-            for (int d = 0; d < GT_RING; ++d) {
-                if (d < U) gat_cp16(ring + d * (GT_THREADS * VW), rows + (int64_t)sm.u_id[d] * HC + c);
-                gat_cp_commit();
-            }
-        }
+        // eight independent row loads in flight per thread (the batch is hoisted above the FMAs); a software prefetch into L1
+        // (prefetch.global.L1, distance 8 / 16) and three CTAs per SM at unroll 4 were measured and change nothing (+-3 %)
 #pragma unroll 8
         for (int u = 0; u < U; ++u) {
             T v[W];
-            if constexpr (W == VW) {
-                gat_cp_wait<GT_RING - 1>();                          // the group of row u (and every older one) has landed
-                T* slot = ring + (u % GT_RING) * (GT_THREADS * VW);
-                vec_load(slot, v);
-                if (u + GT_RING < U) gat_cp16(slot, rows + (int64_t)sm.u_id[u + GT_RING] * HC + c);
-                gat_cp_commit();                                     // one group per iteration, empty or not
-            } else {
-                v[0] = rows[(int64_t)sm.u_id[u] * HC + c];
-            }
+            if constexpr (W == 1) v[0] = rows[(int64_t)sm.u_id[u] * HC + c];
+            else vec_load(rows + (int64_t)sm.u_id[u] * HC + c, *reinterpret_cast<T(*)[Vec<T>::W]>(&v[0]));
             T a[GT_TD];
+            constexpr int VW = Vec<T>::W;
 #pragma unroll
             for (int t = 0; t < GT_TD; t += VW) vec_load(&sm.w[h][u][t], *reinterpret_cast<T(*)[VW]>(&a[t]));
 #pragma unroll
@@ -439,13 +397,12 @@ __device__ __forceinline__ void gat_tile_aggregate(S& sm, const T* __restrict__ 
 #pragma unroll
                 for (int q = 0; q < W; ++q) acc[t][q] += a[t] * v[q];
         }
-        if constexpr (W == VW) gat_cp_wait<0>();
 #pragma unroll
         for (int t = 0; t < GT_TD; ++t) {
             const int64_t node = sm.node[t];
             if (node < 0) continue;
             if constexpr (W == 1) out[node * HC + c] = acc[t][0];
-            else vec_store(out + node * HC + c, acc[t]);
+            else vec_store(out + node * HC + c, *reinterpret_cast<T(*)[Vec<T>::W]>(&acc[t][0]));
         }
     }
 }
@@ -463,8 +420,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_agg_kernel(const T* __
                                                                      const int32_t* __restrict__ order, int64_t n, int H, int C, T slope,
                                                                      T* __restrict__ alpha, const T* __restrict__ dlogit,
                                                                      T* __restrict__ out, T* __restrict__ grad_a) {
-    using S = GatTile<T, GT_HMAX, GT_UMAX, GT_RING_BYTES - gat_edge_state_bytes<T>()>;
-    GAT_TILE_LAYOUT_CHECK(S);
+    using S = GatTile<T, GT_HMAX, GT_UMAX>;
     S& sm = *reinterpret_cast<S*>(gat_smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t e_limit = e_limit_ptr ? *e_limit_ptr : INT64_MAX;
@@ -553,8 +509,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* _
                                                                       int64_t n, int H, int C, T slope, const T* __restrict__ alpha,
                                                                       const T* __restrict__ grad_out, T* __restrict__ dlogit,
                                                                       T* __restrict__ grad_a_dst) {
-    using S = GatTile<T, GT_THREADS / 32, GT_UCHUNK, GT_RING_BYTES>;
-    static_assert(offsetof(S, pad) % 16 == 0 && sizeof(((S*)nullptr)->pad) >= GT_RING_BYTES, "row ring of the by-destination kernel");
+    using S = GatTile<T, GT_THREADS / 32, GT_UCHUNK>;
     S& sm = *reinterpret_cast<S*>(gat_smem_raw);
     constexpr int W = Vec<T>::W;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -592,30 +547,12 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* _
         }
         for (int ub = 0; ub < U; ub += GT_UCHUNK) {
         const int ue = min(U, ub + GT_UCHUNK);
-        // private cp.async ring, GT_RING_B rows (two 16-byte pieces each) in flight per thread
-        T* const ring = reinterpret_cast<T*>(sm.pad) + tid * (2 * W);                // slot d at ring + d * GT_THREADS * 2W
-#pragma unroll
-        for (int d = 0; d < GT_RING_B; ++d) {
-            if (ub + d < ue) {
-                const T* row = feat + (int64_t)sm.u_id[ub + d] * HC;
-                gat_cp16(ring + d * (GT_THREADS * 2 * W), row + c0);
-                gat_cp16(ring + d * (GT_THREADS * 2 * W) + W, row + c1);
-            }
-            gat_cp_commit();
-        }
-#pragma unroll 4
+#pragma unroll 2
         for (int u = ub; u < ue; ++u) {
             T v[2 * W];
-            gat_cp_wait<GT_RING_B - 1>();
-            T* slot = ring + ((u - ub) % GT_RING_B) * (GT_THREADS * 2 * W);
-            vec_load(slot, *reinterpret_cast<T(*)[W]>(&v[0]));
-            vec_load(slot + W, *reinterpret_cast<T(*)[W]>(&v[W]));
-            if (u + GT_RING_B < ue) {
-                const T* row = feat + (int64_t)sm.u_id[u + GT_RING_B] * HC;
-                gat_cp16(slot, row + c0);
-                gat_cp16(slot + W, row + c1);
-            }
-            gat_cp_commit();
+            const T* row = feat + (int64_t)sm.u_id[u] * HC;
+            vec_load(row + c0, *reinterpret_cast<T(*)[W]>(&v[0]));
+            vec_load(row + c1, *reinterpret_cast<T(*)[W]>(&v[W]));
             T p[GT_TD];
 #pragma unroll
             for (int t = 0; t < GT_TD; ++t) {
@@ -649,7 +586,6 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* _
             // lane bits 4,3,2 chose members +4, +2, +1
             if ((lane & 3) == 0) sm.w[warp][u - ub][((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = r1;
         }
-        gat_cp_wait<0>();
         __syncthreads();
         for (int i = tid; i < Et * hps; i += GT_THREADS) {              // d alpha of the edges that read these rows, heads of this sweep
             const int s = i / hps, k = i - s * hps;
@@ -708,7 +644,7 @@ static bool gat_bdst_tile_shape(int C) {
 template <typename T, int MODE, typename... Args>
 static int gat_launch_agg(int64_t n, cudaStream_t st, Args... args) {
     static size_t memo[SDB_MAX_DEVICES];
-    using S = GatTile<T, GT_HMAX, GT_UMAX, GT_RING_BYTES - gat_edge_state_bytes<T>()>;
+    using S = GatTile<T, GT_HMAX, GT_UMAX>;
     auto kern = gat_tile_agg_kernel<T, MODE>;
     cudaError_t e = sdb_ensure_smem(kern, sizeof(S), memo);
     if (e != cudaSuccess) return (int)e;
@@ -718,7 +654,7 @@ static int gat_launch_agg(int64_t n, cudaStream_t st, Args... args) {
 template <typename T, typename... Args>
 static int gat_launch_bdst(int64_t n, cudaStream_t st, Args... args) {
     static size_t memo[SDB_MAX_DEVICES];
-    using S = GatTile<T, GT_THREADS / 32, GT_UCHUNK, GT_RING_BYTES>;
+    using S = GatTile<T, GT_THREADS / 32, GT_UCHUNK>;
     auto kern = gat_tile_bdst_kernel<T>;
     cudaError_t e = sdb_ensure_smem(kern, sizeof(S), memo);
     if (e != cudaSuccess) return (int)e;
