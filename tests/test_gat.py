@@ -279,3 +279,25 @@ def test_gat_tile_kernels_equal_the_per_node_kernels(dtype, tol, kind, n, H, C, 
         assert torch.isfinite(b).all(), key
         scale = max(float(a.abs().max()), 1.0)
         assert float((a - b).abs().max()) <= tol * scale, (key, float((a - b).abs().max()), scale)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-13), (torch.float32, 1e-5)])
+def test_attention_scalars_one_gemm_equals_the_elementwise_form(dtype, tol):
+    """gat.attention_scalars (block-diagonal GEMM, one pass over the activations) against PyG's (x * att).sum(-1), values
+    and every gradient, with fewer destinations than sources (prefix layers)."""
+    from spadot_b200 import gat
+    torch.manual_seed(0)
+    N, H, C, n_dst = 57, 4, 24, 31
+    h = torch.randn(N, H, C, dtype=dtype, requires_grad=True)
+    a_s = torch.randn(1, H, C, dtype=dtype, requires_grad=True)
+    a_d = torch.randn(1, H, C, dtype=dtype, requires_grad=True)
+    w1, w2 = torch.randn(N, H, dtype=dtype), torch.randn(n_dst, H, dtype=dtype)
+    want = ((h * a_s).sum(-1), (h[:n_dst] * a_d).sum(-1))
+    got = gat.attention_scalars(h, a_s, a_d, n_dst)
+    assert got[0].shape == (N, H) and got[1].shape == (n_dst, H)
+    for g, w in zip(got, want):
+        assert float((g - w).abs().max()) <= tol * max(1.0, float(w.abs().max()))
+    gw = torch.autograd.grad((want[0] * w1).sum() + (want[1] * w2).sum(), [h, a_s, a_d])
+    gg = torch.autograd.grad((got[0] * w1).sum() + (got[1] * w2).sum(), [h, a_s, a_d])
+    for g, w in zip(gg, gw):
+        assert float((g - w).abs().max()) <= 10 * tol * max(1.0, float(w.abs().max()))
