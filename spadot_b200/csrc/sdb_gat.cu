@@ -502,6 +502,8 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_agg_kernel(const T* __
 
 // By-destination backward in tile form.  Needs C = 2 * W * tph with tph (threads per head) in {32, 64, 128, 256}: every thread
 // owns two W-wide column groups of ONE head, half a head apart, so a warp never straddles heads and the butterfly is uniform.
+// Wider heads (C = S * 2 * W * 256, the aggregate-first layers of spadot_b200/gat.py: C = in_channels) are cut into S column
+// slices of 2 * W * 256 that take turns - the whole CTA on one slice, partial dot products added up in shared memory.
 template <typename T>
 __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
                                                                       const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
@@ -523,16 +525,19 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* _
     }
     const int Et = sm.off[GT_TD], U = sm.n_u;
     const int HC = H * C;
-    const int tph = C / (2 * W);          // threads per head
-    const int hps = GT_THREADS / tph;     // heads per sweep
-    const int wph = tph >> 5;             // warps per head
-    const int hl = tid / tph;             // head slot of this thread within a sweep
+    const int NS = max(1, C / (2 * W * GT_THREADS));   // column slices per head (1 unless a head is wider than the CTA covers)
+    const int Cs = C / NS;                // slice width
+    const int tph = Cs / (2 * W);         // threads per slice
+    const int hps = GT_THREADS / tph;     // slices per sweep (1 when NS > 1)
+    const int wph = tph >> 5;             // warps per slice
+    const int hl = tid / tph;             // slice slot of this thread within a sweep
     const int j = tid - hl * tph;
+    const int n_sl = H * NS;
     __syncthreads();                      // e_loc
-    for (int h0 = 0; h0 < H; h0 += hps) {
-        const int h = h0 + hl;
-        const bool live = h < H;          // uniform per warp (tph is a multiple of 32)
-        const int c0 = (live ? h : 0) * C + j * W, c1 = c0 + (C >> 1);
+    for (int h0 = 0; h0 < n_sl; h0 += hps) {
+        const int sl = h0 + hl;
+        const bool live = sl < n_sl;      // uniform per warp (tph is a multiple of 32)
+        const int c0 = live ? (sl / NS) * C + (sl % NS) * Cs + j * W : j * W, c1 = c0 + (Cs >> 1);
         T go[GT_TD][2 * W];
 #pragma unroll
         for (int t = 0; t < GT_TD; ++t) {
@@ -590,10 +595,12 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* _
         for (int i = tid; i < Et * hps; i += GT_THREADS) {              // d alpha of the edges that read these rows, heads of this sweep
             const int s = i / hps, k = i - s * hps;
             const int loc = sm.e_loc[s];
-            if (h0 + k >= H || loc < ub || loc >= ue) continue;
+            if (h0 + k >= n_sl || loc < ub || loc >= ue) continue;
             T acc = T(0);
             for (int wi = 0; wi < wph; ++wi) acc += sm.w[k * wph + wi][loc - ub][sm.e_own[s]];
-            sm.ev[s][h0 + k] = acc;
+            const int hh = (h0 + k) / NS;
+            if ((h0 + k) % NS == 0) sm.ev[s][hh] = acc;       // first slice of the head (slices of one head never share a sweep)
+            else sm.ev[s][hh] += acc;
         }
         __syncthreads();
         }
@@ -638,6 +645,7 @@ static bool gat_bdst_tile_shape(int C) {
     constexpr int W = Vec<T>::W;
     if (C % (2 * W)) return false;
     const int tph = C / (2 * W);
+    if (tph > GT_THREADS) return tph % GT_THREADS == 0;      // S slices of a full CTA each
     return tph == 32 || tph == 64 || tph == 128 || tph == 256;
 }
 

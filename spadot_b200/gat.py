@@ -186,6 +186,12 @@ class _EdgeSoftmaxAggregate(torch.autograd.Function):
         return grad_feat, grad_a_src, grad_a_dst, None, None
 
 
+# GATConv runs a prefix layer (fewer destinations than sources) aggregate-first when the linear layer on all source rows would
+# cost at least this many flops: below it the layer is launch-bound and the exchange buys nothing (ChickenHeart-sized batches:
+# 1e10; SYN-T's second and third layers: 3.4e11 and 1.4e11).
+AGGREGATE_FIRST_MIN_FLOPS = 4.0e10
+
+
 def attention_scalars(h, att_src, att_dst, n_dst):
     """a_src[n,head] = <h[n,head,:], att_src[head,:]> for every node, a_dst likewise for the first n_dst nodes (PyG GATConv:
     `(x * att).sum(-1)`), both roles in ONE pass over h: a GEMM against the (H*C, 2H) block-diagonal arrangement of the two
@@ -226,13 +232,31 @@ class GATConv(nn.Module):
         `n_dst` (optional): produce only output rows [:n_dst]; `x` then holds the rows [:n_src] those destinations read
         (CsrGraph.prefix_plan) and `edge_index` may be the CsrGraph of the whole batch."""
         H, C, N = self.heads, self.out_channels, x.shape[0]
-        h = self.lin(x).view(N, H, C)
         graph = edge_index if isinstance(edge_index, CsrGraph) else graph_for(edge_index, N, self.add_self_loops, pos)
         n_dst = N if n_dst is None else int(n_dst)
-        a_src, a_dst = attention_scalars(h, self.att_src, self.att_dst, n_dst)
-        out = _EdgeSoftmaxAggregate.apply(h, a_src, a_dst, graph, self.negative_slope)
+        # prefix layers of a large batch: aggregate first, transform the (fewer) aggregated rows afterwards
+        if 2 * n_dst <= N and 2.0 * N * self.in_channels * H * C >= AGGREGATE_FIRST_MIN_FLOPS:
+            out = self._aggregate_first(x, graph, n_dst)
+        else:
+            h = self.lin(x).view(N, H, C)
+            a_src, a_dst = attention_scalars(h, self.att_src, self.att_dst, n_dst)
+            out = _EdgeSoftmaxAggregate.apply(h, a_src, a_dst, graph, self.negative_slope)
         out = out.reshape(n_dst, H * C) if self.concat else out.mean(dim=1)
         return out + self.bias if self.bias is not None else out
+
+    def _aggregate_first(self, x, graph, n_dst):
+        """The same layer with the two linear steps exchanged:  out[i,h,:] = W_h (sum_j alpha^h_ij x_j)  instead of
+        sum_j alpha^h_ij (W_h x_j).  The linear layer then runs on the n_dst aggregated rows per head instead of on all N source
+        rows - n_dst / N of the GEMM work (forward, dX and dW alike) - and the attention scalars come from the projected
+        attention vectors, a_src[j,h] = x_j . (W_h^T att_src[h]), so the (N, H*C) activations are never formed.  The price is
+        an aggregation over in_channels instead of out_channels features per head.  Identical in exact arithmetic."""
+        H, C, N, F_in = self.heads, self.out_channels, x.shape[0], self.in_channels
+        W = self.lin.weight.view(H, C, F_in)
+        att = torch.stack([self.att_src[0], self.att_dst[0]], dim=-1)                          # (H, C, 2)
+        proj = torch.einsum("hcf,hck->fhk", W, att).reshape(F_in, 2 * H)
+        a = (x @ proj).view(N, H, 2)
+        z = _EdgeSoftmaxAggregate.apply(x.unsqueeze(1).expand(N, H, F_in), a[:, :, 0], a[:n_dst, :, 1], graph, self.negative_slope)
+        return torch.einsum("nhf,hcf->nhc", z, W)                                              # (n_dst, H, C)
 
 
 class GATEncoder(nn.Module):

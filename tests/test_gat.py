@@ -158,12 +158,16 @@ def test_gat_coordinate_hint_orders_ctas_on_device_and_keeps_results():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("agg_first", [False, True])
 @pytest.mark.parametrize("hop_ordered", [True, False])
-def test_gat_encoder_seed_rows_only_equals_full_run(hop_ordered):
+def test_gat_encoder_seed_rows_only_equals_full_run(hop_ordered, agg_first, monkeypatch):
     """GATEncoder(n_out=seeds) runs every layer on the rows the next one reads (prefix form of the kernels): the seeds' outputs
     and every parameter gradient equal the full run's; with hop-ordered nodes the prefixes are the hop sets, with arbitrary
     numbering they degrade to (correct) supersets."""
     from spadot_b200 import gat, graph
+    # agg_first: prefix layers with at most half as many destinations as sources run aggregate-first (GATConv._aggregate_first;
+    # by default only for large batches) - same outputs and gradients as the full run
+    monkeypatch.setattr(gat, "AGGREGATE_FIRST_MIN_FLOPS", 0.0 if agg_first else float("inf"))
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(11)
     n_all, bs = 6000, 64
@@ -243,7 +247,8 @@ def _random_graph(kind, n, rng):
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-5)])
 @pytest.mark.parametrize("kind,n,H,C,n_dst", [("knn", 1203, 4, 512, None), ("knn", 1203, 4, 512, 300), ("knn", 500, 3, 24, None),
                                               ("knn", 500, 2, 25, 123), ("random", 900, 4, 128, None), ("random", 900, 4, 64, 400),
-                                              ("hubs", 800, 4, 256, None), ("hubs", 800, 1, 7, None), ("knn", 40, 5, 16, None)])
+                                              ("hubs", 800, 4, 256, None), ("hubs", 800, 1, 7, None), ("knn", 40, 5, 16, None),
+                                              ("knn", 500, 2, 2048, None), ("knn", 300, 1, 4096, 100)])   # heads wider than a CTA sweep
 def test_gat_tile_kernels_equal_the_per_node_kernels(dtype, tol, kind, n, H, C, n_dst):
     """The tile form (8 nodes per CTA, de-duplicated gathers, dense weights; by-destination backward on the butterfly) against
     the per-node form of the same library (SDB_GAT_TILES=0), forward and all three gradients, full and prefix layers."""
@@ -301,3 +306,36 @@ def test_attention_scalars_one_gemm_equals_the_elementwise_form(dtype, tol):
     gg = torch.autograd.grad((got[0] * w1).sum() + (got[1] * w2).sum(), [h, a_s, a_d])
     for g, w in zip(gg, gw):
         assert float((g - w).abs().max()) <= 10 * tol * max(1.0, float(w.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 5e-5)])
+@pytest.mark.parametrize("concat", [True, False])
+def test_gatconv_aggregate_first_equals_transform_first(dtype, tol, concat, monkeypatch):
+    """A prefix layer (300 destinations of 1203 sources) computed as W_h (sum_j alpha x_j) and as sum_j alpha (W_h x_j): same
+    output, same gradients of the input and of every parameter."""
+    from spadot_b200 import gat
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(7)
+    n, n_dst, f_in, C, H = 1203, 300, 48, 32, 4
+    ei = _random_graph("knn", n, rng).to(dev)
+    g = gat.CsrGraph(ei, n, add_self_loops=True)
+    n_src = max(int(g.col[: int(g.rowptr[n_dst])].max()) + 1, n_dst)
+    torch.manual_seed(1)
+    conv = gat.GATConv(f_in, C, heads=H, concat=concat).to(dtype).to(dev)
+    with torch.no_grad():
+        conv.bias.normal_()
+    x = torch.randn(n_src, f_in, dtype=dtype, device=dev)
+    w = torch.randn(n_dst, H * C if concat else C, dtype=dtype, device=dev)
+    res = []
+    for min_flops in (float("inf"), 0.0):
+        monkeypatch.setattr(gat, "AGGREGATE_FIRST_MIN_FLOPS", min_flops)
+        conv.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        out = conv(xi, g, n_dst=n_dst)
+        (out * w).sum().backward()
+        res.append([out.detach(), xi.grad] + [p.grad.clone() for p in conv.parameters()])
+    assert 2 * n_dst <= n_src
+    for a, b in zip(*res):
+        scale = max(float(a.abs().max()), 1.0)
+        assert float((a - b).abs().max()) <= tol * scale
