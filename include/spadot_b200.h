@@ -450,6 +450,21 @@ int sdb_gat_backward_prefix(const void* feat, const void* a_src, const void* a_d
                             const int32_t* order_src, int64_t n_dst, int64_t n_src, int H, int C, double negative_slope,
                             int is_double, const void* alpha, const void* grad_out, void* dlogit, void* grad_feat,
                             void* grad_a_src, void* grad_a_dst, void* stream);
+/* The same message passing with SHARED features: feat is (n_src, C) and every head weighs the same row,
+ *     out[i,h,:] = sum_j alpha^h_ij feat[j,:]            (n, H, C),
+ * which is what a GAT layer needs when the linear map is applied AFTER the aggregation (out_h = W_h sum_j alpha^h_ij x_j equals
+ * sum_j alpha^h_ij W_h x_j; spadot_b200/gat.py does this for prefix layers, where it leaves the GEMM n_dst instead of n_src rows;
+ * ref: model/encoder.py:41-45,56-58 states the layers, torch_geometric's GATConv always transforms first).  a_src / a_dst are
+ * the caller's attention scalars (n_src,H) / (n,H).  Backward: grad_out (n_dst,H,C) -> grad_feat (n_src, C), the sum over the
+ * heads done inside the kernel; everything else as sdb_gat_forward / sdb_gat_backward_prefix. */
+int sdb_gat_forward_shared(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
+                           const int32_t* node_order, int64_t n, int H, int C, double negative_slope, int is_double,
+                           void* out, void* alpha, void* stream);
+int sdb_gat_backward_shared(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
+                            const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, const int32_t* order_dst,
+                            const int32_t* order_src, int64_t n_dst, int64_t n_src, int H, int C, double negative_slope,
+                            int is_double, const void* alpha, const void* grad_out, void* dlogit, void* grad_feat,
+                            void* grad_a_src, void* grad_a_dst, void* stream);
 
 /* k nearest OTHER points (self excluded) of every point, sorted by (distance, index); pts (n,dim) fp64, dim <= 3,
  * k <= 32 and k <= n-1.  out_idx (n,k) int32, out_dist (n,k) fp64 Euclidean distances (may be NULL).

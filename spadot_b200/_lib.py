@@ -83,6 +83,9 @@ SIGNATURES = {
     "sdb_gat_backward": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p],
     "sdb_gat_backward_prefix": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p,
                                 c_p, c_p],
+    "sdb_gat_forward_shared": [c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p],
+    "sdb_gat_backward_shared": [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_l, c_l, c_i, c_i, c_d, c_i, c_p, c_p, c_p, c_p, c_p,
+                                c_p, c_p],
 }
 
 class SweepDesc(ctypes.Structure):

@@ -69,8 +69,11 @@ __device__ __forceinline__ void vec_store(T* p, const T (&v)[Vec<T>::W]) {
 // One node at a time, every thread of the CTA cooperating.  This is the general form (any H, any C, any degree); the tile
 // kernels below call it for the tiles that exceed their shared-memory budget.  Must be called by ALL threads of the CTA.
 
+// SH ("shared features", the aggregate-first layers of spadot_b200/gat.py): the gathered rows are (n, C) and every head reads
+// the SAME row - out[i,h,:] = sum_j alpha^h_ij x_j - instead of its own slice of an (n, H, C) row.
+
 // forward: segment softmax of node i (one warp per head), then the weighted sum of its gathered source rows
-template <typename T>
+template <typename T, bool SH>
 __device__ void gat_fwd_node(const T* __restrict__ feat, const T* __restrict__ a_src, const T* __restrict__ a_dst,
                              const int32_t* __restrict__ col, int64_t i, int64_t e0, int64_t e1, int H, int C, T slope,
                              T* __restrict__ out, T* __restrict__ alpha) {
@@ -107,10 +110,11 @@ __device__ void gat_fwd_node(const T* __restrict__ feat, const T* __restrict__ a
             T acc[W];
 #pragma unroll
             for (int q = 0; q < W; ++q) acc[q] = T(0);
+            const int fc = SH ? c - h * C : c;
             for (int64_t e = e0; e < e1; ++e) {
                 const T a = alpha[e * H + h];
                 T v[W];
-                vec_load(feat + (int64_t)col[e] * HC + c, v);
+                vec_load(feat + (int64_t)col[e] * (SH ? C : HC) + fc, v);
 #pragma unroll
                 for (int q = 0; q < W; ++q) acc[q] += a * v[q];
             }
@@ -120,7 +124,7 @@ __device__ void gat_fwd_node(const T* __restrict__ feat, const T* __restrict__ a
         for (int c = threadIdx.x; c < HC; c += nt) {
             const int h = c / C;
             T acc = T(0);
-            for (int64_t e = e0; e < e1; ++e) acc += alpha[e * H + h] * feat[(int64_t)col[e] * HC + c];
+            for (int64_t e = e0; e < e1; ++e) acc += alpha[e * H + h] * feat[(int64_t)col[e] * (SH ? C : HC) + (SH ? c - h * C : c)];
             out[i * HC + c] = acc;
         }
     }
@@ -128,7 +132,7 @@ __device__ void gat_fwd_node(const T* __restrict__ feat, const T* __restrict__ a
 }
 
 // backward, by destination:  dlogit[e,h] = d loss / d (a_src[j,h] + a_dst[i,h]);  grad_a_dst[i,h] = sum_e dlogit[e,h]
-template <typename T>
+template <typename T, bool SH>
 __device__ void gat_bdst_node(const T* __restrict__ feat, const T* __restrict__ a_src, const T* __restrict__ a_dst,
                               const int32_t* __restrict__ col, int64_t i, int64_t e0, int64_t e1, int H, int C, T slope,
                               const T* __restrict__ alpha, const T* __restrict__ grad_out, T* __restrict__ dlogit,
@@ -141,7 +145,7 @@ __device__ void gat_bdst_node(const T* __restrict__ feat, const T* __restrict__ 
         const int64_t e = e0 + p / H;
         const int h = (int)(p % H);
         const T* go = grad_out + i * HC + h * C;
-        const T* fj = feat + (int64_t)col[e] * HC + h * C;
+        const T* fj = SH ? feat + (int64_t)col[e] * C : feat + (int64_t)col[e] * HC + h * C;
         T acc = T(0);
         constexpr int W = Vec<T>::W;
         if (C % W == 0) {
@@ -221,17 +225,59 @@ __device__ void gat_bsrc_node(const int32_t* __restrict__ src_dst, const int32_t
     }
 }
 
+// by-source backward with shared features: grad_x[j,:] = sum over heads and out-edges of alpha[e,h] * grad_out[i,h,:]  (n_src, C)
 template <typename T>
+__device__ void gat_bsrc_node_shared(const int32_t* __restrict__ src_dst, const int32_t* __restrict__ src_eid, int64_t j, int64_t p0,
+                                     int64_t p1, int64_t e_limit, int H, int C, const T* __restrict__ alpha,
+                                     const T* __restrict__ dlogit, const T* __restrict__ grad_out, T* __restrict__ grad_feat,
+                                     T* __restrict__ grad_a_src) {
+    const int HC = H * C, nt = blockDim.x;
+    constexpr int W = Vec<T>::W;
+    if (C % W == 0) {
+        for (int c = threadIdx.x * W; c < C; c += nt * W) {
+            T acc[W];
+#pragma unroll
+            for (int q = 0; q < W; ++q) acc[q] = T(0);
+            for (int64_t p = p0; p < p1; ++p) {
+                if (src_eid[p] >= e_limit) continue;
+                for (int h = 0; h < H; ++h) {
+                    const T a = alpha[(int64_t)src_eid[p] * H + h];
+                    T v[W];
+                    vec_load(grad_out + (int64_t)src_dst[p] * HC + h * C + c, v);
+#pragma unroll
+                    for (int q = 0; q < W; ++q) acc[q] += a * v[q];
+                }
+            }
+            vec_store(grad_feat + j * C + c, acc);
+        }
+    } else {
+        for (int c = threadIdx.x; c < C; c += nt) {
+            T acc = T(0);
+            for (int64_t p = p0; p < p1; ++p)
+                if (src_eid[p] < e_limit)
+                    for (int h = 0; h < H; ++h) acc += alpha[(int64_t)src_eid[p] * H + h] * grad_out[(int64_t)src_dst[p] * HC + h * C + c];
+            grad_feat[j * C + c] = acc;
+        }
+    }
+    for (int h = threadIdx.x; h < H; h += nt) {
+        T acc = T(0);
+        for (int64_t p = p0; p < p1; ++p)
+            if (src_eid[p] < e_limit) acc += dlogit[(int64_t)src_eid[p] * H + h];
+        grad_a_src[j * H + h] = acc;
+    }
+}
+
+template <typename T, bool SH>
 __global__ void __launch_bounds__(128) gat_fwd_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
                                                       const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
                                                       const int32_t* __restrict__ col, const int32_t* __restrict__ order,
                                                       int64_t n, int H, int C, T slope, T* __restrict__ out,
                                                       T* __restrict__ alpha) {
     const int64_t i = order ? order[blockIdx.x] : blockIdx.x;   // locality order of the CTAs (L2 reuse of gathered rows)
-    gat_fwd_node<T>(feat, a_src, a_dst, col, i, rowptr[i], rowptr[i + 1], H, C, slope, out, alpha);
+    gat_fwd_node<T, SH>(feat, a_src, a_dst, col, i, rowptr[i], rowptr[i + 1], H, C, slope, out, alpha);
 }
 
-template <typename T>
+template <typename T, bool SH>
 __global__ void __launch_bounds__(128) gat_bwd_dst_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
                                                           const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
                                                           const int32_t* __restrict__ col, const int32_t* __restrict__ order,
@@ -239,10 +285,10 @@ __global__ void __launch_bounds__(128) gat_bwd_dst_kernel(const T* __restrict__ 
                                                           const T* __restrict__ grad_out, T* __restrict__ dlogit,
                                                           T* __restrict__ grad_a_dst) {
     const int64_t i = order ? order[blockIdx.x] : blockIdx.x;
-    gat_bdst_node<T>(feat, a_src, a_dst, col, i, rowptr[i], rowptr[i + 1], H, C, slope, alpha, grad_out, dlogit, grad_a_dst);
+    gat_bdst_node<T, SH>(feat, a_src, a_dst, col, i, rowptr[i], rowptr[i + 1], H, C, slope, alpha, grad_out, dlogit, grad_a_dst);
 }
 
-template <typename T>
+template <typename T, bool SH>
 __global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restrict__ src_rowptr, const int32_t* __restrict__ src_dst,
                                                           const int32_t* __restrict__ src_eid, const int32_t* __restrict__ order,
                                                           const int64_t* __restrict__ e_limit_ptr, int H, int C,
@@ -250,8 +296,12 @@ __global__ void __launch_bounds__(128) gat_bwd_src_kernel(const int64_t* __restr
                                                           const T* __restrict__ dlogit, const T* __restrict__ grad_out,
                                                           T* __restrict__ grad_feat, T* __restrict__ grad_a_src) {
     const int64_t j = order ? order[blockIdx.x] : blockIdx.x;
-    gat_bsrc_node<T>(src_dst, src_eid, j, src_rowptr[j], src_rowptr[j + 1], *e_limit_ptr, H, C, alpha, dlogit, grad_out, grad_feat,
-                     grad_a_src);
+    if constexpr (SH)
+        gat_bsrc_node_shared<T>(src_dst, src_eid, j, src_rowptr[j], src_rowptr[j + 1], *e_limit_ptr, H, C, alpha, dlogit, grad_out,
+                                grad_feat, grad_a_src);
+    else
+        gat_bsrc_node<T>(src_dst, src_eid, j, src_rowptr[j], src_rowptr[j + 1], *e_limit_ptr, H, C, alpha, dlogit, grad_out, grad_feat,
+                         grad_a_src);
 }
 
 // ======================================================================================== tile form
@@ -407,12 +457,89 @@ __device__ __forceinline__ void gat_tile_aggregate(const S& sm, const T* __restr
     }
 }
 
+// Shared features, forward: rows are (n, C) and every head weighs the same row.  The CTA is cut into H groups of
+// GT_THREADS / H threads (H in {1, 2, 4}); the groups work on the SAME columns at the same time, so a row piece is fetched
+// from L2 once and served to the other heads by L1, and each thread keeps its eight accumulators of ONE head.
+template <typename T, int W, typename S>
+__device__ __forceinline__ void gat_tile_aggregate_shared_fwd(const S& sm, const T* __restrict__ rows, T* __restrict__ out, int U, int H,
+                                                              int C) {
+    constexpr int VW = Vec<T>::W;
+    const int tpg = GT_THREADS / H;
+    const int h = threadIdx.x / tpg, j = threadIdx.x - h * tpg;
+    for (int c = j * W; c < C; c += tpg * W) {
+        T acc[GT_TD][W];
+#pragma unroll
+        for (int t = 0; t < GT_TD; ++t)
+#pragma unroll
+            for (int q = 0; q < W; ++q) acc[t][q] = T(0);
+#pragma unroll 8
+        for (int u = 0; u < U; ++u) {
+            T v[W];
+            if constexpr (W == 1) v[0] = rows[(int64_t)sm.u_id[u] * C + c];
+            else vec_load(rows + (int64_t)sm.u_id[u] * C + c, v);
+            T a[GT_TD];
+#pragma unroll
+            for (int t = 0; t < GT_TD; t += VW) vec_load(&sm.w[h][u][t], *reinterpret_cast<T(*)[VW]>(&a[t]));
+#pragma unroll
+            for (int t = 0; t < GT_TD; ++t)
+#pragma unroll
+                for (int q = 0; q < W; ++q) acc[t][q] += a[t] * v[q];
+        }
+#pragma unroll
+        for (int t = 0; t < GT_TD; ++t) {
+            const int64_t node = sm.node[t];
+            if (node < 0) continue;
+            if constexpr (W == 1) out[(node * H + h) * C + c] = acc[t][0];
+            else vec_store(out + (node * H + h) * C + c, acc[t]);
+        }
+    }
+}
+
+// Shared features, by-source backward: grad_x[member, cols] = sum over heads and distinct rows of w[h][row][member] *
+// grad_out[row, h, cols] - the heads are summed inside the kernel, the output is (n_src, C).
+template <typename T, int W, typename S>
+__device__ __forceinline__ void gat_tile_aggregate_shared_bsrc(const S& sm, const T* __restrict__ rows, T* __restrict__ out, int U, int H,
+                                                               int C) {
+    constexpr int VW = Vec<T>::W;
+    const int HC = H * C;
+    for (int c = threadIdx.x * W; c < C; c += GT_THREADS * W) {
+        T acc[GT_TD][W];
+#pragma unroll
+        for (int t = 0; t < GT_TD; ++t)
+#pragma unroll
+            for (int q = 0; q < W; ++q) acc[t][q] = T(0);
+#pragma unroll 2
+        for (int u = 0; u < U; ++u) {
+            const T* row = rows + (int64_t)sm.u_id[u] * HC + c;
+            for (int h = 0; h < H; ++h) {
+                T v[W];
+                if constexpr (W == 1) v[0] = row[h * C];
+                else vec_load(row + h * C, v);
+                T a[GT_TD];
+#pragma unroll
+                for (int t = 0; t < GT_TD; t += VW) vec_load(&sm.w[h][u][t], *reinterpret_cast<T(*)[VW]>(&a[t]));
+#pragma unroll
+                for (int t = 0; t < GT_TD; ++t)
+#pragma unroll
+                    for (int q = 0; q < W; ++q) acc[t][q] += a[t] * v[q];
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < GT_TD; ++t) {
+            const int64_t node = sm.node[t];
+            if (node < 0) continue;
+            if constexpr (W == 1) out[node * C + c] = acc[t][0];
+            else vec_store(out + node * C + c, acc[t]);
+        }
+    }
+}
+
 extern __shared__ __align__(16) unsigned char gat_smem_raw[];
 
 // MODE 0: forward.  members = destinations, (ptr, nbr) = by-destination CSR, rows = feat, out = out; alpha is WRITTEN.
 // MODE 1: by-source backward.  members = sources, (ptr, nbr, eid) = by-source lists, rows = grad_out, out = grad_feat;
 //         alpha and dlogit are READ, grad_a (= grad_a_src) is written.
-template <typename T, int MODE>
+template <typename T, int MODE, bool SH>
 __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_agg_kernel(const T* __restrict__ rows, const T* __restrict__ a_src,
                                                                      const T* __restrict__ a_dst, const int64_t* __restrict__ ptr,
                                                                      const int32_t* __restrict__ nbr, const int32_t* __restrict__ eid,
@@ -429,7 +556,8 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_agg_kernel(const T* __
             const int64_t node = sm.node[m];
             if (node < 0) continue;
             const int64_t p0 = sm.p0[m], p1 = ptr[node + 1];
-            if constexpr (MODE == 0) gat_fwd_node<T>(rows, a_src, a_dst, nbr, node, p0, p1, H, C, slope, out, alpha);
+            if constexpr (MODE == 0) gat_fwd_node<T, SH>(rows, a_src, a_dst, nbr, node, p0, p1, H, C, slope, out, alpha);
+            else if constexpr (SH) gat_bsrc_node_shared<T>(nbr, eid, node, p0, p1, e_limit, H, C, alpha, dlogit, rows, out, grad_a);
             else gat_bsrc_node<T>(nbr, eid, node, p0, p1, e_limit, H, C, alpha, dlogit, rows, out, grad_a);
         }
         return;
@@ -496,15 +624,23 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_agg_kernel(const T* __
         if (sm.e_nbr[s] >= 0) atomicAdd(&sm.w[h][sm.e_loc[s]][sm.e_own[s]], sm.ev[s][h]);
     }
     __syncthreads();
-    if (C % Vec<T>::W == 0) gat_tile_aggregate<T, Vec<T>::W>(sm, rows, out, U, H, C);
-    else gat_tile_aggregate<T, 1>(sm, rows, out, U, H, C);
+    if constexpr (SH && MODE == 0) {
+        if (C % Vec<T>::W == 0) gat_tile_aggregate_shared_fwd<T, Vec<T>::W>(sm, rows, out, U, H, C);
+        else gat_tile_aggregate_shared_fwd<T, 1>(sm, rows, out, U, H, C);
+    } else if constexpr (SH) {
+        if (C % Vec<T>::W == 0) gat_tile_aggregate_shared_bsrc<T, Vec<T>::W>(sm, rows, out, U, H, C);
+        else gat_tile_aggregate_shared_bsrc<T, 1>(sm, rows, out, U, H, C);
+    } else {
+        if (C % Vec<T>::W == 0) gat_tile_aggregate<T, Vec<T>::W>(sm, rows, out, U, H, C);
+        else gat_tile_aggregate<T, 1>(sm, rows, out, U, H, C);
+    }
 }
 
 // By-destination backward in tile form.  Needs C = 2 * W * tph with tph (threads per head) in {32, 64, 128, 256}: every thread
 // owns two W-wide column groups of ONE head, half a head apart, so a warp never straddles heads and the butterfly is uniform.
 // Wider heads (C = S * 2 * W * 256, the aggregate-first layers of spadot_b200/gat.py: C = in_channels) are cut into S column
 // slices of 2 * W * 256 that take turns - the whole CTA on one slice, partial dot products added up in shared memory.
-template <typename T>
+template <typename T, bool SH>
 __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* __restrict__ feat, const T* __restrict__ a_src,
                                                                       const T* __restrict__ a_dst, const int64_t* __restrict__ rowptr,
                                                                       const int32_t* __restrict__ col, const int32_t* __restrict__ order,
@@ -519,7 +655,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* _
         for (int m = 0; m < GT_TD; ++m) {
             const int64_t node = sm.node[m];
             if (node < 0) continue;
-            gat_bdst_node<T>(feat, a_src, a_dst, col, node, sm.p0[m], rowptr[node + 1], H, C, slope, alpha, grad_out, dlogit, grad_a_dst);
+            gat_bdst_node<T, SH>(feat, a_src, a_dst, col, node, sm.p0[m], rowptr[node + 1], H, C, slope, alpha, grad_out, dlogit, grad_a_dst);
         }
         return;
     }
@@ -538,6 +674,9 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* _
         const int sl = h0 + hl;
         const bool live = sl < n_sl;      // uniform per warp (tph is a multiple of 32)
         const int c0 = live ? (sl / NS) * C + (sl % NS) * Cs + j * W : j * W, c1 = c0 + (Cs >> 1);
+        // column of the gathered row: the head's slice of an (n, H, C) row, or the same (n, C) row for every head
+        const int r0 = SH ? (live ? (sl % NS) * Cs + j * W : j * W) : c0, r1c = r0 + (Cs >> 1);
+        const int RS = SH ? C : HC;
         T go[GT_TD][2 * W];
 #pragma unroll
         for (int t = 0; t < GT_TD; ++t) {
@@ -555,9 +694,9 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* _
 #pragma unroll 2
         for (int u = ub; u < ue; ++u) {
             T v[2 * W];
-            const T* row = feat + (int64_t)sm.u_id[u] * HC;
-            vec_load(row + c0, *reinterpret_cast<T(*)[W]>(&v[0]));
-            vec_load(row + c1, *reinterpret_cast<T(*)[W]>(&v[W]));
+            const T* row = feat + (int64_t)sm.u_id[u] * RS;
+            vec_load(row + r0, *reinterpret_cast<T(*)[W]>(&v[0]));
+            vec_load(row + r1c, *reinterpret_cast<T(*)[W]>(&v[W]));
             T p[GT_TD];
 #pragma unroll
             for (int t = 0; t < GT_TD; ++t) {
@@ -649,63 +788,65 @@ static bool gat_bdst_tile_shape(int C) {
     return tph == 32 || tph == 64 || tph == 128 || tph == 256;
 }
 
-template <typename T, int MODE, typename... Args>
+template <typename T, int MODE, bool SH, typename... Args>
 static int gat_launch_agg(int64_t n, cudaStream_t st, Args... args) {
     static size_t memo[SDB_MAX_DEVICES];
     using S = GatTile<T, GT_HMAX, GT_UMAX>;
-    auto kern = gat_tile_agg_kernel<T, MODE>;
+    auto kern = gat_tile_agg_kernel<T, MODE, SH>;
     cudaError_t e = sdb_ensure_smem(kern, sizeof(S), memo);
     if (e != cudaSuccess) return (int)e;
     kern<<<(unsigned)((n + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(args...);
     SDB_LAUNCH_STATUS();
 }
-template <typename T, typename... Args>
+template <typename T, bool SH, typename... Args>
 static int gat_launch_bdst(int64_t n, cudaStream_t st, Args... args) {
     static size_t memo[SDB_MAX_DEVICES];
     using S = GatTile<T, GT_THREADS / 32, GT_UCHUNK>;
-    auto kern = gat_tile_bdst_kernel<T>;
+    auto kern = gat_tile_bdst_kernel<T, SH>;
     cudaError_t e = sdb_ensure_smem(kern, sizeof(S), memo);
     if (e != cudaSuccess) return (int)e;
     kern<<<(unsigned)((n + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(args...);
     SDB_LAUNCH_STATUS();
 }
 
-template <typename T>
+// SH: feat is (n_src, C), shared by the heads; out (n, H, C).  The shared forward's tile form splits the CTA into H groups.
+template <typename T, bool SH>
 int gat_forward_t(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
                   const int32_t* order, int64_t n, int H, int C, double slope, void* out, void* alpha, cudaStream_t st) {
-    if (gat_use_tiles(H, order))
-        return gat_launch_agg<T, 0>(n, st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, (const int32_t*)nullptr,
-                                            (const int64_t*)nullptr, order, n, H, C, (T)slope, (T*)alpha, (const T*)nullptr, (T*)out,
-                                            (T*)nullptr);
-    gat_fwd_kernel<T><<<(unsigned)n, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order, n, H, C,
-                                                  (T)slope, (T*)out, (T*)alpha);
+    if (gat_use_tiles(H, order) && (!SH || GT_THREADS % H == 0))
+        return gat_launch_agg<T, 0, SH>(n, st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, (const int32_t*)nullptr,
+                                        (const int64_t*)nullptr, order, n, H, C, (T)slope, (T*)alpha, (const T*)nullptr, (T*)out,
+                                        (T*)nullptr);
+    gat_fwd_kernel<T, SH><<<(unsigned)n, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order, n, H, C,
+                                                      (T)slope, (T*)out, (T*)alpha);
     SDB_LAUNCH_STATUS();
 }
 
-template <typename T>
+// SH: grad_feat is (n_src, C) - the sum over the heads happens inside the by-source kernel.
+template <typename T, bool SH>
 int gat_backward_t(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
                    const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, const int32_t* order_dst,
                    const int32_t* order_src, int64_t n_dst, int64_t n_src, int H, int C, double slope, const void* alpha,
                    const void* grad_out, void* dlogit, void* grad_feat, void* grad_a_src, void* grad_a_dst, cudaStream_t st) {
     cudaError_t e;
     if (gat_use_tiles(H, order_dst) && gat_bdst_tile_shape<T>(C)) {
-        const int rc = gat_launch_bdst<T>(n_dst, st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst, n_dst,
-                                                  H, C, (T)slope, (const T*)alpha, (const T*)grad_out, (T*)dlogit, (T*)grad_a_dst);
+        const int rc = gat_launch_bdst<T, SH>(n_dst, st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst, n_dst,
+                                              H, C, (T)slope, (const T*)alpha, (const T*)grad_out, (T*)dlogit, (T*)grad_a_dst);
         if (rc) return rc;
     } else {
-        gat_bwd_dst_kernel<T><<<(unsigned)n_dst, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst,
-                                                              n_dst, H, C, (T)slope, (const T*)alpha, (const T*)grad_out, (T*)dlogit,
-                                                              (T*)grad_a_dst);
+        gat_bwd_dst_kernel<T, SH><<<(unsigned)n_dst, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col,
+                                                                  order_dst, n_dst, H, C, (T)slope, (const T*)alpha, (const T*)grad_out,
+                                                                  (T*)dlogit, (T*)grad_a_dst);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (gat_use_tiles(H, order_src))
-        return gat_launch_agg<T, 1>(n_src, st, (const T*)grad_out, (const T*)nullptr, (const T*)nullptr, src_rowptr, src_dst, src_eid,
-                                            rowptr + n_dst, order_src, n_src, H, C, (T)slope, const_cast<T*>((const T*)alpha),
-                                            (const T*)dlogit, (T*)grad_feat, (T*)grad_a_src);
-    gat_bwd_src_kernel<T><<<(unsigned)n_src, 128, 0, st>>>(src_rowptr, src_dst, src_eid, order_src, rowptr + n_dst, H, C,
-                                                          (const T*)alpha, (const T*)dlogit, (const T*)grad_out, (T*)grad_feat,
-                                                          (T*)grad_a_src);
+        return gat_launch_agg<T, 1, SH>(n_src, st, (const T*)grad_out, (const T*)nullptr, (const T*)nullptr, src_rowptr, src_dst, src_eid,
+                                        rowptr + n_dst, order_src, n_src, H, C, (T)slope, const_cast<T*>((const T*)alpha),
+                                        (const T*)dlogit, (T*)grad_feat, (T*)grad_a_src);
+    gat_bwd_src_kernel<T, SH><<<(unsigned)n_src, 128, 0, st>>>(src_rowptr, src_dst, src_eid, order_src, rowptr + n_dst, H, C,
+                                                              (const T*)alpha, (const T*)dlogit, (const T*)grad_out, (T*)grad_feat,
+                                                              (T*)grad_a_src);
     SDB_LAUNCH_STATUS();
 }
 
@@ -719,8 +860,8 @@ int sdb_gat_forward(const void* feat, const void* a_src, const void* a_dst, cons
     SDB_CHECK_ARG(feat && a_src && a_dst && rowptr && col && out && alpha && n >= 0 && H > 0 && C > 0);
     if (n == 0) return 0;
     if (n > 2147483647LL) return SDB_E_UNSUPPORTED;
-    return is_double ? gat_forward_t<double>(feat, a_src, a_dst, rowptr, col, node_order, n, H, C, negative_slope, out, alpha, sdb_stream(stream))
-                     : gat_forward_t<float>(feat, a_src, a_dst, rowptr, col, node_order, n, H, C, negative_slope, out, alpha, sdb_stream(stream));
+    return is_double ? gat_forward_t<double, false>(feat, a_src, a_dst, rowptr, col, node_order, n, H, C, negative_slope, out, alpha, sdb_stream(stream))
+                     : gat_forward_t<float, false>(feat, a_src, a_dst, rowptr, col, node_order, n, H, C, negative_slope, out, alpha, sdb_stream(stream));
 }
 
 int sdb_gat_backward_prefix(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
@@ -733,12 +874,40 @@ int sdb_gat_backward_prefix(const void* feat, const void* a_src, const void* a_d
     if (n_src == 0) return 0;
     if (n_src > 2147483647LL) return SDB_E_UNSUPPORTED;
     if (n_dst == 0) return SDB_E_INVALID;                 // a layer without destinations has no backward
-    return is_double ? gat_backward_t<double>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, order_dst, order_src,
+    return is_double ? gat_backward_t<double, false>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, order_dst, order_src,
                                               n_dst, n_src, H, C, negative_slope, alpha, grad_out, dlogit, grad_feat, grad_a_src,
                                               grad_a_dst, sdb_stream(stream))
-                     : gat_backward_t<float>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, order_dst, order_src,
+                     : gat_backward_t<float, false>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, order_dst, order_src,
                                              n_dst, n_src, H, C, negative_slope, alpha, grad_out, dlogit, grad_feat, grad_a_src,
                                              grad_a_dst, sdb_stream(stream));
+}
+
+int sdb_gat_forward_shared(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
+                           const int32_t* node_order, int64_t n, int H, int C, double negative_slope, int is_double, void* out,
+                           void* alpha, void* stream) {
+    SDB_CHECK_ARG(feat && a_src && a_dst && rowptr && col && out && alpha && n >= 0 && H > 0 && C > 0);
+    if (n == 0) return 0;
+    if (n > 2147483647LL) return SDB_E_UNSUPPORTED;
+    return is_double ? gat_forward_t<double, true>(feat, a_src, a_dst, rowptr, col, node_order, n, H, C, negative_slope, out, alpha, sdb_stream(stream))
+                     : gat_forward_t<float, true>(feat, a_src, a_dst, rowptr, col, node_order, n, H, C, negative_slope, out, alpha, sdb_stream(stream));
+}
+
+int sdb_gat_backward_shared(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
+                            const int64_t* src_rowptr, const int32_t* src_dst, const int32_t* src_eid, const int32_t* order_dst,
+                            const int32_t* order_src, int64_t n_dst, int64_t n_src, int H, int C, double negative_slope,
+                            int is_double, const void* alpha, const void* grad_out, void* dlogit, void* grad_feat,
+                            void* grad_a_src, void* grad_a_dst, void* stream) {
+    SDB_CHECK_ARG(feat && a_src && a_dst && rowptr && col && src_rowptr && src_dst && src_eid && alpha && grad_out && dlogit &&
+                  grad_feat && grad_a_src && grad_a_dst && n_dst >= 0 && n_src >= n_dst && H > 0 && C > 0);
+    if (n_src == 0) return 0;
+    if (n_src > 2147483647LL) return SDB_E_UNSUPPORTED;
+    if (n_dst == 0) return SDB_E_INVALID;
+    return is_double ? gat_backward_t<double, true>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, order_dst, order_src,
+                                                    n_dst, n_src, H, C, negative_slope, alpha, grad_out, dlogit, grad_feat, grad_a_src,
+                                                    grad_a_dst, sdb_stream(stream))
+                     : gat_backward_t<float, true>(feat, a_src, a_dst, rowptr, col, src_rowptr, src_dst, src_eid, order_dst, order_src,
+                                                   n_dst, n_src, H, C, negative_slope, alpha, grad_out, dlogit, grad_feat, grad_a_src,
+                                                   grad_a_dst, sdb_stream(stream));
 }
 
 int sdb_gat_backward(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,

@@ -141,15 +141,22 @@ def _st(t):
 
 class _EdgeSoftmaxAggregate(torch.autograd.Function):
     """feat (n_src,H,C), a_src (n_src,H), a_dst (n_dst,H) -> out (n_dst,H,C); n_dst < n_src is the prefix form (the layer's
-    destinations are the first n_dst nodes of `graph`, see CsrGraph.prefix_plan)."""
+    destinations are the first n_dst nodes of `graph`, see CsrGraph.prefix_plan).
+
+    feat (n_src,C) - two dimensions - is the SHARED form: every head weighs the same row, out[i,h,:] = sum_j alpha^h_ij feat[j,:]
+    (the aggregate-first layers of GATConv); its gradient comes back as (n_src,C), summed over the heads inside the kernel."""
 
     @staticmethod
     def forward(ctx, feat, a_src, a_dst, graph, slope):
         _lib.require_device()
         if not feat.is_cuda:
             raise RuntimeError("spadot_b200.gat needs CUDA tensors; there is no CPU fallback")
-        n_src, H, C = feat.shape
+        shared = feat.dim() == 2
+        n_src, H = a_src.shape
+        C = feat.shape[-1]
         n_dst = a_dst.shape[0]
+        if feat.shape[0] != n_src or (not shared and feat.shape[1] != H):
+            raise ValueError(f"GAT features {tuple(feat.shape)} do not match attention scalars {tuple(a_src.shape)}")
         if not (0 < n_dst <= n_src <= graph.n):
             raise ValueError(f"GAT layer with {n_dst} destinations and {n_src} sources on a graph of {graph.n} nodes")
         feat, a_src, a_dst = feat.contiguous(), a_src.contiguous(), a_dst.contiguous()
@@ -159,18 +166,19 @@ class _EdgeSoftmaxAggregate(torch.autograd.Function):
         if feat.dtype not in (torch.float32, torch.float64):
             raise TypeError("GATConv supports float32 and float64")
         order = graph.order_prefix(n_dst)
-        _lib.call("sdb_gat_forward", feat.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(), graph.rowptr.data_ptr(),
-                  graph.col.data_ptr(), 0 if order is None else order.data_ptr(), n_dst, H, C, float(slope), is_double,
-                  out.data_ptr(), alpha.data_ptr(), _st(feat))
+        _lib.call("sdb_gat_forward_shared" if shared else "sdb_gat_forward", feat.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(),
+                  graph.rowptr.data_ptr(), graph.col.data_ptr(), 0 if order is None else order.data_ptr(), n_dst, H, C, float(slope),
+                  is_double, out.data_ptr(), alpha.data_ptr(), _st(feat))
         ctx.save_for_backward(feat, a_src, a_dst, alpha)
-        ctx.graph, ctx.slope, ctx.is_double = graph, float(slope), is_double
+        ctx.graph, ctx.slope, ctx.is_double, ctx.shared = graph, float(slope), is_double, shared
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         feat, a_src, a_dst, alpha = ctx.saved_tensors
         g = ctx.graph
-        n_src, H, C = feat.shape
+        n_src, H = a_src.shape
+        C = feat.shape[-1]
         n_dst = a_dst.shape[0]
         grad_out = grad_out.contiguous()
         dlogit = torch.empty_like(alpha)
@@ -178,10 +186,10 @@ class _EdgeSoftmaxAggregate(torch.autograd.Function):
         grad_a_src = torch.empty_like(a_src)
         grad_a_dst = torch.empty_like(a_dst)
         o_dst, o_src = g.order_prefix(n_dst), g.order_prefix(n_src)
-        _lib.call("sdb_gat_backward_prefix", feat.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(), g.rowptr.data_ptr(),
-                  g.col.data_ptr(), g.src_rowptr.data_ptr(), g.src_dst.data_ptr(), g.src_eid.data_ptr(),
-                  0 if o_dst is None else o_dst.data_ptr(), 0 if o_src is None else o_src.data_ptr(), n_dst, n_src, H, C,
-                  ctx.slope, ctx.is_double, alpha.data_ptr(), grad_out.data_ptr(), dlogit.data_ptr(), grad_feat.data_ptr(),
+        _lib.call("sdb_gat_backward_shared" if ctx.shared else "sdb_gat_backward_prefix", feat.data_ptr(), a_src.data_ptr(),
+                  a_dst.data_ptr(), g.rowptr.data_ptr(), g.col.data_ptr(), g.src_rowptr.data_ptr(), g.src_dst.data_ptr(),
+                  g.src_eid.data_ptr(), 0 if o_dst is None else o_dst.data_ptr(), 0 if o_src is None else o_src.data_ptr(), n_dst, n_src,
+                  H, C, ctx.slope, ctx.is_double, alpha.data_ptr(), grad_out.data_ptr(), dlogit.data_ptr(), grad_feat.data_ptr(),
                   grad_a_src.data_ptr(), grad_a_dst.data_ptr(), _st(feat))
         return grad_feat, grad_a_src, grad_a_dst, None, None
 
@@ -255,7 +263,7 @@ class GATConv(nn.Module):
         att = torch.stack([self.att_src[0], self.att_dst[0]], dim=-1)                          # (H, C, 2)
         proj = torch.einsum("hcf,hck->fhk", W, att).reshape(F_in, 2 * H)
         a = (x @ proj).view(N, H, 2)
-        z = _EdgeSoftmaxAggregate.apply(x.unsqueeze(1).expand(N, H, F_in), a[:, :, 0], a[:n_dst, :, 1], graph, self.negative_slope)
+        z = _EdgeSoftmaxAggregate.apply(x, a[:, :, 0], a[:n_dst, :, 1], graph, self.negative_slope)   # shared rows: (n_dst, H, F_in)
         return torch.einsum("nhf,hcf->nhc", z, W)                                              # (n_dst, H, C)
 
 

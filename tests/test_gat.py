@@ -339,3 +339,47 @@ def test_gatconv_aggregate_first_equals_transform_first(dtype, tol, concat, monk
     for a, b in zip(*res):
         scale = max(float(a.abs().max()), 1.0)
         assert float((a - b).abs().max()) <= tol * scale
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tiles", ["0", "1"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-12), (torch.float32, 2e-5)])
+@pytest.mark.parametrize("kind,n,H,C,n_dst", [("knn", 1203, 4, 512, 300), ("knn", 1203, 4, 2048, 200), ("knn", 500, 3, 24, None),
+                                              ("knn", 500, 2, 25, 123), ("random", 900, 4, 128, 400), ("hubs", 800, 4, 256, None),
+                                              ("hubs", 800, 1, 7, None), ("knn", 300, 5, 16, 100)])
+def test_gat_shared_feature_form_equals_the_expanded_features(tiles, dtype, tol, kind, n, H, C, n_dst):
+    """sdb_gat_forward_shared / sdb_gat_backward_shared (rows (n, C) read by every head, head sum of the feature gradient inside
+    the kernel) against the per-head kernels fed with the same row copied H times - in the tile and in the per-node form."""
+    import os
+    from spadot_b200 import gat
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(n + H + C + 1)
+    ei = _random_graph(kind, n, rng).to(dev)
+    g = gat.CsrGraph(ei, n, add_self_loops=(kind != "hubs"))
+    if n_dst is not None:
+        n_src = max(int(g.col[: int(g.rowptr[n_dst])].max()) + 1 if int(g.rowptr[n_dst]) else n_dst, n_dst)
+    else:
+        n_dst = n_src = n
+    torch.manual_seed(0)
+    x = torch.randn(n_src, C, dtype=dtype, device=dev)
+    a_s = torch.randn(n_src, H, dtype=dtype, device=dev)
+    a_d = torch.randn(n_dst, H, dtype=dtype, device=dev)
+    go = torch.randn(n_dst, H, C, dtype=dtype, device=dev)
+    res = []
+    os.environ["SDB_GAT_TILES"] = tiles
+    try:
+        for shared in (False, True):
+            xi, s, d = (t.clone().requires_grad_(True) for t in (x, a_s, a_d))
+            feat = xi if shared else xi.unsqueeze(1).expand(n_src, H, C)
+            out = gat._EdgeSoftmaxAggregate.apply(feat, s, d, g, 0.2)
+            out.backward(go)
+            torch.cuda.synchronize()
+            res.append(dict(out=out.detach(), grad_x=xi.grad, grad_a_src=s.grad, grad_a_dst=d.grad))
+    finally:
+        os.environ.pop("SDB_GAT_TILES", None)
+    assert res[1]["grad_x"].shape == (n_src, C)
+    for key in res[0]:
+        a, b = res[0][key], res[1][key]
+        assert torch.isfinite(b).all(), key
+        scale = max(float(a.abs().max()), 1.0)
+        assert float((a - b).abs().max()) <= tol * scale, (key, float((a - b).abs().max()), scale)
