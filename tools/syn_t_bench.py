@@ -25,6 +25,7 @@ def main(argv=None):
     ap.add_argument("--inducing", type=int, default=150)
     ap.add_argument("--batches", type=int, default=4)
     ap.add_argument("--name", default="SYN-T")
+    ap.add_argument("--top-kernels", type=int, default=0, help="print the N kernels with the most device time of one step to stderr")
     ap.add_argument("--host-profile", action="store_true", help="cProfile one more step and print the top host-side entries to stderr")
     a = ap.parse_args(argv)
     dev = torch.device("cuda:0")
@@ -96,6 +97,11 @@ def main(argv=None):
             else:
                 k = "elementwise / reductions / indexing (torch)"
             fam[k] = fam.get(k, 0.0) + float(t)
+        if a.top_kernels:
+            top = sorted(((float(getattr(ev, "device_time_total", None) or getattr(ev, "cuda_time_total", 0.0)), ev.count, ev.key)
+                          for ev in prof.key_averages()), reverse=True)[:a.top_kernels]
+            for t, cnt, name in top:
+                print(f"{t / 1e3:8.3f} ms  x{cnt:<4d} {name[:150]}", file=sys.stderr)
         tot = sum(fam.values())
         breakdown = {k: dict(ms=v / 1e3, share=v / tot) for k, v in sorted(fam.items(), key=lambda kv: -kv[1])}
     except Exception as exc:
