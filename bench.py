@@ -440,6 +440,22 @@ def gpu_main(a):
                 line["aux_train_epoch"] = train_epoch_bench.run(dev)
             except Exception as exc:       # the aux number must never take the headline down
                 line["aux_train_epoch"] = dict(error=repr(exc)[:200])
+            # BASELINE configs[2] ("SVGP+GAT training throughput" at 100k spots x 2000 SVGs): one timepoint of that shape, six
+            # optimiser steps on 512-seed 2-hop batches (tools/syn_t_bench.py); the reference cannot run this shape at all
+            try:
+                import statistics
+                import syn_t_bench
+                torch.cuda.empty_cache()
+                r = syn_t_bench.run(["--batches", "6"])
+                line["aux_syn_t_step"] = dict(workload=r["workload"], subgraph_nodes=r["subgraph_nodes"], subgraph_edges=r["subgraph_edges"],
+                                              train_step_ms_median=1e3 * statistics.median(r["step_times_s"]),
+                                              step_times_s=r["step_times_s"], seeds_per_s_median=512.0 / statistics.median(r["step_times_s"]),
+                                              graph_build_s=r["graph_build_s"], sample_batch_s=r["sample_batch_s"],
+                                              all_latent_samples_s=r["all_latent_samples_s"], peak_mem_gb=r["peak_mem_gb"],
+                                              device_time_ms={k: round(v["ms"], 3) for k, v in (r["step_breakdown_device_time"] or {}).items()
+                                                              if isinstance(v, dict)})
+            except Exception as exc:
+                line["aux_syn_t_step"] = dict(error=repr(exc)[:200])
         print(json.dumps(line))
     if world > 1:
         td.destroy_process_group()

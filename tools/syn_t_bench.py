@@ -16,7 +16,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from spadot_b200 import graph, model as product  # noqa: E402
 
 
-def main(argv=None):
+def run(argv=None):
+    """One measurement; returns the result dict (bench.py's aux_syn_t_step calls this with a short batch list)."""
     import argparse
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=100_000)
@@ -126,11 +127,15 @@ def main(argv=None):
     lat = net.all_latent_samples(loc, y, ei, "t")
     torch.cuda.synchronize()
     t_inf = time.perf_counter() - t0
-    print(json.dumps(dict(workload=f"{a.name} one timepoint: {n} spots x {genes} genes, z={z}, {m_ind} inducing, k=30, fp64",
+    return dict(workload=f"{a.name} one timepoint: {n} spots x {genes} genes, z={z}, {m_ind} inducing, k=30, fp64",
                           graph_build_s=t_graph, sample_batch_s=t_sample, subgraph_nodes=sub_nodes, subgraph_edges=sub_edges,
                           train_step_s=dt, step_times_s=[round(t, 4) for t in step_times], seeds_per_s=512 / dt, losses=losses, all_latent_samples_s=t_inf,
                           latent_shape=list(lat.shape), peak_mem_gb=torch.cuda.max_memory_allocated() / 1e9,
-                          step_breakdown_device_time=breakdown)))
+                          step_breakdown_device_time=breakdown)
+
+
+def main(argv=None):
+    print(json.dumps(run(argv)))
 
 
 if __name__ == "__main__":
