@@ -383,3 +383,59 @@ def test_gat_shared_feature_form_equals_the_expanded_features(tiles, dtype, tol,
         assert torch.isfinite(b).all(), key
         scale = max(float(a.abs().max()), 1.0)
         assert float((a - b).abs().max()) <= tol * scale, (key, float((a - b).abs().max()), scale)
+
+
+class _DenseAggregateStandIn:
+    """CPU stand-in for gat._EdgeSoftmaxAggregate (plain torch, autograd through it): softmax over each destination's incoming
+    edges of leaky_relu(a_src[j] + a_dst[i]), then the weighted sum of per-head (n,H,C) or shared (n,C) rows."""
+
+    @staticmethod
+    def apply(feat, a_src, a_dst, graph, slope):
+        n_src, n_dst, H = a_src.shape[0], a_dst.shape[0], a_src.shape[1]
+        E = int(graph.rowptr[n_dst])
+        src = graph.col[:E].long()
+        dst = torch.repeat_interleave(torch.arange(n_dst), (graph.rowptr[1:n_dst + 1] - graph.rowptr[:n_dst]))
+        logit = torch.nn.functional.leaky_relu(a_src[src] + a_dst[dst], slope)                       # (E, H)
+        mask = torch.zeros(n_dst, n_src, dtype=torch.bool)
+        mask[dst, src] = True
+        dense = torch.full((n_dst, n_src, H), float("-inf"), dtype=feat.dtype).index_put((dst, src), logit)
+        alpha = torch.softmax(dense, dim=1).masked_fill(~mask[:, :, None], 0.0)
+        rows = feat if feat.dim() == 3 else feat.unsqueeze(1).expand(n_src, H, feat.shape[-1])
+        return torch.einsum("inh,nhc->ihc", alpha, rows)
+
+
+@pytest.mark.parametrize("concat", [True, False])
+def test_gatconv_host_logic_aggregate_first_on_cpu(concat, monkeypatch):
+    """The host side of GATConv without the CUDA kernels: with a dense torch stand-in for the aggregation, the aggregate-first
+    form (projected attention vectors, shared rows, per-head linear map afterwards) equals the transform-first form in output and
+    in every gradient, and the rule that picks it looks at destinations / sources and at the GEMM size."""
+    from spadot_b200 import gat
+    monkeypatch.setattr(gat, "_EdgeSoftmaxAggregate", _DenseAggregateStandIn)
+    rng = np.random.default_rng(2)
+    n, n_dst, f_in, C, H = 90, 30, 11, 6, 3
+    coords = rng.uniform(0, 10, size=(n, 2))
+    g = gat.CsrGraph(torch.from_numpy(graph_ref.spatial_edge_index(coords, 5)), n, add_self_loops=True)
+    n_src = max(int(g.col[: int(g.rowptr[n_dst])].max()) + 1, n_dst)
+    assert 2 * n_dst <= n_src
+    torch.manual_seed(3)
+    conv = gat.GATConv(f_in, C, heads=H, concat=concat).double()
+    with torch.no_grad():
+        conv.bias.normal_()
+    x = torch.randn(n_src, f_in, dtype=torch.float64)
+    w = torch.randn(n_dst, H * C if concat else C, dtype=torch.float64)
+    res, used = [], []
+    real = gat.GATConv._aggregate_first
+    monkeypatch.setattr(gat.GATConv, "_aggregate_first", lambda self, *a: (used.append(True), real(self, *a))[1])
+    for min_flops in (float("inf"), 0.0):
+        monkeypatch.setattr(gat, "AGGREGATE_FIRST_MIN_FLOPS", min_flops)
+        conv.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        out = conv(xi, g, n_dst=n_dst)
+        (out * w).sum().backward()
+        res.append([out.detach(), xi.grad] + [p.grad.clone() for p in conv.parameters()])
+    assert used == [True]                                   # only the second run took the exchanged form
+    for a, b in zip(*res):
+        assert float((a - b).abs().max()) <= 1e-12 * max(1.0, float(a.abs().max()))
+    used.clear()
+    conv(torch.randn(n, f_in, dtype=torch.float64), g)       # a full layer (as many destinations as sources): never exchanged
+    assert used == []
