@@ -424,7 +424,7 @@ __device__ bool gat_tile_edges(S& sm, const int64_t* __restrict__ ptr, const int
 template <typename T, int W, typename S>
 __device__ __forceinline__ void gat_tile_aggregate(const S& sm, const T* __restrict__ rows, T* __restrict__ out, int U, int H, int C) {
     const int HC = H * C;
-    for (int c = threadIdx.x * W; c < HC; c += GT_THREADS * W) {
+    for (int c = (blockIdx.y * GT_THREADS + threadIdx.x) * W; c < HC; c += gridDim.y * GT_THREADS * W) {
         const int h = c / C;
         T acc[GT_TD][W];
 #pragma unroll
@@ -466,7 +466,7 @@ __device__ __forceinline__ void gat_tile_aggregate_shared_fwd(const S& sm, const
     constexpr int VW = Vec<T>::W;
     const int tpg = GT_THREADS / H;
     const int h = threadIdx.x / tpg, j = threadIdx.x - h * tpg;
-    for (int c = j * W; c < C; c += tpg * W) {
+    for (int c = (blockIdx.y * tpg + j) * W; c < C; c += gridDim.y * tpg * W) {
         T acc[GT_TD][W];
 #pragma unroll
         for (int t = 0; t < GT_TD; ++t)
@@ -502,7 +502,7 @@ __device__ __forceinline__ void gat_tile_aggregate_shared_bsrc(const S& sm, cons
                                                                int C) {
     constexpr int VW = Vec<T>::W;
     const int HC = H * C;
-    for (int c = threadIdx.x * W; c < C; c += GT_THREADS * W) {
+    for (int c = (blockIdx.y * GT_THREADS + threadIdx.x) * W; c < C; c += gridDim.y * GT_THREADS * W) {
         T acc[GT_TD][W];
 #pragma unroll
         for (int t = 0; t < GT_TD; ++t)
@@ -670,7 +670,10 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* _
     const int j = tid - hl * tph;
     const int n_sl = H * NS;
     __syncthreads();                      // e_loc
+    // gridDim.y > 1 (few tiles, hps == 1): CTA y takes the heads h with h % gridDim.y == y - their slices here, their
+    // softmax backward below
     for (int h0 = 0; h0 < n_sl; h0 += hps) {
+        if (gridDim.y > 1 && (h0 / NS) % (int)gridDim.y != (int)blockIdx.y) continue;
         const int sl = h0 + hl;
         const bool live = sl < n_sl;      // uniform per warp (tph is a multiple of 32)
         const int c0 = live ? (sl / NS) * C + (sl % NS) * Cs + j * W : j * W, c1 = c0 + (Cs >> 1);
@@ -747,7 +750,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gat_tile_bdst_kernel(const T* _
     // softmax backward per (member, head): dlogit = alpha (d alpha - sum alpha d alpha), through the LeakyReLU
     {   // eight lanes per (member, head): all segments of the tile side by side
         const int seg = tid >> 3, gl = tid & 7;
-        const bool on = seg < GT_TD * H;
+        const bool on = seg < GT_TD * H && (gridDim.y == 1 || (seg % H) % (int)gridDim.y == (int)blockIdx.y);
         const int m = on ? seg / H : 0, h = on ? seg - m * H : 0;
         const int64_t node = on ? sm.node[m] : -1;
         const int s0 = node >= 0 ? sm.off[m] : 0, s1 = node >= 0 ? sm.off[m + 1] : 0;
@@ -788,24 +791,32 @@ static bool gat_bdst_tile_shape(int C) {
     return tph == 32 || tph == 64 || tph == 128 || tph == 256;
 }
 
+// Few tiles (a prefix layer with 512 destinations is 64 tiles on 148 SMs): the column sweeps of a tile are dealt over
+// gridDim.y CTAs, each of which repeats the tile's (cheap) phase A; `sweeps` = column sweeps one CTA would otherwise do.
+static int gat_column_splits(int64_t n, int sweeps) {
+    const int64_t tiles = (n + GT_TD - 1) / GT_TD;
+    const int64_t want = (4 * 148 + tiles - 1) / tiles;
+    return (int)max((int64_t)1, min((int64_t)sweeps, min(want, (int64_t)16)));
+}
+
 template <typename T, int MODE, bool SH, typename... Args>
-static int gat_launch_agg(int64_t n, cudaStream_t st, Args... args) {
+static int gat_launch_agg(int64_t n, int ny, cudaStream_t st, Args... args) {
     static size_t memo[SDB_MAX_DEVICES];
     using S = GatTile<T, GT_HMAX, GT_UMAX>;
     auto kern = gat_tile_agg_kernel<T, MODE, SH>;
     cudaError_t e = sdb_ensure_smem(kern, sizeof(S), memo);
     if (e != cudaSuccess) return (int)e;
-    kern<<<(unsigned)((n + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(args...);
+    kern<<<dim3((unsigned)((n + GT_TD - 1) / GT_TD), (unsigned)ny), GT_THREADS, sizeof(S), st>>>(args...);
     SDB_LAUNCH_STATUS();
 }
 template <typename T, bool SH, typename... Args>
-static int gat_launch_bdst(int64_t n, cudaStream_t st, Args... args) {
+static int gat_launch_bdst(int64_t n, int ny, cudaStream_t st, Args... args) {
     static size_t memo[SDB_MAX_DEVICES];
     using S = GatTile<T, GT_THREADS / 32, GT_UCHUNK>;
     auto kern = gat_tile_bdst_kernel<T, SH>;
     cudaError_t e = sdb_ensure_smem(kern, sizeof(S), memo);
     if (e != cudaSuccess) return (int)e;
-    kern<<<(unsigned)((n + GT_TD - 1) / GT_TD), GT_THREADS, sizeof(S), st>>>(args...);
+    kern<<<dim3((unsigned)((n + GT_TD - 1) / GT_TD), (unsigned)ny), GT_THREADS, sizeof(S), st>>>(args...);
     SDB_LAUNCH_STATUS();
 }
 
@@ -814,7 +825,9 @@ template <typename T, bool SH>
 int gat_forward_t(const void* feat, const void* a_src, const void* a_dst, const int64_t* rowptr, const int32_t* col,
                   const int32_t* order, int64_t n, int H, int C, double slope, void* out, void* alpha, cudaStream_t st) {
     if (gat_use_tiles(H, order) && (!SH || GT_THREADS % H == 0))
-        return gat_launch_agg<T, 0, SH>(n, st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, (const int32_t*)nullptr,
+        return gat_launch_agg<T, 0, SH>(n, gat_column_splits(n, SH ? (C * H + GT_THREADS * (int)Vec<T>::W - 1) / (GT_THREADS * (int)Vec<T>::W)
+                                                                      : (H * C + GT_THREADS * (int)Vec<T>::W - 1) / (GT_THREADS * (int)Vec<T>::W)),
+                                        st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, (const int32_t*)nullptr,
                                         (const int64_t*)nullptr, order, n, H, C, (T)slope, (T*)alpha, (const T*)nullptr, (T*)out,
                                         (T*)nullptr);
     gat_fwd_kernel<T, SH><<<(unsigned)n, 128, 0, st>>>((const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order, n, H, C,
@@ -830,7 +843,14 @@ int gat_backward_t(const void* feat, const void* a_src, const void* a_dst, const
                    const void* grad_out, void* dlogit, void* grad_feat, void* grad_a_src, void* grad_a_dst, cudaStream_t st) {
     cudaError_t e;
     if (gat_use_tiles(H, order_dst) && gat_bdst_tile_shape<T>(C)) {
-        const int rc = gat_launch_bdst<T, SH>(n_dst, st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst, n_dst,
+        // heads over gridDim.y only when one slice fills the CTA (threads per head >= GT_THREADS) and H splits evenly
+        const int tph = C / (2 * (int)Vec<T>::W);
+        int ny = 1;
+        if (tph >= GT_THREADS) {
+            ny = gat_column_splits(n_dst, H);
+            while (H % ny) --ny;
+        }
+        const int rc = gat_launch_bdst<T, SH>(n_dst, ny, st, (const T*)feat, (const T*)a_src, (const T*)a_dst, rowptr, col, order_dst, n_dst,
                                               H, C, (T)slope, (const T*)alpha, (const T*)grad_out, (T*)dlogit, (T*)grad_a_dst);
         if (rc) return rc;
     } else {
@@ -841,7 +861,8 @@ int gat_backward_t(const void* feat, const void* a_src, const void* a_dst, const
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (gat_use_tiles(H, order_src))
-        return gat_launch_agg<T, 1, SH>(n_src, st, (const T*)grad_out, (const T*)nullptr, (const T*)nullptr, src_rowptr, src_dst, src_eid,
+        return gat_launch_agg<T, 1, SH>(n_src, gat_column_splits(n_src, ((SH ? C : H * C) + GT_THREADS * (int)Vec<T>::W - 1) / (GT_THREADS * (int)Vec<T>::W)),
+                                        st, (const T*)grad_out, (const T*)nullptr, (const T*)nullptr, src_rowptr, src_dst, src_eid,
                                         rowptr + n_dst, order_src, n_src, H, C, (T)slope, const_cast<T*>((const T*)alpha),
                                         (const T*)dlogit, (T*)grad_feat, (T*)grad_a_src);
     gat_bwd_src_kernel<T, SH><<<(unsigned)n_src, 128, 0, st>>>(src_rowptr, src_dst, src_eid, order_src, rowptr + n_dst, H, C,
