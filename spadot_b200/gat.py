@@ -42,6 +42,7 @@ class CsrGraph:
         self.src_rowptr[1:] = torch.cumsum(torch.bincount(self.col.long(), minlength=num_nodes), 0)
         self.order = None
         self._closures, self._orders = {}, {}
+        self._base_tensors = (self.col, self.rowptr, self.src_eid, self.src_dst, self.src_rowptr)
         if num_nodes >= self.REORDER_MIN_NODES and pos is not None:
             # locality order for the CTAs from the spots' coordinates: a Z-curve sort on the device (tens of microseconds;
             # the sampled sub-graph of every training batch is a new graph, so this runs once per optimiser step)
@@ -54,6 +55,12 @@ class CsrGraph:
             A = sp.csr_matrix((np.ones(s_np.size, dtype=np.int8), (s_np, d_np)), shape=(num_nodes, num_nodes))
             perm = reverse_cuthill_mckee((A + A.T).tocsr(), symmetric_mode=True)
             self.order = torch.from_numpy(np.ascontiguousarray(perm).astype(np.int32)).to(edge_index.device)
+
+
+def _graph_nbytes(self):
+    """Device bytes held by the graph (CSR both ways, CTA order, cached prefix data)."""
+    extra = [t for t in (self.order, getattr(self, "_col_cummax", None)) if t is not None] + list(self._orders.values())
+    return int(sum(t.numel() * t.element_size() for t in list(self._base_tensors) + [t for t in extra if t is not None]))
 
 
 def _graph_prefix_plan(self, n_out, n_layers):
@@ -90,6 +97,7 @@ def _graph_order_prefix(self, p):
 
 
 CsrGraph.prefix_plan = _graph_prefix_plan
+CsrGraph.nbytes = _graph_nbytes
 CsrGraph.order_prefix = _graph_order_prefix
 
 
@@ -283,8 +291,11 @@ class GATEncoder(nn.Module):
         runs on the rows the next one reads and no others: same values for those rows, less work (at SYN-T's 512-seed
         batches the third layer's GEMMs shrink from 40.7k to 16.4k rows and its aggregation from 40.7k to 512)."""
         N = x.shape[0]
+        if isinstance(edge_index, CsrGraph) and edge_index.n != N:
+            raise ValueError(f"CsrGraph of {edge_index.n} nodes for {N} feature rows")
         if n_out is not None and 0 < int(n_out) < N and x.is_cuda:
-            graph = graph_for(edge_index, N, True, pos)
+            # a prebuilt CsrGraph (graph.TwoHopBatches keeps one per mini-batch across epochs) carries its CTA order and prefix plans
+            graph = edge_index if isinstance(edge_index, CsrGraph) else graph_for(edge_index, N, True, pos)
             (d1, s1), (d2, s2), (d3, s3) = graph.prefix_plan(int(n_out), 3)
             h = F.leaky_relu(self.gat1(x[:s1], graph, n_dst=d1))
             h = F.leaky_relu(self.gat2(h[:s2], graph, n_dst=d2))

@@ -120,3 +120,48 @@ def two_hop_batches(edge_index, num_nodes, batch_size=512, num_hops=2):
         lei = torch.stack([local[s[keep]], local[t[keep]]])
         local[nodes] = -1
         yield nodes, lei, int(seeds.numel())
+
+
+class TwoHopBatches:
+    """The mini-batches of one timepoint as (node_ids, gat.CsrGraph of the induced sub-graph, n_seeds), sampled ONCE and kept.
+
+    The reference builds its NeighborLoader without shuffling over a static graph (utils/_train_utils.py:80-85), so every
+    epoch walks the same sequence of seed blocks and - with the fan-out above every in-degree - the same sub-graphs; PyG
+    re-samples them anyway.  Here the first pass through the loader samples each batch (two_hop_batches) and prepares its graph
+    for the GAT kernels (CSR by destination and by source, the Z-curve CTA order from `pos`, later the prefix plans the encoder
+    asks for); from the second epoch on a step starts with everything in place.  Batches are kept while they fit `max_cache_bytes`
+    of device memory (SYN-T: ~35 MB per 40k-node batch), otherwise every epoch re-samples like the reference.
+    `spadot_b200.gat.GATEncoder` / `GATConv` take the CsrGraph wherever they take an edge_index."""
+
+    def __init__(self, edge_index, num_nodes, batch_size=512, num_hops=2, pos=None, max_cache_bytes=8 << 30):
+        self.edge_index, self.num_nodes, self.batch_size, self.num_hops = edge_index, int(num_nodes), int(batch_size), int(num_hops)
+        self.pos = None if pos is None else torch.as_tensor(pos, device=edge_index.device)
+        self.max_cache_bytes = int(max_cache_bytes)
+        self.cached_bytes = 0
+        self._cache = None
+
+    def __len__(self):
+        return -(-self.num_nodes // self.batch_size)
+
+    @property
+    def cached(self):
+        return self._cache is not None
+
+    def __iter__(self):
+        if self._cache is not None:
+            yield from self._cache
+            return
+        from . import gat
+        kept, nbytes = [], 0
+        for nodes, lei, ns in two_hop_batches(self.edge_index, self.num_nodes, self.batch_size, self.num_hops):
+            g = gat.CsrGraph(lei, int(nodes.numel()), True, None if self.pos is None else self.pos[nodes])
+            item = (nodes, g, ns)
+            if kept is not None:
+                nbytes += nodes.numel() * nodes.element_size() + g.nbytes()
+                if nbytes > self.max_cache_bytes:
+                    kept = None                      # does not fit: stream this and every later epoch
+                else:
+                    kept.append(item)
+            yield item
+        if kept is not None:                         # only a COMPLETE pass becomes the cache
+            self._cache, self.cached_bytes = kept, nbytes

@@ -439,3 +439,52 @@ def test_gatconv_host_logic_aggregate_first_on_cpu(concat, monkeypatch):
     used.clear()
     conv(torch.randn(n, f_in, dtype=torch.float64), g)       # a full layer (as many destinations as sources): never exchanged
     assert used == []
+
+
+def test_two_hop_batches_loader_samples_once_and_keeps_the_graphs():
+    """graph.TwoHopBatches: same node sets and induced edges as two_hop_batches, a prepared CsrGraph per batch, the very same
+    objects on the second epoch; an interrupted first pass or a budget that is too small leaves nothing cached."""
+    from spadot_b200 import gat, graph
+    rng = np.random.default_rng(8)
+    n = 700
+    coords = rng.uniform(0, 40, size=(n, 2))
+    ei = torch.as_tensor(np.asarray(graph_ref.spatial_edge_index(coords, 6)), dtype=torch.long)
+    plain = list(graph.two_hop_batches(ei, n, batch_size=128))
+    loader = graph.TwoHopBatches(ei, n, batch_size=128, pos=torch.from_numpy(coords))
+    assert len(loader) == len(plain) == 6 and not loader.cached
+    first = list(loader)
+    assert loader.cached and loader.cached_bytes > 0
+    for (nodes_a, lei, ns_a), (nodes_b, g, ns_b) in zip(plain, first):
+        assert ns_a == ns_b and torch.equal(nodes_a, nodes_b) and isinstance(g, gat.CsrGraph) and g.n == nodes_a.numel()
+        # the CSR holds the induced edges plus one self loop per node (existing self loops replaced)
+        src, dst = lei[0], lei[1]
+        keep = src != dst
+        want = set(zip(src[keep].tolist(), dst[keep].tolist())) | {(i, i) for i in range(g.n)}
+        dst_of_edge = torch.repeat_interleave(torch.arange(g.n), g.rowptr[1:] - g.rowptr[:-1])
+        assert set(zip(g.col.tolist(), dst_of_edge.tolist())) == want
+    second = list(loader)
+    assert all(a[1] is b[1] and a[0] is b[0] for a, b in zip(first, second))          # nothing re-sampled, nothing rebuilt
+    partial = graph.TwoHopBatches(ei, n, batch_size=128)
+    next(iter(partial))
+    assert not partial.cached
+    small = graph.TwoHopBatches(ei, n, batch_size=128, max_cache_bytes=1000)
+    assert len(list(small)) == 6 and not small.cached and len(list(small)) == 6
+
+
+def test_gat_encoder_takes_a_prebuilt_graph_on_cpu(monkeypatch):
+    """GATEncoder / GATConv accept a gat.CsrGraph wherever they accept an edge_index (what graph.TwoHopBatches hands out); with
+    the dense stand-in for the kernels the two calls agree, and a graph of the wrong size is refused."""
+    from spadot_b200 import gat
+    monkeypatch.setattr(gat, "_EdgeSoftmaxAggregate", _DenseAggregateStandIn)
+    rng = np.random.default_rng(4)
+    n = 80
+    ei = torch.from_numpy(graph_ref.spatial_edge_index(rng.uniform(0, 10, size=(n, 2)), 5))
+    torch.manual_seed(9)
+    enc = gat.GATEncoder(13, 4, hidden_dim=8, num_heads=2).double()
+    x = torch.randn(n, 13, dtype=torch.float64)
+    mu_a, var_a = enc(x, ei)
+    mu_b, var_b = enc(x, gat.CsrGraph(ei, n, add_self_loops=True))
+    np.testing.assert_allclose(mu_b.detach().numpy(), mu_a.detach().numpy(), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(var_b.detach().numpy(), var_a.detach().numpy(), rtol=1e-12, atol=1e-14)
+    with pytest.raises(ValueError):
+        enc(x[:50], gat.CsrGraph(ei, n, add_self_loops=True))
