@@ -488,3 +488,37 @@ def test_gat_encoder_takes_a_prebuilt_graph_on_cpu(monkeypatch):
     np.testing.assert_allclose(var_b.detach().numpy(), var_a.detach().numpy(), rtol=1e-12, atol=1e-14)
     with pytest.raises(ValueError):
         enc(x[:50], gat.CsrGraph(ei, n, add_self_loops=True))
+
+
+@pytest.mark.gpu
+def test_loader_batches_with_prebuilt_graphs_train_like_plain_batches():
+    """graph.TwoHopBatches on the device: the encoder fed with a kept (nodes, CsrGraph, n_seeds) batch returns what it returns for
+    the plain (nodes, edge_index, n_seeds) batch, forward and parameter gradients, on the first and on the second epoch."""
+    from spadot_b200 import gat, graph
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(21)
+    n_all = 3000
+    coords = torch.from_numpy(rng.uniform(0, 60, size=(n_all, 2))).to(dev)
+    ei_all = graph.spatial_edge_index(coords.cpu().numpy(), 8, device=dev)
+    loader = graph.TwoHopBatches(ei_all, n_all, batch_size=256, pos=coords)
+    plain = list(graph.two_hop_batches(ei_all, n_all, batch_size=256))
+    torch.manual_seed(2)
+    enc = gat.GATEncoder(20, 4, hidden_dim=16, num_heads=4).double().to(dev)
+    feats = torch.randn(n_all, 20, dtype=torch.float64, device=dev)
+
+    def run(x, g, ns):
+        enc.zero_grad()
+        mu, var = enc(x, g, pos=None, n_out=ns)
+        ((mu ** 2).sum() + var.sum()).backward()
+        return mu.detach().clone(), [p.grad.clone() for p in enc.parameters()]
+
+    for epoch in range(2):
+        for (nodes_a, lei, ns_a), (nodes_b, g, ns_b) in zip(plain[:3], loader):
+            assert torch.equal(nodes_a, nodes_b) and ns_a == ns_b
+            mu_a, ga = run(feats[nodes_a], lei, ns_a)
+            mu_b, gb = run(feats[nodes_b], g, ns_b)
+            np.testing.assert_allclose(mu_b.cpu().numpy(), mu_a.cpu().numpy(), rtol=1e-11, atol=1e-13)
+            for a, b in zip(ga, gb):
+                assert float((a - b).abs().max()) <= 1e-11 * (float(a.abs().max()) + 1e-30)
+    assert not loader.cached                  # both epochs were cut short after three batches: nothing is kept
+    assert len(list(loader)) == len(plain) and loader.cached
