@@ -238,6 +238,20 @@ if __name__ == "__main__" and "--graph-only" in sys.argv:
     sys.exit(0)
 
 
+def sweep_cases(ref):
+    """BASELINE configs[4], the corners of the epsilon / unbalance sweep (eps 0.01-0.1, lambda 1-50), at a size the
+    reference solves in seconds: pins the oracle where the exponent scale 1/eps is largest and where the near-balanced
+    problem needs thousands of iterations."""
+    for tag, eps, l1, l2, seed in (("e001_l1_1", 0.01, 1.0, 1.0, 31), ("e001_l1_50", 0.01, 1.0, 50.0, 32), ("e01_l50_50", 0.1, 50.0, 50.0, 33)):
+        ot_case(ref, f"ot_sweep_{tag}_120x100_d32", 120, 100, 32, seed, dict(CFG, lambda1=l1, lambda2=l2, epsilon=eps), full_plan=False)
+
+
+if __name__ == "__main__" and "--sweep-only" in sys.argv:
+    assert reference_loader.available(), "reference not mounted"
+    sweep_cases(reference_loader.load_ot_solvers())
+    sys.exit(0)
+
+
 if __name__ == "__main__" and "--model-only" in sys.argv:
     model_case()
 
@@ -251,6 +265,7 @@ if __name__ == "__main__" and "--model-only" not in sys.argv:
     ot_case(ref, "ot_medium_300x411_d20", 300, 411, 20, 1993, CFG, full_plan=False)
     wot_cfg = dict(CFG, lambda1=1.0, lambda2=50.0, epsilon=0.02)
     ot_case(ref, "ot_wotcfg_130x97_d32", 130, 97, 32, 13, wot_cfg, full_plan=False)
+    sweep_cases(ref)
     svgp_case(reference_loader.load_svgp())
     model_case()
     graph_case("graph_visium_747", 747, 21, "visium")
